@@ -1,0 +1,80 @@
+// Shared host/device descriptors of libc3cuda.
+#pragma once
+#include <cstdint>
+
+namespace c3 {
+
+// One child edge of an internal node, as seen by the pruning kernels.
+//   src : the child's rows.  Internal child: its partial likelihoods
+//         [rows][K][MP].  Tip child: the pre-multiplied table
+//         tip_inner[u][b][:] = P_b . indicator_u  (numpy.inner(tip rows, psub),
+//         evolve/likelihood_calculation.py:86 applied to a tip), written by the
+//         expm kernels.
+//   idx : LikelihoodTreeEdge.indexes[c] narrowed to int32 [parent rows].
+//   P   : P[b][i][j] of the edge for an internal child, nullptr when src is
+//         already multiplied by P (tips).
+struct ChildRef {
+  const double* src;
+  const int32_t* idx;
+  const double* P;
+  int64_t src_rows;
+};
+
+struct NodeDesc {
+  double* out;       // [rows][K][MP]
+  int64_t n_rows;    // P+1
+  int32_t child_begin;
+  int32_t n_children;
+  int32_t fixed_motif;  // -1: none (PartialLikelihoodProductDefnFixedMotif)
+  int32_t is_root;
+};
+
+// per edge (node with a branch above it)
+struct EdgeDesc {
+  double* P;                // [K][MP][MP]
+  const double* tip_table;  // [tip_rows][MP] indicator rows, nullptr for internal
+  double* tip_inner;        // [tip_rows][K][MP]
+  int64_t tip_rows;
+};
+
+enum ExpmMode : int32_t {
+  EXPM_EIGEN_REAL = 0,
+  EXPM_EIGEN_COMPLEX = 1,
+  EXPM_PADE = 2,
+  EXPM_FIXED = 3,  // P supplied by the host; only the tip table is refreshed
+};
+
+struct ExpmJob {
+  int32_t node;
+  int32_t bin;
+  int32_t slot;
+  int32_t mode;
+  double t;
+};
+
+struct PruneArgs {
+  const NodeDesc* nodes;
+  const ChildRef* childs;
+  const int32_t* work_node;    // dirty nodes of this level
+  const int32_t* tile_prefix;  // [n_work+1] first tile of each work item
+  int32_t n_work;
+  int32_t total_tiles;
+  int32_t K;
+  int32_t M;
+  const double* pi;  // root only: [MP] (zero padded)
+  double* lh_out;    // root only: [rows][K]
+};
+
+constexpr int PRUNE4_THREADS = 256;
+constexpr int PRUNE4_UNROLL = 1;
+#ifndef PRUNE4_MIN_BLOCKS
+#define PRUNE4_MIN_BLOCKS 4
+#endif
+constexpr int DMMA_THREADS = 256;
+constexpr int DMMA_TILE_ROWS = 64;
+constexpr int REDUCE_THREADS = 256;
+constexpr int REDUCE_ROWS_PER_TILE = 1024;
+
+inline int prune4_rows_per_tile(int K) { return (PRUNE4_THREADS / K) * PRUNE4_UNROLL; }
+
+}  // namespace c3

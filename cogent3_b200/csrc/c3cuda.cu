@@ -1,0 +1,991 @@
+// libc3cuda: host side of the engine + the C ABI declared in include/c3cuda.h.
+//
+// One c3_engine holds, resident in HBM for the life of a likelihood function:
+//   * the pattern tables of every node (int32 gather indexes, tip indicator rows),
+//   * the partial likelihoods of every internal node, FP64, [row][bin][MP],
+//   * every P[edge][bin] and the pre-multiplied tip tables,
+//   * the eigen-systems / rate matrices ("q slots") the P's are derived from.
+// An evaluation uploads ONE small parameter block (dirty expm jobs, per-level dirty
+// node lists, pi, bin probs), then launches: batched expm -> one pruning kernel per
+// dirty tree level -> the site-weighted reduction, and reads one double back.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/c3cuda.h"
+#include "c3_types.cuh"
+#include "expm_kernels.cuh"
+#include "prune_kernels.cuh"
+
+using namespace c3;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define C3_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t err__ = (call);                                                            \
+    if (err__ != cudaSuccess) {                                                            \
+      const int code__ = (err__ == cudaErrorMemoryAllocation) ? C3_ERR_MEMORY : C3_ERR_CUDA; \
+      return fail(code__, std::string(#call) + ": " + cudaGetErrorString(err__));          \
+    }                                                                                      \
+  } while (0)
+
+#define C3_REQUIRE(cond, msg)                              \
+  do {                                                     \
+    if (!(cond)) return fail(C3_ERR_INVALID, (msg));       \
+  } while (0)
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct Slot {
+  int mode = -1;  // ExpmMode or -1 (unset)
+  std::vector<double> data;
+  bool dirty = false;
+};
+
+}  // namespace
+
+struct c3_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int n_sm = 148;
+
+  int n_nodes = 0, M = 0, MP = 0, K = 0, root = 0, n_levels = 0;
+  bool use_dmma = false;
+  std::vector<std::vector<int>> children;
+  std::vector<int> parent, level, child_begin;
+  std::vector<std::vector<int>> level_nodes;  // internal nodes per level
+
+  // host copies of the pattern tables until finalize
+  std::vector<int64_t> n_rows;
+  std::vector<std::vector<double>> tip_table;
+  std::vector<std::vector<int32_t>> idx32;
+  std::vector<double> counts;
+  bool finalized = false;
+
+  // device memory
+  char* d_pool = nullptr;  // everything sized at finalize
+  int64_t pool_bytes = 0, partial_bytes = 0;
+  std::vector<double*> d_rows;      // per node: partials (internal) / tip_inner (tips)
+  std::vector<double*> d_tip_table;
+  std::vector<int32_t*> d_idx;
+  double* d_P = nullptr;
+  NodeDesc* d_nodes = nullptr;
+  ChildRef* d_childs = nullptr;
+  EdgeDesc* d_edges = nullptr;
+  double* d_counts = nullptr;
+  double* d_lh = nullptr;
+  double* d_tile_sums = nullptr;
+  unsigned int* d_counter = nullptr;
+  double* d_lnl = nullptr;
+  std::vector<NodeDesc> h_nodes;
+  bool nodes_dirty = false;
+
+  double* d_slots = nullptr;
+  int64_t slot_stride = 0;
+  int n_slots_alloc = 0;
+  std::vector<Slot> slots;
+
+  // per-evaluation parameter block
+  char* h_block = nullptr;  // pinned
+  char* d_block = nullptr;
+  int64_t block_bytes = 0;
+  int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0;
+  cudaEvent_t block_copied = nullptr;
+  double* h_lnl = nullptr;  // mapped pinned result
+  double* h_lnl_dev = nullptr;
+
+  // model state (host)
+  std::vector<int32_t> qslot;       // [n_nodes*K]
+  std::vector<double> dist;         // [n_nodes*K]
+  std::vector<char> pdirty;         // [n_nodes*K] P must be recomputed
+  std::vector<char> pfixed;         // [n_nodes*K] P supplied by host
+  std::vector<char> node_dirty;     // [n_nodes]
+  std::vector<double> pi, bprobs;
+  std::vector<int32_t> fixed_motif;
+  bool reduce_dirty = true;
+  bool have_pi = false, have_dist = false;
+  double cached_lnl = NAN;
+  bool have_cached = false;
+
+  c3_stats stats{};
+};
+
+namespace {
+
+template <typename Kern>
+int set_max_smem(Kern kern, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+  }
+  return C3_OK;
+}
+
+template <int MP>
+int launch_dmma(c3_engine* e, const PruneArgs& a, bool is_root, int grid) {
+  const size_t smem = DmmaCfg<MP>::SMEM_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_max_smem(prune_dmma_kernel<MP, false>, smem);
+    if (rc) return rc;
+    rc = set_max_smem(prune_dmma_kernel<MP, true>, smem);
+    if (rc) return rc;
+    configured = true;
+  }
+  if (is_root)
+    prune_dmma_kernel<MP, true><<<grid, DMMA_THREADS, smem, e->stream>>>(a);
+  else
+    prune_dmma_kernel<MP, false><<<grid, DMMA_THREADS, smem, e->stream>>>(a);
+  return C3_OK;
+}
+
+int dmma_blocks_per_sm(int MP) {
+  const size_t smem = (size_t)(DMMA_TILE_ROWS * (MP + 4) + 2 * MP * (MP + 4)) * sizeof(double);
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  return std::max(1, std::min(per_sm, 2048 / DMMA_THREADS));
+}
+
+int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root) {
+  if (a.total_tiles <= 0) return C3_OK;
+  if (!e->use_dmma) {
+    const int grid = std::min(a.total_tiles, e->n_sm * 32);
+#define C3_P4(KT)                                                                    \
+  do {                                                                               \
+    if (is_root)                                                                     \
+      prune4_kernel<KT, true><<<grid, PRUNE4_THREADS, 0, e->stream>>>(a);            \
+    else                                                                             \
+      prune4_kernel<KT, false><<<grid, PRUNE4_THREADS, 0, e->stream>>>(a);           \
+  } while (0)
+    switch (e->K) {
+      case 1: C3_P4(1); break;
+      case 2: C3_P4(2); break;
+      case 4: C3_P4(4); break;
+      default: C3_P4(0); break;
+    }
+#undef C3_P4
+  } else {
+    const int grid = std::min(a.total_tiles, e->n_sm * dmma_blocks_per_sm(e->MP));
+    int rc = C3_OK;
+    switch (e->MP) {
+      case 8: rc = launch_dmma<8>(e, a, is_root, grid); break;
+      case 16: rc = launch_dmma<16>(e, a, is_root, grid); break;
+      case 24: rc = launch_dmma<24>(e, a, is_root, grid); break;
+      case 32: rc = launch_dmma<32>(e, a, is_root, grid); break;
+      case 40: rc = launch_dmma<40>(e, a, is_root, grid); break;
+      case 48: rc = launch_dmma<48>(e, a, is_root, grid); break;
+      case 56: rc = launch_dmma<56>(e, a, is_root, grid); break;
+      case 64: rc = launch_dmma<64>(e, a, is_root, grid); break;
+      default: return fail(C3_ERR_INVALID, "unsupported padded state count");
+    }
+    if (rc) return rc;
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("prune launch: ") + cudaGetErrorString(err));
+  return C3_OK;
+}
+
+int64_t tiles_of_node(const c3_engine* e, int n) {
+  if (!e->use_dmma) {
+    const int rpt = prune4_rows_per_tile(e->K);
+    return (e->n_rows[n] + rpt - 1) / rpt;
+  }
+  return (int64_t)e->K * ((e->n_rows[n] + DMMA_TILE_ROWS - 1) / DMMA_TILE_ROWS);
+}
+
+int ensure_slots(c3_engine* e, int n) {
+  if ((int)e->slots.size() < n) e->slots.resize(n);
+  if (n <= e->n_slots_alloc) return C3_OK;
+  const int new_n = std::max(n, std::max(4, 2 * e->n_slots_alloc));
+  double* fresh = nullptr;
+  C3_CUDA(cudaMalloc(&fresh, (size_t)new_n * e->slot_stride * sizeof(double)));
+  if (e->d_slots) {
+    C3_CUDA(cudaStreamSynchronize(e->stream));
+    C3_CUDA(cudaMemcpy(fresh, e->d_slots, (size_t)e->n_slots_alloc * e->slot_stride * sizeof(double),
+                       cudaMemcpyDeviceToDevice));
+    C3_CUDA(cudaFree(e->d_slots));
+  }
+  e->stats.device_bytes += (int64_t)(new_n - e->n_slots_alloc) * e->slot_stride * sizeof(double);
+  e->d_slots = fresh;
+  e->n_slots_alloc = new_n;
+  return C3_OK;
+}
+
+int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out);
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int c3_abi_version(void) { return C3_ABI_VERSION; }
+const char* c3_last_error(void) { return g_last_error.c_str(); }
+
+int c3_device_count(int* n) {
+  C3_REQUIRE(n != nullptr, "null out pointer");
+  cudaError_t err = cudaGetDeviceCount(n);
+  if (err != cudaSuccess) {
+    *n = 0;
+    return fail(C3_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
+  }
+  return C3_OK;
+}
+
+int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* child_ptr,
+              const int32_t* child_idx, c3_engine** out) {
+  C3_REQUIRE(out != nullptr && child_ptr != nullptr, "null pointer");
+  C3_REQUIRE(n_nodes >= 2, "need at least two nodes");
+  C3_REQUIRE(n_states >= 2 && n_states <= 64, "n_states must be in [2, 64] (cogent3 asserts < 65)");
+  C3_REQUIRE(n_bins >= 1 && n_bins <= 64, "n_bins must be in [1, 64]");
+  int n_dev = 0;
+  C3_CUDA(cudaGetDeviceCount(&n_dev));
+  if (n_dev == 0) return fail(C3_ERR_CUDA, "no CUDA device: libc3cuda has no CPU fallback");
+  C3_REQUIRE(device >= 0 && device < n_dev, "bad device ordinal");
+  C3_CUDA(cudaSetDevice(device));
+  c3_engine* e = new c3_engine();
+  e->device = device;
+  e->n_nodes = n_nodes;
+  e->M = n_states;
+  e->K = n_bins;
+  e->use_dmma = (n_states != 4);
+  if (const char* env = getenv("C3_FORCE_DMMA")) e->use_dmma = e->use_dmma || atoi(env) != 0;
+  e->MP = e->use_dmma ? (int)align_up(n_states, 8) : 4;
+  e->root = n_nodes - 1;
+  e->children.resize(n_nodes);
+  e->parent.assign(n_nodes, -1);
+  e->level.assign(n_nodes, 0);
+  e->child_begin.assign(n_nodes, 0);
+  int running = 0;
+  for (int n = 0; n < n_nodes; ++n) {
+    e->child_begin[n] = running;
+    for (int k = child_ptr[n]; k < child_ptr[n + 1]; ++k) {
+      const int c = child_idx[k];
+      if (c < 0 || c >= n) {
+        delete e;
+        return fail(C3_ERR_INVALID, "nodes must be in post-order (child id < parent id)");
+      }
+      if (e->parent[c] != -1) {
+        delete e;
+        return fail(C3_ERR_INVALID, "node has two parents");
+      }
+      e->parent[c] = n;
+      e->children[n].push_back(c);
+      e->level[n] = std::max(e->level[n], e->level[c] + 1);
+      ++running;
+    }
+  }
+  for (int n = 0; n < n_nodes - 1; ++n)
+    if (e->parent[n] < 0) {
+      delete e;
+      return fail(C3_ERR_INVALID, "only the last node may be the root");
+    }
+  if (e->children[e->root].empty()) {
+    delete e;
+    return fail(C3_ERR_INVALID, "root has no children");
+  }
+  e->n_levels = e->level[e->root];
+  e->level_nodes.resize(e->n_levels + 1);
+  for (int n = 0; n < n_nodes; ++n)
+    if (!e->children[n].empty()) e->level_nodes[e->level[n]].push_back(n);
+  e->n_rows.assign(n_nodes, 0);
+  e->tip_table.resize(n_nodes);
+  e->idx32.resize(n_nodes);
+  e->qslot.assign((size_t)n_nodes * n_bins, 0);
+  e->dist.assign((size_t)n_nodes * n_bins, NAN);
+  e->pdirty.assign((size_t)n_nodes * n_bins, 1);
+  e->pfixed.assign((size_t)n_nodes * n_bins, 0);
+  e->node_dirty.assign(n_nodes, 1);
+  e->pi.assign(e->MP, 0.0);
+  e->bprobs.assign(n_bins, 1.0 / n_bins);
+  e->fixed_motif.assign(n_nodes, -1);
+  e->slot_stride = 2 * (int64_t)n_states + 4 * (int64_t)n_states * n_states;
+  cudaDeviceProp prop;
+  C3_CUDA(cudaGetDeviceProperties(&prop, device));
+  e->n_sm = prop.multiProcessorCount;
+  C3_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->own_stream = true;
+  C3_CUDA(cudaEventCreateWithFlags(&e->block_copied, cudaEventDisableTiming));
+  C3_CUDA(cudaHostAlloc(&e->h_lnl, sizeof(double), cudaHostAllocMapped));
+  C3_CUDA(cudaHostGetDevicePointer(&e->h_lnl_dev, e->h_lnl, 0));
+  e->stats.n_levels = e->n_levels;
+  e->stats.padded_states = e->MP;
+  *out = e;
+  return C3_OK;
+}
+
+int c3_destroy(c3_engine* e) {
+  if (!e) return C3_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->d_pool) cudaFree(e->d_pool);
+  if (e->d_slots) cudaFree(e->d_slots);
+  if (e->d_block) cudaFree(e->d_block);
+  if (e->h_block) cudaFreeHost(e->h_block);
+  if (e->h_lnl) cudaFreeHost(e->h_lnl);
+  if (e->block_copied) cudaEventDestroy(e->block_copied);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return C3_OK;
+}
+
+int c3_set_stream(c3_engine* e, void* cuda_stream) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  C3_CUDA(cudaSetDevice(e->device));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->own_stream) {
+    C3_CUDA(cudaStreamDestroy(e->stream));
+    e->own_stream = false;
+  }
+  if (cuda_stream == nullptr) {
+    C3_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+  } else {
+    e->stream = (cudaStream_t)cuda_stream;
+  }
+  return C3_OK;
+}
+
+int c3_set_tip(c3_engine* e, int node, const double* table, int64_t n_rows) {
+  C3_REQUIRE(e && table, "null pointer");
+  C3_REQUIRE(!e->finalized, "pattern tables are frozen after c3_finalize");
+  C3_REQUIRE(node >= 0 && node < e->n_nodes && e->children[node].empty(), "not a tip node");
+  C3_REQUIRE(n_rows >= 1 && n_rows < INT32_MAX, "bad row count");
+  e->n_rows[node] = n_rows;
+  std::vector<double>& t = e->tip_table[node];
+  t.assign((size_t)n_rows * e->MP, 0.0);
+  for (int64_t u = 0; u < n_rows; ++u)
+    for (int j = 0; j < e->M; ++j) t[u * e->MP + j] = table[u * e->M + j];
+  return C3_OK;
+}
+
+int c3_set_node_patterns(c3_engine* e, int node, const int64_t* indexes, int64_t n_rows) {
+  C3_REQUIRE(e && indexes, "null pointer");
+  C3_REQUIRE(!e->finalized, "pattern tables are frozen after c3_finalize");
+  C3_REQUIRE(node >= 0 && node < e->n_nodes && !e->children[node].empty(), "not an internal node");
+  C3_REQUIRE(n_rows >= 1 && n_rows < INT32_MAX, "bad row count");
+  const size_t C = e->children[node].size();
+  e->n_rows[node] = n_rows;
+  std::vector<int32_t>& ix = e->idx32[node];
+  ix.resize(C * (size_t)n_rows);
+  for (size_t c = 0; c < C; ++c) {
+    const int child = e->children[node][c];
+    const int64_t child_rows = e->n_rows[child];
+    C3_REQUIRE(child_rows > 0, "set the children's tables before their parent's");
+    for (int64_t p = 0; p < n_rows; ++p) {
+      const int64_t v = indexes[c * n_rows + p];
+      if (v < 0 || v >= child_rows) return fail(C3_ERR_INVALID, "child row index out of range");
+      ix[c * n_rows + p] = (int32_t)v;
+    }
+  }
+  return C3_OK;
+}
+
+int c3_set_root_counts(c3_engine* e, const double* counts, int64_t n_rows) {
+  C3_REQUIRE(e && counts, "null pointer");
+  C3_REQUIRE(!e->finalized, "pattern tables are frozen after c3_finalize");
+  C3_REQUIRE(n_rows == e->n_rows[e->root], "counts length must equal the root's row count");
+  e->counts.assign(counts, counts + n_rows);
+  return C3_OK;
+}
+
+int c3_finalize(c3_engine* e) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  C3_REQUIRE(!e->finalized, "already finalized");
+  C3_CUDA(cudaSetDevice(e->device));
+  const int N = e->n_nodes, K = e->K, MP = e->MP;
+  for (int n = 0; n < N; ++n) C3_REQUIRE(e->n_rows[n] > 0, "a node has no pattern table");
+  C3_REQUIRE(!e->counts.empty(), "root counts not set");
+
+  // ---- carve one pool -----------------------------------------------------
+  int64_t off = 0;
+  auto carve = [&](int64_t bytes) {
+    const int64_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  std::vector<int64_t> o_rows(N), o_tab(N, -1), o_idx(N, -1);
+  int64_t n_child_total = 0, partial_bytes = 0;
+  for (int n = 0; n < N; ++n) {
+    const int64_t bytes = e->n_rows[n] * K * MP * (int64_t)sizeof(double);
+    o_rows[n] = carve(bytes);
+    if (e->children[n].empty()) {
+      o_tab[n] = carve(e->n_rows[n] * MP * (int64_t)sizeof(double));
+    } else {
+      partial_bytes += bytes;
+      o_idx[n] = carve((int64_t)e->children[n].size() * e->n_rows[n] * (int64_t)sizeof(int32_t));
+      n_child_total += (int64_t)e->children[n].size();
+    }
+  }
+  const int64_t o_P = carve((int64_t)N * K * MP * MP * sizeof(double));
+  const int64_t o_nodes = carve((int64_t)N * sizeof(NodeDesc));
+  const int64_t o_childs = carve(n_child_total * sizeof(ChildRef));
+  const int64_t o_edges = carve((int64_t)N * sizeof(EdgeDesc));
+  const int64_t root_rows = e->n_rows[e->root];
+  const int64_t o_counts = carve(root_rows * sizeof(double));
+  const int64_t o_lh = carve(root_rows * K * sizeof(double));
+  const int64_t n_red_tiles = (root_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE;
+  const int64_t o_tiles = carve(n_red_tiles * sizeof(double));
+  const int64_t o_counter = carve(256);
+  const int64_t o_lnl = carve(256);
+
+  size_t free_b = 0, total_b = 0;
+  C3_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  if ((size_t)off > free_b) {
+    char msg[256];
+    snprintf(msg, sizeof msg,
+             "engine needs %.2f GB of device memory (%.2f GB partial likelihoods) but only %.2f GB is free",
+             off / 1e9, partial_bytes / 1e9, free_b / 1e9);
+    return fail(C3_ERR_MEMORY, msg);
+  }
+  C3_CUDA(cudaMalloc(&e->d_pool, (size_t)off));
+  e->pool_bytes = off;
+  e->partial_bytes = partial_bytes;
+  C3_CUDA(cudaMemsetAsync(e->d_pool + o_P, 0, (size_t)N * K * MP * MP * sizeof(double), e->stream));
+  C3_CUDA(cudaMemsetAsync(e->d_pool + o_counter, 0, 512, e->stream));
+
+  e->d_rows.resize(N);
+  e->d_tip_table.assign(N, nullptr);
+  e->d_idx.assign(N, nullptr);
+  for (int n = 0; n < N; ++n) {
+    e->d_rows[n] = reinterpret_cast<double*>(e->d_pool + o_rows[n]);
+    if (o_tab[n] >= 0) {
+      e->d_tip_table[n] = reinterpret_cast<double*>(e->d_pool + o_tab[n]);
+      C3_CUDA(cudaMemcpyAsync(e->d_tip_table[n], e->tip_table[n].data(),
+                              e->tip_table[n].size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      // padded tip_inner columns must be zero
+      C3_CUDA(cudaMemsetAsync(e->d_rows[n], 0, (size_t)e->n_rows[n] * K * MP * sizeof(double), e->stream));
+    } else {
+      e->d_idx[n] = reinterpret_cast<int32_t*>(e->d_pool + o_idx[n]);
+      C3_CUDA(cudaMemcpyAsync(e->d_idx[n], e->idx32[n].data(), e->idx32[n].size() * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, e->stream));
+    }
+  }
+  e->d_P = reinterpret_cast<double*>(e->d_pool + o_P);
+  e->d_nodes = reinterpret_cast<NodeDesc*>(e->d_pool + o_nodes);
+  e->d_childs = reinterpret_cast<ChildRef*>(e->d_pool + o_childs);
+  e->d_edges = reinterpret_cast<EdgeDesc*>(e->d_pool + o_edges);
+  e->d_counts = reinterpret_cast<double*>(e->d_pool + o_counts);
+  e->d_lh = reinterpret_cast<double*>(e->d_pool + o_lh);
+  e->d_tile_sums = reinterpret_cast<double*>(e->d_pool + o_tiles);
+  e->d_counter = reinterpret_cast<unsigned int*>(e->d_pool + o_counter);
+  e->d_lnl = reinterpret_cast<double*>(e->d_pool + o_lnl);
+  C3_CUDA(cudaMemcpyAsync(e->d_counts, e->counts.data(), root_rows * sizeof(double),
+                          cudaMemcpyHostToDevice, e->stream));
+
+  // ---- descriptors -----------------------------------------------------------
+  e->h_nodes.assign(N, NodeDesc{});
+  std::vector<ChildRef> h_childs((size_t)n_child_total);
+  std::vector<EdgeDesc> h_edges(N);
+  for (int n = 0; n < N; ++n) {
+    NodeDesc& nd = e->h_nodes[n];
+    nd.out = e->children[n].empty() ? nullptr : e->d_rows[n];
+    nd.n_rows = e->n_rows[n];
+    nd.child_begin = e->child_begin[n];
+    nd.n_children = (int)e->children[n].size();
+    nd.fixed_motif = -1;
+    nd.is_root = (n == e->root);
+    for (size_t c = 0; c < e->children[n].size(); ++c) {
+      const int ch = e->children[n][c];
+      ChildRef& cr = h_childs[e->child_begin[n] + c];
+      cr.src = e->d_rows[ch];
+      cr.idx = e->d_idx[n] + c * e->n_rows[n];
+      cr.P = e->children[ch].empty() ? nullptr : e->d_P + (int64_t)ch * K * MP * MP;
+      cr.src_rows = e->n_rows[ch];
+    }
+    EdgeDesc& ed = h_edges[n];
+    ed.P = e->d_P + (int64_t)n * K * MP * MP;
+    ed.tip_table = e->d_tip_table[n];
+    ed.tip_inner = e->children[n].empty() ? e->d_rows[n] : nullptr;
+    ed.tip_rows = e->children[n].empty() ? e->n_rows[n] : 0;
+  }
+  C3_CUDA(cudaMemcpyAsync(e->d_nodes, e->h_nodes.data(), N * sizeof(NodeDesc), cudaMemcpyHostToDevice, e->stream));
+  C3_CUDA(cudaMemcpyAsync(e->d_childs, h_childs.data(), h_childs.size() * sizeof(ChildRef),
+                          cudaMemcpyHostToDevice, e->stream));
+  C3_CUDA(cudaMemcpyAsync(e->d_edges, h_edges.data(), N * sizeof(EdgeDesc), cudaMemcpyHostToDevice, e->stream));
+
+  // ---- per-evaluation parameter block -------------------------------------
+  int n_internal = 0;
+  for (int n = 0; n < N; ++n) n_internal += !e->children[n].empty();
+  int64_t b = 0;
+  // the expm job list goes last: one copy of [0, end of used jobs) per evaluation
+  e->off_pi = b;      b += align_up(MP * sizeof(double), 16);
+  e->off_bprobs = b;  b += align_up(K * sizeof(double), 16);
+  e->off_work = b;    b += align_up((int64_t)n_internal * sizeof(int32_t), 16);
+  e->off_prefix = b;  b += align_up((int64_t)(n_internal + e->n_levels + 2) * sizeof(int32_t), 16);
+  e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
+  e->block_bytes = b;
+  C3_CUDA(cudaHostAlloc(&e->h_block, (size_t)b, cudaHostAllocDefault));
+  C3_CUDA(cudaMalloc(&e->d_block, (size_t)b));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+
+  // host copies no longer needed
+  for (auto& v : e->tip_table) std::vector<double>().swap(v);
+  for (auto& v : e->idx32) std::vector<int32_t>().swap(v);
+  e->stats.device_bytes += off + b;
+  e->stats.partial_bytes = partial_bytes;
+  e->finalized = true;
+  return C3_OK;
+}
+
+int c3_set_eigen(c3_engine* e, int q_slot, const double* roots, const double* evT, const double* evI,
+                 int is_complex) {
+  C3_REQUIRE(e && roots && evT && evI, "null pointer");
+  C3_REQUIRE(q_slot >= 0 && q_slot < (1 << 20), "bad q slot");
+  C3_CUDA(cudaSetDevice(e->device));
+  int rc = ensure_slots(e, q_slot + 1);
+  if (rc) return rc;
+  Slot& s = e->slots[q_slot];
+  const int M = e->M, MM = M * M;
+  s.mode = is_complex ? EXPM_EIGEN_COMPLEX : EXPM_EIGEN_REAL;
+  s.data.assign((size_t)e->slot_stride, 0.0);
+  const int w = is_complex ? 2 : 1;
+  std::memcpy(s.data.data(), roots, sizeof(double) * w * M);
+  std::memcpy(s.data.data() + 2 * M, evT, sizeof(double) * w * MM);
+  std::memcpy(s.data.data() + 2 * M + 2 * MM, evI, sizeof(double) * w * MM);
+  s.dirty = true;
+  return C3_OK;
+}
+
+int c3_set_Q(c3_engine* e, int q_slot, const double* Q) {
+  C3_REQUIRE(e && Q, "null pointer");
+  C3_REQUIRE(q_slot >= 0 && q_slot < (1 << 20), "bad q slot");
+  C3_CUDA(cudaSetDevice(e->device));
+  int rc = ensure_slots(e, q_slot + 1);
+  if (rc) return rc;
+  Slot& s = e->slots[q_slot];
+  s.mode = EXPM_PADE;
+  s.data.assign((size_t)e->slot_stride, 0.0);
+  std::memcpy(s.data.data(), Q, sizeof(double) * e->M * e->M);
+  s.dirty = true;
+  return C3_OK;
+}
+
+int c3_set_edge_qslots(c3_engine* e, const int32_t* q) {
+  C3_REQUIRE(e && q, "null pointer");
+  for (int n = 0; n < e->n_nodes - 1; ++n)
+    for (int b = 0; b < e->K; ++b) {
+      const size_t i = (size_t)n * e->K + b;
+      C3_REQUIRE(q[i] >= 0, "negative q slot");
+      if (q[i] != e->qslot[i] || e->pfixed[i]) {
+        e->qslot[i] = q[i];
+        e->pfixed[i] = 0;
+        e->pdirty[i] = 1;
+      }
+    }
+  return C3_OK;
+}
+
+int c3_set_psub(c3_engine* e, int node, int bin, const double* P) {
+  C3_REQUIRE(e && P, "null pointer");
+  C3_REQUIRE(e->finalized, "call c3_finalize first");
+  C3_REQUIRE(node >= 0 && node < e->n_nodes - 1 && bin >= 0 && bin < e->K, "bad edge / bin");
+  C3_CUDA(cudaSetDevice(e->device));
+  const int M = e->M, MP = e->MP;
+  std::vector<double> padded((size_t)MP * MP, 0.0);
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j < M; ++j) padded[i * MP + j] = P[i * M + j];
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  C3_CUDA(cudaMemcpy(e->d_P + ((int64_t)node * e->K + bin) * MP * MP, padded.data(),
+                     padded.size() * sizeof(double), cudaMemcpyHostToDevice));
+  const size_t i = (size_t)node * e->K + bin;
+  e->pfixed[i] = 1;
+  e->pdirty[i] = 1;
+  return C3_OK;
+}
+
+int c3_set_distances(c3_engine* e, const double* d) {
+  C3_REQUIRE(e && d, "null pointer");
+  const size_t n = (size_t)(e->n_nodes - 1) * e->K;
+  for (size_t i = 0; i < n; ++i) {
+    // bitwise compare: NaN (the initial state) is always "changed"
+    if (std::memcmp(&d[i], &e->dist[i], sizeof(double)) != 0) {
+      e->dist[i] = d[i];
+      if (!e->pfixed[i]) e->pdirty[i] = 1;
+    }
+  }
+  e->have_dist = true;
+  return C3_OK;
+}
+
+int c3_set_root_mprobs(c3_engine* e, const double* pi) {
+  C3_REQUIRE(e && pi, "null pointer");
+  bool changed = !e->have_pi;
+  for (int i = 0; i < e->M; ++i) changed = changed || (pi[i] != e->pi[i]);
+  if (changed) {
+    std::fill(e->pi.begin(), e->pi.end(), 0.0);
+    std::copy(pi, pi + e->M, e->pi.begin());
+    e->node_dirty[e->root] = 1;
+    e->have_pi = true;
+  }
+  return C3_OK;
+}
+
+int c3_set_bin_probs(c3_engine* e, const double* bp) {
+  C3_REQUIRE(e && bp, "null pointer");
+  for (int b = 0; b < e->K; ++b)
+    if (bp[b] != e->bprobs[b]) {
+      e->bprobs[b] = bp[b];
+      e->reduce_dirty = true;
+    }
+  return C3_OK;
+}
+
+int c3_set_fixed_motifs(c3_engine* e, const int32_t* fm) {
+  C3_REQUIRE(e && fm, "null pointer");
+  C3_REQUIRE(e->finalized, "call c3_finalize first");
+  for (int n = 0; n < e->n_nodes; ++n) {
+    const int32_t v = (fm[n] < 0) ? -1 : fm[n];
+    C3_REQUIRE(v < e->M, "fixed motif out of range");
+    if (v != e->fixed_motif[n]) {
+      e->fixed_motif[n] = v;
+      if (!e->children[n].empty()) {
+        e->h_nodes[n].fixed_motif = v;
+        e->node_dirty[n] = 1;
+        e->nodes_dirty = true;
+      }
+    }
+  }
+  return C3_OK;
+}
+
+int c3_invalidate(c3_engine* e) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  for (size_t i = 0; i < e->pdirty.size(); ++i) e->pdirty[i] = 1;
+  std::fill(e->node_dirty.begin(), e->node_dirty.end(), 1);
+  e->reduce_dirty = true;
+  e->have_cached = false;
+  return C3_OK;
+}
+
+int c3_evaluate(c3_engine* e, double* lnL) {
+  C3_REQUIRE(e && lnL, "null pointer");
+  return run_evaluation(e, nullptr, true, lnL);
+}
+
+int c3_evaluate_device(c3_engine* e, double* device_lnL) {
+  C3_REQUIRE(e && device_lnL, "null pointer");
+  return run_evaluation(e, device_lnL, false, nullptr);
+}
+
+int c3_update(c3_engine* e, const double* d, double* lnL) {
+  int rc = c3_set_distances(e, d);
+  if (rc) return rc;
+  return c3_evaluate(e, lnL);
+}
+
+int c3_get_lh(c3_engine* e, int bin, double* out, int64_t n_rows) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_REQUIRE(e->finalized && e->have_cached, "no evaluation yet");
+  C3_REQUIRE(bin >= 0 && bin < e->K, "bad bin");
+  C3_REQUIRE(n_rows == e->n_rows[e->root], "bad row count");
+  C3_CUDA(cudaSetDevice(e->device));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  C3_CUDA(cudaMemcpy2D(out, sizeof(double), e->d_lh + bin, e->K * sizeof(double), sizeof(double),
+                       (size_t)n_rows, cudaMemcpyDeviceToHost));
+  return C3_OK;
+}
+
+int c3_get_psub(c3_engine* e, int node, int bin, double* out) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_REQUIRE(e->finalized && e->have_cached, "no evaluation yet");
+  C3_REQUIRE(node >= 0 && node < e->n_nodes - 1 && bin >= 0 && bin < e->K, "bad edge / bin");
+  C3_CUDA(cudaSetDevice(e->device));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  const int M = e->M, MP = e->MP;
+  C3_CUDA(cudaMemcpy2D(out, M * sizeof(double), e->d_P + ((int64_t)node * e->K + bin) * MP * MP,
+                       MP * sizeof(double), M * sizeof(double), M, cudaMemcpyDeviceToHost));
+  return C3_OK;
+}
+
+int c3_get_partials(c3_engine* e, int node, int bin, double* out, int64_t n_rows) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_REQUIRE(e->finalized && e->have_cached, "no evaluation yet");
+  C3_REQUIRE(node >= 0 && node < e->n_nodes && bin >= 0 && bin < e->K, "bad node / bin");
+  C3_REQUIRE(n_rows == e->n_rows[node], "bad row count");
+  C3_CUDA(cudaSetDevice(e->device));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  const int M = e->M, MP = e->MP;
+  // rows are [row][bin][MP]; for a tip this returns the P-multiplied tip table
+  C3_CUDA(cudaMemcpy2D(out, M * sizeof(double), e->d_rows[node] + (int64_t)bin * MP,
+                       (size_t)e->K * MP * sizeof(double), M * sizeof(double), (size_t)n_rows,
+                       cudaMemcpyDeviceToHost));
+  return C3_OK;
+}
+
+int c3_get_stats(c3_engine* e, c3_stats* out) {
+  C3_REQUIRE(e && out, "null pointer");
+  *out = e->stats;
+  return C3_OK;
+}
+
+int c3_measure_dmma_peak(int device, double* tflops) {
+  C3_REQUIRE(tflops != nullptr, "null pointer");
+  C3_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  C3_CUDA(cudaGetDeviceProperties(&prop, device));
+  double* d_out = nullptr;
+  C3_CUDA(cudaMalloc(&d_out, 64));
+  cudaEvent_t a, b;
+  C3_CUDA(cudaEventCreate(&a));
+  C3_CUDA(cudaEventCreate(&b));
+  const int grid = prop.multiProcessorCount * 8, iters = 20000;
+  dmma_peak_kernel<<<grid, 256>>>(d_out, 200);
+  C3_CUDA(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    C3_CUDA(cudaEventRecord(a));
+    dmma_peak_kernel<<<grid, 256>>>(d_out, iters);
+    C3_CUDA(cudaEventRecord(b));
+    C3_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    C3_CUDA(cudaEventElapsedTime(&ms, a, b));
+    best = std::min(best, ms);
+  }
+  const double flops = (double)grid * 8 /*warps*/ * iters * 8 /*dmma per iter*/ * (2.0 * 8 * 8 * 4);
+  *tflops = flops / (best * 1e-3) / 1e12;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d_out);
+  return C3_OK;
+}
+
+}  // extern "C"
+
+// =========================================================================================
+// evaluation
+// =========================================================================================
+namespace {
+
+int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out) {
+  C3_REQUIRE(e->finalized, "call c3_finalize first");
+  C3_REQUIRE(e->have_pi, "root motif probabilities not set");
+  C3_CUDA(cudaSetDevice(e->device));
+  const int N = e->n_nodes, K = e->K, M = e->M, MP = e->MP;
+
+  // slots whose contents changed dirty every (edge, bin) that uses them
+  bool any_slot_dirty = false;
+  for (const Slot& s : e->slots) any_slot_dirty = any_slot_dirty || s.dirty;
+  if (any_slot_dirty) {
+    for (int n = 0; n < N - 1; ++n)
+      for (int b = 0; b < K; ++b) {
+        const size_t i = (size_t)n * K + b;
+        if (!e->pfixed[i] && e->qslot[i] < (int)e->slots.size() && e->slots[e->qslot[i]].dirty)
+          e->pdirty[i] = 1;
+      }
+  }
+
+  // ---- expm jobs ----------------------------------------------------------------
+  C3_CUDA(cudaEventSynchronize(e->block_copied));  // staging buffer free again
+  ExpmJob* jobs = reinterpret_cast<ExpmJob*>(e->h_block + e->off_jobs);
+  int n_eigen = 0, n_pade = 0;
+  std::vector<char> edge_touched(N, 0);
+  // first pass: eigen-type and fixed jobs, second: Pade (two launches)
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int n = 0; n < N - 1; ++n)
+      for (int b = 0; b < K; ++b) {
+        const size_t i = (size_t)n * K + b;
+        if (!e->pdirty[i]) continue;
+        int mode;
+        if (e->pfixed[i]) {
+          mode = EXPM_FIXED;
+        } else {
+          const int s = e->qslot[i];
+          if (s >= (int)e->slots.size() || e->slots[s].mode < 0)
+            return fail(C3_ERR_INVALID, "an (edge, bin) uses a q slot that was never set");
+          if (!e->have_dist || std::isnan(e->dist[i]))
+            return fail(C3_ERR_INVALID, "distances not set");
+          mode = e->slots[s].mode;
+        }
+        const bool is_pade = (mode == EXPM_PADE);
+        if (is_pade != (pass == 1)) continue;
+        ExpmJob& j = jobs[n_eigen + n_pade];
+        j.node = n;
+        j.bin = b;
+        j.slot = e->pfixed[i] ? 0 : e->qslot[i];
+        j.mode = mode;
+        j.t = e->pfixed[i] ? 0.0 : e->dist[i];
+        if (is_pade) ++n_pade; else ++n_eigen;
+        edge_touched[n] = 1;
+      }
+  }
+
+  // ---- dirty nodes, level by level --------------------------------------------------
+  std::vector<char> recompute(N, 0);
+  int n_dirty_nodes = 0;
+  for (int n = 0; n < N; ++n) {
+    if (e->children[n].empty()) continue;
+    bool d = e->node_dirty[n] != 0;
+    for (int c : e->children[n]) d = d || edge_touched[c] || recompute[c];
+    if (d) {
+      recompute[n] = 1;
+      ++n_dirty_nodes;
+    }
+  }
+  if (n_dirty_nodes == 0 && n_eigen + n_pade == 0 && !e->reduce_dirty && e->have_cached) {
+    if (host_out) *host_out = e->cached_lnl;
+    if (device_out)
+      C3_CUDA(cudaMemcpyAsync(device_out, e->d_lnl, sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    e->stats.last_launches = 0;
+    return C3_OK;
+  }
+
+  int32_t* work = reinterpret_cast<int32_t*>(e->h_block + e->off_work);
+  int32_t* prefix = reinterpret_cast<int32_t*>(e->h_block + e->off_prefix);
+  struct LevelLaunch { int work_off, prefix_off, n_work, total_tiles; bool is_root; };
+  std::vector<LevelLaunch> launches;
+  int w_off = 0, p_off = 0;
+  int64_t node_rows = 0, alg_bytes = 0, flops = 0;
+  for (int l = 1; l <= e->n_levels; ++l) {
+    LevelLaunch ll{w_off, p_off, 0, 0, false};
+    int64_t tiles = 0;
+    for (int n : e->level_nodes[l]) {
+      if (!recompute[n]) continue;
+      work[w_off + ll.n_work] = n;
+      prefix[p_off + ll.n_work] = (int32_t)tiles;
+      tiles += tiles_of_node(e, n);
+      if (tiles > INT32_MAX) return fail(C3_ERR_INVALID, "too many tiles in one level");
+      ++ll.n_work;
+      ll.is_root = ll.is_root || (n == e->root);
+      const int64_t rows = e->n_rows[n];
+      node_rows += rows;
+      alg_bytes += rows * K * M * 8;  // write
+      for (int c : e->children[n]) {
+        alg_bytes += e->n_rows[c] * K * M * 8 + rows * 4;  // child rows once + gather index
+        if (!e->children[c].empty()) flops += rows * K * 2 * (int64_t)(e->use_dmma ? MP * MP : M * M);
+      }
+      if (n == e->root) alg_bytes += rows * K * 8;
+    }
+    if (ll.n_work == 0) continue;
+    prefix[p_off + ll.n_work] = (int32_t)tiles;
+    ll.total_tiles = (int)tiles;
+    w_off += ll.n_work;
+    p_off += ll.n_work + 1;
+    launches.push_back(ll);
+  }
+
+  // ---- upload: dirty slots, descriptors, the parameter block -------------------------
+  for (size_t s = 0; s < e->slots.size(); ++s) {
+    Slot& sl = e->slots[s];
+    if (!sl.dirty) continue;
+    // the vector stays alive and unmodified until the next set_* call; pageable copies
+    // are staged by the runtime before the call returns
+    C3_CUDA(cudaMemcpyAsync(e->d_slots + (int64_t)s * e->slot_stride, sl.data.data(),
+                            (size_t)e->slot_stride * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    sl.dirty = false;
+  }
+  if (e->nodes_dirty) {
+    C3_CUDA(cudaMemcpyAsync(e->d_nodes, e->h_nodes.data(), N * sizeof(NodeDesc), cudaMemcpyHostToDevice,
+                            e->stream));
+    e->nodes_dirty = false;
+  }
+  std::memcpy(e->h_block + e->off_pi, e->pi.data(), MP * sizeof(double));
+  std::memcpy(e->h_block + e->off_bprobs, e->bprobs.data(), K * sizeof(double));
+  // one contiguous copy of the used part of the block
+  const int64_t used = e->off_jobs + (int64_t)(n_eigen + n_pade) * sizeof(ExpmJob);
+  C3_CUDA(cudaMemcpyAsync(e->d_block, e->h_block, (size_t)std::min(used, e->block_bytes),
+                          cudaMemcpyHostToDevice, e->stream));
+  C3_CUDA(cudaEventRecord(e->block_copied, e->stream));
+
+  int64_t n_launch = 0;
+  const ExpmJob* d_jobs = reinterpret_cast<const ExpmJob*>(e->d_block + e->off_jobs);
+  if (n_eigen > 0) {
+    const int threads = (M <= 4) ? 32 : (M <= 16 ? 64 : 256);
+    const size_t smem = (size_t)(MP * MP + 2 * M) * sizeof(double);
+    static bool cfg = false;
+    if (!cfg) { int rc = set_max_smem(expm_eigen_kernel, 64 * 64 * 8 + 1024); if (rc) return rc; cfg = true; }
+    expm_eigen_kernel<<<n_eigen, threads, smem, e->stream>>>(d_jobs, e->d_slots, e->slot_stride, e->d_edges,
+                                                            M, MP, K);
+    ++n_launch;
+  }
+  if (n_pade > 0) {
+    const int threads = (M <= 4) ? 32 : (M <= 16 ? 128 : 256);
+    const size_t smem = (size_t)5 * MP * MP * sizeof(double);
+    static bool cfg = false;
+    if (!cfg) { int rc = set_max_smem(expm_pade_kernel, (size_t)5 * 64 * 64 * 8); if (rc) return rc; cfg = true; }
+    expm_pade_kernel<<<n_pade, threads, smem, e->stream>>>(d_jobs + n_eigen, e->d_slots, e->slot_stride,
+                                                          e->d_edges, M, MP, K);
+    ++n_launch;
+  }
+  {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("expm launch: ") + cudaGetErrorString(err));
+  }
+
+  const int32_t* d_work = reinterpret_cast<const int32_t*>(e->d_block + e->off_work);
+  const int32_t* d_prefix = reinterpret_cast<const int32_t*>(e->d_block + e->off_prefix);
+  for (const LevelLaunch& ll : launches) {
+    PruneArgs a;
+    a.nodes = e->d_nodes;
+    a.childs = e->d_childs;
+    a.work_node = d_work + ll.work_off;
+    a.tile_prefix = d_prefix + ll.prefix_off;
+    a.n_work = ll.n_work;
+    a.total_tiles = ll.total_tiles;
+    a.K = K;
+    a.M = M;
+    a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
+    a.lh_out = e->d_lh;
+    int rc = launch_prune(e, a, ll.is_root);
+    if (rc) return rc;
+    ++n_launch;
+  }
+  {
+    const int64_t rows = e->n_rows[e->root];
+    const int n_tiles = (int)((rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
+    const int grid = std::min(n_tiles, e->n_sm * 8);
+    lnl_reduce_kernel<<<grid, REDUCE_THREADS, 0, e->stream>>>(
+        e->d_lh, reinterpret_cast<const double*>(e->d_block + e->off_bprobs), e->d_counts, rows, K, n_tiles,
+        e->d_tile_sums, e->d_counter, e->d_lnl, device_out, blocking ? e->h_lnl_dev : nullptr);
+    ++n_launch;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(err));
+  }
+
+  // bookkeeping: everything launched is now clean
+  std::fill(e->pdirty.begin(), e->pdirty.end(), 0);
+  std::fill(e->node_dirty.begin(), e->node_dirty.end(), 0);
+  e->reduce_dirty = false;
+  e->stats.evaluations += 1;
+  e->stats.kernel_launches += n_launch;
+  e->stats.last_launches = n_launch;
+  e->stats.last_expm_jobs = n_eigen + n_pade;
+  e->stats.last_nodes = n_dirty_nodes;
+  e->stats.last_node_rows = node_rows;
+  e->stats.last_alg_bytes = alg_bytes;
+  e->stats.last_flops = flops;
+
+  if (blocking) {
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) {
+      e->have_cached = false;
+      c3_invalidate(e);
+      return fail(C3_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(err));
+    }
+    e->cached_lnl = *e->h_lnl;
+    e->have_cached = true;
+    if (host_out) *host_out = e->cached_lnl;
+  } else {
+    e->have_cached = true;  // value lives in d_lnl; the host copy is refreshed lazily
+    e->cached_lnl = NAN;
+    e->reduce_dirty = true;  // a later blocking call must re-run the reduction for the host value
+  }
+  return C3_OK;
+}
+
+}  // namespace

@@ -1,0 +1,271 @@
+// Batched P(t) = expm(Q t): one CTA per dirty (edge, rate class), all of them in
+// one launch per exponentiator kind.
+//
+//   eigen : P = max(Re(evT . diag(exp(t roots)) . evI^T), 0)
+//           -- EigenExponentiator.__call__, maths/matrix_exponentiation.py:35-40.
+//           The eigen-decomposition itself stays on the host (numpy.linalg.eig /
+//           inv, :132-146) so that roots / vectors are bit-identical to the
+//           reference's; see DESIGN.md.
+//   Pade  : scaling-and-squaring with the reference's data-dependent order
+//           -- PadeExponentiator.__call__, maths/matrix_exponentiation.py:92-129.
+//
+// For a tip edge the CTA also refreshes the pre-multiplied tip table
+// tip_inner[u][b][i] = sum_j P_b[i][j] table[u][j], which is numpy.inner(tip
+// rows, psub) (evolve/likelihood_calculation.py:86) on the <= U+1 distinct tip
+// rows -- the "column gather of P" of SURVEY §7 step 6.
+#pragma once
+#include "c3_types.cuh"
+
+namespace c3 {
+
+__device__ __forceinline__ void tip_inner_update(const EdgeDesc& ed, const double* sP, int bin,
+                                                 int M, int MP, int K) {
+  if (ed.tip_table == nullptr) return;
+  const int64_t total = ed.tip_rows * M;
+  for (int64_t o = threadIdx.x; o < total; o += blockDim.x) {
+    const int64_t u = o / M;
+    const int i = (int)(o - u * M);
+    const double* row = ed.tip_table + u * MP;
+    double s = 0.0;
+    for (int j = 0; j < M; ++j) s = fma(row[j], sP[i * MP + j], s);
+    ed.tip_inner[(u * K + bin) * MP + i] = s;
+  }
+}
+
+// slot layout (doubles): roots[2M] | evT[2 M M] | evI[2 M M]   (complex interleaved; the
+// real variant uses the first M / M M entries of each region)  -- or Q[M M] for Pade.
+__global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double* __restrict__ slots,
+                                  int64_t slot_stride, const EdgeDesc* __restrict__ edges, int M,
+                                  int MP, int K) {
+  extern __shared__ double smem[];
+  double* sP = smem;              // [MP*MP]
+  double* s_er = sP + MP * MP;    // [M] exp(t re) cos(t im)
+  double* s_ei = s_er + M;        // [M] exp(t re) sin(t im)
+  const ExpmJob job = jobs[blockIdx.x];
+  const EdgeDesc ed = edges[job.node];
+  double* Pout = ed.P + (int64_t)job.bin * MP * MP;
+  const int MM = M * M;
+
+  if (job.mode == EXPM_FIXED) {
+    for (int o = threadIdx.x; o < MP * MP; o += blockDim.x) sP[o] = Pout[o];
+    __syncthreads();
+    tip_inner_update(ed, sP, job.bin, M, MP, K);
+    return;
+  }
+  const double* slot = slots + (int64_t)job.slot * slot_stride;
+  const double t = job.t;
+  if (job.mode == EXPM_EIGEN_COMPLEX) {
+    const double* roots = slot;
+    const double* evT = slot + 2 * M;
+    const double* evI = evT + 2 * MM;
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+      const double mag = exp(t * roots[2 * k]);
+      double s, c;
+      sincos(t * roots[2 * k + 1], &s, &c);
+      s_er[k] = mag * c;
+      s_ei[k] = mag * s;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < MM; o += blockDim.x) {
+      const int i = o / M, j = o - i * M;
+      double acc = 0.0;
+      for (int k = 0; k < M; ++k) {
+        const double ar = evT[2 * (i * M + k)], ai = evT[2 * (i * M + k) + 1];
+        const double er = s_er[k], ei = s_ei[k];
+        // w = evT[i,k] * exp_roots[k]   (numpy: self.evT * exp_roots)
+        const double wr = ar * er - ai * ei;
+        const double wi = ar * ei + ai * er;
+        const double br = evI[2 * (j * M + k)], bi = evI[2 * (j * M + k) + 1];
+        // Re(w * evI[j,k])             (numpy.inner(...).real)
+        acc += wr * br - wi * bi;
+      }
+      acc = fmax(acc, 0.0);
+      sP[i * MP + j] = acc;
+      Pout[i * MP + j] = acc;
+    }
+  } else {
+    const double* roots = slot;
+    const double* evT = slot + 2 * M;
+    const double* evI = evT + 2 * MM;
+    for (int k = threadIdx.x; k < M; k += blockDim.x) s_er[k] = exp(t * roots[k]);
+    __syncthreads();
+    for (int o = threadIdx.x; o < MM; o += blockDim.x) {
+      const int i = o / M, j = o - i * M;
+      double acc = 0.0;
+      for (int k = 0; k < M; ++k) acc += (evT[i * M + k] * s_er[k]) * evI[j * M + k];
+      acc = fmax(acc, 0.0);
+      sP[i * MP + j] = acc;
+      Pout[i * MP + j] = acc;
+    }
+  }
+  // zero the padding of sP so the tip table never sees garbage
+  for (int o = threadIdx.x; o < MP * MP; o += blockDim.x) {
+    const int i = o / MP, j = o - i * MP;
+    if (i >= M || j >= M) sP[o] = 0.0;
+  }
+  __syncthreads();
+  tip_inner_update(ed, sP, job.bin, M, MP, K);
+}
+
+// C = A . B for M x M matrices with row stride MP held in shared memory
+__device__ __forceinline__ void smem_matmul(double* __restrict__ C, const double* __restrict__ A,
+                                            const double* __restrict__ B, int M, int MP) {
+  for (int o = threadIdx.x; o < M * M; o += blockDim.x) {
+    const int i = o / M, j = o - i * M;
+    double s = 0.0;
+    for (int k = 0; k < M; ++k) s = fma(A[i * MP + k], B[k * MP + j], s);
+    C[i * MP + j] = s;
+  }
+}
+
+__global__ void expm_pade_kernel(const ExpmJob* __restrict__ jobs, const double* __restrict__ slots,
+                                 int64_t slot_stride, const EdgeDesc* __restrict__ edges, int M,
+                                 int MP, int K) {
+  extern __shared__ double smem[];
+  const int S = MP * MP;
+  double* A = smem;
+  double* X = A + S;
+  double* T = X + S;
+  double* N = T + S;
+  double* D = N + S;
+  __shared__ double s_red[64];
+  __shared__ int s_j, s_q, s_piv;
+  __shared__ double s_norm;
+
+  const ExpmJob job = jobs[blockIdx.x];
+  const EdgeDesc ed = edges[job.node];
+  double* Pout = ed.P + (int64_t)job.bin * S;
+  const double* Q = slots + (int64_t)job.slot * slot_stride;
+  const double t = job.t;
+  const int tid = threadIdx.x;
+
+  for (int o = tid; o < S; o += blockDim.x) {
+    const int i = o / MP, j = o - i * MP;
+    A[o] = (i < M && j < M) ? Q[i * M + j] * t : 0.0;  // A = self.Q * t  (:94)
+  }
+  __syncthreads();
+  // norm = max row sum of |A|  (:97)
+  if (tid < M) {
+    double s = 0.0;
+    for (int j = 0; j < M; ++j) s += fabs(A[tid * MP + j]);
+    s_red[tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double norm = s_red[0];
+    for (int i = 1; i < M; ++i) norm = fmax(norm, s_red[i]);
+    // j = int(floor(log(max(norm, 0.5)) / log(2.0))) + 1   (:98)
+    const int j = (int)floor(log(fmax(norm, 0.5)) / log(2.0)) + 1;
+    // order q: while e > 1e-12 ...  (:103-109)
+    double e = 1.0, qf = 1.0;
+    int q = 0;
+    const double scaled = norm / exp2((double)j);
+    while (e > 1e-12) {
+      q += 1;
+      const double q2 = 2.0 * q;
+      qf *= ((double)q * q) / (q2 * (q2 - 1) * q2 * (q2 + 1));
+      e = 8 * pow(scaled, 2.0 * q) * qf;
+    }
+    s_j = j;
+    s_q = q;
+    s_norm = norm;
+  }
+  __syncthreads();
+  const int jj = s_j, q = s_q;
+  const double inv_scale = exp2((double)jj);
+  for (int o = tid; o < S; o += blockDim.x) A[o] = A[o] / inv_scale;  // A = A / 2.0**j (:99)
+  __syncthreads();
+  double c = 0.5;
+  for (int o = tid; o < S; o += blockDim.x) {
+    const int i = o / MP, j = o - i * MP;
+    const double id = (i == j && i < M) ? 1.0 : 0.0;
+    X[o] = A[o];
+    N[o] = id + c * A[o];
+    D[o] = id - c * A[o];
+  }
+  __syncthreads();
+  for (int k = 2; k <= q; ++k) {
+    c = c * (q - k + 1) / (double)(k * (2 * q - k + 1));
+    smem_matmul(T, A, X, M, MP);  // X = dot(A, X)
+    __syncthreads();
+    double* tmp = X;
+    X = T;
+    T = tmp;
+    const bool plus = (k % 2) == 0;
+    for (int o = tid; o < M * M; o += blockDim.x) {
+      const int i = o / M, j = o - i * M;
+      const double cX = c * X[i * MP + j];
+      N[i * MP + j] += cX;
+      D[i * MP + j] = plus ? D[i * MP + j] + cX : D[i * MP + j] - cX;
+    }
+    __syncthreads();
+  }
+  // F = solve(D, N): LU with partial pivoting (what numpy.linalg.solve -> LAPACK dgesv does)
+  for (int k = 0; k < M; ++k) {
+    if (tid == 0) {
+      int piv = k;
+      double best = fabs(D[k * MP + k]);
+      for (int i = k + 1; i < M; ++i) {
+        const double v = fabs(D[i * MP + k]);
+        if (v > best) { best = v; piv = i; }
+      }
+      s_piv = piv;
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    if (piv != k) {
+      for (int j = tid; j < 2 * M; j += blockDim.x) {
+        double* Mx = j < M ? D : N;
+        const int jc = j < M ? j : j - M;
+        const double a = Mx[k * MP + jc];
+        Mx[k * MP + jc] = Mx[piv * MP + jc];
+        Mx[piv * MP + jc] = a;
+      }
+      __syncthreads();
+    }
+    const double pivot = D[k * MP + k];
+    for (int i = k + 1 + tid; i < M; i += blockDim.x) D[i * MP + k] = D[i * MP + k] / pivot;
+    __syncthreads();
+    const int rows = M - k - 1;
+    for (int o = tid; o < rows * (2 * M); o += blockDim.x) {
+      const int i = k + 1 + o / (2 * M);
+      const int j = o % (2 * M);
+      const double l = D[i * MP + k];
+      if (j < M) {
+        if (j > k) D[i * MP + j] -= l * D[k * MP + j];
+      } else {
+        N[i * MP + (j - M)] -= l * N[k * MP + (j - M)];
+      }
+    }
+    __syncthreads();
+  }
+  // back substitution, one right-hand-side column per thread
+  for (int j = tid; j < M; j += blockDim.x) {
+    for (int i = M - 1; i >= 0; --i) {
+      double s = N[i * MP + j];
+      for (int m = i + 1; m < M; ++m) s -= D[i * MP + m] * N[m * MP + j];
+      N[i * MP + j] = s / D[i * MP + i];
+    }
+  }
+  __syncthreads();
+  double* F = N;
+  double* G = D;
+  for (int k = 1; k <= jj; ++k) {  // F = dot(F, F), j times (:127-128)
+    smem_matmul(G, F, F, M, MP);
+    __syncthreads();
+    double* tmp = F;
+    F = G;
+    G = tmp;
+  }
+  // the Pade path is NOT clamped at zero by the reference (only the eigen path is)
+  for (int o = tid; o < S; o += blockDim.x) {
+    const int i = o / MP, j = o - i * MP;
+    const double v = (i < M && j < M) ? F[o] : 0.0;
+    A[o] = v;
+    if (i < M && j < M) Pout[o] = v;
+  }
+  __syncthreads();
+  tip_inner_update(ed, A, job.bin, M, MP, K);
+}
+
+}  // namespace c3

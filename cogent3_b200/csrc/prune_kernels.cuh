@@ -1,0 +1,460 @@
+// Felsenstein pruning over compressed site patterns, one launch per tree level.
+//
+// For every dirty internal node n of the level and every pattern row p, bin b:
+//     plh_n[p, b, :] = prod_c  ( P_c,b . plh_c[idx_c[p], b, :] )
+// i.e. the reference's per-edge numpy.inner(child_plh, psub)
+// (evolve/likelihood_calculation.py:86) FUSED with the gather-product
+// sum_input_likelihoods (evolve/likelihood_tree_numba.py:7-25): the [P_child x M]
+// "inner" intermediates are never materialised; each child row is read once
+// (gathered through idx, 4 B per parent row), each parent row written once.
+// Children are multiplied in tree order like the reference (child 0 assigns, the
+// others multiply).  The fixed-motif mask of
+// PartialLikelihoodProductDefnFixedMotif (likelihood_calculation.py:50-59) and, at
+// the root, lh = numpy.inner(plh_root, pi) (:147-148) are fused in.
+//
+// Layout: partial rows are [row][bin][MP] doubles, so the K rate classes of one
+// pattern are contiguous (K*M*8 = 128 B for GTR+G4: one gathered row = one cache
+// line, the gather index is read once for all bins).
+//
+// prune4_kernel : M = 4.  HBM-bound; one thread per (row, bin), 256-bit
+//                 LDG/STG, P matrices staged in shared memory, register FMA.
+// prune_dmma_kernel<MP> : any M <= 64 padded to MP (multiple of 8).  Internal
+//                 children are a real [rows x MP] . [MP x MP] FP64 contraction:
+//                 gathered rows staged in shared memory with cp.async, P in
+//                 shared memory, mma.sync m8n8k4 f64 (DMMA) accumulating in
+//                 registers; tip children are a gather of pre-multiplied rows.
+#pragma once
+#include "c3_types.cuh"
+
+namespace c3 {
+
+struct __align__(32) d4 {
+  double x, y, z, w;
+};
+
+__device__ __forceinline__ d4 ld256_nc(const double* p) {
+  d4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256(double* p, const d4& r) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.x), "d"(r.y), "d"(r.z),
+               "d"(r.w)
+               : "memory");
+}
+
+__device__ __forceinline__ int find_work(const int32_t* __restrict__ prefix, int n_work, int t) {
+  int lo = 0, hi = n_work;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (prefix[mid] <= t) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------
+// 4-state kernel
+// ---------------------------------------------------------------------------------------
+constexpr int P4_MAXC = 4;      // children whose P is staged in shared memory
+constexpr int P4_MAXK = 8;
+constexpr int P4_PSTRIDE = 18;  // 16 + pad: bins land in different banks
+
+__device__ __forceinline__ d4 matvec4(const double* __restrict__ P, const d4& x) {
+  d4 y;
+  y.x = fma(x.w, P[3], fma(x.z, P[2], fma(x.y, P[1], x.x * P[0])));
+  y.y = fma(x.w, P[7], fma(x.z, P[6], fma(x.y, P[5], x.x * P[4])));
+  y.z = fma(x.w, P[11], fma(x.z, P[10], fma(x.y, P[9], x.x * P[8])));
+  y.w = fma(x.w, P[15], fma(x.z, P[14], fma(x.y, P[13], x.x * P[12])));
+  return y;
+}
+
+template <int NC, int UNROLL, bool ROOT>
+__device__ __forceinline__ void prune4_tile(const PruneArgs& a, const NodeDesc& nd,
+                                            const ChildRef* __restrict__ s_child,
+                                            const double* __restrict__ sP, int64_t row0, int rl,
+                                            int b, int K, int rows_per_pass) {
+  int64_t p[UNROLL];
+  bool ok[UNROLL];
+  int32_t r[UNROLL][NC];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    p[u] = row0 + (int64_t)u * rows_per_pass + rl;
+    ok[u] = p[u] < nd.n_rows;
+    const int64_t pp = ok[u] ? p[u] : nd.n_rows - 1;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) r[u][c] = __ldg(s_child[c].idx + pp);
+  }
+  d4 x[UNROLL][NC];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      x[u][c] = ld256_nc(s_child[c].src + ((int64_t)r[u][c] * K + b) * 4);
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    d4 acc = matvec4(sP + (0 * K + b) * P4_PSTRIDE, x[u][0]);
+#pragma unroll
+    for (int c = 1; c < NC; ++c) {
+      const d4 y = matvec4(sP + (c * K + b) * P4_PSTRIDE, x[u][c]);
+      acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w;
+    }
+    if (nd.fixed_motif >= 0) {
+      if (nd.fixed_motif != 0) acc.x = 0.0;
+      if (nd.fixed_motif != 1) acc.y = 0.0;
+      if (nd.fixed_motif != 2) acc.z = 0.0;
+      if (nd.fixed_motif != 3) acc.w = 0.0;
+    }
+    if (ok[u]) {
+      st256(nd.out + (p[u] * K + b) * 4, acc);
+      if (ROOT) {
+        // lh = numpy.inner(plh_root, pi)
+        const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
+        a.lh_out[p[u] * K + b] = lh;
+      }
+    }
+  }
+}
+
+// generic child count (polytomies): children handled one after the other
+template <int UNROLL, bool ROOT>
+__device__ __forceinline__ void prune4_tile_generic(const PruneArgs& a, const NodeDesc& nd,
+                                                    const double* __restrict__ sP, bool p_in_smem,
+                                                    int64_t row0, int rl, int b, int K,
+                                                    int rows_per_pass) {
+#pragma unroll 1
+  for (int u = 0; u < UNROLL; ++u) {
+    const int64_t p = row0 + (int64_t)u * rows_per_pass + rl;
+    if (p >= nd.n_rows) continue;
+    d4 acc;
+#pragma unroll 1
+    for (int c = 0; c < nd.n_children; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + c];
+      const int32_t r = __ldg(ch.idx + p);
+      const d4 x = ld256_nc(ch.src + ((int64_t)r * K + b) * 4);
+      d4 y;
+      if (p_in_smem) {
+        y = matvec4(sP + (c * K + b) * P4_PSTRIDE, x);
+      } else if (ch.P != nullptr) {
+        y = matvec4(ch.P + b * 16, x);
+      } else {
+        y = x;
+      }
+      if (c == 0) acc = y;
+      else { acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w; }
+    }
+    if (nd.fixed_motif >= 0) {
+      if (nd.fixed_motif != 0) acc.x = 0.0;
+      if (nd.fixed_motif != 1) acc.y = 0.0;
+      if (nd.fixed_motif != 2) acc.z = 0.0;
+      if (nd.fixed_motif != 3) acc.w = 0.0;
+    }
+    st256(nd.out + (p * K + b) * 4, acc);
+    if (ROOT) {
+      const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
+      a.lh_out[p * K + b] = lh;
+    }
+  }
+}
+
+template <int KT, bool ROOT>
+__global__ void __launch_bounds__(PRUNE4_THREADS, PRUNE4_MIN_BLOCKS) prune4_kernel(const PruneArgs a) {
+  constexpr int UNROLL = PRUNE4_UNROLL;
+  const int K = KT > 0 ? KT : a.K;
+  const int rows_per_pass = PRUNE4_THREADS / K;
+  const int rows_per_tile = rows_per_pass * UNROLL;
+  __shared__ ChildRef s_child[P4_MAXC];
+  __shared__ double sP[P4_MAXC * P4_MAXK * P4_PSTRIDE];
+  const int tid = threadIdx.x;
+  const int b = tid % K;
+  const int rl = tid / K;
+  const bool active = rl < rows_per_pass;
+
+  for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    const int w = find_work(a.tile_prefix, a.n_work, t);
+    const NodeDesc nd = a.nodes[a.work_node[w]];
+    const int64_t row0 = (int64_t)(t - a.tile_prefix[w]) * rows_per_tile;
+    const int nc = nd.n_children;
+    const bool p_in_smem = nc <= P4_MAXC && K <= P4_MAXK;
+    __syncthreads();
+    if (p_in_smem) {
+      if (tid < nc) s_child[tid] = a.childs[nd.child_begin + tid];
+      for (int o = tid; o < nc * K * 16; o += PRUNE4_THREADS) {
+        const int c = o / (K * 16);
+        const int rem = o - c * (K * 16);
+        const int bb = rem >> 4, e = rem & 15;
+        const double* P = a.childs[nd.child_begin + c].P;
+        // pre-multiplied children (tips) use the identity: 1*x + 0*... is exact
+        sP[(c * K + bb) * P4_PSTRIDE + e] = P ? P[bb * 16 + e] : ((e % 5 == 0) ? 1.0 : 0.0);
+      }
+    }
+    __syncthreads();
+    if (!active) continue;
+    if (p_in_smem && nc == 2) {
+      prune4_tile<2, UNROLL, ROOT>(a, nd, s_child, sP, row0, rl, b, K, rows_per_pass);
+    } else {
+      prune4_tile_generic<UNROLL, ROOT>(a, nd, sP, p_in_smem, row0, rl, b, K, rows_per_pass);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 tensor-core (DMMA) kernel, MP = padded state count (multiple of 8, <= 64)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int MP>
+struct DmmaCfg {
+  static constexpr int LDS = MP + 4;  // row stride (doubles): conflict-free fragment loads
+  static constexpr int NI = MP / 8;   // n-blocks of 8 columns
+  static constexpr int KS = MP / 4;   // k-steps of 4
+  static constexpr int A_DOUBLES = DMMA_TILE_ROWS * LDS;
+  static constexpr int B_DOUBLES = MP * LDS;
+  static constexpr int NB = 2;  // resident P matrices
+  static constexpr size_t SMEM_BYTES = (size_t)(A_DOUBLES + NB * B_DOUBLES) * sizeof(double);
+};
+
+template <int MP>
+__device__ __forceinline__ void load_P_to_smem(double* __restrict__ sB, const double* __restrict__ P) {
+  constexpr int LDS = DmmaCfg<MP>::LDS;
+  for (int o = threadIdx.x; o < MP * MP / 2; o += DMMA_THREADS) {
+    const int i = (2 * o) / MP, j = (2 * o) - i * MP;
+    const double2 v = *reinterpret_cast<const double2*>(P + i * MP + j);
+    *reinterpret_cast<double2*>(sB + i * LDS + j) = v;
+  }
+}
+
+template <int MP, bool ROOT>
+__global__ void __launch_bounds__(DMMA_THREADS) prune_dmma_kernel(const PruneArgs a) {
+  using Cfg = DmmaCfg<MP>;
+  constexpr int LDS = Cfg::LDS, NI = Cfg::NI, KS = Cfg::KS;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;
+  double* sB = smem + Cfg::A_DOUBLES;  // [NB][MP*LDS]
+  const int K = a.K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;  // fragment row group / quad lane
+
+  int cur_node = -1, cur_bin = -1;
+  for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    const int w = find_work(a.tile_prefix, a.n_work, t);
+    const int node_id = a.work_node[w];
+    const NodeDesc nd = a.nodes[node_id];
+    const int64_t row_tiles = (nd.n_rows + DMMA_TILE_ROWS - 1) / DMMA_TILE_ROWS;
+    const int local = t - a.tile_prefix[w];
+    const int b = (int)(local / row_tiles);
+    const int64_t row0 = (int64_t)(local - b * row_tiles) * DMMA_TILE_ROWS;
+    const int nc = nd.n_children;
+
+    // which children need the contraction; the first NB of them keep P resident
+    if (node_id != cur_node || b != cur_bin) {
+      __syncthreads();
+      int slot = 0;
+      for (int c = 0; c < nc && slot < Cfg::NB; ++c) {
+        const double* P = a.childs[nd.child_begin + c].P;
+        if (P != nullptr) {
+          load_P_to_smem<MP>(sB + slot * Cfg::B_DOUBLES, P + (int64_t)b * MP * MP);
+          ++slot;
+        }
+      }
+      cur_node = node_id;
+      cur_bin = b;
+      __syncthreads();
+    }
+
+    const int64_t my_row = row0 + warp * 8 + g;  // the C-fragment row of this thread
+    const bool row_ok = my_row < nd.n_rows;
+    const int64_t my_row_c = row_ok ? my_row : nd.n_rows - 1;
+
+    double prod[NI][2];
+    int dmma_seen = 0;
+    for (int c = 0; c < nc; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + c];
+      double cur[NI][2];
+      if (ch.P == nullptr) {
+        // pre-multiplied (tip) child: gather the finished row straight into the C layout
+        const int32_t r = __ldg(ch.idx + my_row_c);
+        const double* src = ch.src + ((int64_t)r * K + b) * MP + 2 * q;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          const double2 v = __ldg(reinterpret_cast<const double2*>(src + 8 * ni));
+          cur[ni][0] = v.x;
+          cur[ni][1] = v.y;
+        }
+      } else {
+        const double* sBc;
+        if (dmma_seen < Cfg::NB) {
+          sBc = sB + dmma_seen * Cfg::B_DOUBLES;
+        } else {
+          // more contraction children than resident slots (e.g. a trifurcating root of
+          // internal nodes): stream this P through slot 0, restore on the next tile
+          __syncthreads();
+          load_P_to_smem<MP>(sB, ch.P + (int64_t)b * MP * MP);
+          cur_node = -1;
+          sBc = sB;
+        }
+        ++dmma_seen;
+        // gather 64 child rows into shared memory (16 B per lane, coalesced per row)
+        constexpr int CHUNKS = MP / 2;  // 16-byte chunks per row
+        for (int o = tid; o < DMMA_TILE_ROWS * CHUNKS; o += DMMA_THREADS) {
+          const int rr = o / CHUNKS, ck = o - rr * CHUNKS;
+          int64_t p = row0 + rr;
+          if (p >= nd.n_rows) p = nd.n_rows - 1;
+          const int32_t r = __ldg(ch.idx + p);
+          cp_async16(sA + rr * LDS + 2 * ck, ch.src + ((int64_t)r * K + b) * MP + 2 * ck);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) cur[ni][0] = cur[ni][1] = 0.0;
+        const double* aRow = sA + (warp * 8 + g) * LDS + q;
+        const double* bRow = sBc + g * LDS + q;
+#pragma unroll 4
+        for (int ks = 0; ks < KS; ++ks) {
+          const double av = aRow[4 * ks];
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) {
+            const double bv = bRow[(8 * ni) * LDS + 4 * ks];
+            dmma_m8n8k4(cur[ni][0], cur[ni][1], av, bv);
+          }
+        }
+        __syncthreads();  // sA (and a streamed sB) may be overwritten by the next child
+      }
+      if (c == 0) {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) { prod[ni][0] = cur[ni][0]; prod[ni][1] = cur[ni][1]; }
+      } else {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) { prod[ni][0] *= cur[ni][0]; prod[ni][1] *= cur[ni][1]; }
+      }
+    }
+    if (nd.fixed_motif >= 0) {
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        if (8 * ni + 2 * q != nd.fixed_motif) prod[ni][0] = 0.0;
+        if (8 * ni + 2 * q + 1 != nd.fixed_motif) prod[ni][1] = 0.0;
+      }
+    }
+    if (row_ok) {
+      double* dst = nd.out + ((int64_t)my_row * K + b) * MP + 2 * q;
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni)
+        *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(prod[ni][0], prod[ni][1]);
+    }
+    if (ROOT) {
+      double s = 0.0;
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        s = fma(prod[ni][0], a.pi[8 * ni + 2 * q], s);
+        s = fma(prod[ni][1], a.pi[8 * ni + 2 * q + 1], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (row_ok && q == 0) a.lh_out[my_row * K + b] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// site-weighted log-likelihood reduction
+//   mix[p] = sum_b bprob_b lh_b[p]     BinnedSiteDistribution.get_weighted_sum_lh
+//                                      (evolve/likelihood_calculation.py:178-185)
+//   lnL    = sum_p log(mix[p]) counts[p]   get_log_sum_across_sites
+//                                      (evolve/likelihood_tree_numba.py:36-42)
+// Deterministic: fixed tile size, fixed in-tile tree, tiles summed in index order by the
+// last CTA to finish -- the result does not depend on the grid or on timing.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* s_warp) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  double total = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) total += s_warp[i];
+  }
+  return total;  // valid on thread 0
+}
+
+__global__ void __launch_bounds__(REDUCE_THREADS)
+lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bprobs,
+                  const double* __restrict__ counts, int64_t n_rows, int K, int n_tiles,
+                  double* __restrict__ tile_sums, unsigned int* __restrict__ counter,
+                  double* __restrict__ d_lnl, double* __restrict__ d_lnl2,
+                  volatile double* __restrict__ h_lnl) {
+  __shared__ double s_warp[REDUCE_THREADS / 32];
+  __shared__ bool s_last;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    double acc = 0.0;
+    const int64_t base = (int64_t)tile * REDUCE_ROWS_PER_TILE;
+#pragma unroll
+    for (int u = 0; u < REDUCE_ROWS_PER_TILE / REDUCE_THREADS; ++u) {
+      const int64_t p = base + u * REDUCE_THREADS + threadIdx.x;
+      if (p < n_rows) {
+        double mix;
+        if (K == 1) {
+          mix = lh[p];
+        } else {
+          mix = 0.0;
+          for (int b = 0; b < K; ++b) mix = __dadd_rn(mix, __dmul_rn(lh[p * K + b], bprobs[b]));
+        }
+        acc += log(mix) * counts[p];
+      }
+    }
+    const double total = block_sum(acc, s_warp);
+    if (threadIdx.x == 0) tile_sums[tile] = total;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_tiles; i += REDUCE_THREADS) acc += __ldcg(tile_sums + i);
+  const double total = block_sum(acc, s_warp);
+  if (threadIdx.x == 0) {
+    *d_lnl = total;
+    if (d_lnl2) *d_lnl2 = total;
+    if (h_lnl) *h_lnl = total;
+    *counter = 0u;
+    __threadfence_system();
+  }
+}
+
+// sustained DMMA rate microbenchmark (roofline denominator of the codon kernel)
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+  double acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+}  // namespace c3

@@ -1,0 +1,187 @@
+"""LikelihoodEngine: Python handle on one ``c3_engine`` (include/c3cuda.h).
+
+The engine owns all device buffers (pattern tables, resident partial likelihoods,
+P matrices); Python keeps only small parameter arrays.  Mirrors what the
+reference's Defn cells hold for one locus (a10-a15) but with the
+whole post-order sweep behind one call.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_void_p
+
+import numpy as np
+
+from . import _lib
+from .patterns import PatternTree
+
+
+def _dptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(c_double))
+
+
+def _i32ptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+def _i64ptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+
+
+class LikelihoodEngine:
+    """GPU-resident Felsenstein pruning for one alignment on one device."""
+
+    def __init__(self, patterns: PatternTree, n_bins: int = 1, device: int = 0, stream=None):
+        self._lib = _lib.load()
+        self._h = c_void_p()
+        self.patterns = patterns
+        topo = patterns.topo
+        self.topo = topo
+        self.n_states = int(patterns.n_states)
+        self.n_bins = int(n_bins)
+        self.n_nodes = topo.n_nodes
+        ptr, idx = topo.child_csr()
+        _lib.check(
+            self._lib.c3_create(
+                device, topo.n_nodes, self.n_states, self.n_bins, _i32ptr(ptr), _i32ptr(idx),
+                byref(self._h),
+            )
+        )  # fmt: skip
+        try:
+            if stream is not None:
+                self.set_stream(stream)
+            for n, nd in enumerate(patterns.nodes):
+                if nd.is_tip:
+                    tab = np.ascontiguousarray(nd.table, dtype=np.float64)
+                    _lib.check(self._lib.c3_set_tip(self._h, n, _dptr(tab), tab.shape[0]))
+                else:
+                    ix = np.ascontiguousarray(nd.indexes, dtype=np.int64)
+                    _lib.check(
+                        self._lib.c3_set_node_patterns(self._h, n, _i64ptr(ix), ix.shape[1])
+                    )
+            counts = np.ascontiguousarray(patterns.root.counts, dtype=np.float64)
+            _lib.check(self._lib.c3_set_root_counts(self._h, _dptr(counts), counts.shape[0]))
+            _lib.check(self._lib.c3_finalize(self._h))
+        except Exception:
+            self.close()
+            raise
+        self.root_rows = int(patterns.root.n_rows)
+        self._dist = np.zeros((self.n_nodes, self.n_bins), np.float64)
+
+    # -- lifetime ------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.c3_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        """``stream``: a ``torch.cuda.Stream`` / raw cudaStream_t int / None"""
+        raw = getattr(stream, "cuda_stream", stream)
+        _lib.check(self._lib.c3_set_stream(self._h, c_void_p(raw) if raw else None))
+
+    # -- model state ---------------------------------------------------------
+    def set_eigen(self, slot, roots, evT, evI):
+        """eigen-system of one distinct Q (EigenExponentiator state)."""
+        is_complex = any(np.iscomplexobj(a) for a in (roots, evT, evI))
+        dt = np.complex128 if is_complex else np.float64
+        roots = np.ascontiguousarray(roots, dtype=dt)
+        evT = np.ascontiguousarray(evT, dtype=dt)
+        evI = np.ascontiguousarray(evI, dtype=dt)
+        M = self.n_states
+        assert roots.shape == (M,) and evT.shape == (M, M) and evI.shape == (M, M)
+        f = lambda a: a.view(np.float64).ctypes.data_as(ctypes.POINTER(c_double))  # noqa: E731
+        _lib.check(
+            self._lib.c3_set_eigen(self._h, slot, f(roots), f(evT), f(evI), int(is_complex))
+        )
+
+    def set_Q(self, slot, Q):
+        """rate matrix for the Pade path."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        assert Q.shape == (self.n_states, self.n_states)
+        _lib.check(self._lib.c3_set_Q(self._h, slot, _dptr(Q)))
+
+    def set_edge_qslots(self, qslots):
+        q = np.ascontiguousarray(np.broadcast_to(qslots, (self.n_nodes, self.n_bins)), np.int32)
+        _lib.check(self._lib.c3_set_edge_qslots(self._h, _i32ptr(q)))
+
+    def set_psub(self, node, bin_, P):
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        _lib.check(self._lib.c3_set_psub(self._h, int(node), int(bin_), _dptr(P)))
+
+    def set_distances(self, dist):
+        """``dist[n_nodes, n_bins]`` = length[edge] * rate[bin] (root row ignored)."""
+        d = np.ascontiguousarray(np.broadcast_to(dist, (self.n_nodes, self.n_bins)), np.float64)
+        self._dist = d
+        _lib.check(self._lib.c3_set_distances(self._h, _dptr(d)))
+
+    def set_root_mprobs(self, pi):
+        pi = np.ascontiguousarray(pi, dtype=np.float64)
+        assert pi.shape == (self.n_states,)
+        _lib.check(self._lib.c3_set_root_mprobs(self._h, _dptr(pi)))
+
+    def set_bin_probs(self, bprobs):
+        bp = np.ascontiguousarray(bprobs, dtype=np.float64)
+        assert bp.shape == (self.n_bins,)
+        _lib.check(self._lib.c3_set_bin_probs(self._h, _dptr(bp)))
+
+    def set_fixed_motifs(self, fixed):
+        fm = np.full(self.n_nodes, -1, np.int32)
+        if fixed is not None:
+            fm[:] = np.asarray(fixed, np.int32)
+        _lib.check(self._lib.c3_set_fixed_motifs(self._h, _i32ptr(fm)))
+
+    def invalidate(self):
+        _lib.check(self._lib.c3_invalidate(self._h))
+
+    # -- evaluation ----------------------------------------------------------
+    def evaluate(self) -> float:
+        out = c_double(0.0)
+        _lib.check(self._lib.c3_evaluate(self._h, byref(out)))
+        return out.value
+
+    def update(self, dist) -> float:
+        d = np.ascontiguousarray(np.broadcast_to(dist, (self.n_nodes, self.n_bins)), np.float64)
+        out = c_double(0.0)
+        _lib.check(self._lib.c3_update(self._h, _dptr(d), byref(out)))
+        return out.value
+
+    def evaluate_device(self, device_ptr: int):
+        """asynchronous; writes lnL to ``device_ptr`` (a double in device memory)"""
+        _lib.check(self._lib.c3_evaluate_device(self._h, c_void_p(device_ptr)))
+
+    # -- accessors -------------------------------------------------------------
+    def get_lh(self, bin_=0):
+        out = np.empty(self.root_rows, np.float64)
+        _lib.check(self._lib.c3_get_lh(self._h, int(bin_), _dptr(out), out.shape[0]))
+        return out
+
+    def get_psub(self, node, bin_=0):
+        M = self.n_states
+        out = np.empty((M, M), np.float64)
+        _lib.check(self._lib.c3_get_psub(self._h, int(node), int(bin_), _dptr(out)))
+        return out
+
+    def get_partials(self, node, bin_=0):
+        rows = int(self.patterns.nodes[node].n_rows)
+        out = np.empty((rows, self.n_states), np.float64)
+        _lib.check(self._lib.c3_get_partials(self._h, int(node), int(bin_), _dptr(out), rows))
+        return out
+
+    def stats(self):
+        st = _lib.C3Stats()
+        _lib.check(self._lib.c3_get_stats(self._h, byref(st)))
+        return st.as_dict()
+
+
+def measure_dmma_peak(device=0) -> float:
+    """sustained FP64 tensor-core TFLOP/s of this GPU (DMMA m8n8k4 issue loop)."""
+    out = c_double(0.0)
+    _lib.check(_lib.load().c3_measure_dmma_peak(device, byref(out)))
+    return out.value

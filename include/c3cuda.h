@@ -1,0 +1,154 @@
+/*
+ * libc3cuda -- C ABI of the B200-native likelihood engine for cogent3's
+ * substitution-model hot path.
+ *
+ * This is the drop-in boundary.  cogent3 has no FFI for this
+ * path (it is pure Python + numba); every entry point below therefore cites the
+ * reference function whose arithmetic it replaces (paths relative to
+ * /root/reference/src/cogent3).  The binding a cogent3 maintainer would add is a
+ * ctypes stub -- see INTEGRATION.md and cogent3_b200/_lib.py.
+ *
+ * Conventions
+ *   - all functions return C3_OK (0) or a C3_ERR_* code; c3_last_error() gives a
+ *     thread-local message.  No exceptions cross the ABI.
+ *   - plain pointers and sizes only; host pointers unless the name says "device".
+ *   - nodes are numbered in post-order (every child id < its parent id), the root
+ *     is node n_nodes-1; "the edge of node n" is the branch above node n.
+ *   - a node's pattern table has n_rows = P+1 rows; the last is the all-gap row
+ *     with count 0 (evolve/likelihood_tree.py:49-51, 230-232).
+ *   - P[i*M + j] = Pr(i -> j) (maths/matrix_exponentiation.py:35-40).
+ *   - per-(edge, bin) arrays are laid out [node][bin] (node-major).
+ */
+#ifndef C3CUDA_H
+#define C3CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C3_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define C3_API __attribute__((visibility("default")))
+#else
+#define C3_API
+#endif
+
+#define C3_OK 0
+#define C3_ERR_INVALID 1 /* bad argument / call order                           */
+#define C3_ERR_CUDA 2    /* CUDA runtime error                                  */
+#define C3_ERR_MEMORY 3  /* device memory exhausted                             */
+#define C3_ERR_NUMERIC 4 /* recoverable numeric failure -> ArithmeticError      */
+
+typedef struct c3_engine c3_engine;
+
+typedef struct c3_stats {
+  int64_t evaluations;        /* c3_evaluate* calls that launched work          */
+  int64_t kernel_launches;    /* kernels launched since creation                */
+  int64_t last_launches;      /* kernels launched by the last evaluation        */
+  int64_t last_expm_jobs;     /* P matrices recomputed by the last evaluation   */
+  int64_t last_nodes;         /* internal nodes recomputed by the last eval     */
+  int64_t last_node_rows;     /* sum of pattern rows over those nodes           */
+  int64_t last_alg_bytes;     /* algorithmic bytes of the pruning kernels (§8d) */
+  int64_t last_flops;         /* executed FP64 flops of the pruning kernels     */
+  int64_t device_bytes;       /* device memory owned by the engine              */
+  int64_t partial_bytes;      /* ... of which resident partial likelihoods      */
+  int32_t n_levels;           /* tree levels (kernel launches of a full sweep)  */
+  int32_t padded_states;      /* row stride of a partial row, in doubles        */
+} c3_stats;
+
+C3_API int c3_abi_version(void);
+C3_API const char* c3_last_error(void);
+C3_API int c3_device_count(int* n);
+
+/* ---- construction --------------------------------------------------------
+ * replaces the Defn sub-DAG built by make_total_loglikelihood_defn
+ * (evolve/likelihood_calculation.py:125-167): one engine per (locus) likelihood
+ * function.  child_ptr[n_nodes+1] / child_idx[] is the CSR list of ordered
+ * children (PhyloNode.children order, likelihood_calculation.py:83-87).        */
+C3_API int c3_create(int device, int n_nodes, int n_states, int n_bins,
+              const int32_t* child_ptr, const int32_t* child_idx, c3_engine** out);
+C3_API int c3_destroy(c3_engine* e);
+/* run on the caller's CUDA stream (e.g. torch's current stream); NULL = own    */
+C3_API int c3_set_stream(c3_engine* e, void* cuda_stream);
+
+/* ---- pattern tables (set once per alignment) -------------------------------
+ * c3_set_tip: LikelihoodTreeLeaf.input_likelihoods [n_rows x M]
+ *             (evolve/likelihood_tree.py:223-278; LeafPartialLikelihoodDefn
+ *             likelihood_calculation.py:32-37)
+ * c3_set_node_patterns: LikelihoodTreeEdge.indexes int64 [C x n_rows],
+ *             C-contiguous (evolve/likelihood_tree.py:55-58)
+ * c3_set_root_counts: root LikelihoodTreeEdge.counts (likelihood_tree.py:62)
+ * c3_finalize: allocates the resident partial-likelihood arrays in HBM
+ *             (make_partial_likelihoods_array, likelihood_tree.py:133-134).    */
+C3_API int c3_set_tip(c3_engine* e, int node, const double* table, int64_t n_rows);
+C3_API int c3_set_node_patterns(c3_engine* e, int node, const int64_t* indexes, int64_t n_rows);
+C3_API int c3_set_root_counts(c3_engine* e, const double* counts, int64_t n_rows);
+C3_API int c3_finalize(c3_engine* e);
+
+/* ---- model state -------------------------------------------------------------
+ * A "q slot" is one distinct rate matrix (one value of the Q / Qd Defns,
+ * evolve/substitution_model.py:636-641).
+ * c3_set_eigen: the EigenExponentiator state (maths/matrix_exponentiation.py:23-40)
+ *             as produced by Fast/CheckedExponentiator (:132-146): roots[M],
+ *             evT[M x M], evI[M x M]; complex128 interleaved (re, im) when
+ *             is_complex != 0, float64 otherwise.
+ * c3_set_Q:   the rate matrix for the Pade path (PadeExponentiator :92-129).
+ * c3_set_edge_qslots: which slot each (edge, bin) exponentiates [n_nodes x K].
+ * c3_set_psub: a P matrix supplied directly (discrete-time models,
+ *             evolve/discrete_markov.py:15-80); the (edge, bin) stops using expm.
+ * c3_set_distances: distance[edge, bin] = length * rate (ProductDefn,
+ *             recalculation/definition.py:679-683; psubs = Qd(distance),
+ *             substitution_model.py:702-710).  The engine diffs against the
+ *             previous values: only changed edges are re-exponentiated and only
+ *             their ancestors re-pruned (the role of Calculator.change,
+ *             recalculation/calculation.py:402-477).
+ * c3_set_root_mprobs / c3_set_bin_probs / c3_set_fixed_motifs: the other inputs
+ *             of the lh / tll / plh Defns (likelihood_calculation.py:50-59,
+ *             147-148, 174-185).                                               */
+C3_API int c3_set_eigen(c3_engine* e, int q_slot, const double* roots, const double* evT,
+                 const double* evI, int is_complex);
+C3_API int c3_set_Q(c3_engine* e, int q_slot, const double* Q);
+C3_API int c3_set_edge_qslots(c3_engine* e, const int32_t* q_slot_of_edge_bin);
+C3_API int c3_set_psub(c3_engine* e, int node, int bin, const double* P);
+C3_API int c3_set_distances(c3_engine* e, const double* distance_of_edge_bin);
+C3_API int c3_set_root_mprobs(c3_engine* e, const double* pi);
+C3_API int c3_set_bin_probs(c3_engine* e, const double* bprobs);
+C3_API int c3_set_fixed_motifs(c3_engine* e, const int32_t* fixed_motif_of_node);
+C3_API int c3_invalidate(c3_engine* e); /* force a full recomputation next time        */
+
+/* ---- evaluation ----------------------------------------------------------------
+ * c3_evaluate: batched expm for the dirty (edge, bin)s, level-by-level pruning of
+ *             the dirty nodes, site-weighted reduction; blocks for the scalar
+ *             (replaces Calculator.__call__'s cell sweep for the psubs / inner /
+ *             plh / lh / tll cells and get_log_sum_across_sites,
+ *             evolve/likelihood_tree_numba.py:36-42).
+ * c3_evaluate_device: same, asynchronous on the engine's stream; the scalar is
+ *             written to device memory (input of the NCCL all-reduce when site
+ *             patterns are sharded over GPUs).
+ * c3_update:  distances + evaluate in one call (one FFI crossing per optimiser
+ *             step).                                                           */
+C3_API int c3_evaluate(c3_engine* e, double* lnL);
+C3_API int c3_evaluate_device(c3_engine* e, double* device_lnL);
+C3_API int c3_update(c3_engine* e, const double* distance_of_edge_bin, double* lnL);
+
+/* ---- accessors (what likelihood_function.py reads back) -------------------------
+ * c3_get_lh: per-pattern root likelihood of one bin, "lh" Defn
+ *             (likelihood_function.py:415-425); n_rows = root rows.
+ * c3_get_psub: "psubs" value (likelihood_function.py:272-320).
+ * c3_get_partials: "plh" of one node and bin [n_rows x M].                     */
+C3_API int c3_get_lh(c3_engine* e, int bin, double* out, int64_t n_rows);
+C3_API int c3_get_psub(c3_engine* e, int node, int bin, double* out);
+C3_API int c3_get_partials(c3_engine* e, int node, int bin, double* out, int64_t n_rows);
+C3_API int c3_get_stats(c3_engine* e, c3_stats* out);
+
+/* ---- calibration helper: sustained FP64 tensor (DMMA) rate of this GPU, used as
+ * the roofline denominator of the 61-state kernel.                 */
+C3_API int c3_measure_dmma_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C3CUDA_H */

@@ -1,0 +1,233 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors of the
+live reference and against the CPU oracle on the same inputs.
+
+Tolerances are the north-star's: pattern tables bit-exact (checked on the CPU side),
+total lnL <= 1e-9 relative, per-pattern likelihoods <= 1e-12 absolute."""
+
+import numpy as np
+import pytest
+from goldenutil import Golden, golden_cases
+from lfutil import lf_from_golden
+from oracle_engine import OracleEngine
+
+from cogent3_b200 import models as hostmodels
+from cogent3_b200.likelihood import LikelihoodFunction
+from cogent3_b200.synthetic import make_workload
+
+pytestmark = pytest.mark.gpu
+CASES = golden_cases()
+REL_LNL = 1e-9
+ABS_LH = 1e-12
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_golden_lnL_lh_psubs(case):
+    g = Golden(case)
+    lf = lf_from_golden(g)
+    lnL = lf.get_log_likelihood()
+    assert abs(lnL - g.lnL) <= REL_LNL * abs(g.lnL), (lnL, g.lnL)
+    for b in range(g.n_bins):
+        lh = lf.engine.get_lh(b)
+        assert np.max(np.abs(lh - g.lh[b])) <= ABS_LH
+        for n in g.topo.edges:
+            P = lf.engine.get_psub(n, b)
+            np.testing.assert_allclose(P, g.psubs[b, n], rtol=0, atol=1e-13)
+    if "pinned_lnL" in g.meta:
+        np.testing.assert_allclose(lnL, g.meta["pinned_lnL"], rtol=1e-7)
+    st = lf.engine.stats()
+    assert st["last_launches"] >= 3  # expm + >=1 level + reduction: the CUDA path ran
+
+
+@pytest.mark.parametrize("case", ["c2_gtr_gamma4_small", "c4_cnfgtr_small", "c3_gn_pade_small"])
+def test_partials_match_oracle(case):
+    g = Golden(case)
+    lf = lf_from_golden(g)
+    ref = lf_from_golden(g, engine_factory=OracleEngine)
+    lf.get_log_likelihood()
+    ref.get_log_likelihood()
+    for n in range(g.topo.n_nodes):
+        for b in range(g.n_bins):
+            got = lf.engine.get_partials(n, b)
+            want = ref.engine.get_partials(n, b)
+            np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-300)
+
+
+@pytest.mark.parametrize("case", ["c1_brca1_hky85_default", "c2_gtr_gamma4_mid", "c4_cnfgtr_small"])
+def test_partial_update_equals_full_recompute(case):
+    g = Golden(case)
+    lf = lf_from_golden(g)
+    ref = lf_from_golden(g, engine_factory=OracleEngine)
+    lf.get_log_likelihood()
+    rng = np.random.default_rng(3)
+    for n in rng.choice(g.topo.edges, size=4, replace=False):
+        name = g.topo.names[n]
+        v = float(rng.uniform(0.01, 0.5))
+        lf.set_param_rule("length", edge=name, value=v)
+        ref.set_param_rule("length", edge=name, value=v)
+        got = lf.get_log_likelihood()
+        st = lf.engine.stats()
+        assert st["last_expm_jobs"] == g.n_bins  # only that edge was re-exponentiated
+        assert st["last_nodes"] == len(g.topo.ancestors(n))  # only its ancestors re-pruned
+        want = ref.get_log_likelihood()
+        assert abs(got - want) <= REL_LNL * abs(want)
+        lf.engine.invalidate()
+        full = lf.get_log_likelihood()
+        assert got == full  # dirty-path result is bit-identical to a full sweep
+
+
+def test_rate_param_and_mprobs_changes():
+    g = Golden("c2_gtr_gamma4_small")
+    lf = lf_from_golden(g)
+    ref = lf_from_golden(g, engine_factory=OracleEngine)
+    for setter in (
+        lambda f: f.set_param_rule("A/G", value=2.2),
+        lambda f: f.set_param_rule("rate_shape", value=1.3),
+        lambda f: f.set_motif_probs(np.array([0.1, 0.2, 0.3, 0.4])),
+        lambda f: f.set_param_rule("bprobs", value=np.array([0.4, 0.3, 0.2, 0.1])),
+    ):
+        setter(lf)
+        setter(ref)
+        got, want = lf.get_log_likelihood(), ref.get_log_likelihood()
+        assert abs(got - want) <= REL_LNL * abs(want)
+
+
+def test_fixed_motif_masks_like_reference():
+    g = Golden("c2_gtr_gamma4_small")
+    lf = lf_from_golden(g)
+    ref = lf_from_golden(g, engine_factory=OracleEngine)
+    lf.get_log_likelihood()
+    ref.get_log_likelihood()
+    node = g.topo.n_nodes - 2 if not g.topo.is_tip[g.topo.n_nodes - 2] else g.topo.root
+    for motif in range(4):
+        fixed = np.full(g.topo.n_nodes, -1)
+        fixed[node] = motif
+        lf.engine.set_fixed_motifs(fixed)
+        ref.engine.set_fixed_motifs(list(fixed))
+        lf.engine.evaluate()
+        ref.engine.evaluate()
+        for b in range(g.n_bins):
+            assert np.max(np.abs(lf.engine.get_lh(b) - ref.engine.get_lh(b))) <= ABS_LH
+
+
+def test_direct_psub_edges():
+    """P supplied by the host (discrete-time edges) bypasses expm"""
+    g = Golden("c5_hky85_gamma4_small")
+    lf = lf_from_golden(g)
+    ref = lf_from_golden(g, engine_factory=OracleEngine)
+    lf.get_log_likelihood()
+    ref.get_log_likelihood()
+    rng = np.random.default_rng(0)
+    P = rng.random((4, 4))
+    P /= P.sum(axis=1, keepdims=True)
+    for b in range(g.n_bins):
+        lf.engine.set_psub(2, b, P)
+        ref.engine.set_psub(2, b, P)
+    got, want = lf.engine.evaluate(), ref.engine.evaluate()
+    assert abs(got - want) <= REL_LNL * abs(want)
+    np.testing.assert_array_equal(lf.engine.get_psub(2, 1), P)
+
+
+@pytest.mark.parametrize("force_dmma", [False, True])
+def test_four_state_through_both_kernels(force_dmma, monkeypatch):
+    """the 4-state register kernel and the generic DMMA kernel (MP=8) agree"""
+    if force_dmma:
+        monkeypatch.setenv("C3_FORCE_DMMA", "1")
+    g = Golden("c2_gtr_gamma4_mid")
+    lf = lf_from_golden(g)
+    lnL = lf.get_log_likelihood()
+    assert lf.engine.stats()["padded_states"] == (8 if force_dmma else 4)
+    assert abs(lnL - g.lnL) <= REL_LNL * abs(g.lnL)
+
+
+@pytest.mark.parametrize(
+    "model,n_tips,L,bins,kind",
+    [
+        ("GTR", 24, 50_000, 4, "evolved"),
+        ("HKY85", 16, 30_000, 1, "dense"),
+        ("GN", 12, 20_000, 1, "evolved"),
+        ("CNFGTR", 10, 4_000, 1, "evolved"),
+        ("CNFGTR", 8, 2_000, 2, "dense"),
+    ],
+)
+def test_synthetic_against_oracle(model, n_tips, L, bins, kind):
+    m = hostmodels.get_model(model)
+    topo, lengths, codes = make_workload(n_tips, L, m.n_states, kind=kind, seed=99)
+    rows = np.eye(m.n_states)
+    kw = {"expm": "pade"} if model == "GN" else {}
+    lfs = []
+    for factory in (None, OracleEngine):
+        lf = LikelihoodFunction(m, topo, bins=bins, engine_factory=factory, **kw)
+        lf.set_alignment(codes.astype(np.int64), rows)
+        lf.set_motif_probs_from_data()
+        lf.lengths[:-1] = lengths[:-1]
+        for k, p in enumerate(m.parameter_order):
+            lf.set_param_rule(p, value=0.5 + 0.37 * k)
+        if bins > 1:
+            lf.set_param_rule("rate_shape", value=0.6)
+        lfs.append(lf)
+    got, want = lfs[0].get_log_likelihood(), lfs[1].get_log_likelihood()
+    assert abs(got - want) <= REL_LNL * abs(want), (got, want)
+    for b in range(bins):
+        assert np.max(np.abs(lfs[0].engine.get_lh(b) - lfs[1].engine.get_lh(b))) <= ABS_LH
+
+
+def test_polytomy_and_many_bins():
+    """5-way polytomy at the root, K=3 (generic-K kernel path)"""
+    from cogent3_b200.tree import Topology
+
+    topo, _ = Topology.from_newick("(a:0.1,b:0.2,c:0.15,(d:0.1,e:0.3):0.05,f:0.2);")
+    rng = np.random.default_rng(5)
+    codes = rng.integers(0, 4, size=(6, 700))
+    lfs = []
+    for factory in (None, OracleEngine):
+        lf = LikelihoodFunction("HKY85", topo, bins=3, engine_factory=factory)
+        lf.set_alignment(codes, np.eye(4))
+        lf.lengths[:-1] = [0.1, 0.2, 0.15, 0.1, 0.3, 0.05, 0.2]
+        lf.set_param_rule("kappa", value=2.5)
+        lf.set_param_rule("rate_shape", value=0.8)
+        lfs.append(lf)
+    got, want = lfs[0].get_log_likelihood(), lfs[1].get_log_likelihood()
+    assert abs(got - want) <= REL_LNL * abs(want)
+
+
+def test_empty_and_single_column_alignments():
+    from cogent3_b200.tree import Topology
+
+    topo, _ = Topology.from_newick("((a:0.1,b:0.2):0.1,c:0.3,d:0.2);")
+    for L in (0, 1):
+        codes = np.zeros((4, L), np.int64)
+        lfs = []
+        for factory in (None, OracleEngine):
+            lf = LikelihoodFunction("HKY85", topo, engine_factory=factory)
+            lf.set_alignment(codes, np.eye(4))
+            lf.lengths[:-1] = 0.2
+            lfs.append(lf)
+        got, want = lfs[0].get_log_likelihood(), lfs[1].get_log_likelihood()
+        assert got == pytest.approx(want, rel=1e-12, abs=1e-15)
+
+
+def test_determinism_repeated_and_recreated():
+    g = Golden("c2_gtr_gamma4_mid")
+    vals = set()
+    for _ in range(3):
+        lf = lf_from_golden(g)
+        vals.add(lf.get_log_likelihood())
+        lf.engine.invalidate()
+        vals.add(lf.get_log_likelihood())
+    assert len(vals) == 1
+
+
+def test_optimise_improves_and_matches_oracle_path():
+    g = Golden("c2_gtr_gamma4_small")
+    lf = lf_from_golden(g)
+    before = lf.get_log_likelihood()
+    after = lf.optimise(max_evaluations=400)
+    assert after > before
+    # the optimum found on the GPU evaluates to the same lnL on the oracle
+    ref = lf_from_golden(g, engine_factory=OracleEngine)
+    ref.lengths[:] = lf.lengths
+    ref.params = dict(lf.params)
+    ref.rate_shape = lf.rate_shape
+    ref._dirty_q = ref._dirty_model = True
+    want = ref.get_log_likelihood()
+    assert abs(after - want) <= REL_LNL * abs(want)
