@@ -34,6 +34,7 @@ class C3Stats(ctypes.Structure):
         ("last_node_rows", c_int64),
         ("last_alg_bytes", c_int64),
         ("last_flops", c_int64),
+        ("last_h2d_bytes", c_int64),
         ("device_bytes", c_int64),
         ("partial_bytes", c_int64),
         ("n_levels", c_int32),
@@ -76,6 +77,8 @@ SIGNATURES = {
     "c3_get_psub": (c_int, [c_void_p, c_int, c_int, _pd]),
     "c3_get_partials": (c_int, [c_void_p, c_int, c_int, _pd, c_int64]),
     "c3_get_stats": (c_int, [c_void_p, POINTER(C3Stats)]),
+    "c3_set_profiling": (c_int, [c_void_p, c_int]),
+    "c3_get_launch_profile": (c_int, [c_void_p, c_int, _pi32, _pd, _pi64, _pi64, POINTER(c_int)]),
     "c3_measure_dmma_peak": (c_int, [c_int, _pd]),
 }
 

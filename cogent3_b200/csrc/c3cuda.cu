@@ -123,6 +123,13 @@ struct c3_engine {
   bool have_cached = false;
 
   c3_stats stats{};
+
+  // per-launch profiling
+  bool profiling = false;
+  struct LaunchRec { int kind; int64_t bytes, flops; cudaEvent_t a, b; float ms; };
+  std::vector<LaunchRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
 };
 
 namespace {
@@ -226,6 +233,29 @@ int ensure_slots(c3_engine* e, int n) {
 }
 
 int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out);
+
+cudaEvent_t next_event(c3_engine* e) {
+  if (e->events_used == e->event_pool.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    e->event_pool.push_back(ev);
+  }
+  return e->event_pool[e->events_used++];
+}
+
+struct ProfScope {
+  c3_engine* e;
+  bool on;
+  ProfScope(c3_engine* e_, int kind, int64_t bytes, int64_t flops) : e(e_), on(e_->profiling) {
+    if (!on) return;
+    c3_engine::LaunchRec r{kind, bytes, flops, next_event(e), next_event(e), 0.f};
+    cudaEventRecord(r.a, e->stream);
+    e->prof.push_back(r);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(e->prof.back().b, e->stream);
+  }
+};
 
 }  // namespace
 
@@ -339,6 +369,7 @@ int c3_destroy(c3_engine* e) {
   if (e->h_block) cudaFreeHost(e->h_block);
   if (e->h_lnl) cudaFreeHost(e->h_lnl);
   if (e->block_copied) cudaEventDestroy(e->block_copied);
+  for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return C3_OK;
@@ -734,6 +765,26 @@ int c3_get_stats(c3_engine* e, c3_stats* out) {
   return C3_OK;
 }
 
+int c3_set_profiling(c3_engine* e, int on) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  e->profiling = on != 0;
+  return C3_OK;
+}
+
+int c3_get_launch_profile(c3_engine* e, int max_n, int32_t* kind, double* ms, int64_t* alg_bytes,
+                          int64_t* flops, int* n) {
+  C3_REQUIRE(e && kind && ms && alg_bytes && flops && n, "null pointer");
+  const int m = std::min<int>(max_n, (int)e->prof.size());
+  for (int i = 0; i < m; ++i) {
+    kind[i] = e->prof[i].kind;
+    ms[i] = e->prof[i].ms;
+    alg_bytes[i] = e->prof[i].bytes;
+    flops[i] = e->prof[i].flops;
+  }
+  *n = m;
+  return C3_OK;
+}
+
 int c3_measure_dmma_peak(int device, double* tflops) {
   C3_REQUIRE(tflops != nullptr, "null pointer");
   C3_CUDA(cudaSetDevice(device));
@@ -847,13 +898,14 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
 
   int32_t* work = reinterpret_cast<int32_t*>(e->h_block + e->off_work);
   int32_t* prefix = reinterpret_cast<int32_t*>(e->h_block + e->off_prefix);
-  struct LevelLaunch { int work_off, prefix_off, n_work, total_tiles; bool is_root; };
+  struct LevelLaunch { int work_off, prefix_off, n_work, total_tiles; bool is_root; int64_t bytes, flops; };
   std::vector<LevelLaunch> launches;
   int w_off = 0, p_off = 0;
   int64_t node_rows = 0, alg_bytes = 0, flops = 0;
   for (int l = 1; l <= e->n_levels; ++l) {
-    LevelLaunch ll{w_off, p_off, 0, 0, false};
+    LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0};
     int64_t tiles = 0;
+    const int64_t bytes0 = alg_bytes, flops0 = flops;
     for (int n : e->level_nodes[l]) {
       if (!recompute[n]) continue;
       work[w_off + ll.n_work] = n;
@@ -872,6 +924,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       if (n == e->root) alg_bytes += rows * K * 8;
     }
     if (ll.n_work == 0) continue;
+    ll.bytes = alg_bytes - bytes0;
+    ll.flops = flops - flops0;
     prefix[p_off + ll.n_work] = (int32_t)tiles;
     ll.total_tiles = (int)tiles;
     w_off += ll.n_work;
@@ -880,9 +934,11 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   }
 
   // ---- upload: dirty slots, descriptors, the parameter block -------------------------
+  int64_t h2d_bytes = 0;
   for (size_t s = 0; s < e->slots.size(); ++s) {
     Slot& sl = e->slots[s];
     if (!sl.dirty) continue;
+    h2d_bytes += e->slot_stride * (int64_t)sizeof(double);
     // the vector stays alive and unmodified until the next set_* call; pageable copies
     // are staged by the runtime before the call returns
     C3_CUDA(cudaMemcpyAsync(e->d_slots + (int64_t)s * e->slot_stride, sl.data.data(),
@@ -901,14 +957,18 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   C3_CUDA(cudaMemcpyAsync(e->d_block, e->h_block, (size_t)std::min(used, e->block_bytes),
                           cudaMemcpyHostToDevice, e->stream));
   C3_CUDA(cudaEventRecord(e->block_copied, e->stream));
+  h2d_bytes += std::min(used, e->block_bytes);
 
   int64_t n_launch = 0;
+  e->prof.clear();
+  e->events_used = 0;
   const ExpmJob* d_jobs = reinterpret_cast<const ExpmJob*>(e->d_block + e->off_jobs);
   if (n_eigen > 0) {
     const int threads = (M <= 4) ? 32 : (M <= 16 ? 64 : 256);
     const size_t smem = (size_t)(MP * MP + 2 * M) * sizeof(double);
     static bool cfg = false;
     if (!cfg) { int rc = set_max_smem(expm_eigen_kernel, 64 * 64 * 8 + 1024); if (rc) return rc; cfg = true; }
+    ProfScope ps(e, 0, 0, 0);
     expm_eigen_kernel<<<n_eigen, threads, smem, e->stream>>>(d_jobs, e->d_slots, e->slot_stride, e->d_edges,
                                                             M, MP, K);
     ++n_launch;
@@ -918,6 +978,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     const size_t smem = (size_t)5 * MP * MP * sizeof(double);
     static bool cfg = false;
     if (!cfg) { int rc = set_max_smem(expm_pade_kernel, (size_t)5 * 64 * 64 * 8); if (rc) return rc; cfg = true; }
+    ProfScope ps(e, 1, 0, 0);
     expm_pade_kernel<<<n_pade, threads, smem, e->stream>>>(d_jobs + n_eigen, e->d_slots, e->slot_stride,
                                                           e->d_edges, M, MP, K);
     ++n_launch;
@@ -941,6 +1002,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     a.M = M;
     a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
     a.lh_out = e->d_lh;
+    ProfScope ps(e, ll.is_root ? 3 : 2, ll.bytes, ll.flops);
     int rc = launch_prune(e, a, ll.is_root);
     if (rc) return rc;
     ++n_launch;
@@ -949,6 +1011,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     const int64_t rows = e->n_rows[e->root];
     const int n_tiles = (int)((rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
     const int grid = std::min(n_tiles, e->n_sm * 8);
+    ProfScope ps(e, 4, rows * (K + 1) * 8, 0);
     lnl_reduce_kernel<<<grid, REDUCE_THREADS, 0, e->stream>>>(
         e->d_lh, reinterpret_cast<const double*>(e->d_block + e->off_bprobs), e->d_counts, rows, K, n_tiles,
         e->d_tile_sums, e->d_counter, e->d_lnl, device_out, blocking ? e->h_lnl_dev : nullptr);
@@ -969,6 +1032,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   e->stats.last_node_rows = node_rows;
   e->stats.last_alg_bytes = alg_bytes;
   e->stats.last_flops = flops;
+  e->stats.last_h2d_bytes = h2d_bytes;
 
   if (blocking) {
     cudaError_t err = cudaStreamSynchronize(e->stream);
@@ -977,6 +1041,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       c3_invalidate(e);
       return fail(C3_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(err));
     }
+    for (auto& r : e->prof) cudaEventElapsedTime(&r.ms, r.a, r.b);
     e->cached_lnl = *e->h_lnl;
     e->have_cached = true;
     if (host_out) *host_out = e->cached_lnl;

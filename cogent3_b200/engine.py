@@ -174,6 +174,30 @@ class LikelihoodEngine:
         _lib.check(self._lib.c3_get_partials(self._h, int(node), int(bin_), _dptr(out), rows))
         return out
 
+    def set_profiling(self, on=True):
+        _lib.check(self._lib.c3_set_profiling(self._h, int(bool(on))))
+
+    KIND_NAMES = ("expm_eigen", "expm_pade", "prune", "prune_root", "reduce")
+
+    def launch_profile(self):
+        """per-launch (kind, ms, algorithmic bytes, executed flops) of the last evaluation"""
+        n_max = 4 * self.n_nodes + 8
+        kind = np.zeros(n_max, np.int32)
+        ms = np.zeros(n_max, np.float64)
+        nbytes = np.zeros(n_max, np.int64)
+        flops = np.zeros(n_max, np.int64)
+        n = ctypes.c_int(0)
+        _lib.check(
+            self._lib.c3_get_launch_profile(
+                self._h, n_max, _i32ptr(kind), _dptr(ms), _i64ptr(nbytes), _i64ptr(flops), byref(n)
+            )
+        )
+        return [
+            {"kind": self.KIND_NAMES[kind[i]], "ms": float(ms[i]), "bytes": int(nbytes[i]),
+             "flops": int(flops[i])}
+            for i in range(n.value)
+        ]  # fmt: skip
+
     def stats(self):
         st = _lib.C3Stats()
         _lib.check(self._lib.c3_get_stats(self._h, byref(st)))

@@ -53,6 +53,7 @@ typedef struct c3_stats {
   int64_t last_node_rows;     /* sum of pattern rows over those nodes           */
   int64_t last_alg_bytes;     /* algorithmic bytes of the pruning kernels (§8d) */
   int64_t last_flops;         /* executed FP64 flops of the pruning kernels     */
+  int64_t last_h2d_bytes;     /* host->device bytes copied by the last evaluation */
   int64_t device_bytes;       /* device memory owned by the engine              */
   int64_t partial_bytes;      /* ... of which resident partial likelihoods      */
   int32_t n_levels;           /* tree levels (kernel launches of a full sweep)  */
@@ -143,6 +144,15 @@ C3_API int c3_get_lh(c3_engine* e, int bin, double* out, int64_t n_rows);
 C3_API int c3_get_psub(c3_engine* e, int node, int bin, double* out);
 C3_API int c3_get_partials(c3_engine* e, int node, int bin, double* out, int64_t n_rows);
 C3_API int c3_get_stats(c3_engine* e, c3_stats* out);
+
+/* ---- per-launch timing (CUDA events on the engine's stream) ----------------------
+ * With profiling on, every kernel launch of a blocking c3_evaluate is bracketed by
+ * events.  c3_get_launch_profile returns, for the last evaluation and per launch:
+ * kind (0 expm-eigen, 1 expm-pade, 2 prune level, 3 prune root level, 4 reduction),
+ * duration in ms, algorithmic bytes and executed flops of that launch.            */
+C3_API int c3_set_profiling(c3_engine* e, int on);
+C3_API int c3_get_launch_profile(c3_engine* e, int max_n, int32_t* kind, double* ms,
+                                 int64_t* alg_bytes, int64_t* flops, int* n);
 
 /* ---- calibration helper: sustained FP64 tensor (DMMA) rate of this GPU, used as
  * the roofline denominator of the 61-state kernel.                 */
