@@ -66,7 +66,9 @@ struct PruneArgs {
 };
 
 constexpr int PRUNE4_THREADS = 256;
-constexpr int PRUNE4_UNROLL = 1;
+#ifndef PRUNE4_UNROLL
+#define PRUNE4_UNROLL 1
+#endif
 #ifndef PRUNE4_MIN_BLOCKS
 #define PRUNE4_MIN_BLOCKS 4
 #endif

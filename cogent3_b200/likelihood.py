@@ -55,6 +55,7 @@ class LikelihoodFunction:
         self._dirty_model = True
         self._slot_of_edge = np.zeros(topo.n_nodes, np.int32)
         self._slot_keys: list = []
+        self._slot_map_sent = None
         self._n_evals = 0
 
     # ------------------------------------------------------------------ data
@@ -76,6 +77,7 @@ class LikelihoodFunction:
             patterns, self.n_bins, device=self.device, stream=self.stream
         )
         self._dirty_q = self._dirty_model = True
+        self._slot_keys, self._slot_map_sent = [], None
         return self
 
     def set_motif_probs(self, mprobs):
@@ -169,24 +171,34 @@ class LikelihoodFunction:
     def rates(self):
         if self.n_bins == 1:
             return np.ones(1)
-        return hostmodels.gamma_rates(self.n_bins, self.rate_shape, self.bprobs)
+        key = (self.rate_shape, self.bprobs.tobytes())
+        if getattr(self, "_rates_key", None) != key:  # scipy's gamma.ppf is slow: cache
+            self._rates = hostmodels.gamma_rates(self.n_bins, self.rate_shape, self.bprobs)
+            self._rates_key = key
+        return self._rates
 
     # ------------------------------------------------------------ evaluation
     def _sync_q(self):
         """(re)build the distinct rate matrices and their exponentiator state."""
+        order = self.model.parameter_order
         keys, slot_of_edge = {}, np.zeros(self.topo.n_nodes, np.int32)
-        for n in self.topo.edges:
-            p = self._params_of_edge(n)
-            key = tuple(p[k] for k in self.model.parameter_order)
-            slot_of_edge[n] = keys.setdefault(key, len(keys))
+        if not self.edge_params:  # one Q for the whole tree (the common case)
+            keys[tuple(self.params[k] for k in order)] = 0
+        else:
+            for n in self.topo.edges:
+                p = self._params_of_edge(n)
+                slot_of_edge[n] = keys.setdefault(tuple(p[k] for k in order), len(keys))
+        mp = self.mprobs.tobytes()
         for key, slot in keys.items():
-            if slot < len(self._slot_keys) and self._slot_keys[slot] == (key, self.mprobs.tobytes()):
+            if slot < len(self._slot_keys) and self._slot_keys[slot] == (key, mp):
                 continue
-            Q = self.model.calcQ(self.mprobs, dict(zip(self.model.parameter_order, key, strict=True)))
+            Q = self.model.calcQ(self.mprobs, dict(zip(order, key, strict=True)))
             self._upload_exponentiator(slot, Q)
-        self._slot_keys = [(k, self.mprobs.tobytes()) for k in keys]
+        self._slot_keys = [(k, mp) for k in keys]
+        if self._slot_map_sent is None or not np.array_equal(slot_of_edge, self._slot_map_sent):
+            self.engine.set_edge_qslots(np.repeat(slot_of_edge[:, None], self.n_bins, axis=1))
+            self._slot_map_sent = slot_of_edge
         self._slot_of_edge = slot_of_edge
-        self.engine.set_edge_qslots(np.repeat(slot_of_edge[:, None], self.n_bins, axis=1))
         self._dirty_q = False
 
     def _upload_exponentiator(self, slot, Q):
