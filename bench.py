@@ -374,16 +374,19 @@ def run_ours(args):
     # ---- roofline of the pruning kernels (per-launch CUDA events) -------------------
     eng.set_profiling(True)
     prof_rows = []
-    for k in range(3):
-        eng.update(np.nan_to_num(step_lengths(base, k + 3))[:, None] * rates[None, :])
-        prof_rows.append(eng.launch_profile())
+    for k in range(6):
+        # alternate two length vectors so that every profiled step is a full evaluation
+        eng.update(np.nan_to_num(base * (1.0 + 1e-3 * (1 + k % 2)))[:, None] * rates[None, :])
+        rows = eng.launch_profile()
+        if rows and k >= 1:
+            prof_rows.append(rows)
     eng.set_profiling(False)
     prof = prof_rows[-1]
     prune = [[r for r in rows if r["kind"].startswith("prune")] for rows in prof_rows]
-    prune_ms = float(np.mean([sum(r["ms"] for r in rows) for rows in prune]))
+    prune_ms = float(np.median([sum(r["ms"] for r in rows) for rows in prune]))
     prune_bytes = sum(r["bytes"] for r in prune[-1])
     prune_flops = sum(r["flops"] for r in prune[-1])
-    step_ms = float(np.mean([sum(r["ms"] for r in rows) for rows in prof_rows]))
+    step_ms = float(np.median([sum(r["ms"] for r in rows) for rows in prof_rows]))
     hbm_peak, peak_src = peaks()
     st = eng.stats()
     M = lf.model.n_states
@@ -405,7 +408,8 @@ def run_ours(args):
         "launches_per_step": len(prune[-1]), "kernel_ms_per_step": prune_ms,
         "kernel_share_of_step": prune_ms / step_ms if step_ms else None,
         "alg_bytes_per_step": prune_bytes, "executed_flops_per_step": prune_flops,
-        "per_launch": [{"kind": r["kind"], "ms": round(r["ms"], 5), "bytes": r["bytes"]} for r in prof],
+        "per_launch": [{"kind": r["kind"], "ms": round(r["ms"], 5), "bytes": r["bytes"],
+                        "GBps": round(r["bytes"] / r["ms"] / 1e6, 1) if r["ms"] > 0 else None} for r in prof],
     })  # fmt: skip
 
     # ---- partial updates: one branch length at a time (the optimiser's inner loop) --

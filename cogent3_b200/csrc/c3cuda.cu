@@ -66,6 +66,7 @@ struct c3_engine {
 
   int n_nodes = 0, M = 0, MP = 0, K = 0, root = 0, n_levels = 0;
   bool use_dmma = false;
+  bool use_strip = true;  // pipelined 4-state kernel (C3_NO_STRIP=1 selects the first version)
   std::vector<std::vector<int>> children;
   std::vector<int> parent, level, child_begin;
   std::vector<std::vector<int>> level_nodes;  // internal nodes per level
@@ -167,9 +168,45 @@ int dmma_blocks_per_sm(int MP) {
   return std::max(1, std::min(per_sm, 2048 / DMMA_THREADS));
 }
 
-int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root) {
+template <int K, int NC>
+int launch_strip(c3_engine* e, const PruneArgs& a, bool is_root) {
+  using Cfg = P4SCfg<K, NC>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_max_smem(prune4_strip_kernel<K, NC, false>, Cfg::SMEM_BYTES);
+    if (rc) return rc;
+    rc = set_max_smem(prune4_strip_kernel<K, NC, true>, Cfg::SMEM_BYTES);
+    if (rc) return rc;
+    configured = true;
+  }
+  // one CTA per SM (shared memory bound); never more warps than strips
+  const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + Cfg::WARPS - 1) / Cfg::WARPS));
+  if (is_root)
+    prune4_strip_kernel<K, NC, true><<<grid, Cfg::WARPS * 32, Cfg::SMEM_BYTES, e->stream>>>(a);
+  else
+    prune4_strip_kernel<K, NC, false><<<grid, Cfg::WARPS * 32, Cfg::SMEM_BYTES, e->stream>>>(a);
+  return C3_OK;
+}
+
+// kind: 0 = generic kernels (prune4_kernel / prune_dmma_kernel); 2, 3 = strip kernel for
+// nodes with that many children (4-state, K in {1,2,4})
+int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
   if (a.total_tiles <= 0) return C3_OK;
-  if (!e->use_dmma) {
+  if (kind >= 2) {
+    int rc = C3_ERR_INVALID;
+#define C3_STRIP(KK)                                                         \
+  case KK:                                                                   \
+    rc = (kind == 2) ? launch_strip<KK, 2>(e, a, is_root) : launch_strip<KK, 3>(e, a, is_root); \
+    break;
+    switch (e->K) {
+      C3_STRIP(1)
+      C3_STRIP(2)
+      C3_STRIP(4)
+      default: return fail(C3_ERR_INVALID, "strip kernel: unsupported K");
+    }
+#undef C3_STRIP
+    if (rc) return rc;
+  } else if (!e->use_dmma) {
     const int grid = std::min(a.total_tiles, e->n_sm * 32);
 #define C3_P4(KT)                                                                    \
   do {                                                                               \
@@ -206,7 +243,19 @@ int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root) {
   return C3_OK;
 }
 
-int64_t tiles_of_node(const c3_engine* e, int n) {
+// which kernel family handles node n (see launch_prune)
+int kind_of_node(const c3_engine* e, int n) {
+  if (e->use_dmma || !e->use_strip) return 0;
+  if (e->K != 1 && e->K != 2 && e->K != 4) return 0;
+  const int nc = (int)e->children[n].size();
+  return (nc == 2 || nc == 3) ? nc : 0;
+}
+
+int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
+  if (kind >= 2) {
+    const int rows = 128 / e->K;
+    return (e->n_rows[n] + rows - 1) / rows;
+  }
   if (!e->use_dmma) {
     const int rpt = prune4_rows_per_tile(e->K);
     return (e->n_rows[n] + rpt - 1) / rpt;
@@ -296,6 +345,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   e->use_dmma = (n_states != 4);
   if (const char* env = getenv("C3_FORCE_DMMA")) e->use_dmma = e->use_dmma || atoi(env) != 0;
   e->MP = e->use_dmma ? (int)align_up(n_states, 8) : 4;
+  if (const char* env = getenv("C3_NO_STRIP")) e->use_strip = atoi(env) == 0;
   e->root = n_nodes - 1;
   e->children.resize(n_nodes);
   e->parent.assign(n_nodes, -1);
@@ -558,7 +608,7 @@ int c3_finalize(c3_engine* e) {
   e->off_pi = b;      b += align_up(MP * sizeof(double), 16);
   e->off_bprobs = b;  b += align_up(K * sizeof(double), 16);
   e->off_work = b;    b += align_up((int64_t)n_internal * sizeof(int32_t), 16);
-  e->off_prefix = b;  b += align_up((int64_t)(n_internal + e->n_levels + 2) * sizeof(int32_t), 16);
+  e->off_prefix = b;  b += align_up((int64_t)(n_internal + 3 * e->n_levels + 4) * sizeof(int32_t), 16);
   e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
   e->block_bytes = b;
   C3_CUDA(cudaHostAlloc(&e->h_block, (size_t)b, cudaHostAllocDefault));
@@ -898,39 +948,41 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
 
   int32_t* work = reinterpret_cast<int32_t*>(e->h_block + e->off_work);
   int32_t* prefix = reinterpret_cast<int32_t*>(e->h_block + e->off_prefix);
-  struct LevelLaunch { int work_off, prefix_off, n_work, total_tiles; bool is_root; int64_t bytes, flops; };
+  struct LevelLaunch { int work_off, prefix_off, n_work, total_tiles; bool is_root; int64_t bytes, flops; int kind; };
   std::vector<LevelLaunch> launches;
   int w_off = 0, p_off = 0;
   int64_t node_rows = 0, alg_bytes = 0, flops = 0;
   for (int l = 1; l <= e->n_levels; ++l) {
-    LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0};
-    int64_t tiles = 0;
-    const int64_t bytes0 = alg_bytes, flops0 = flops;
-    for (int n : e->level_nodes[l]) {
-      if (!recompute[n]) continue;
-      work[w_off + ll.n_work] = n;
-      prefix[p_off + ll.n_work] = (int32_t)tiles;
-      tiles += tiles_of_node(e, n);
-      if (tiles > INT32_MAX) return fail(C3_ERR_INVALID, "too many tiles in one level");
-      ++ll.n_work;
-      ll.is_root = ll.is_root || (n == e->root);
-      const int64_t rows = e->n_rows[n];
-      node_rows += rows;
-      alg_bytes += rows * K * M * 8;  // write
-      for (int c : e->children[n]) {
-        alg_bytes += e->n_rows[c] * K * M * 8 + rows * 4;  // child rows once + gather index
-        if (!e->children[c].empty()) flops += rows * K * 2 * (int64_t)(e->use_dmma ? MP * MP : M * M);
+    for (int kind : {0, 2, 3}) {
+      LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, kind};
+      int64_t tiles = 0;
+      const int64_t bytes0 = alg_bytes, flops0 = flops;
+      for (int n : e->level_nodes[l]) {
+        if (!recompute[n] || kind_of_node(e, n) != kind) continue;
+        work[w_off + ll.n_work] = n;
+        prefix[p_off + ll.n_work] = (int32_t)tiles;
+        tiles += tiles_of_node(e, n, kind);
+        if (tiles > INT32_MAX) return fail(C3_ERR_INVALID, "too many tiles in one level");
+        ++ll.n_work;
+        ll.is_root = ll.is_root || (n == e->root);
+        const int64_t rows = e->n_rows[n];
+        node_rows += rows;
+        alg_bytes += rows * K * M * 8;  // write
+        for (int c : e->children[n]) {
+          alg_bytes += e->n_rows[c] * K * M * 8 + rows * 4;  // child rows once + gather index
+          if (!e->children[c].empty()) flops += rows * K * 2 * (int64_t)(e->use_dmma ? MP * MP : M * M);
+        }
+        if (n == e->root) alg_bytes += rows * K * 8;
       }
-      if (n == e->root) alg_bytes += rows * K * 8;
+      if (ll.n_work == 0) continue;
+      ll.bytes = alg_bytes - bytes0;
+      ll.flops = flops - flops0;
+      prefix[p_off + ll.n_work] = (int32_t)tiles;
+      ll.total_tiles = (int)tiles;
+      w_off += ll.n_work;
+      p_off += ll.n_work + 1;
+      launches.push_back(ll);
     }
-    if (ll.n_work == 0) continue;
-    ll.bytes = alg_bytes - bytes0;
-    ll.flops = flops - flops0;
-    prefix[p_off + ll.n_work] = (int32_t)tiles;
-    ll.total_tiles = (int)tiles;
-    w_off += ll.n_work;
-    p_off += ll.n_work + 1;
-    launches.push_back(ll);
   }
 
   // ---- upload: dirty slots, descriptors, the parameter block -------------------------
@@ -1003,7 +1055,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
     a.lh_out = e->d_lh;
     ProfScope ps(e, ll.is_root ? 3 : 2, ll.bytes, ll.flops);
-    int rc = launch_prune(e, a, ll.is_root);
+    int rc = launch_prune(e, a, ll.is_root, ll.kind);
     if (rc) return rc;
     ++n_launch;
   }

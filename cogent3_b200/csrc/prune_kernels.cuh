@@ -200,6 +200,259 @@ __global__ void __launch_bounds__(PRUNE4_THREADS, PRUNE4_MIN_BLOCKS) prune4_kern
 }
 
 // ---------------------------------------------------------------------------------------
+// 4-state kernel, pipelined ("strip") version -- the production path for K in {1,2,4} and
+// nodes with 2 or 3 children.
+//
+// The first version above is latency bound (ncu: long-scoreboard stalls, 0.4 eligible
+// warps/cycle, L1 data pipe 70% busy of which 2/3 are LDS of the P matrices): a thread
+// waits for its gather index, then for the gathered rows, and block-wide barriers per
+// tile serialise the warps.  Here every WARP runs its own software pipeline:
+//   * a strip = 128 (row, bin) units = 128/K pattern rows; per child that is 4 KB of
+//     gathered rows, fetched with cp.async (LDGSTS, 16 B per lane, no registers held)
+//     into a warp-private ring of P4S_STAGES stages in shared memory;
+//   * the gather indexes of strip s+STAGES are loaded (coalesced, one int per lane)
+//     while strip s+STAGES-1.. are in flight, so neither latency is exposed;
+//   * compute: each lane owns one bin and 4 rows of the strip (register tiling: each
+//     P element read from shared memory is used for 4 rows), FMA in registers, one
+//     256-bit coalesced store per row;
+//   * no block barrier anywhere: only __syncwarp around the warp's own ring.
+// ---------------------------------------------------------------------------------------
+#ifndef P4S_WARPS
+#define P4S_WARPS 8
+#endif
+#ifndef P4S_STAGES_NC2
+#define P4S_STAGES_NC2 2
+#endif
+#ifndef P4S_WARPS_NC3
+#define P4S_WARPS_NC3 6
+#endif
+constexpr int P4S_U = 4;         // rows per lane per strip
+constexpr int P4S_PSTRIDE = 18;  // doubles per P matrix in shared memory (16 + pad)
+
+template <int K, int NC>
+struct P4SCfg {
+  static constexpr int ROWS = 128 / K;  // pattern rows per strip
+  // lo halves (first 16 B) of the 128 units, then -- 64 B further, so that the cp.async
+  // writes of one quarter-warp fall into distinct banks -- the hi halves
+  static constexpr int HI_OFFSET = 2048 + 64;
+  static constexpr int CHILD_BYTES = 4096 + 128;
+  static constexpr int STAGES = (NC <= 2) ? P4S_STAGES_NC2 : 2;  // ring depth (shared memory bound)
+  static constexpr int WARPS = (NC <= 2) ? P4S_WARPS : P4S_WARPS_NC3;
+  static constexpr int STAGE_BYTES = NC * CHILD_BYTES;
+  static constexpr int P_DOUBLES = NC * K * P4S_PSTRIDE;  // warp-private copy of the node's P's
+  static constexpr int WARP_BYTES = STAGES * STAGE_BYTES + ((P_DOUBLES * 8 + 127) / 128) * 128;
+  static constexpr size_t SMEM_BYTES = (size_t)WARPS * WARP_BYTES;
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16_cg(unsigned smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+// .ca: allocate in L1.  Small child tables (tips, shallow nodes) are gathered from by every
+// row of a large parent; with .cg all SMs hammer the same few L2 lines (measured 6x slower).
+__device__ __forceinline__ void cp_async16_ca(unsigned smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// cursor over the strips of one launch: strips are numbered across the work list; a warp
+// visits strips gw, gw+GW, ...  The cursor only moves forward, so the node lookup is a
+// short scan of the prefix array instead of a binary search per strip.
+template <int NC>
+struct StripCursor {
+  int w = -1;          // current work item
+  int first = 0;       // first strip of work item w
+  int next_first = 0;  // first strip of work item w+1
+  const double* src[NC];
+  const int32_t* idx[NC];
+  int64_t n_rows = 0;
+  __device__ __forceinline__ bool seek(const PruneArgs& a, int s) {  // true if the node changed
+    if (s < next_first) return false;
+    do {
+      ++w;
+      first = next_first;
+      next_first = a.tile_prefix[w + 1];
+    } while (s >= next_first);
+    const NodeDesc& nd = a.nodes[a.work_node[w]];
+    n_rows = nd.n_rows;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const ChildRef& ch = a.childs[nd.child_begin + c];
+      src[c] = ch.src;
+      idx[c] = ch.idx;
+    }
+    return true;
+  }
+};
+
+template <int K, int NC, bool ROOT>
+__global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_kernel(const PruneArgs a) {
+  using Cfg = P4SCfg<K, NC>;
+  constexpr int ROWS = Cfg::ROWS;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int NQ = (ROWS + 31) / 32;  // gather-index registers per lane and child
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + (size_t)warp * Cfg::WARP_BYTES;
+  double* sP = reinterpret_cast<double*>(wbase + STAGES * Cfg::STAGE_BYTES);
+  const unsigned ring = (unsigned)__cvta_generic_to_shared(wbase);
+
+  const int gw = blockIdx.x * Cfg::WARPS + warp;
+  const int GW = gridDim.x * Cfg::WARPS;
+  const int total = a.total_tiles;  // strips in this launch
+  const int b = lane % K;           // this lane's rate class
+  const int slot = lane / K;        // its row slot within a pass (32/K slots)
+
+  StripCursor<NC> fc;  // fetch cursor, runs STAGES strips ahead
+  int32_t f_idx[NC][NQ];
+  auto load_idx = [&](int s) {
+    const int64_t row0 = (int64_t)(s - fc.first) * ROWS;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        int64_t p = row0 + q * 32 + lane;
+        if (p >= fc.n_rows) p = fc.n_rows - 1;
+        f_idx[c][q] = __ldg(fc.idx[c] + p);
+      }
+  };
+  // gathers of one strip into ring stage st: row r of the strip has its index in lane
+  // r%32, register r/32
+  auto issue = [&](int st) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const unsigned dst0 = ring + st * Cfg::STAGE_BYTES + c * Cfg::CHILD_BYTES;
+      constexpr int CHUNKS_PER_ROW = K * 2;                // 16-byte chunks per pattern row
+      constexpr int ROWS_PER_INSTR = 32 / CHUNKS_PER_ROW;  // rows per warp-wide cp.async
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = j * ROWS_PER_INSTR + lane / CHUNKS_PER_ROW;  // row within the strip
+        const int k = lane % CHUNKS_PER_ROW;                       // chunk within the row
+        const int32_t src_row = __shfl_sync(0xffffffffu, f_idx[c][(j * ROWS_PER_INSTR) / 32], r % 32);
+        const int unit = r * K + (k >> 1);  // (row, bin) unit index, 0..127
+        const unsigned dst = dst0 + ((k & 1) ? (unsigned)Cfg::HI_OFFSET : 0u) + (unsigned)unit * 16u;
+        cp_async16_ca(dst, fc.src[c] + ((int64_t)src_row * K) * 4 + k * 2);
+      }
+    }
+  };
+
+  // ---- prologue: fill the ring ----------------------------------------------------------
+  int s_fetch = gw;
+#pragma unroll 1
+  for (int st = 0; st < STAGES; ++st) {
+    if (s_fetch < total) {
+      fc.seek(a, s_fetch);
+      load_idx(s_fetch);
+      issue(st);
+    }
+    cp_async_commit();
+    s_fetch += GW;
+  }
+  bool have_next = s_fetch < total;
+  if (have_next) {  // idx of the next strip to fetch, loaded one iteration early
+    fc.seek(a, s_fetch);
+    load_idx(s_fetch);
+  }
+
+  // ---- main loop ----------------------------------------------------------------------------
+  int c_w = -1, c_first = 0, c_next = 0;  // compute cursor
+  int64_t c_rows = 0;
+  double* c_out = nullptr;
+  int c_fixed = -1;
+  int st = 0;
+#pragma unroll 1
+  for (int s = gw; s < total; s += GW) {
+    if (s >= c_next) {
+      do {
+        ++c_w;
+        c_first = c_next;
+        c_next = a.tile_prefix[c_w + 1];
+      } while (s >= c_next);
+      const NodeDesc& nd = a.nodes[a.work_node[c_w]];
+      c_rows = nd.n_rows;
+      c_out = nd.out;
+      c_fixed = nd.fixed_motif;
+      __syncwarp();
+      for (int o = lane; o < NC * K * 16; o += 32) {
+        const int c = o / (K * 16);
+        const int rem = o - c * (K * 16);  // bin * 16 + element
+        const double* P = a.childs[nd.child_begin + c].P;
+        // pre-multiplied children (tips) use the identity: 1*x + 0*... is exact
+        sP[(c * K + (rem >> 4)) * P4S_PSTRIDE + (rem & 15)] =
+            P ? P[rem] : (((rem & 15) % 5 == 0) ? 1.0 : 0.0);
+      }
+      __syncwarp();
+    }
+    const int64_t node_row0 = (int64_t)(s - c_first) * ROWS;
+    cp_async_wait_group<STAGES - 1>();
+    __syncwarp();
+
+    const unsigned char* stage = wbase + st * Cfg::STAGE_BYTES;
+    d4 acc[P4S_U];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      d4 x[P4S_U];
+#pragma unroll
+      for (int u = 0; u < P4S_U; ++u) {
+        const int unit = u * 32 + lane;  // == (u*(32/K) + slot) * K + b
+        const double2 lo = *reinterpret_cast<const double2*>(stage + c * Cfg::CHILD_BYTES + unit * 16);
+        const double2 hi =
+            *reinterpret_cast<const double2*>(stage + c * Cfg::CHILD_BYTES + Cfg::HI_OFFSET + unit * 16);
+        x[u].x = lo.x; x[u].y = lo.y; x[u].z = hi.x; x[u].w = hi.y;
+      }
+      const double* Pc = sP + (c * K + b) * P4S_PSTRIDE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double2 p01 = *reinterpret_cast<const double2*>(Pc + 4 * i);
+        const double2 p23 = *reinterpret_cast<const double2*>(Pc + 4 * i + 2);
+#pragma unroll
+        for (int u = 0; u < P4S_U; ++u) {
+          const double y = fma(x[u].w, p23.y, fma(x[u].z, p23.x, fma(x[u].y, p01.y, x[u].x * p01.x)));
+          double& t = (i == 0) ? acc[u].x : (i == 1) ? acc[u].y : (i == 2) ? acc[u].z : acc[u].w;
+          t = (c == 0) ? y : t * y;
+        }
+      }
+    }
+    __syncwarp();  // every lane is done reading this stage
+
+    // refill the stage with the strip STAGES ahead (its idx was loaded last iteration)
+    if (have_next) issue(st);
+    cp_async_commit();
+    s_fetch += GW;
+    have_next = s_fetch < total;
+    if (have_next) {
+      fc.seek(a, s_fetch);
+      load_idx(s_fetch);
+    }
+
+#pragma unroll
+    for (int u = 0; u < P4S_U; ++u) {
+      const int64_t p = node_row0 + u * (32 / K) + slot;
+      if (c_fixed >= 0) {
+        if (c_fixed != 0) acc[u].x = 0.0;
+        if (c_fixed != 1) acc[u].y = 0.0;
+        if (c_fixed != 2) acc[u].z = 0.0;
+        if (c_fixed != 3) acc[u].w = 0.0;
+      }
+      if (p < c_rows) {
+        st256(c_out + (p * K + b) * 4, acc[u]);
+        if (ROOT) {
+          const double lh =
+              fma(acc[u].w, a.pi[3], fma(acc[u].z, a.pi[2], fma(acc[u].y, a.pi[1], acc[u].x * a.pi[0])));
+          a.lh_out[p * K + b] = lh;
+        }
+      }
+    }
+    st = (st + 1 == STAGES) ? 0 : st + 1;
+  }
+  cp_async_wait_group<0>();
+}
+
+// ---------------------------------------------------------------------------------------
 // FP64 tensor-core (DMMA) kernel, MP = padded state count (multiple of 8, <= 64)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -209,11 +462,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+  cp_async16_cg((unsigned)__cvta_generic_to_shared(smem_dst), gsrc);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int MP>
 struct DmmaCfg {

@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    "c2": [{"PRUNE4_UNROLL": u, "PRUNE4_MIN_BLOCKS": mb} for u, mb in
-           [(1, 3), (1, 4), (1, 5), (1, 6), (1, 8), (2, 2), (2, 3), (2, 4)]],
+    "c2": [{"P4S_WARPS": w, "P4S_STAGES_NC2": st, "P4S_WARPS_NC3": w3} for w, st, w3 in
+           [(8, 2, 8), (6, 2, 6), (10, 2, 5), (7, 2, 4), (5, 2, 7), (9, 2, 8)]],
 }
 
 
