@@ -662,7 +662,7 @@ int c3_set_edge_qslots(c3_engine* e, const int32_t* q) {
   for (int n = 0; n < e->n_nodes - 1; ++n)
     for (int b = 0; b < e->K; ++b) {
       const size_t i = (size_t)n * e->K + b;
-      C3_REQUIRE(q[i] >= 0, "negative q slot");
+      if (q[i] < 0) continue;  // negative: leave this (edge, bin) as it is (e.g. a supplied P)
       if (q[i] != e->qslot[i] || e->pfixed[i]) {
         e->qslot[i] = q[i];
         e->pfixed[i] = 0;

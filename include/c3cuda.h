@@ -97,7 +97,8 @@ C3_API int c3_finalize(c3_engine* e);
  *             evT[M x M], evI[M x M]; complex128 interleaved (re, im) when
  *             is_complex != 0, float64 otherwise.
  * c3_set_Q:   the rate matrix for the Pade path (PadeExponentiator :92-129).
- * c3_set_edge_qslots: which slot each (edge, bin) exponentiates [n_nodes x K].
+ * c3_set_edge_qslots: which slot each (edge, bin) exponentiates [n_nodes x K]; a
+ *             negative entry leaves that (edge, bin) unchanged (e.g. a supplied P).
  * c3_set_psub: a P matrix supplied directly (discrete-time models,
  *             evolve/discrete_markov.py:15-80); the (edge, bin) stops using expm.
  * c3_set_distances: distance[edge, bin] = length * rate (ProductDefn,

@@ -96,7 +96,10 @@ class OracleEngine:
         self.slots[slot] = oracle.PadeExponentiator(np.array(Q))
 
     def set_edge_qslots(self, q):
-        self.qslots = np.broadcast_to(q, (self.n_nodes, self.n_bins)).copy()
+        q = np.broadcast_to(q, (self.n_nodes, self.n_bins))
+        for n, b in zip(*np.nonzero(q >= 0), strict=True):  # negative: leave as is
+            self.qslots[n, b] = q[n, b]
+            self.fixed_psub.pop((int(n), int(b)), None)
 
     def set_psub(self, node, bin_, P):
         self.fixed_psub[(node, bin_)] = np.array(P)
@@ -173,12 +176,23 @@ class OracleEngine:
                     ix.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _pd(out), ptrs, len(kids),
                     out.shape[0], M,
                 )  # fmt: skip
+                self._apply_fixed(n, out)
                 plh[n] = out
             lhs.append(np.inner(plh[-1], self.pi))
         self._lhs = lhs
         mix = oracle.weighted_sum_lh(self.bprobs, lhs) if self.n_bins > 1 else lhs[0]
         counts = self.lht[-1].counts
         return float(lib.c3o_log_sum_across_sites(_pd(np.ascontiguousarray(mix)), _pd(counts), len(counts)))
+
+    def _apply_fixed(self, n, out):
+        """fixed-motif mask of PartialLikelihoodProductDefnFixedMotif
+        (evolve/likelihood_calculation.py:50-59)"""
+        if self.fixed is None or self.fixed[n] in (None, -1):
+            return
+        keep = int(self.fixed[n])
+        for m in range(out.shape[-1]):
+            if m != keep:
+                out[..., m] = 0.0
 
     def _init_fused(self):
         K, M = self.n_bins, self.n_states
@@ -211,6 +225,7 @@ class OracleEngine:
             Ps = (PD * C)(*[_pd(Pall[k]) if Pall[k] is not None else None for k in kids])
             lib.c3o_fused_node(_pd(self._rows[n]), self._rows[n].shape[0], K, M, C, src, idx, Ps,
                                self.n_threads)  # fmt: skip
+            self._apply_fixed(n, self._rows[n])
         root = self._rows[-1]
         self._lhs = [root[:, b, :] @ self.pi for b in range(K)]
         counts = self.lht[-1].counts

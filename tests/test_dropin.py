@@ -1,0 +1,164 @@
+"""The drop-in glue under the REAL cogent3 objects (build container only: needs
+/root/reference).  The engine is the CPU oracle test double here (no GPU), so what is
+tested is the host logic of cogent3_b200/dropin.py: the replaced Defn sub-graph, slot /
+distance / fixed-motif plumbing, accessors, optimiser protocol.  The same tests run with
+the CUDA engine when a GPU and the reference are both present (never on the GPU box)."""
+
+import functools
+
+import numpy as np
+import pytest
+from refutil import import_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="needs /root/reference")
+
+if reference_available():
+    cogent3 = import_reference()
+    from cogent3 import get_dataset, get_model, make_aligned_seqs, make_tree
+
+    from cogent3_b200.dropin import make_likelihood_function
+    from oracle.engine import OracleEngine
+
+    FACTORY = functools.partial(OracleEngine, mode="port")
+
+
+def small_problem(n_tips=7, L=240, n_states=4, seed=5):
+    from cogent3_b200 import models as hostmodels
+    from cogent3_b200.synthetic import evolved_alignment
+    from cogent3_b200.tree import random_join_tree
+
+    rng = np.random.default_rng(seed)
+    topo, lengths = random_join_tree(n_tips, rng)
+    codes = evolved_alignment(topo, lengths, L, n_states, rng)
+    symbols = hostmodels.dna_symbol_rows()[0] if n_states == 4 else hostmodels.codon_symbol_rows()[0]
+    data = {n: "".join(symbols[c] for c in row) for n, row in zip(topo.tip_names, codes, strict=True)}
+    return make_tree(topo.to_newick(lengths)), make_aligned_seqs(data, moltype="dna")
+
+
+def pair(model_factory, tree, aln, **kw):
+    ref = model_factory().make_likelihood_function(tree, **kw)
+    ref.set_alignment(aln)
+    lf = make_likelihood_function(model_factory(), tree, engine_factory=FACTORY, **kw)
+    lf.set_alignment(aln)
+    return ref, lf
+
+
+def assert_same(ref, lf, rel=1e-12):
+    a, b = ref.get_log_likelihood(), lf.get_log_likelihood()
+    assert abs(a - b) <= rel * abs(a), (a, b)
+
+
+def test_brca1_hky85_matches_reference_and_survey_value():
+    aln, tree = get_dataset("brca1"), get_dataset("mammal-tree")
+    ref, lf = pair(lambda: get_model("HKY85"), tree, aln)
+    assert lf.get_log_likelihood() == pytest.approx(-193293.46430542142, rel=1e-12)
+    assert_same(ref, lf)
+    for f in (ref, lf):
+        f.set_param_rule("kappa", value=3.3)
+        f.set_param_rule("length", edge="Human", value=0.07)
+    assert_same(ref, lf)
+    assert lf.get_num_free_params() == ref.get_num_free_params() == 108
+    np.testing.assert_allclose(
+        lf.get_full_length_likelihoods(), ref.get_full_length_likelihoods(), rtol=0, atol=1e-15
+    )
+    np.testing.assert_array_equal(
+        lf.get_psub_for_edge("Human").to_array(), ref.get_psub_for_edge("Human").to_array()
+    )
+
+
+def test_gtr_gamma_bins_and_posteriors():
+    tree, aln = small_problem()
+    mk = lambda: get_model("GTR", ordered_param="rate", distribution="gamma")  # noqa: E731
+    ref, lf = pair(mk, tree, aln, bins=4)
+    for f in (ref, lf):
+        f.set_param_rule("bprobs", is_constant=True)
+        f.set_param_rule("rate_shape", value=0.5)
+        f.set_param_rule("A/G", value=3.2)
+    assert_same(ref, lf)
+    np.testing.assert_allclose(lf.get_bin_probs().array, ref.get_bin_probs().array, atol=1e-13)
+    np.testing.assert_allclose(
+        lf.get_full_length_likelihoods(), ref.get_full_length_likelihoods(), atol=1e-15
+    )
+    assert lf.get_G_statistic() == pytest.approx(ref.get_G_statistic(), rel=1e-10)
+
+
+def test_gn_time_heterogeneous_pade():
+    tree, aln = small_problem(n_tips=6, L=150, seed=8)
+    ref, lf = pair(lambda: get_model("GN"), tree, aln, expm="pade")
+    rng = np.random.default_rng(0)
+    for f in (ref, lf):
+        f.set_time_heterogeneity(is_independent=True, upper=50)
+    names = [e.name for e in tree.get_edge_vector(include_root=False)]
+    for name in names:
+        for p in lf.model.get_param_list():
+            v = float(rng.uniform(0.3, 3.0))
+            for f in (ref, lf):
+                f.set_param_rule(p, edge=name, value=v)
+    assert_same(ref, lf, rel=1e-11)
+
+
+def test_codon_model():
+    tree, aln = small_problem(n_tips=5, L=40, n_states=61, seed=3)
+    ref, lf = pair(lambda: get_model("CNFGTR"), tree, aln)
+    for f in (ref, lf):
+        f.set_param_rule("omega", value=0.4)
+        f.set_param_rule("C/T", value=3.6)
+    assert_same(ref, lf, rel=1e-11)
+
+
+def test_discrete_edges_use_supplied_psubs():
+    tree, aln = small_problem(n_tips=5, L=200, seed=11)
+    tip = tree.get_tip_names()[0]
+    ref, lf = pair(lambda: get_model("HKY85"), tree, aln, discrete_edges=[tip])
+    assert_same(ref, lf, rel=1e-11)
+
+
+def test_ancestral_reconstruction_uses_fixed_motifs():
+    tree, aln = small_problem(n_tips=5, L=60, seed=2)
+    ref, lf = pair(lambda: get_model("F81"), tree, aln)
+    a = ref.reconstruct_ancestral_seqs()
+    b = lf.reconstruct_ancestral_seqs()
+    assert set(a) == set(b)
+    for edge in a:
+        np.testing.assert_allclose(b[edge].array, a[edge].array, atol=1e-13)
+
+
+def test_optimise_powell_follows_the_same_path():
+    tree, aln = small_problem(n_tips=6, L=300, seed=4)
+    ref, lf = pair(lambda: get_model("HKY85"), tree, aln)
+    for f in (ref, lf):
+        f.optimise(local=True, show_progress=False, max_evaluations=250, limit_action="ignore")
+    assert_same(ref, lf, rel=1e-9)
+    assert lf.get_param_value("kappa") == pytest.approx(ref.get_param_value("kappa"), rel=1e-6)
+
+
+def test_multi_locus_sum():
+    tree, aln = small_problem(n_tips=5, L=200, seed=6)
+    half = len(aln) // 2
+    alns = [aln[:half], aln[half:]]
+    ref = get_model("HKY85").make_likelihood_function(tree, loci=["a", "b"])
+    ref.set_alignment(alns)
+    lf = make_likelihood_function(get_model("HKY85"), tree, loci=["a", "b"], engine_factory=FACTORY)
+    lf.set_alignment(alns)
+    assert_same(ref, lf)
+
+
+def test_set_alignment_twice_reuses_the_function():
+    tree, aln = small_problem(n_tips=5, L=100, seed=7)
+    _, aln2 = small_problem(n_tips=5, L=130, seed=7)
+    ref, lf = pair(lambda: get_model("HKY85"), tree, aln)
+    assert_same(ref, lf)
+    ref.set_alignment(aln2)
+    lf.set_alignment(aln2)
+    assert_same(ref, lf)
+
+
+def test_product_default_engine_has_no_cpu_fallback():
+    from cogent3_b200 import _lib
+
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    tree, aln = small_problem(n_tips=4, L=30, seed=1)
+    lf = make_likelihood_function(get_model("HKY85"), tree)  # default engine = CUDA
+    with pytest.raises((_lib.C3Error, RuntimeError)):
+        lf.set_alignment(aln)
