@@ -65,6 +65,21 @@ struct PruneArgs {
   double* lh_out;    // root only: [rows][K]
 };
 
+// one tree level inside a fused "small levels" launch
+struct SmallLevel {
+  int32_t work_off;    // into PruneArgs::work_node
+  int32_t prefix_off;  // into PruneArgs::tile_prefix (prefix in (row, bin) units)
+  int32_t n_work;
+  int32_t total_units;
+};
+
+constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_CLUSTER = 8;            // CTAs (SMs) cooperating on the small levels
+constexpr int SMALL_LEVEL_UNITS = SMALL_THREADS * SMALL_CLUSTER;  // one unit per thread and level
+constexpr int SMALL_MAX_WORK = 384;  // work items whose descriptors are staged in shared memory
+constexpr int SMALL_MAX_LEVELS = 64;
+constexpr int SMALL_STAGED_CHILDREN = 3;
+
 constexpr int PRUNE4_THREADS = 256;
 #ifndef PRUNE4_UNROLL
 #define PRUNE4_UNROLL 1

@@ -105,7 +105,8 @@ struct c3_engine {
   char* h_block = nullptr;  // pinned
   char* d_block = nullptr;
   int64_t block_bytes = 0;
-  int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0;
+  int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0, off_small = 0;
+  bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
   cudaEvent_t block_copied = nullptr;
   double* h_lnl = nullptr;  // mapped pinned result
   double* h_lnl_dev = nullptr;
@@ -346,6 +347,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_FORCE_DMMA")) e->use_dmma = e->use_dmma || atoi(env) != 0;
   e->MP = e->use_dmma ? (int)align_up(n_states, 8) : 4;
   if (const char* env = getenv("C3_NO_STRIP")) e->use_strip = atoi(env) == 0;
+  if (const char* env = getenv("C3_NO_SMALL")) e->use_small = atoi(env) == 0;
   e->root = n_nodes - 1;
   e->children.resize(n_nodes);
   e->parent.assign(n_nodes, -1);
@@ -609,6 +611,7 @@ int c3_finalize(c3_engine* e) {
   e->off_bprobs = b;  b += align_up(K * sizeof(double), 16);
   e->off_work = b;    b += align_up((int64_t)n_internal * sizeof(int32_t), 16);
   e->off_prefix = b;  b += align_up((int64_t)(n_internal + 3 * e->n_levels + 4) * sizeof(int32_t), 16);
+  e->off_small = b;   b += align_up((int64_t)(e->n_levels + 1) * sizeof(SmallLevel), 16);
   e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
   e->block_bytes = b;
   C3_CUDA(cudaHostAlloc(&e->h_block, (size_t)b, cudaHostAllocDefault));
@@ -948,13 +951,75 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
 
   int32_t* work = reinterpret_cast<int32_t*>(e->h_block + e->off_work);
   int32_t* prefix = reinterpret_cast<int32_t*>(e->h_block + e->off_prefix);
-  struct LevelLaunch { int work_off, prefix_off, n_work, total_tiles; bool is_root; int64_t bytes, flops; int kind; };
+  // kind: 0 generic, 1 fused small levels, 2/3 strip kernel (see launch_prune)
+  struct LevelLaunch {
+    int work_off, prefix_off, n_work, total_tiles;
+    bool is_root;
+    int64_t bytes, flops;
+    int kind;
+    int small_off, n_small;  // kind 1: range of SmallLevel records
+  };
   std::vector<LevelLaunch> launches;
+  SmallLevel* small = reinterpret_cast<SmallLevel*>(e->h_block + e->off_small);
+  int n_small_total = 0;
   int w_off = 0, p_off = 0;
   int64_t node_rows = 0, alg_bytes = 0, flops = 0;
+  auto account = [&](int n) {
+    const int64_t rows = e->n_rows[n];
+    node_rows += rows;
+    alg_bytes += rows * K * M * 8;  // write
+    for (int c : e->children[n]) {
+      alg_bytes += e->n_rows[c] * K * M * 8 + rows * 4;  // child rows once + gather index
+      if (!e->children[c].empty()) flops += rows * K * 2 * (int64_t)(e->use_dmma ? MP * MP : M * M);
+    }
+    if (n == e->root) alg_bytes += rows * K * 8;
+  };
+  int open_small = -1;  // index into launches of the small group being extended
   for (int l = 1; l <= e->n_levels; ++l) {
+    int64_t units = 0;
+    int n_dirty = 0;
+    for (int n : e->level_nodes[l])
+      if (recompute[n]) {
+        units += e->n_rows[n] * K;
+        ++n_dirty;
+      }
+    if (n_dirty == 0) continue;
+    if (e->use_small && !e->use_dmma && units <= SMALL_LEVEL_UNITS) {
+      // extend (or open) a fused launch covering consecutive small levels
+      if (open_small < 0) {
+        launches.push_back(LevelLaunch{w_off, p_off, 0, 0, false, 0, 0, 1, n_small_total, 0});
+        open_small = (int)launches.size() - 1;
+      }
+      LevelLaunch& g = launches[open_small];
+      SmallLevel& sl = small[n_small_total++];
+      sl.work_off = w_off - g.work_off;
+      sl.prefix_off = p_off - g.prefix_off;
+      sl.n_work = 0;
+      int64_t u = 0;
+      const int64_t bytes0 = alg_bytes, flops0 = flops;
+      for (int n : e->level_nodes[l]) {
+        if (!recompute[n]) continue;
+        work[w_off + sl.n_work] = n;
+        prefix[p_off + sl.n_work] = (int32_t)u;
+        u += e->n_rows[n] * K;
+        ++sl.n_work;
+        g.is_root = g.is_root || (n == e->root);
+        account(n);
+      }
+      prefix[p_off + sl.n_work] = (int32_t)u;
+      sl.total_units = (int32_t)u;
+      w_off += sl.n_work;
+      p_off += sl.n_work + 1;
+      g.n_work += sl.n_work;
+      g.n_small += 1;
+      g.total_tiles += (int)u;
+      g.bytes += alg_bytes - bytes0;
+      g.flops += flops - flops0;
+      continue;
+    }
+    open_small = -1;
     for (int kind : {0, 2, 3}) {
-      LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, kind};
+      LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, kind, 0, 0};
       int64_t tiles = 0;
       const int64_t bytes0 = alg_bytes, flops0 = flops;
       for (int n : e->level_nodes[l]) {
@@ -965,14 +1030,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
         if (tiles > INT32_MAX) return fail(C3_ERR_INVALID, "too many tiles in one level");
         ++ll.n_work;
         ll.is_root = ll.is_root || (n == e->root);
-        const int64_t rows = e->n_rows[n];
-        node_rows += rows;
-        alg_bytes += rows * K * M * 8;  // write
-        for (int c : e->children[n]) {
-          alg_bytes += e->n_rows[c] * K * M * 8 + rows * 4;  // child rows once + gather index
-          if (!e->children[c].empty()) flops += rows * K * 2 * (int64_t)(e->use_dmma ? MP * MP : M * M);
-        }
-        if (n == e->root) alg_bytes += rows * K * 8;
+        account(n);
       }
       if (ll.n_work == 0) continue;
       ll.bytes = alg_bytes - bytes0;
@@ -1055,8 +1113,36 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
     a.lh_out = e->d_lh;
     ProfScope ps(e, ll.is_root ? 3 : 2, ll.bytes, ll.flops);
-    int rc = launch_prune(e, a, ll.is_root, ll.kind);
-    if (rc) return rc;
+    if (ll.kind == 1) {
+      const SmallLevel* d_small = reinterpret_cast<const SmallLevel*>(e->d_block + e->off_small) + ll.small_off;
+      // one cluster; fewer CTAs when there is little work (cluster size must divide the grid)
+      int ctas = SMALL_CLUSTER;
+      while (ctas > 1 && (int64_t)(ctas / 2) * SMALL_THREADS >= ll.total_tiles / std::max(1, ll.n_small)) ctas /= 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(ctas);
+      cfg.blockDim = dim3(SMALL_THREADS);
+      cfg.dynamicSmemBytes = sizeof(SmallSmem);
+      static bool small_cfg = false;
+      if (!small_cfg) {
+        int rc = set_max_smem(prune4_small_kernel, sizeof(SmallSmem));
+        if (rc) return rc;
+        small_cfg = true;
+      }
+      cfg.stream = e->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = ctas;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel, a, d_small, ll.n_small, ll.n_work,
+                                           ll.n_work + ll.n_small);
+      if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("small-level launch: ") + cudaGetErrorString(err));
+    } else {
+      int rc = launch_prune(e, a, ll.is_root, ll.kind);
+      if (rc) return rc;
+    }
     ++n_launch;
   }
   {

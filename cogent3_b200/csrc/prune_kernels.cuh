@@ -453,6 +453,113 @@ __global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_ker
 }
 
 // ---------------------------------------------------------------------------------------
+// 4-state kernel for SMALL levels: several consecutive tree levels in ONE launch.
+//
+// Real alignments (brca1: 2763 root patterns, 11 levels) and the shallow levels of big
+// ones are latency bound: a launch per level costs ~8 us of dependent-load latency for a
+// few thousand rows.  Here one thread-block cluster (8 CTAs = 8 SMs) walks the levels in
+// order, one (row, bin) unit per thread per step, with a cluster barrier between levels
+// (barrier.cluster release/acquire makes the previous level's rows visible).  Arithmetic
+// is identical to the strip kernel (same FMA order), so the results are bit-identical
+// whichever kernel a node is assigned to.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// plain (coherent) 256-bit load: the rows may have been written earlier in this launch
+__device__ __forceinline__ d4 ld256(const double* p) {
+  d4 r;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
+struct SmallSmem {
+  SmallLevel levels[SMALL_MAX_LEVELS];
+  int32_t prefix[SMALL_MAX_WORK + SMALL_MAX_LEVELS];
+  NodeDesc nodes[SMALL_MAX_WORK];
+  ChildRef childs[SMALL_MAX_WORK * SMALL_STAGED_CHILDREN];
+};
+
+// n_work_total / n_prefix_total: sizes of the launch's work and prefix arrays.  When they
+// fit, every descriptor the units need is staged in shared memory first, so the
+// dependent-load chain per level is just  gather index -> child row  (P and the
+// descriptors no longer sit on it).
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, int n_levels,
+                    int n_work_total, int n_prefix_total) {
+  extern __shared__ __align__(16) unsigned char small_raw[];
+  SmallSmem& sm = *reinterpret_cast<SmallSmem*>(small_raw);
+  const int K = a.K;
+  const unsigned nthreads = cluster_nctarank() * SMALL_THREADS;
+  const unsigned tid = cluster_ctarank() * SMALL_THREADS + threadIdx.x;
+  bool staged = n_work_total <= SMALL_MAX_WORK && n_levels <= SMALL_MAX_LEVELS;
+  if (staged) {
+    for (int i = threadIdx.x; i < n_levels; i += SMALL_THREADS) sm.levels[i] = levels[i];
+    for (int i = threadIdx.x; i < n_prefix_total; i += SMALL_THREADS) sm.prefix[i] = a.tile_prefix[i];
+    for (int i = threadIdx.x; i < n_work_total; i += SMALL_THREADS) {
+      const NodeDesc nd = a.nodes[a.work_node[i]];
+      sm.nodes[i] = nd;
+      for (int c = 0; c < nd.n_children && c < SMALL_STAGED_CHILDREN; ++c)
+        sm.childs[i * SMALL_STAGED_CHILDREN + c] = a.childs[nd.child_begin + c];
+    }
+    __syncthreads();
+  }
+  for (int li = 0; li < n_levels; ++li) {
+    const SmallLevel L = staged ? sm.levels[li] : levels[li];
+    const int32_t* prefix = (staged ? sm.prefix : a.tile_prefix) + L.prefix_off;
+    for (int u = (int)tid; u < L.total_units; u += (int)nthreads) {
+      const int w = find_work(prefix, L.n_work, u);
+      const int wi = L.work_off + w;
+      const NodeDesc nd = staged ? sm.nodes[wi] : a.nodes[a.work_node[wi]];
+      const int local = u - prefix[w];
+      const int64_t p = local / K;
+      const int b = local - (int)p * K;
+      d4 acc;
+      for (int c = 0; c < nd.n_children; ++c) {
+        const ChildRef ch = (staged && c < SMALL_STAGED_CHILDREN) ? sm.childs[wi * SMALL_STAGED_CHILDREN + c]
+                                                                  : a.childs[nd.child_begin + c];
+        const int32_t r = ch.idx[p];
+        const d4 x = ld256(ch.src + ((int64_t)r * K + b) * 4);
+        d4 y;
+        if (ch.P != nullptr) {
+          y = matvec4(ch.P + b * 16, x);
+        } else {
+          y = x;  // pre-multiplied rows; same value as the strip kernel's identity product
+        }
+        if (c == 0) acc = y;
+        else { acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w; }
+      }
+      if (nd.fixed_motif >= 0) {
+        if (nd.fixed_motif != 0) acc.x = 0.0;
+        if (nd.fixed_motif != 1) acc.y = 0.0;
+        if (nd.fixed_motif != 2) acc.z = 0.0;
+        if (nd.fixed_motif != 3) acc.w = 0.0;
+      }
+      st256(nd.out + (p * K + b) * 4, acc);
+      if (nd.is_root) {
+        const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
+        a.lh_out[p * K + b] = lh;
+      }
+    }
+    if (li + 1 < n_levels) cluster_barrier();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // FP64 tensor-core (DMMA) kernel, MP = padded state count (multiple of 8, <= 64)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
