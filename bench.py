@@ -438,7 +438,19 @@ def run_ours(args):
 
     cpu_rec = None
     if world == 1 and not args.no_cpu:
-        cpu_rec = cpu_arm(problem, budget_s=20.0, sample_columns=args.cpu_sample)
+        # in a fresh process: torch's OpenMP runtime settings must not throttle the CPU arm
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+               "--kind", args.kind]  # fmt: skip
+        if args.columns:
+            cmd += ["--columns", str(args.columns)]
+        if args.cpu_sample:
+            cmd += ["--cpu-sample", str(args.cpu_sample)]
+        env = {k: v for k, v in os.environ.items() if not k.startswith("OMP_")}
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            cpu_rec = json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as err:  # noqa: BLE001 - the GPU line must still be printed
+            cpu_rec = {"error": f"cpu baseline failed: {err!r}"}
 
     value = total_units * args.steps / dev_s
     line = {
@@ -489,10 +501,30 @@ def main():
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29533",
                os.path.abspath(__file__), *sys.argv[1:]]  # fmt: skip
         raise SystemExit(subprocess.call(cmd))
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_ours(args)
+    # Everything libraries print (NCCL's version banner, warnings) goes to stderr; the real
+    # stdout receives exactly one JSON line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    captured = []
+    builtin_print = print
+
+    def emit(line):
+        captured.append(line)
+
+    globals()["print"] = lambda *a, **k: emit(" ".join(str(x) for x in a))
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_ours(args)
+    finally:
+        globals()["print"] = builtin_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in captured:
+        builtin_print(line, flush=True)
 
 
 if __name__ == "__main__":
