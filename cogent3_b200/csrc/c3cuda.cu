@@ -1074,17 +1074,18 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   e->events_used = 0;
   const ExpmJob* d_jobs = reinterpret_cast<const ExpmJob*>(e->d_block + e->off_jobs);
   if (n_eigen > 0) {
-    const int threads = (M <= 4) ? 32 : (M <= 16 ? 64 : 256);
-    const size_t smem = (size_t)(MP * MP + 2 * M) * sizeof(double);
+    const int threads = (M <= 4) ? 32 : (M <= 16 ? 64 : (M <= 32 ? 256 : 1024));
+    // sP + exp(roots) + (large M) the staged W / evI planes, complex-capable
+    const size_t smem = (size_t)(MP * MP + 2 * M + (M > 8 ? 4 * M * (M | 1) : 0)) * sizeof(double);
     static bool cfg = false;
-    if (!cfg) { int rc = set_max_smem(expm_eigen_kernel, 64 * 64 * 8 + 1024); if (rc) return rc; cfg = true; }
+    if (!cfg) { int rc = set_max_smem(expm_eigen_kernel, (size_t)(64 * 64 + 128 + 4 * 64 * 65) * 8); if (rc) return rc; cfg = true; }
     ProfScope ps(e, 0, 0, 0);
     expm_eigen_kernel<<<n_eigen, threads, smem, e->stream>>>(d_jobs, e->d_slots, e->slot_stride, e->d_edges,
                                                             M, MP, K);
     ++n_launch;
   }
   if (n_pade > 0) {
-    const int threads = (M <= 4) ? 32 : (M <= 16 ? 128 : 256);
+    const int threads = (M <= 4) ? 32 : (M <= 16 ? 128 : (M <= 32 ? 256 : 1024));
     const size_t smem = (size_t)5 * MP * MP * sizeof(double);
     static bool cfg = false;
     if (!cfg) { int rc = set_max_smem(expm_pade_kernel, (size_t)5 * 64 * 64 * 8); if (rc) return rc; cfg = true; }

@@ -26,8 +26,15 @@ __device__ __forceinline__ void tip_inner_update(const EdgeDesc& ed, const doubl
     const int64_t u = o / M;
     const int i = (int)(o - u * M);
     const double* row = ed.tip_table + u * MP;
+    // the j loop starts at i: consecutive lanes (consecutive i) then read different shared
+    // memory banks of sP (row stride MP is a multiple of the bank count); the rows are 0/1
+    // indicators, so the rotated summation order only matters for ambiguity codes (~1 ulp)
     double s = 0.0;
-    for (int j = 0; j < M; ++j) s = fma(row[j], sP[i * MP + j], s);
+    int j = (MP > 8) ? i : 0;
+    for (int n = 0; n < M; ++n) {
+      s = fma(row[j], sP[i * MP + j], s);
+      j = (j + 1 == M) ? 0 : j + 1;
+    }
     ed.tip_inner[(u * K + bin) * MP + i] = s;
   }
 }
@@ -54,6 +61,12 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
   }
   const double* slot = slots + (int64_t)job.slot * slot_stride;
   const double t = job.t;
+  // Large alphabets (codons): stage W = evT * exp(t roots) and evI in shared memory so the
+  // M^3 contraction reads shared memory (odd row stride: conflict free) instead of
+  // uncoalesced global memory.  sW / sI live behind sP in the dynamic allocation.
+  const bool staged = M > 8;
+  const int LD = M | 1;  // odd stride
+  double* sW = s_ei + M;             // [M*LD] (real) or [2*M*LD] (complex: re, im planes)
   if (job.mode == EXPM_EIGEN_COMPLEX) {
     const double* roots = slot;
     const double* evT = slot + 2 * M;
@@ -66,22 +79,48 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
       s_ei[k] = mag * s;
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < MM; o += blockDim.x) {
-      const int i = o / M, j = o - i * M;
-      double acc = 0.0;
-      for (int k = 0; k < M; ++k) {
-        const double ar = evT[2 * (i * M + k)], ai = evT[2 * (i * M + k) + 1];
+    if (staged) {
+      double* sWr = sW;
+      double* sWi = sW + M * LD;
+      double* sIr = sWi + M * LD;
+      double* sIi = sIr + M * LD;
+      for (int o = threadIdx.x; o < MM; o += blockDim.x) {
+        const int i = o / M, k = o - i * M;
+        const double ar = evT[2 * o], ai = evT[2 * o + 1];
         const double er = s_er[k], ei = s_ei[k];
-        // w = evT[i,k] * exp_roots[k]   (numpy: self.evT * exp_roots)
-        const double wr = ar * er - ai * ei;
-        const double wi = ar * ei + ai * er;
-        const double br = evI[2 * (j * M + k)], bi = evI[2 * (j * M + k) + 1];
-        // Re(w * evI[j,k])             (numpy.inner(...).real)
-        acc += wr * br - wi * bi;
+        sWr[i * LD + k] = ar * er - ai * ei;  // w = evT[i,k] * exp_roots[k]
+        sWi[i * LD + k] = ar * ei + ai * er;
+        sIr[i * LD + k] = evI[2 * o];
+        sIi[i * LD + k] = evI[2 * o + 1];
       }
-      acc = fmax(acc, 0.0);
-      sP[i * MP + j] = acc;
-      Pout[i * MP + j] = acc;
+      __syncthreads();
+      for (int o = threadIdx.x; o < MM; o += blockDim.x) {
+        const int i = o / M, j = o - i * M;
+        double acc = 0.0;
+        for (int k = 0; k < M; ++k)
+          acc += sWr[i * LD + k] * sIr[j * LD + k] - sWi[i * LD + k] * sIi[j * LD + k];
+        acc = fmax(acc, 0.0);
+        sP[i * MP + j] = acc;
+        Pout[i * MP + j] = acc;
+      }
+    } else {
+      for (int o = threadIdx.x; o < MM; o += blockDim.x) {
+        const int i = o / M, j = o - i * M;
+        double acc = 0.0;
+        for (int k = 0; k < M; ++k) {
+          const double ar = evT[2 * (i * M + k)], ai = evT[2 * (i * M + k) + 1];
+          const double er = s_er[k], ei = s_ei[k];
+          // w = evT[i,k] * exp_roots[k]   (numpy: self.evT * exp_roots)
+          const double wr = ar * er - ai * ei;
+          const double wi = ar * ei + ai * er;
+          const double br = evI[2 * (j * M + k)], bi = evI[2 * (j * M + k) + 1];
+          // Re(w * evI[j,k])             (numpy.inner(...).real)
+          acc += wr * br - wi * bi;
+        }
+        acc = fmax(acc, 0.0);
+        sP[i * MP + j] = acc;
+        Pout[i * MP + j] = acc;
+      }
     }
   } else {
     const double* roots = slot;
@@ -89,13 +128,31 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
     const double* evI = evT + 2 * MM;
     for (int k = threadIdx.x; k < M; k += blockDim.x) s_er[k] = exp(t * roots[k]);
     __syncthreads();
-    for (int o = threadIdx.x; o < MM; o += blockDim.x) {
-      const int i = o / M, j = o - i * M;
-      double acc = 0.0;
-      for (int k = 0; k < M; ++k) acc += (evT[i * M + k] * s_er[k]) * evI[j * M + k];
-      acc = fmax(acc, 0.0);
-      sP[i * MP + j] = acc;
-      Pout[i * MP + j] = acc;
+    if (staged) {
+      double* sI = sW + M * LD;
+      for (int o = threadIdx.x; o < MM; o += blockDim.x) {
+        const int i = o / M, k = o - i * M;
+        sW[i * LD + k] = evT[o] * s_er[k];
+        sI[i * LD + k] = evI[o];
+      }
+      __syncthreads();
+      for (int o = threadIdx.x; o < MM; o += blockDim.x) {
+        const int i = o / M, j = o - i * M;
+        double acc = 0.0;
+        for (int k = 0; k < M; ++k) acc += sW[i * LD + k] * sI[j * LD + k];
+        acc = fmax(acc, 0.0);
+        sP[i * MP + j] = acc;
+        Pout[i * MP + j] = acc;
+      }
+    } else {
+      for (int o = threadIdx.x; o < MM; o += blockDim.x) {
+        const int i = o / M, j = o - i * M;
+        double acc = 0.0;
+        for (int k = 0; k < M; ++k) acc += (evT[i * M + k] * s_er[k]) * evI[j * M + k];
+        acc = fmax(acc, 0.0);
+        sP[i * MP + j] = acc;
+        Pout[i * MP + j] = acc;
+      }
     }
   }
   // zero the padding of sP so the tip table never sees garbage
