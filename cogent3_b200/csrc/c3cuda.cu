@@ -107,6 +107,7 @@ struct c3_engine {
   int64_t block_bytes = 0;
   int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0, off_small = 0;
   bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
+  bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
   cudaEvent_t block_copied = nullptr;
   double* h_lnl = nullptr;  // mapped pinned result
   double* h_lnl_dev = nullptr;
@@ -182,10 +183,21 @@ int launch_strip(c3_engine* e, const PruneArgs& a, bool is_root) {
   }
   // one CTA per SM (shared memory bound); never more warps than strips
   const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + Cfg::WARPS - 1) / Cfg::WARPS));
-  if (is_root)
-    prune4_strip_kernel<K, NC, true><<<grid, Cfg::WARPS * 32, Cfg::SMEM_BYTES, e->stream>>>(a);
-  else
-    prune4_strip_kernel<K, NC, false><<<grid, Cfg::WARPS * 32, Cfg::SMEM_BYTES, e->stream>>>(a);
+  // programmatic dependent launch: this kernel's descriptor staging and first index loads
+  // overlap the tail of the previous launch (it calls griddepcontrol.wait before gathering)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::WARPS * 32);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune4_strip_kernel<K, NC, true>, a)
+                            : cudaLaunchKernelEx(&cfg, prune4_strip_kernel<K, NC, false>, a);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("strip launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
 
@@ -348,6 +360,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   e->MP = e->use_dmma ? (int)align_up(n_states, 8) : 4;
   if (const char* env = getenv("C3_NO_STRIP")) e->use_strip = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_SMALL")) e->use_small = atoi(env) == 0;
+  if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
   e->root = n_nodes - 1;
   e->children.resize(n_nodes);
   e->parent.assign(n_nodes, -1);
@@ -610,7 +623,7 @@ int c3_finalize(c3_engine* e) {
   e->off_pi = b;      b += align_up(MP * sizeof(double), 16);
   e->off_bprobs = b;  b += align_up(K * sizeof(double), 16);
   e->off_work = b;    b += align_up((int64_t)n_internal * sizeof(int32_t), 16);
-  e->off_prefix = b;  b += align_up((int64_t)(n_internal + 3 * e->n_levels + 4) * sizeof(int32_t), 16);
+  e->off_prefix = b;  b += align_up((int64_t)(2 * n_internal + 3 * e->n_levels + 8) * sizeof(int32_t), 16);
   e->off_small = b;   b += align_up((int64_t)(e->n_levels + 1) * sizeof(SmallLevel), 16);
   e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
   e->block_bytes = b;
@@ -1021,9 +1034,23 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     for (int kind : {0, 2, 3}) {
       LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, kind, 0, 0};
       int64_t tiles = 0;
-      const int64_t bytes0 = alg_bytes, flops0 = flops;
+      int64_t bytes0 = alg_bytes, flops0 = flops;
       for (int n : e->level_nodes[l]) {
         if (!recompute[n] || kind_of_node(e, n) != kind) continue;
+        if (kind >= 2 && ll.n_work == P4S_MAXW) {
+          // the strip kernel stages at most P4S_MAXW descriptors: close this launch, open another
+          ll.bytes = alg_bytes - bytes0;
+          ll.flops = flops - flops0;
+          prefix[p_off + ll.n_work] = (int32_t)tiles;
+          ll.total_tiles = (int)tiles;
+          w_off += ll.n_work;
+          p_off += ll.n_work + 1;
+          launches.push_back(ll);
+          ll = LevelLaunch{w_off, p_off, 0, 0, false, 0, 0, kind, 0, 0};
+          tiles = 0;
+          bytes0 = alg_bytes;
+          flops0 = flops;
+        }
         work[w_off + ll.n_work] = n;
         prefix[p_off + ll.n_work] = (int32_t)tiles;
         tiles += tiles_of_node(e, n, kind);

@@ -48,6 +48,7 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
   double* sP = smem;              // [MP*MP]
   double* s_er = sP + MP * MP;    // [M] exp(t re) cos(t im)
   double* s_ei = s_er + M;        // [M] exp(t re) sin(t im)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // see pdl_trigger()
   const ExpmJob job = jobs[blockIdx.x];
   const EdgeDesc ed = edges[job.node];
   double* Pout = ed.P + (int64_t)job.bin * MP * MP;
@@ -189,6 +190,7 @@ __global__ void expm_pade_kernel(const ExpmJob* __restrict__ jobs, const double*
   __shared__ int s_j, s_q, s_piv;
   __shared__ double s_norm;
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // see pdl_trigger()
   const ExpmJob job = jobs[blockIdx.x];
   const EdgeDesc ed = edges[job.node];
   double* Pout = ed.P + (int64_t)job.bin * S;

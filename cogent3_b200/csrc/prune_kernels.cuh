@@ -45,6 +45,12 @@ __device__ __forceinline__ void st256(double* p, const d4& r) {
                : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor drains; pdl_wait() blocks until the predecessor
+// has completed and its writes are visible, pdl_trigger() lets the successor start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ int find_work(const int32_t* __restrict__ prefix, int n_work, int t) {
   int lo = 0, hi = n_work;
   while (hi - lo > 1) {
@@ -259,34 +265,26 @@ __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// cursor over the strips of one launch: strips are numbered across the work list; a warp
-// visits strips gw, gw+GW, ...  The cursor only moves forward, so the node lookup is a
-// short scan of the prefix array instead of a binary search per strip.
+// Descriptors of the launch's work items, staged once per CTA in shared memory: the
+// per-strip node lookup, the child pointers and the P staging then never wait on global
+// memory (measured: ~20 us of dependent-load latency per launch before this).
+constexpr int P4S_MAXW = 64;  // work items (dirty nodes) per strip launch; the host splits longer lists
+
 template <int NC>
-struct StripCursor {
-  int w = -1;          // current work item
-  int first = 0;       // first strip of work item w
-  int next_first = 0;  // first strip of work item w+1
+struct WorkDesc {
+  double* out;
+  int64_t n_rows;
   const double* src[NC];
   const int32_t* idx[NC];
-  int64_t n_rows = 0;
-  __device__ __forceinline__ bool seek(const PruneArgs& a, int s) {  // true if the node changed
-    if (s < next_first) return false;
-    do {
-      ++w;
-      first = next_first;
-      next_first = a.tile_prefix[w + 1];
-    } while (s >= next_first);
-    const NodeDesc& nd = a.nodes[a.work_node[w]];
-    n_rows = nd.n_rows;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const ChildRef& ch = a.childs[nd.child_begin + c];
-      src[c] = ch.src;
-      idx[c] = ch.idx;
-    }
-    return true;
-  }
+  const double* P[NC];
+  int32_t fixed_motif;
+  int32_t pad;
+};
+
+template <int NC>
+struct StripSmem {
+  WorkDesc<NC> work[P4S_MAXW];
+  int32_t prefix[P4S_MAXW + 1];
 };
 
 template <int K, int NC, bool ROOT>
@@ -296,10 +294,30 @@ __global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_ker
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NQ = (ROWS + 31) / 32;  // gather-index registers per lane and child
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ StripSmem<NC> sd;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * Cfg::WARP_BYTES;
   double* sP = reinterpret_cast<double*>(wbase + STAGES * Cfg::STAGE_BYTES);
   const unsigned ring = (unsigned)__cvta_generic_to_shared(wbase);
+
+  pdl_trigger();
+  // ---- stage the descriptors (static data: may overlap the previous level's tail) ---------
+  for (int i = threadIdx.x; i <= a.n_work; i += blockDim.x) sd.prefix[i] = a.tile_prefix[i];
+  for (int i = threadIdx.x; i < a.n_work; i += blockDim.x) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    WorkDesc<NC>& wd = sd.work[i];
+    wd.out = nd.out;
+    wd.n_rows = nd.n_rows;
+    wd.fixed_motif = nd.fixed_motif;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + c];
+      wd.src[c] = ch.src;
+      wd.idx[c] = ch.idx;
+      wd.P[c] = ch.P;
+    }
+  }
+  __syncthreads();
 
   const int gw = blockIdx.x * Cfg::WARPS + warp;
   const int GW = gridDim.x * Cfg::WARPS;
@@ -307,25 +325,33 @@ __global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_ker
   const int b = lane % K;           // this lane's rate class
   const int slot = lane / K;        // its row slot within a pass (32/K slots)
 
-  StripCursor<NC> fc;  // fetch cursor, runs STAGES strips ahead
+  // fetch cursor (runs STAGES strips ahead of the compute cursor); strips are numbered
+  // across the work list and a warp only moves forward, so the lookup is a short scan
+  int f_w = 0;
+  auto f_seek = [&](int s) {
+    while (s >= sd.prefix[f_w + 1]) ++f_w;
+  };
   int32_t f_idx[NC][NQ];
   auto load_idx = [&](int s) {
-    const int64_t row0 = (int64_t)(s - fc.first) * ROWS;
+    const WorkDesc<NC>& wd = sd.work[f_w];
+    const int64_t row0 = (int64_t)(s - sd.prefix[f_w]) * ROWS;
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         int64_t p = row0 + q * 32 + lane;
-        if (p >= fc.n_rows) p = fc.n_rows - 1;
-        f_idx[c][q] = __ldg(fc.idx[c] + p);
+        if (p >= wd.n_rows) p = wd.n_rows - 1;
+        f_idx[c][q] = __ldg(wd.idx[c] + p);
       }
   };
   // gathers of one strip into ring stage st: row r of the strip has its index in lane
   // r%32, register r/32
   auto issue = [&](int st) {
+    const WorkDesc<NC>& wd = sd.work[f_w];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const unsigned dst0 = ring + st * Cfg::STAGE_BYTES + c * Cfg::CHILD_BYTES;
+      const double* src = wd.src[c];
       constexpr int CHUNKS_PER_ROW = K * 2;                // 16-byte chunks per pattern row
       constexpr int ROWS_PER_INSTR = 32 / CHUNKS_PER_ROW;  // rows per warp-wide cp.async
 #pragma unroll
@@ -335,59 +361,59 @@ __global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_ker
         const int32_t src_row = __shfl_sync(0xffffffffu, f_idx[c][(j * ROWS_PER_INSTR) / 32], r % 32);
         const int unit = r * K + (k >> 1);  // (row, bin) unit index, 0..127
         const unsigned dst = dst0 + ((k & 1) ? (unsigned)Cfg::HI_OFFSET : 0u) + (unsigned)unit * 16u;
-        cp_async16_ca(dst, fc.src[c] + ((int64_t)src_row * K) * 4 + k * 2);
+        cp_async16_ca(dst, src + ((int64_t)src_row * K) * 4 + k * 2);
       }
     }
   };
 
   // ---- prologue: fill the ring ----------------------------------------------------------
   int s_fetch = gw;
+  bool waited = false;
 #pragma unroll 1
   for (int st = 0; st < STAGES; ++st) {
     if (s_fetch < total) {
-      fc.seek(a, s_fetch);
-      load_idx(s_fetch);
+      f_seek(s_fetch);
+      load_idx(s_fetch);  // gather indexes are static too
+      if (!waited) {
+        pdl_wait();  // the child rows are the previous launches' output
+        waited = true;
+      }
       issue(st);
     }
     cp_async_commit();
     s_fetch += GW;
   }
+  if (!waited) pdl_wait();
   bool have_next = s_fetch < total;
   if (have_next) {  // idx of the next strip to fetch, loaded one iteration early
-    fc.seek(a, s_fetch);
+    f_seek(s_fetch);
     load_idx(s_fetch);
   }
 
   // ---- main loop ----------------------------------------------------------------------------
-  int c_w = -1, c_first = 0, c_next = 0;  // compute cursor
-  int64_t c_rows = 0;
-  double* c_out = nullptr;
-  int c_fixed = -1;
+  int c_w = 0, p_w = -1;  // compute cursor; node whose P matrices are in sP
   int st = 0;
 #pragma unroll 1
   for (int s = gw; s < total; s += GW) {
-    if (s >= c_next) {
-      do {
-        ++c_w;
-        c_first = c_next;
-        c_next = a.tile_prefix[c_w + 1];
-      } while (s >= c_next);
-      const NodeDesc& nd = a.nodes[a.work_node[c_w]];
-      c_rows = nd.n_rows;
-      c_out = nd.out;
-      c_fixed = nd.fixed_motif;
+    while (s >= sd.prefix[c_w + 1]) ++c_w;
+    const WorkDesc<NC>& wd = sd.work[c_w];
+    if (c_w != p_w) {
       __syncwarp();
       for (int o = lane; o < NC * K * 16; o += 32) {
         const int c = o / (K * 16);
         const int rem = o - c * (K * 16);  // bin * 16 + element
-        const double* P = a.childs[nd.child_begin + c].P;
+        const double* P = wd.P[c];
         // pre-multiplied children (tips) use the identity: 1*x + 0*... is exact
         sP[(c * K + (rem >> 4)) * P4S_PSTRIDE + (rem & 15)] =
             P ? P[rem] : (((rem & 15) % 5 == 0) ? 1.0 : 0.0);
       }
+      p_w = c_w;
       __syncwarp();
     }
-    const int64_t node_row0 = (int64_t)(s - c_first) * ROWS;
+    const int64_t node_row0 = (int64_t)(s - sd.prefix[c_w]) * ROWS;
+    const int64_t c_rows = wd.n_rows;
+    double* c_out = wd.out;
+    const int c_fixed = wd.fixed_motif;
     cp_async_wait_group<STAGES - 1>();
     __syncwarp();
 
@@ -425,7 +451,7 @@ __global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_ker
     s_fetch += GW;
     have_next = s_fetch < total;
     if (have_next) {
-      fc.seek(a, s_fetch);
+      f_seek(s_fetch);
       load_idx(s_fetch);
     }
 
@@ -503,6 +529,7 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
                     int n_work_total, int n_prefix_total) {
   extern __shared__ __align__(16) unsigned char small_raw[];
   SmallSmem& sm = *reinterpret_cast<SmallSmem*>(small_raw);
+  pdl_trigger();
   const int K = a.K;
   const unsigned nthreads = cluster_nctarank() * SMALL_THREADS;
   const unsigned tid = cluster_ctarank() * SMALL_THREADS + threadIdx.x;
