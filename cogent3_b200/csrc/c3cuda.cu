@@ -108,6 +108,7 @@ struct c3_engine {
   int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0, off_small = 0;
   bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
   bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
+  bool use_dmma_pipe = false;
   cudaEvent_t block_copied = nullptr;
   double* h_lnl = nullptr;  // mapped pinned result
   double* h_lnl_dev = nullptr;
@@ -164,6 +165,35 @@ int launch_dmma(c3_engine* e, const PruneArgs& a, bool is_root, int grid) {
   return C3_OK;
 }
 
+template <int MP>
+int launch_dmma_pipe(c3_engine* e, const PruneArgs& a, bool is_root) {
+  const size_t smem = DPipeCfg<MP>::SMEM_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_max_smem(prune_dmma_pipe_kernel<MP, false>, smem);
+    if (rc) return rc;
+    rc = set_max_smem(prune_dmma_pipe_kernel<MP, true>, smem);
+    if (rc) return rc;
+    configured = true;
+  }
+  const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + sizeof(DSmem) + 1024))));
+  const int grid = std::max(1, std::min(a.total_tiles, e->n_sm * per_sm));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(DMMA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune_dmma_pipe_kernel<MP, true>, a)
+                            : cudaLaunchKernelEx(&cfg, prune_dmma_pipe_kernel<MP, false>, a);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("dmma launch: ") + cudaGetErrorString(err));
+  return C3_OK;
+}
+
 int dmma_blocks_per_sm(int MP) {
   const size_t smem = (size_t)(DMMA_TILE_ROWS * (MP + 4) + 2 * MP * (MP + 4)) * sizeof(double);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -205,7 +235,21 @@ int launch_strip(c3_engine* e, const PruneArgs& a, bool is_root) {
 // nodes with that many children (4-state, K in {1,2,4})
 int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
   if (a.total_tiles <= 0) return C3_OK;
-  if (kind >= 2) {
+  if (kind == 4) {
+    int rc = C3_OK;
+    switch (e->MP) {
+      case 8: rc = launch_dmma_pipe<8>(e, a, is_root); break;
+      case 16: rc = launch_dmma_pipe<16>(e, a, is_root); break;
+      case 24: rc = launch_dmma_pipe<24>(e, a, is_root); break;
+      case 32: rc = launch_dmma_pipe<32>(e, a, is_root); break;
+      case 40: rc = launch_dmma_pipe<40>(e, a, is_root); break;
+      case 48: rc = launch_dmma_pipe<48>(e, a, is_root); break;
+      case 56: rc = launch_dmma_pipe<56>(e, a, is_root); break;
+      case 64: rc = launch_dmma_pipe<64>(e, a, is_root); break;
+      default: return fail(C3_ERR_INVALID, "unsupported padded state count");
+    }
+    if (rc) return rc;
+  } else if (kind >= 2) {
     int rc = C3_ERR_INVALID;
 #define C3_STRIP(KK)                                                         \
   case KK:                                                                   \
@@ -258,13 +302,18 @@ int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
 
 // which kernel family handles node n (see launch_prune)
 int kind_of_node(const c3_engine* e, int n) {
-  if (e->use_dmma || !e->use_strip) return 0;
+  // the pipelined DMMA kernel is an experiment that measured SLOWER than the first version
+  // (1.48 vs 1.40 ms on C4: one CTA of 8 warps per SM hides less latency than two CTAs);
+  // it stays selectable (C3_DMMA_PIPE=1) for the next round's tuning
+  if (e->use_dmma) return (e->use_dmma_pipe && (int)e->children[n].size() <= DP_MAXC) ? 4 : 0;
+  if (!e->use_strip) return 0;
   if (e->K != 1 && e->K != 2 && e->K != 4) return 0;
   const int nc = (int)e->children[n].size();
   return (nc == 2 || nc == 3) ? nc : 0;
 }
 
 int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
+  if (kind == 4) return (int64_t)e->K * ((e->n_rows[n] + DP_TILE_ROWS - 1) / DP_TILE_ROWS);
   if (kind >= 2) {
     const int rows = 128 / e->K;
     return (e->n_rows[n] + rows - 1) / rows;
@@ -361,6 +410,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_STRIP")) e->use_strip = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_SMALL")) e->use_small = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
+  if (const char* env = getenv("C3_DMMA_PIPE")) e->use_dmma_pipe = atoi(env) != 0;
   e->root = n_nodes - 1;
   e->children.resize(n_nodes);
   e->parent.assign(n_nodes, -1);
@@ -623,7 +673,7 @@ int c3_finalize(c3_engine* e) {
   e->off_pi = b;      b += align_up(MP * sizeof(double), 16);
   e->off_bprobs = b;  b += align_up(K * sizeof(double), 16);
   e->off_work = b;    b += align_up((int64_t)n_internal * sizeof(int32_t), 16);
-  e->off_prefix = b;  b += align_up((int64_t)(2 * n_internal + 3 * e->n_levels + 8) * sizeof(int32_t), 16);
+  e->off_prefix = b;  b += align_up((int64_t)(2 * n_internal + 4 * e->n_levels + 8) * sizeof(int32_t), 16);
   e->off_small = b;   b += align_up((int64_t)(e->n_levels + 1) * sizeof(SmallLevel), 16);
   e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
   e->block_bytes = b;
@@ -1031,13 +1081,13 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       continue;
     }
     open_small = -1;
-    for (int kind : {0, 2, 3}) {
+    for (int kind : {0, 2, 3, 4}) {
       LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, kind, 0, 0};
       int64_t tiles = 0;
       int64_t bytes0 = alg_bytes, flops0 = flops;
       for (int n : e->level_nodes[l]) {
         if (!recompute[n] || kind_of_node(e, n) != kind) continue;
-        if (kind >= 2 && ll.n_work == P4S_MAXW) {
+        if (kind >= 2 && ll.n_work == (kind == 4 ? DP_MAXW : P4S_MAXW)) {
           // the strip kernel stages at most P4S_MAXW descriptors: close this launch, open another
           ll.bytes = alg_bytes - bytes0;
           ll.flops = flops - flops0;

@@ -753,6 +753,287 @@ __global__ void __launch_bounds__(DMMA_THREADS) prune_dmma_kernel(const PruneArg
 }
 
 // ---------------------------------------------------------------------------------------
+// DMMA kernel, pipelined version (the production path for M != 4, nodes with <= 4 children).
+//
+// ncu on the first version: FP64 tensor pipe 50-63 % active, the rest long-scoreboard stalls:
+// each child's 64 gathered rows were fetched and waited for before its contraction started.
+// Here the CTA walks the sequence of (tile, contraction-child) units with a fetch cursor that
+// runs DP_NBUF-1 units ahead of the compute cursor: the rows of the next units are landing in
+// the other A buffers (cp.async) while the current one feeds the tensor cores.  One block
+// barrier per unit.  Descriptors are staged in shared memory; launched with programmatic
+// dependent launch like the strip kernel.
+// ---------------------------------------------------------------------------------------
+#ifndef DP_NBUF
+#define DP_NBUF 2
+#endif
+#ifndef DP_WM
+#define DP_WM 2  // 8-row blocks per warp: each B fragment feeds DP_WM DMMAs
+#endif
+constexpr int DP_TILE_ROWS = (DMMA_THREADS / 32) * 8 * DP_WM;
+constexpr int DP_MAXC = 4;   // children per node handled here (more: first version)
+constexpr int DP_MAXW = 48;  // work items per launch (the host splits longer lists)
+
+struct DWork {
+  double* out;
+  int64_t n_rows;
+  int64_t row_tiles;
+  const double* src[DP_MAXC];
+  const int32_t* idx[DP_MAXC];
+  const double* P[DP_MAXC];
+  int32_t nc;
+  int32_t fixed_motif;
+};
+struct DSmem {
+  DWork work[DP_MAXW];
+  int32_t prefix[DP_MAXW + 1];
+};
+
+template <int MP>
+struct DPipeCfg {
+  static constexpr int LDS = MP + 4;
+  static constexpr int NI = MP / 8;
+  static constexpr int KS = MP / 4;
+  static constexpr int A_DOUBLES = DP_TILE_ROWS * LDS;
+  static constexpr int B_DOUBLES = MP * LDS;
+  static constexpr size_t SMEM_BYTES = (size_t)(DP_NBUF * A_DOUBLES + 2 * B_DOUBLES) * sizeof(double);
+};
+
+struct DCursor {  // position in the (tile, child) sequence of one CTA
+  int t;          // tile
+  int w;          // work item of tile t
+  int b;          // rate class
+  int64_t row0;   // first row
+  int c;          // child
+};
+
+template <int MP, bool ROOT>
+__global__ void __launch_bounds__(DMMA_THREADS) prune_dmma_pipe_kernel(const PruneArgs a) {
+  using Cfg = DPipeCfg<MP>;
+  constexpr int LDS = Cfg::LDS, NI = Cfg::NI, KS = Cfg::KS;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ DSmem sd;
+  double* sA = smem;                                // [DP_NBUF][64*LDS]
+  double* sB = smem + DP_NBUF * Cfg::A_DOUBLES;     // [2][MP*LDS]
+  const int K = a.K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+
+  pdl_trigger();
+  for (int i = tid; i <= a.n_work; i += DMMA_THREADS) sd.prefix[i] = a.tile_prefix[i];
+  for (int i = tid; i < a.n_work; i += DMMA_THREADS) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    DWork& wd = sd.work[i];
+    wd.out = nd.out;
+    wd.n_rows = nd.n_rows;
+    wd.row_tiles = (nd.n_rows + DP_TILE_ROWS - 1) / DP_TILE_ROWS;
+    wd.nc = nd.n_children;
+    wd.fixed_motif = nd.fixed_motif;
+    for (int c = 0; c < nd.n_children && c < DP_MAXC; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + c];
+      wd.src[c] = ch.src;
+      wd.idx[c] = ch.idx;
+      wd.P[c] = ch.P;
+    }
+  }
+  __syncthreads();
+
+  auto place = [&](DCursor& cur) {  // fill w / b / row0 for cur.t (t < total)
+    while (cur.t >= sd.prefix[cur.w + 1]) ++cur.w;
+    const DWork& wd = sd.work[cur.w];
+    const int local = cur.t - sd.prefix[cur.w];
+    cur.b = (int)(local / wd.row_tiles);
+    cur.row0 = (int64_t)(local - cur.b * wd.row_tiles) * DP_TILE_ROWS;
+  };
+  // advance to the next contraction child at or after (t, c); false when the CTA is done
+  auto seek_unit = [&](DCursor& cur) -> bool {
+    while (cur.t < a.total_tiles) {
+      const DWork& wd = sd.work[cur.w];
+      while (cur.c < wd.nc) {
+        if (wd.P[cur.c] != nullptr) return true;
+        ++cur.c;
+      }
+      cur.t += gridDim.x;
+      cur.c = 0;
+      if (cur.t < a.total_tiles) place(cur);
+    }
+    return false;
+  };
+
+  DCursor fc{(int)blockIdx.x, 0, 0, 0, 0};
+  if (fc.t < a.total_tiles) place(fc);
+  int n_issued = 0;
+  constexpr int CHUNKS = MP / 2;                       // 16-byte chunks per row
+  constexpr int PASSES = DP_TILE_ROWS * CHUNKS / DMMA_THREADS;
+  // gather indexes of the NEXT unit to issue (this thread's chunks), loaded one unit early
+  // so that their latency hides behind the current contraction
+  int32_t nidx[PASSES];
+  bool f_valid = false;
+  auto prefetch_idx = [&]() {
+    f_valid = seek_unit(fc);
+    if (f_valid) {
+      const DWork& wd = sd.work[fc.w];
+      const int32_t* idx = wd.idx[fc.c];
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) {
+        const int rr = (tid + i * DMMA_THREADS) / CHUNKS;
+        int64_t p = fc.row0 + rr;
+        if (p >= wd.n_rows) p = wd.n_rows - 1;
+        nidx[i] = __ldg(idx + p);
+      }
+    }
+  };
+  auto issue_next = [&]() {
+    if (f_valid) {
+      const DWork& wd = sd.work[fc.w];
+      double* dstA = sA + (n_issued % DP_NBUF) * Cfg::A_DOUBLES;
+      const double* src = wd.src[fc.c];
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) {
+        const int o = tid + i * DMMA_THREADS;
+        const int rr = o / CHUNKS, ck = o - rr * CHUNKS;
+        cp_async16(dstA + rr * LDS + 2 * ck, src + ((int64_t)nidx[i] * K + fc.b) * MP + 2 * ck);
+      }
+      ++fc.c;
+    }
+    cp_async_commit();
+    ++n_issued;
+    prefetch_idx();
+  };
+
+  pdl_wait();
+  prefetch_idx();
+#pragma unroll 1
+  for (int i = 0; i < DP_NBUF - 1; ++i) issue_next();
+
+  int n_consumed = 0;
+  int res_w = -1, res_b = -1;  // (work item, bin) whose first two P matrices are resident
+  DCursor cc{(int)blockIdx.x, 0, 0, 0, 0};
+#pragma unroll 1
+  for (; cc.t < a.total_tiles; cc.t += gridDim.x) {
+    place(cc);
+    const DWork& wd = sd.work[cc.w];
+    const int b = cc.b;
+    const int nc = wd.nc;
+    if (cc.w != res_w || b != res_b) {
+      __syncthreads();
+      int slot = 0;
+      for (int c = 0; c < nc && slot < 2; ++c)
+        if (wd.P[c] != nullptr) {
+          load_P_to_smem<MP>(sB + slot * Cfg::B_DOUBLES, wd.P[c] + (int64_t)b * MP * MP);
+          ++slot;
+        }
+      res_w = cc.w;
+      res_b = b;
+      __syncthreads();
+    }
+    // this thread's C-fragment rows: DP_WM blocks of 8 rows per warp
+    int64_t my_row[DP_WM];
+    bool row_ok[DP_WM];
+    int64_t my_row_c[DP_WM];
+#pragma unroll
+    for (int m = 0; m < DP_WM; ++m) {
+      my_row[m] = cc.row0 + (warp * DP_WM + m) * 8 + g;
+      row_ok[m] = my_row[m] < wd.n_rows;
+      my_row_c[m] = row_ok[m] ? my_row[m] : wd.n_rows - 1;
+    }
+
+    double prod[DP_WM][NI][2];
+    int dmma_seen = 0;
+    for (int c = 0; c < nc; ++c) {
+      double cur[DP_WM][NI][2];
+      if (wd.P[c] == nullptr) {
+#pragma unroll
+        for (int m = 0; m < DP_WM; ++m) {
+          const int32_t r = __ldg(wd.idx[c] + my_row_c[m]);
+          const double* src = wd.src[c] + ((int64_t)r * K + b) * MP + 2 * q;
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(src + 8 * ni));
+            cur[m][ni][0] = v.x;
+            cur[m][ni][1] = v.y;
+          }
+        }
+      } else {
+        const double* sBc;
+        if (dmma_seen < 2) {
+          sBc = sB + dmma_seen * Cfg::B_DOUBLES;
+        } else {
+          // third / fourth contraction child: stream its P through slot 0
+          __syncthreads();
+          load_P_to_smem<MP>(sB, wd.P[c] + (int64_t)b * MP * MP);
+          res_w = -1;
+          sBc = sB;
+        }
+        ++dmma_seen;
+        cp_async_wait_group<DP_NBUF - 2>();
+        __syncthreads();  // unit landed; everyone is done with the previous unit's buffer
+        const double* sAc = sA + (n_consumed % DP_NBUF) * Cfg::A_DOUBLES;
+        ++n_consumed;
+        issue_next();     // refill the buffer the previous unit used
+#pragma unroll
+        for (int m = 0; m < DP_WM; ++m)
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) cur[m][ni][0] = cur[m][ni][1] = 0.0;
+        const double* aRow = sAc + ((warp * DP_WM) * 8 + g) * LDS + q;
+        const double* bRow = sBc + g * LDS + q;
+#pragma unroll 2
+        for (int ks = 0; ks < KS; ++ks) {
+          double av[DP_WM];
+#pragma unroll
+          for (int m = 0; m < DP_WM; ++m) av[m] = aRow[m * 8 * LDS + 4 * ks];
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) {
+            const double bv = bRow[(8 * ni) * LDS + 4 * ks];
+#pragma unroll
+            for (int m = 0; m < DP_WM; ++m) dmma_m8n8k4(cur[m][ni][0], cur[m][ni][1], av[m], bv);
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < DP_WM; ++m)
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          if (c == 0) {
+            prod[m][ni][0] = cur[m][ni][0];
+            prod[m][ni][1] = cur[m][ni][1];
+          } else {
+            prod[m][ni][0] *= cur[m][ni][0];
+            prod[m][ni][1] *= cur[m][ni][1];
+          }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < DP_WM; ++m) {
+      if (wd.fixed_motif >= 0) {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          if (8 * ni + 2 * q != wd.fixed_motif) prod[m][ni][0] = 0.0;
+          if (8 * ni + 2 * q + 1 != wd.fixed_motif) prod[m][ni][1] = 0.0;
+        }
+      }
+      if (row_ok[m]) {
+        double* dst = wd.out + ((int64_t)my_row[m] * K + b) * MP + 2 * q;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni)
+          *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(prod[m][ni][0], prod[m][ni][1]);
+      }
+      if (ROOT) {
+        double sdot = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          sdot = fma(prod[m][ni][0], a.pi[8 * ni + 2 * q], sdot);
+          sdot = fma(prod[m][ni][1], a.pi[8 * ni + 2 * q + 1], sdot);
+        }
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+        if (row_ok[m] && q == 0) a.lh_out[my_row[m] * K + b] = sdot;
+      }
+    }
+  }
+  cp_async_wait_group<0>();
+}
+
+// ---------------------------------------------------------------------------------------
 // site-weighted log-likelihood reduction
 //   mix[p] = sum_b bprob_b lh_b[p]     BinnedSiteDistribution.get_weighted_sum_lh
 //                                      (evolve/likelihood_calculation.py:178-185)

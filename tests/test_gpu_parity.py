@@ -177,6 +177,17 @@ def test_synthetic_against_oracle(model, n_tips, L, bins, kind):
         assert np.max(np.abs(lfs[0].engine.get_lh(b) - lfs[1].engine.get_lh(b))) <= ABS_LH
 
 
+def test_dmma_pipelined_variant_matches(monkeypatch):
+    """the (non-default) pipelined DMMA kernel gives the same numbers as the default one"""
+    monkeypatch.setenv("C3_DMMA_PIPE", "1")
+    for case in ("c4_cnfgtr_mid", "c4_cnfgtr_small"):
+        g = Golden(case)
+        lf = lf_from_golden(g)
+        lnL = lf.get_log_likelihood()
+        assert abs(lnL - g.lnL) <= REL_LNL * abs(g.lnL)
+        assert np.max(np.abs(lf.engine.get_lh(0) - g.lh[0])) <= ABS_LH
+
+
 def test_polytomy_and_many_bins():
     """5-way polytomy at the root, K=3 (generic-K kernel path)"""
     from cogent3_b200.tree import Topology
