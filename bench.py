@@ -403,6 +403,17 @@ def run_ours(args):
                     "frac": achieved / dmma_peak, "traffic": None,
                     "peak_source": "FP64 DMMA issue-loop microbenchmark on this GPU (c3_measure_dmma_peak)",
                     "hbm_gbs_achieved": prune_bytes / (prune_ms * 1e-3) / 1e9}  # fmt: skip
+    # DRAM traffic of the dominant launch from the committed ncu capture (per launch, like
+    # `achieved` is per launch); null when no capture exists for this config
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f).get(args.config)
+        if tr and args.kind == "evolved" and not args.columns:
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_note"] = (f"{tr['kernel']}: algorithmic {tr['algorithmic_bytes']} B per launch; "
+                                        "profiles/r1_prune4_strip_ncu.txt")
+    except (OSError, ValueError, KeyError):
+        pass
     roofline.update({
         "kernel": "prune4_kernel" if M == 4 else "prune_dmma_kernel",
         "launches_per_step": len(prune[-1]), "kernel_ms_per_step": prune_ms,
