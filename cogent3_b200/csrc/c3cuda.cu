@@ -109,6 +109,7 @@ struct c3_engine {
   bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
   bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
   bool use_dmma_pipe = false;
+  bool use_ring = false;  // C3_RING=1: the cp.async shared-memory ring version of the strip kernel
   cudaEvent_t block_copied = nullptr;
   double* h_lnl = nullptr;  // mapped pinned result
   double* h_lnl_dev = nullptr;
@@ -231,6 +232,26 @@ int launch_strip(c3_engine* e, const PruneArgs& a, bool is_root) {
   return C3_OK;
 }
 
+template <int K, int NC>
+int launch_reg(c3_engine* e, const PruneArgs& a, bool is_root) {
+  constexpr int WARPS = RegCfg<NC>::WARPS;
+  const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + WARPS - 1) / WARPS));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune4_reg_kernel<K, NC, true>, a)
+                            : cudaLaunchKernelEx(&cfg, prune4_reg_kernel<K, NC, false>, a);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("regpipe launch: ") + cudaGetErrorString(err));
+  return C3_OK;
+}
+
 // kind: 0 = generic kernels (prune4_kernel / prune_dmma_kernel); 2, 3 = strip kernel for
 // nodes with that many children (4-state, K in {1,2,4})
 int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
@@ -251,9 +272,12 @@ int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
     if (rc) return rc;
   } else if (kind >= 2) {
     int rc = C3_ERR_INVALID;
-#define C3_STRIP(KK)                                                         \
-  case KK:                                                                   \
-    rc = (kind == 2) ? launch_strip<KK, 2>(e, a, is_root) : launch_strip<KK, 3>(e, a, is_root); \
+#define C3_STRIP(KK)                                                                              \
+  case KK:                                                                                        \
+    if (e->use_ring)                                                                              \
+      rc = (kind == 2) ? launch_strip<KK, 2>(e, a, is_root) : launch_strip<KK, 3>(e, a, is_root); \
+    else                                                                                          \
+      rc = (kind == 2) ? launch_reg<KK, 2>(e, a, is_root) : launch_reg<KK, 3>(e, a, is_root);     \
     break;
     switch (e->K) {
       C3_STRIP(1)
@@ -411,6 +435,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_SMALL")) e->use_small = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
   if (const char* env = getenv("C3_DMMA_PIPE")) e->use_dmma_pipe = atoi(env) != 0;
+  if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   e->root = n_nodes - 1;
   e->children.resize(n_nodes);
   e->parent.assign(n_nodes, -1);

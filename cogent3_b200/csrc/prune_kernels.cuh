@@ -479,6 +479,156 @@ __global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_ker
 }
 
 // ---------------------------------------------------------------------------------------
+// 4-state kernel, register-pipelined version ("regpipe").
+//
+// ncu on the cp.async ring version: DRAM 56 %, L1 data pipe 74 % -- the pipe that moves the
+// gathered rows global -> shared (LDGSTS) and shared -> registers (LDS) plus the P matrices
+// is the binding unit, and the ring's shared memory leaves little L1 for the small child
+// tables.  Here the gathered rows go straight to registers with 256-bit loads and the
+// software pipeline lives in registers: while a warp computes strip s from x_cur it already
+// has the 8 (4 rows x 2 children) 32-byte loads of strip s+1 in flight into x_next, and the
+// gather indexes of strip s+2.  No shared-memory ring => ~1/3 fewer L1 wavefronts per strip
+// and ~200 KB of L1 for the child tables.  Same arithmetic (bit-identical results), same
+// strip numbering, same staged descriptors and programmatic dependent launch as the ring
+// version.
+// ---------------------------------------------------------------------------------------
+template <int NC>
+struct RegCfg {
+  static constexpr int WARPS = (NC <= 2) ? 8 : 6;
+};
+
+template <int K, int NC, bool ROOT>
+__global__ void __launch_bounds__(RegCfg<NC>::WARPS * 32, 1) prune4_reg_kernel(const PruneArgs a) {
+  constexpr int ROWS = 128 / K;
+  constexpr int WARPS = RegCfg<NC>::WARPS;
+  __shared__ StripSmem<NC> sd;
+  __shared__ __align__(16) double sPall[WARPS][NC * K * P4S_PSTRIDE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sP = sPall[warp];
+
+  pdl_trigger();
+  for (int i = threadIdx.x; i <= a.n_work; i += blockDim.x) sd.prefix[i] = a.tile_prefix[i];
+  for (int i = threadIdx.x; i < a.n_work; i += blockDim.x) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    WorkDesc<NC>& wd = sd.work[i];
+    wd.out = nd.out;
+    wd.n_rows = nd.n_rows;
+    wd.fixed_motif = nd.fixed_motif;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + c];
+      wd.src[c] = ch.src;
+      wd.idx[c] = ch.idx;
+      wd.P[c] = ch.P;
+    }
+  }
+  __syncthreads();
+
+  const int gw = blockIdx.x * WARPS + warp;
+  const int GW = gridDim.x * WARPS;
+  const int total = a.total_tiles;
+  const int b = lane % K;
+  const int slot = lane / K;
+
+  // idx cursor runs two strips ahead, gather cursor one strip ahead of the compute cursor
+  int i_w = 0, g_w = 0, c_w = 0, p_w = -1;
+  int32_t idx_n[NC][P4S_U];  // gather rows of the strip after next
+  auto load_idx = [&](int s) {
+    while (s >= sd.prefix[i_w + 1]) ++i_w;
+    const WorkDesc<NC>& wd = sd.work[i_w];
+    const int64_t row0 = (int64_t)(s - sd.prefix[i_w]) * ROWS;
+#pragma unroll
+    for (int u = 0; u < P4S_U; ++u) {
+      int64_t p = row0 + u * (32 / K) + slot;
+      if (p >= wd.n_rows) p = wd.n_rows - 1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) idx_n[c][u] = __ldg(wd.idx[c] + p);
+    }
+  };
+  d4 x_n[NC][P4S_U];  // rows of the next strip, in flight
+  auto gather = [&](int s) {
+    while (s >= sd.prefix[g_w + 1]) ++g_w;
+    const WorkDesc<NC>& wd = sd.work[g_w];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int u = 0; u < P4S_U; ++u)
+        x_n[c][u] = ld256_nc(wd.src[c] + ((int64_t)idx_n[c][u] * K + b) * 4);
+  };
+
+  pdl_wait();
+  if (gw < total) {
+    load_idx(gw);
+    gather(gw);
+  }
+  if (gw + GW < total) load_idx(gw + GW);
+
+#pragma unroll 1
+  for (int s = gw; s < total; s += GW) {
+    while (s >= sd.prefix[c_w + 1]) ++c_w;
+    const WorkDesc<NC>& wd = sd.work[c_w];
+    if (c_w != p_w) {
+      __syncwarp();
+      for (int o = lane; o < NC * K * 16; o += 32) {
+        const int c = o / (K * 16);
+        const int rem = o - c * (K * 16);
+        const double* P = wd.P[c];
+        sP[(c * K + (rem >> 4)) * P4S_PSTRIDE + (rem & 15)] =
+            P ? P[rem] : (((rem & 15) % 5 == 0) ? 1.0 : 0.0);
+      }
+      p_w = c_w;
+      __syncwarp();
+    }
+    // take over the rows that were in flight, start the next strip's loads
+    d4 x[NC][P4S_U];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int u = 0; u < P4S_U; ++u) x[c][u] = x_n[c][u];
+    if (s + GW < total) gather(s + GW);
+    if (s + 2 * GW < total) load_idx(s + 2 * GW);
+
+    d4 acc[P4S_U];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double* Pc = sP + (c * K + b) * P4S_PSTRIDE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double2 p01 = *reinterpret_cast<const double2*>(Pc + 4 * i);
+        const double2 p23 = *reinterpret_cast<const double2*>(Pc + 4 * i + 2);
+#pragma unroll
+        for (int u = 0; u < P4S_U; ++u) {
+          const double y =
+              fma(x[c][u].w, p23.y, fma(x[c][u].z, p23.x, fma(x[c][u].y, p01.y, x[c][u].x * p01.x)));
+          double& t = (i == 0) ? acc[u].x : (i == 1) ? acc[u].y : (i == 2) ? acc[u].z : acc[u].w;
+          t = (c == 0) ? y : t * y;
+        }
+      }
+    }
+    const int64_t node_row0 = (int64_t)(s - sd.prefix[c_w]) * ROWS;
+    const int c_fixed = wd.fixed_motif;
+#pragma unroll
+    for (int u = 0; u < P4S_U; ++u) {
+      const int64_t p = node_row0 + u * (32 / K) + slot;
+      if (c_fixed >= 0) {
+        if (c_fixed != 0) acc[u].x = 0.0;
+        if (c_fixed != 1) acc[u].y = 0.0;
+        if (c_fixed != 2) acc[u].z = 0.0;
+        if (c_fixed != 3) acc[u].w = 0.0;
+      }
+      if (p < wd.n_rows) {
+        st256(wd.out + (p * K + b) * 4, acc[u]);
+        if (ROOT) {
+          const double lh =
+              fma(acc[u].w, a.pi[3], fma(acc[u].z, a.pi[2], fma(acc[u].y, a.pi[1], acc[u].x * a.pi[0])));
+          a.lh_out[p * K + b] = lh;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // 4-state kernel for SMALL levels: several consecutive tree levels in ONE launch.
 //
 // Real alignments (brca1: 2763 root patterns, 11 levels) and the shallow levels of big
