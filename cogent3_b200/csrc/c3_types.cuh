@@ -80,6 +80,8 @@ constexpr int SMALL_MAX_WORK = 384;  // work items whose descriptors are staged 
 constexpr int SMALL_MAX_LEVELS = 64;
 constexpr int SMALL_STAGED_CHILDREN = 3;
 
+constexpr int FLOW_MAXW = 256;  // work items (dirty nodes) per dataflow launch
+
 constexpr int PRUNE4_THREADS = 256;
 #ifndef PRUNE4_UNROLL
 #define PRUNE4_UNROLL 1

@@ -39,6 +39,15 @@ __device__ __forceinline__ d4 ld256_nc(const double* p) {
                : "l"(p));
   return r;
 }
+// plain (coherent) 256-bit load: the rows may have been written earlier in this launch
+__device__ __forceinline__ d4 ld256(const double* p) {
+  d4 r;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
 __device__ __forceinline__ void st256(double* p, const d4& r) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.x), "d"(r.y), "d"(r.z),
                "d"(r.w)
@@ -629,6 +638,248 @@ __global__ void __launch_bounds__(RegCfg<NC>::WARPS * 32, 1) prune4_reg_kernel(c
 }
 
 // ---------------------------------------------------------------------------------------
+// 4-state DATAFLOW kernel: several consecutive tree levels in ONE persistent launch.
+//
+// Per-level launches cost ~15 us each of ramp-up / tail / launch latency (fit over the C2
+// levels: time = 15-20 us + bytes / 6 TB/s), a third of a C2 step.  Here the dirty binary
+// nodes of a whole run of levels form one work list in level order; strips are numbered
+// across it and dealt to the resident warps round-robin, exactly as in the regpipe kernel.
+// Instead of a kernel boundary between levels, every node has a completion counter:
+//   * when a warp leaves node n (its next strip belongs to another node) it does
+//     fence.acq_rel.gpu + red.relaxed  node_done[n] += (strips of n it stored)  (the fence
+//     is cumulative over the other lanes' stores through __syncwarp);
+//   * before a warp gathers rows for a strip of node n it makes sure, once per node, that
+//     node_done[child] == strips(child) for the children computed in this launch
+//     (ld.acquire.gpu poll).
+// Deadlock freedom: strips are in level order and every warp visits its strips in
+// increasing order; a warp only ever blocks when it ENTERS a node, and by then it has
+// signalled everything it stored; inside a node (whose children are complete) it never
+// blocks.  So the owner of the smallest unfinished strip can always proceed.  The one trap
+// -- a warp PREFETCHING strip s+GW must not block on a dependency before it has stored and
+// signalled strip s -- is avoided by prefetching early only when the dependency is already
+// satisfied, and otherwise gathering after the signal.  All CTAs are resident (grid <= SM
+// count, one CTA per SM).
+// Measured and dropped: a release per strip (the MEMBAR.GPU is a store round trip per strip:
+// 20 % slower), and strip-granular dependencies through "super-round" counters so that level
+// l+1 streams in right behind level l (cogent3's first-seen pattern numbering guarantees
+// idx[p] <= p): 4-10 % slower than node granularity at 4..32 rounds per signal -- the
+// kernel is issue bound and the level transitions were not where the time goes.  Walking
+// odd levels downwards so that parents first gather what is still in L2: no change.
+// ---------------------------------------------------------------------------------------
+struct FlowWork {
+  double* out;
+  int64_t n_rows;
+  const double* src[2];
+  const int32_t* idx[2];
+  const double* P[2];
+  int32_t dep[2];  // work item producing child c in this launch, -1: nothing to wait for
+  int32_t fixed_motif;
+  int32_t is_root;
+  int32_t n_strips;
+  int32_t pad;
+};
+struct FlowSmem {
+  FlowWork work[FLOW_MAXW];
+  int32_t prefix[FLOW_MAXW + 1];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 1)
+prune4_flow_kernel(const PruneArgs a, const int32_t* __restrict__ dep, unsigned* __restrict__ node_done) {
+  constexpr int ROWS = 128 / K;
+  constexpr int WARPS = 8;
+  constexpr int NC = 2;
+  extern __shared__ __align__(16) unsigned char flow_raw[];
+  FlowSmem& sd = *reinterpret_cast<FlowSmem*>(flow_raw);
+  __shared__ __align__(16) double sPall[WARPS][NC * K * P4S_PSTRIDE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sP = sPall[warp];
+
+  pdl_trigger();
+  for (int i = threadIdx.x; i <= a.n_work; i += blockDim.x) sd.prefix[i] = a.tile_prefix[i];
+  for (int i = threadIdx.x; i < a.n_work; i += blockDim.x) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    FlowWork& wd = sd.work[i];
+    wd.out = nd.out;
+    wd.n_rows = nd.n_rows;
+    wd.fixed_motif = nd.fixed_motif;
+    wd.is_root = nd.is_root;
+    wd.n_strips = a.tile_prefix[i + 1] - a.tile_prefix[i];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + c];
+      wd.src[c] = ch.src;
+      wd.idx[c] = ch.idx;
+      wd.P[c] = ch.P;
+      wd.dep[c] = dep[2 * i + c];
+    }
+  }
+  __syncthreads();
+
+  const int gw = blockIdx.x * WARPS + warp;
+  const int GW = gridDim.x * WARPS;
+  const int total = a.total_tiles;
+  const int b = lane % K;
+  const int slot = lane / K;
+
+  int i_w = 0, g_w = 0, c_w = 0, p_w = -1;
+  int ready_w = -1;  // last work item whose children are known to be complete
+  // is every child of work item w complete?  Uniform across the warp (same-address polls).
+  auto deps_done = [&](int w) -> bool {
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int d = sd.work[w].dep[c];
+      if (d >= 0 && ld_acquire_gpu(node_done + d) < (unsigned)sd.work[d].n_strips) ok = false;
+    }
+    __syncwarp();
+    return ok;
+  };
+  auto strip_row0 = [&](int s, int w) -> int64_t { return (int64_t)(s - sd.prefix[w]) * ROWS; };
+  int32_t idx_n[NC][P4S_U];
+  auto load_idx = [&](int s) {
+    while (s >= sd.prefix[i_w + 1]) ++i_w;
+    const FlowWork& wd = sd.work[i_w];
+    const int64_t row0 = strip_row0(s, i_w);
+#pragma unroll
+    for (int u = 0; u < P4S_U; ++u) {
+      int64_t p = row0 + u * (32 / K) + slot;
+      if (p >= wd.n_rows) p = wd.n_rows - 1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) idx_n[c][u] = __ldg(wd.idx[c] + p);
+    }
+  };
+  d4 x_n[NC][P4S_U];
+  // rows written earlier in this launch: plain (coherent) loads, never the .nc path
+  auto gather = [&]() {
+    const FlowWork& wd = sd.work[g_w];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int u = 0; u < P4S_U; ++u)
+        x_n[c][u] = ld256(wd.src[c] + ((int64_t)idx_n[c][u] * K + b) * 4);
+  };
+  // make strip s the gather target; returns whether its dependencies are satisfied
+  auto seek_gather = [&](int s, bool block) -> bool {
+    while (s >= sd.prefix[g_w + 1]) ++g_w;
+    if (g_w == ready_w) return true;
+    bool ok = deps_done(g_w);
+    while (!ok && block) {
+      __nanosleep(100);
+      ok = deps_done(g_w);
+    }
+    if (ok) ready_w = g_w;
+    return ok;
+  };
+
+  if (gw < total) load_idx(gw);  // gather indexes are static: may overlap the previous launch
+  pdl_wait();
+  bool pending = false;   // the next strip's gather still has to be issued (dependency not ready)
+  int n_unsignalled = 0;  // strips of the current node stored but not yet added to node_done[]
+  if (gw < total) {
+    seek_gather(gw, true);
+    gather();
+  }
+  if (gw + GW < total) load_idx(gw + GW);
+
+#pragma unroll 1
+  for (int s = gw; s < total; s += GW) {
+    while (s >= sd.prefix[c_w + 1]) ++c_w;
+    const FlowWork& wd = sd.work[c_w];
+    if (c_w != p_w) {
+      __syncwarp();
+      for (int o = lane; o < NC * K * 16; o += 32) {
+        const int c = o / (K * 16);
+        const int rem = o - c * (K * 16);
+        const double* P = wd.P[c];
+        sP[(c * K + (rem >> 4)) * P4S_PSTRIDE + (rem & 15)] =
+            P ? P[rem] : (((rem & 15) % 5 == 0) ? 1.0 : 0.0);
+      }
+      p_w = c_w;
+      __syncwarp();
+    }
+    d4 x[NC][P4S_U];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int u = 0; u < P4S_U; ++u) x[c][u] = x_n[c][u];
+    // prefetch the next strip now if its node's children are complete, else after the signal
+    pending = false;
+    const bool more = s + GW < total;
+    if (more) {
+      if (seek_gather(s + GW, false)) gather();
+      else pending = true;
+    }
+    const bool more_idx = s + 2 * GW < total;
+    if (more_idx && !pending) load_idx(s + 2 * GW);
+
+    d4 acc[P4S_U];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double* Pc = sP + (c * K + b) * P4S_PSTRIDE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double2 p01 = *reinterpret_cast<const double2*>(Pc + 4 * i);
+        const double2 p23 = *reinterpret_cast<const double2*>(Pc + 4 * i + 2);
+#pragma unroll
+        for (int u = 0; u < P4S_U; ++u) {
+          const double y =
+              fma(x[c][u].w, p23.y, fma(x[c][u].z, p23.x, fma(x[c][u].y, p01.y, x[c][u].x * p01.x)));
+          double& t = (i == 0) ? acc[u].x : (i == 1) ? acc[u].y : (i == 2) ? acc[u].z : acc[u].w;
+          t = (c == 0) ? y : t * y;
+        }
+      }
+    }
+    const int64_t node_row0 = strip_row0(s, c_w);
+    const int c_fixed = wd.fixed_motif;
+#pragma unroll
+    for (int u = 0; u < P4S_U; ++u) {
+      const int64_t p = node_row0 + u * (32 / K) + slot;
+      if (c_fixed >= 0) {
+        if (c_fixed != 0) acc[u].x = 0.0;
+        if (c_fixed != 1) acc[u].y = 0.0;
+        if (c_fixed != 2) acc[u].z = 0.0;
+        if (c_fixed != 3) acc[u].w = 0.0;
+      }
+      if (p < wd.n_rows) {
+        st256(wd.out + (p * K + b) * 4, acc[u]);
+        if (wd.is_root) {
+          const double lh =
+              fma(acc[u].w, a.pi[3], fma(acc[u].z, a.pi[2], fma(acc[u].y, a.pi[1], acc[u].x * a.pi[0])));
+          a.lh_out[p * K + b] = lh;
+        }
+      }
+    }
+    // signal the strips this warp stored for node c_w -- once, when it leaves the node
+    ++n_unsignalled;
+    if (!more || g_w != c_w) {
+      __syncwarp();
+      if (lane == 0) {
+        fence_acq_rel_gpu();
+        red_relaxed_gpu_add(node_done + c_w, (unsigned)n_unsignalled);
+      }
+      n_unsignalled = 0;
+    }
+    if (pending) {
+      // the next strip's node was not ready before: now it is safe to block
+      seek_gather(s + GW, true);
+      gather();
+      if (more_idx) load_idx(s + 2 * GW);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // 4-state kernel for SMALL levels: several consecutive tree levels in ONE launch.
 //
 // Real alignments (brca1: 2763 root patterns, 11 levels) and the shallow levels of big
@@ -651,15 +902,6 @@ __device__ __forceinline__ unsigned cluster_ctarank() {
 __device__ __forceinline__ unsigned cluster_nctarank() {
   unsigned r;
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-// plain (coherent) 256-bit load: the rows may have been written earlier in this launch
-__device__ __forceinline__ d4 ld256(const double* p) {
-  d4 r;
-  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
-               : "l"(p)
-               : "memory");
   return r;
 }
 

@@ -177,6 +177,67 @@ def test_synthetic_against_oracle(model, n_tips, L, bins, kind):
         assert np.max(np.abs(lfs[0].engine.get_lh(b) - lfs[1].engine.get_lh(b))) <= ABS_LH
 
 
+@pytest.mark.parametrize(
+    "model,n_tips,L,bins,kind,rooted",
+    [
+        ("GTR", 24, 50_000, 4, "evolved", False),
+        ("HKY85", 16, 30_000, 1, "dense", False),
+        ("HKY85", 20, 40_000, 2, "evolved", False),
+        ("HKY85", 9, 60_000, 4, "dense", True),
+    ],
+)
+def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, rooted, monkeypatch):
+    """per-level regpipe (default), dataflow, cp.async ring and thread-per-unit kernels do the
+    same arithmetic in the same order: every partial row, lh and lnL are bit-identical; so is
+    a dirty-path update inside the dataflow launch"""
+    from cogent3_b200.tree import Topology
+
+    m = hostmodels.get_model(model)
+    topo, lengths, codes = make_workload(n_tips, L, m.n_states, kind=kind, seed=7)
+    if rooted:
+        # bifurcating root: the root itself is computed inside the dataflow launch
+        topo, lengths = Topology.from_newick("(((a:0.1,b:0.2):0.1,(c:0.3,d:0.2):0.05):0.1,((e:0.1,f:0.1):0.2,(g:0.2,(h:0.1,i:0.3):0.1):0.1):0.2);")
+        codes = codes[: int(np.sum(topo.is_tip))]
+
+    def build(env):
+        for k in ("C3_FLOW", "C3_RING", "C3_NO_STRIP", "C3_NO_SMALL"):
+            monkeypatch.delenv(k, raising=False)
+        for k in env:
+            monkeypatch.setenv(k, "1")
+        lf = LikelihoodFunction(m, topo, bins=bins)
+        lf.set_alignment(codes.astype(np.int64), np.eye(4))
+        lf.set_motif_probs_from_data()
+        lf.lengths[:-1] = np.asarray(lengths)[:-1]
+        for k, p in enumerate(m.parameter_order):
+            lf.set_param_rule(p, value=0.5 + 0.37 * k)
+        if bins > 1:
+            lf.set_param_rule("rate_shape", value=0.6)
+        return lf
+
+    variants = [(), ("C3_FLOW",), ("C3_RING",), ("C3_NO_STRIP",), ("C3_NO_SMALL",), ("C3_FLOW", "C3_NO_SMALL")]
+    lfs = [build(v) for v in variants]
+    vals = [lf.get_log_likelihood() for lf in lfs]
+    assert len(set(vals)) == 1, vals
+    for n in range(topo.n_nodes):
+        if topo.is_tip[n]:
+            continue
+        for b in range(bins):
+            want = lfs[0].engine.get_partials(n, b)
+            for lf in lfs[1:]:
+                np.testing.assert_array_equal(lf.engine.get_partials(n, b), want)
+    # dirty path (one branch length at a time) through each family
+    rng = np.random.default_rng(11)
+    for n in rng.choice(topo.edges, size=3, replace=False):
+        v = float(rng.uniform(0.01, 0.5))
+        got = []
+        for lf in lfs:
+            lf.set_param_rule("length", edge=topo.names[n], value=v)
+            got.append(lf.get_log_likelihood())
+        assert len(set(got)) == 1, got
+        lfs[0].engine.invalidate()
+        assert lfs[0].get_log_likelihood() == got[0]
+
+
 def test_dmma_pipelined_variant_matches(monkeypatch):
     """the (non-default) pipelined DMMA kernel gives the same numbers as the default one"""
     monkeypatch.setenv("C3_DMMA_PIPE", "1")
