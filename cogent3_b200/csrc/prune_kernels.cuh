@@ -500,6 +500,11 @@ __global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_ker
 // and ~200 KB of L1 for the child tables.  Same arithmetic (bit-identical results), same
 // strip numbering, same staged descriptors and programmatic dependent launch as the ring
 // version.
+// Measured and dropped: a variant with TWO strips in flight per warp (row buffers refilled in
+// place right after the FMAs that consume them, 244 registers): 0.119 vs 0.109 ms on the largest
+// C2 level, no change for K = 1.  More bytes in flight do not help: the evolved alignments'
+// gathers (rows re-referenced out of order, 128 B each) hold DRAM at ~4.8 TB/s; i.i.d. columns,
+// whose child index is nearly the identity, reach 5.5-5.9 TB/s with the same kernel.
 // ---------------------------------------------------------------------------------------
 template <int NC>
 struct RegCfg {
@@ -881,6 +886,9 @@ prune4_flow_kernel(const PruneArgs a, const int32_t* __restrict__ dep, unsigned*
 
 // ---------------------------------------------------------------------------------------
 // 4-state kernel for SMALL levels: several consecutive tree levels in ONE launch.
+// (Measured and dropped: the whole brca1 evaluation -- expm, 11 levels, reduction -- in one
+// single-CTA launch with block barriers: 71 us vs 75 us for the three launches; one SM has to
+// issue all ~190k warp instructions, which costs what the cluster barriers cost here.)
 //
 // Real alignments (brca1: 2763 root patterns, 11 levels) and the shallow levels of big
 // ones are latency bound: a launch per level costs ~8 us of dependent-load latency for a
