@@ -173,6 +173,20 @@ class SubstitutionModel:
         return dict.fromkeys(self.parameter_order, 1.0)
 
 
+class SuppliedQModel(SubstitutionModel):
+    """a fixed, already calibrated rate matrix (any alphabet up to 64 states): lets the engine
+    be driven with the reference's own Q for models this host layer does not restate
+    (dinucleotide, protein: tests/golden kat_dinucleotide / kat_protein)."""
+
+    def __init__(self, Q, alphabet):
+        Q = np.array(Q, float)
+        super().__init__("supplied-Q", alphabet, (Q != 0) & ~np.eye(len(Q), dtype=bool), {}, True, "tuple")
+        self._Q = Q
+
+    def calcQ(self, mprobs, params):
+        return self._Q.copy()
+
+
 def _nucleotide_mask():
     return 1.0 - np.eye(4)
 

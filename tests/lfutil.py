@@ -2,12 +2,16 @@
 
 from __future__ import annotations
 
+from cogent3_b200 import models as hostmodels
 from cogent3_b200.likelihood import LikelihoodFunction
 
 
 def lf_from_golden(g, engine_factory=None, device=0):
+    model = g.meta["model"]
+    if model == "supplied-Q":
+        model = hostmodels.SuppliedQModel(g.Q[0, 0], g.alphabet)
     lf = LikelihoodFunction(
-        g.meta["model"], g.topo, bins=g.n_bins, expm=g.meta["expm"], engine_factory=engine_factory,
+        model, g.topo, bins=g.n_bins, expm=g.meta["expm"], engine_factory=engine_factory,
         device=device,
     )  # fmt: skip
     lf.set_alignment(g.codes_by_tip(), g.symbol_rows)
