@@ -106,11 +106,16 @@ def make_lf(problem, engine_factory=None, device=0, stream=None, patterns=None):
     lf = LikelihoodFunction(model_name, topo, bins=bins, expm=setup.get("expm", "either"),
                             engine_factory=engine_factory, device=device, stream=stream)  # fmt: skip
     t0 = time.perf_counter()
-    if patterns is None:
-        patterns = compress_alignment(topo, codes, rows)
-    t1 = time.perf_counter()
-    lf.set_alignment(None, patterns=patterns)
-    t2 = time.perf_counter()
+    if patterns is None and engine_factory is None:
+        # the CUDA engine compresses the alignment itself (c3_compress_alignment)
+        lf.set_alignment(codes, rows, compress="device")
+        t1 = t2 = time.perf_counter()
+    else:
+        if patterns is None:
+            patterns = compress_alignment(topo, codes, rows)
+        t1 = time.perf_counter()
+        lf.set_alignment(None, patterns=patterns)
+        t2 = time.perf_counter()
     if "mprobs" in setup:
         lf.set_motif_probs(setup["mprobs"])
     else:
@@ -123,7 +128,8 @@ def make_lf(problem, engine_factory=None, device=0, stream=None, patterns=None):
             lf.set_param_rule(p, edge=n, value=v)
     if "rate_shape" in setup:
         lf.set_param_rule("rate_shape", value=setup["rate_shape"])
-    return lf, {"compress_s": t1 - t0, "upload_s": t2 - t1}
+    return lf, {"compress_s": t1 - t0, "upload_s": t2 - t1,
+                "compress": "device" if (t1 == t2) else "host"}
 
 
 def step_lengths(base, k):

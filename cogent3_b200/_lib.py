@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libc3cuda.so")
@@ -61,6 +61,14 @@ SIGNATURES = {
     "c3_set_node_patterns": (c_int, [c_void_p, c_int, _pi64, c_int64]),
     "c3_set_root_counts": (c_int, [c_void_p, _pd, c_int64]),
     "c3_finalize": (c_int, [c_void_p]),
+    "c3_compress_alignment": (c_int, [c_void_p, POINTER(c_uint8), c_int64, _pd, c_int, c_int]),
+    "c3_get_node_rows": (c_int, [c_void_p, _pi64]),
+    "c3_get_node_indexes": (c_int, [c_void_p, c_int, _pi64]),
+    "c3_get_tip_table": (c_int, [c_void_p, c_int, _pd]),
+    "c3_get_root_counts": (c_int, [c_void_p, _pd]),
+    "c3_get_column_index": (c_int, [c_void_p, c_int, _pi64]),
+    "c3_set_column_index": (c_int, [c_void_p, _pi64, c_int64]),
+    "c3_get_site_lh": (c_int, [c_void_p, c_int, _pd, c_int64]),
     "c3_set_eigen": (c_int, [c_void_p, c_int, _pd, _pd, _pd, c_int]),
     "c3_set_Q": (c_int, [c_void_p, c_int, _pd]),
     "c3_set_edge_qslots": (c_int, [c_void_p, _pi32]),

@@ -20,6 +20,7 @@
 
 #include "../../include/c3cuda.h"
 #include "c3_types.cuh"
+#include "compress_kernels.cuh"
 #include "expm_kernels.cuh"
 #include "prune_kernels.cuh"
 
@@ -77,6 +78,12 @@ struct c3_engine {
   std::vector<std::vector<int32_t>> idx32;
   std::vector<double> counts;
   bool finalized = false;
+
+  // tables built on the device by c3_compress_alignment (moved into the pool by c3_finalize)
+  int64_t n_columns = -1;
+  std::vector<int32_t*> d_index;    // per node: pattern number of every column, int32 [L] (root always kept)
+  std::vector<int32_t*> d_idx_tmp;  // per internal node: gather table int32 [C][rows]
+  int32_t* d_root_index = nullptr;  // == d_index[root]; survives finalize
 
   // device memory
   char* d_pool = nullptr;  // everything sized at finalize
@@ -535,6 +542,10 @@ int c3_destroy(c3_engine* e) {
   if (!e) return C3_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  for (int32_t* p : e->d_index)
+    if (p) cudaFree(p);
+  for (int32_t* p : e->d_idx_tmp)
+    if (p) cudaFree(p);
   if (e->d_pool) cudaFree(e->d_pool);
   if (e->d_slots) cudaFree(e->d_slots);
   if (e->d_block) cudaFree(e->d_block);
@@ -604,6 +615,317 @@ int c3_set_root_counts(c3_engine* e, const double* counts, int64_t n_rows) {
   C3_REQUIRE(!e->finalized, "pattern tables are frozen after c3_finalize");
   C3_REQUIRE(n_rows == e->n_rows[e->root], "counts length must equal the root's row count");
   e->counts.assign(counts, counts + n_rows);
+  return C3_OK;
+}
+
+// ---- device-side pattern compression ------------------------------------------------------
+namespace {
+struct CmpScratch {
+  unsigned long long* keys = nullptr;
+  unsigned* first = nullptr;
+  unsigned* rank = nullptr;
+  int32_t* slot_of_col = nullptr;
+  unsigned* pos = nullptr;
+  unsigned* tile_sums = nullptr;
+  unsigned* total = nullptr;
+  int64_t table_cap = 0;
+  ~CmpScratch() {
+    cudaFree(keys); cudaFree(first); cudaFree(rank); cudaFree(slot_of_col); cudaFree(pos);
+    cudaFree(tile_sums); cudaFree(total);
+  }
+};
+
+// first-seen numbering of key(col) = a[col]*rows_b + b[col] (or codes[col]); writes index[col],
+// leaves pos[col] (first-occurrence columns) in the scratch; returns the number of distinct keys
+int cmp_first_seen(c3_engine* e, CmpScratch& sc, const int32_t* a, const int32_t* b, const uint8_t* codes,
+                   int64_t rows_a, int64_t rows_b, int64_t L, int32_t* index_out, int64_t* n_unique) {
+  if (L == 0) {
+    *n_unique = 0;
+    return C3_OK;
+  }
+  // table size: a power of two >= 2 * (upper bound on distinct keys)
+  const double span = codes ? 256.0 : (double)rows_a * (double)rows_b;
+  const int64_t bound = (int64_t)std::min((double)L, span);
+  int64_t size = 1024;
+  while (size < 2 * bound) size *= 2;
+  if (size > sc.table_cap) return fail(C3_ERR_INVALID, "compression hash table too small (internal)");
+  CmpTable t{sc.keys, sc.first, sc.rank, (unsigned)(size - 1)};
+  C3_CUDA(cudaMemsetAsync(sc.keys, 0xFF, (size_t)size * sizeof(unsigned long long), e->stream));
+  C3_CUDA(cudaMemsetAsync(sc.first, 0xFF, (size_t)size * sizeof(unsigned), e->stream));
+  const int grid = (int)std::min<int64_t>((L + CMP_THREADS - 1) / CMP_THREADS, (int64_t)e->n_sm * 16);
+  const int n_tiles = (int)((L + CMP_SCAN_TILE - 1) / CMP_SCAN_TILE);
+  cmp_insert_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(a, b, codes, rows_b, L, t, sc.slot_of_col);
+  cmp_count_kernel<<<n_tiles, CMP_THREADS, 0, e->stream>>>(L, t, sc.slot_of_col, sc.tile_sums);
+  cmp_scan_tiles_kernel<<<1, CMP_THREADS, 0, e->stream>>>(sc.tile_sums, n_tiles, sc.total);
+  cmp_number_kernel<<<n_tiles, CMP_THREADS, 0, e->stream>>>(L, t, sc.slot_of_col, sc.tile_sums, sc.pos);
+  cmp_index_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(L, t, sc.slot_of_col, index_out);
+  unsigned total = 0;
+  C3_CUDA(cudaMemcpyAsync(&total, sc.total, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  C3_CUDA(cudaGetLastError());
+  *n_unique = total;
+  return C3_OK;
+}
+}  // namespace
+
+int c3_compress_alignment(c3_engine* e, const uint8_t* codes, int64_t n_columns, const double* symbol_rows,
+                          int n_symbols, int keep_index) {
+  C3_REQUIRE(e && symbol_rows && (codes || n_columns == 0), "null pointer");
+  C3_REQUIRE(!e->finalized, "pattern tables are frozen after c3_finalize");
+  C3_REQUIRE(n_columns >= 0 && n_columns < INT32_MAX - 1, "bad column count");
+  C3_REQUIRE(n_symbols >= 1 && n_symbols <= 256, "n_symbols must be in [1, 256]");
+  C3_CUDA(cudaSetDevice(e->device));
+  const int N = e->n_nodes, M = e->M, MP = e->MP;
+  const int64_t L = n_columns;
+  int n_tips = 0;
+  for (int n = 0; n < N; ++n) n_tips += e->children[n].empty();
+
+  CmpScratch sc;
+  {
+    int64_t cap = 1024;
+    while (cap < 2 * std::max<int64_t>(L, 256)) cap *= 2;
+    sc.table_cap = cap;
+    const size_t Lp = (size_t)std::max<int64_t>(L, 1);
+    const size_t tiles = (Lp + CMP_SCAN_TILE - 1) / CMP_SCAN_TILE;
+    C3_CUDA(cudaMalloc(&sc.keys, (size_t)cap * sizeof(unsigned long long)));
+    C3_CUDA(cudaMalloc(&sc.first, (size_t)cap * sizeof(unsigned)));
+    C3_CUDA(cudaMalloc(&sc.rank, (size_t)cap * sizeof(unsigned)));
+    C3_CUDA(cudaMalloc(&sc.slot_of_col, Lp * sizeof(int32_t)));
+    C3_CUDA(cudaMalloc(&sc.pos, Lp * sizeof(unsigned)));
+    C3_CUDA(cudaMalloc(&sc.tile_sums, tiles * sizeof(unsigned)));
+    C3_CUDA(cudaMalloc(&sc.total, sizeof(unsigned)));
+  }
+  for (int32_t* p : e->d_index)
+    if (p) cudaFree(p);
+  for (int32_t* p : e->d_idx_tmp)
+    if (p) cudaFree(p);
+  e->d_index.assign(N, nullptr);
+  e->d_idx_tmp.assign(N, nullptr);
+  e->n_columns = L;
+  const size_t Lb = (size_t)std::max<int64_t>(L, 1);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((L + CMP_THREADS - 1) / CMP_THREADS, (int64_t)e->n_sm * 16));
+
+  uint8_t* d_codes = nullptr;
+  C3_CUDA(cudaMalloc(&d_codes, Lb));
+  int32_t* d_small = nullptr;  // first-seen values of the first columns (<= 256 for a tip)
+  C3_CUDA(cudaMalloc(&d_small, 257 * sizeof(int32_t)));
+  int32_t* d_fold = nullptr;  // intermediate numbering of a polytomy's folded children
+  int rc = C3_OK;
+  int tip_no = 0;
+  for (int n = 0; n < N && rc == C3_OK; ++n) {
+    const std::vector<int>& kids = e->children[n];
+    cudaError_t err = cudaMalloc(&e->d_index[n], Lb * sizeof(int32_t));
+    if (err != cudaSuccess) { rc = fail(C3_ERR_MEMORY, "device memory exhausted during compression"); break; }
+    int64_t U = 0;
+    if (kids.empty()) {
+      // ---- tip (make_likelihood_tree_leaf) ---------------------------------------------------
+      if (L > 0) {
+        err = cudaMemcpyAsync(d_codes, codes + (int64_t)tip_no * L, (size_t)L, cudaMemcpyHostToDevice, e->stream);
+        if (err != cudaSuccess) { rc = fail(C3_ERR_CUDA, cudaGetErrorString(err)); break; }
+      }
+      rc = cmp_first_seen(e, sc, nullptr, nullptr, d_codes, 1, 1, L, e->d_index[n], &U);
+      if (rc) break;
+      std::vector<int32_t> uniq((size_t)U);
+      if (U > 0) {
+        cmp_gather_first_u8_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(L, sc.pos, d_codes, d_small);
+        err = cudaMemcpyAsync(uniq.data(), d_small, (size_t)U * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        if (err != cudaSuccess) { rc = fail(C3_ERR_CUDA, cudaGetErrorString(err)); break; }
+      }
+      e->n_rows[n] = U + 1;
+      std::vector<double>& tab = e->tip_table[n];
+      tab.assign((size_t)(U + 1) * MP, 0.0);
+      for (int64_t u = 0; u < U && rc == C3_OK; ++u) {
+        if (uniq[u] >= n_symbols) rc = fail(C3_ERR_INVALID, "symbol code out of range");
+        else
+          for (int j = 0; j < M; ++j) tab[u * MP + j] = symbol_rows[(int64_t)uniq[u] * M + j];
+      }
+      for (int j = 0; j < M; ++j) tab[U * MP + j] = 1.0;  // the all-gap row
+      ++tip_no;
+    } else {
+      // ---- internal node (LikelihoodTreeEdge.__init__) -------------------------------------
+      const int C = (int)kids.size();
+      const int32_t* acc = e->d_index[kids[0]];
+      int64_t acc_rows = e->n_rows[kids[0]];
+      if (C == 1) {
+        // a single child: patterns are the child's; number them through the same machinery
+        // key = 2 a + a is injective in a; handled like any other key
+        rc = cmp_first_seen(e, sc, acc, acc, nullptr, acc_rows, 2, L, e->d_index[n], &U);
+      }
+      for (int c = 1; c < C && rc == C3_OK; ++c) {
+        const bool last = (c == C - 1);
+        int32_t* out = e->d_index[n];
+        if (!last) {
+          if (!d_fold) {
+            err = cudaMalloc(&d_fold, 2 * Lb * sizeof(int32_t));
+            if (err != cudaSuccess) { rc = fail(C3_ERR_MEMORY, "device memory exhausted during compression"); break; }
+          }
+          out = d_fold + ((c & 1) ? 0 : Lb);  // ping-pong: acc may point at the other half
+        }
+        rc = cmp_first_seen(e, sc, acc, e->d_index[kids[c]], nullptr, acc_rows, e->n_rows[kids[c]], L, out, &U);
+        acc = out;
+        acc_rows = U;  // intermediate numbering has no gap row
+      }
+      if (rc) break;
+      const int64_t rows = U + 1;
+      e->n_rows[n] = rows;
+      err = cudaMalloc(&e->d_idx_tmp[n], (size_t)C * rows * sizeof(int32_t));
+      if (err != cudaSuccess) { rc = fail(C3_ERR_MEMORY, "device memory exhausted during compression"); break; }
+      std::vector<int32_t> gap(C);
+      for (int c = 0; c < C; ++c) {
+        if (L > 0)
+          cmp_gather_first_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(L, sc.pos, e->d_index[kids[c]],
+                                                                      e->d_idx_tmp[n] + (int64_t)c * rows);
+        gap[c] = (int32_t)(e->n_rows[kids[c]] - 1);
+        err = cudaMemcpyAsync(e->d_idx_tmp[n] + (int64_t)c * rows + U, &gap[c], sizeof(int32_t),
+                              cudaMemcpyHostToDevice, e->stream);
+        if (err != cudaSuccess) { rc = fail(C3_ERR_CUDA, cudaGetErrorString(err)); break; }
+      }
+      err = cudaStreamSynchronize(e->stream);
+      if (err != cudaSuccess) { rc = fail(C3_ERR_CUDA, cudaGetErrorString(err)); break; }
+      if (!keep_index)
+        for (int k : kids) {
+          cudaFree(e->d_index[k]);
+          e->d_index[k] = nullptr;
+        }
+      if (n == e->root) {
+        // counts (float64, like the reference's): histogram of the column numbering + the gap row
+        unsigned* d_cnt = nullptr;
+        double* d_cntf = nullptr;
+        err = cudaMalloc(&d_cnt, (size_t)rows * sizeof(unsigned));
+        if (err == cudaSuccess) err = cudaMalloc(&d_cntf, (size_t)rows * sizeof(double));
+        if (err != cudaSuccess) { cudaFree(d_cnt); rc = fail(C3_ERR_MEMORY, "device memory exhausted during compression"); break; }
+        cudaMemsetAsync(d_cnt, 0, (size_t)rows * sizeof(unsigned), e->stream);
+        if (L > 0) cmp_histogram_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(L, e->d_index[n], d_cnt);
+        cmp_counts_to_double_kernel<<<(int)std::min<int64_t>((rows + 255) / 256, 4096), CMP_THREADS, 0, e->stream>>>(
+            rows, d_cnt, d_cntf);
+        e->counts.assign((size_t)rows, 0.0);
+        err = cudaMemcpyAsync(e->counts.data(), d_cntf, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        cudaFree(d_cnt);
+        cudaFree(d_cntf);
+        if (err != cudaSuccess) { rc = fail(C3_ERR_CUDA, cudaGetErrorString(err)); break; }
+      }
+    }
+  }
+  cudaFree(d_codes);
+  cudaFree(d_small);
+  cudaFree(d_fold);
+  if (rc != C3_OK) return rc;
+  e->d_root_index = e->d_index[e->root];
+  return C3_OK;
+}
+
+int c3_get_node_rows(c3_engine* e, int64_t* rows) {
+  C3_REQUIRE(e && rows, "null pointer");
+  for (int n = 0; n < e->n_nodes; ++n) rows[n] = e->n_rows[n];
+  return C3_OK;
+}
+
+int c3_get_node_indexes(c3_engine* e, int node, int64_t* out) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_REQUIRE(node >= 0 && node < e->n_nodes && !e->children[node].empty(), "not an internal node");
+  C3_CUDA(cudaSetDevice(e->device));
+  const size_t n = e->children[node].size() * (size_t)e->n_rows[node];
+  std::vector<int32_t> tmp(n);
+  const int32_t* src = nullptr;
+  if (e->finalized) src = e->d_idx[node];
+  else if (!e->d_idx_tmp.empty() && e->d_idx_tmp[node]) src = e->d_idx_tmp[node];
+  if (src) {
+    C3_CUDA(cudaStreamSynchronize(e->stream));
+    C3_CUDA(cudaMemcpy(tmp.data(), src, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  } else {
+    C3_REQUIRE(e->idx32[node].size() == n, "the node has no pattern table yet");
+    tmp = e->idx32[node];
+  }
+  for (size_t i = 0; i < n; ++i) out[i] = tmp[i];
+  return C3_OK;
+}
+
+int c3_get_tip_table(c3_engine* e, int node, double* out) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_REQUIRE(node >= 0 && node < e->n_nodes && e->children[node].empty(), "not a tip node");
+  C3_CUDA(cudaSetDevice(e->device));
+  const int M = e->M, MP = e->MP;
+  const int64_t rows = e->n_rows[node];
+  std::vector<double> tmp((size_t)rows * MP);
+  if (e->finalized) {
+    C3_CUDA(cudaStreamSynchronize(e->stream));
+    C3_CUDA(cudaMemcpy(tmp.data(), e->d_tip_table[node], tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    C3_REQUIRE(e->tip_table[node].size() == tmp.size(), "the tip has no table yet");
+    tmp = e->tip_table[node];
+  }
+  for (int64_t u = 0; u < rows; ++u)
+    for (int j = 0; j < M; ++j) out[u * M + j] = tmp[u * MP + j];
+  return C3_OK;
+}
+
+int c3_get_root_counts(c3_engine* e, double* out) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_CUDA(cudaSetDevice(e->device));
+  if (e->finalized) {
+    C3_CUDA(cudaStreamSynchronize(e->stream));
+    C3_CUDA(cudaMemcpy(out, e->d_counts, (size_t)e->n_rows[e->root] * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    C3_REQUIRE(!e->counts.empty(), "root counts not set");
+    std::copy(e->counts.begin(), e->counts.end(), out);
+  }
+  return C3_OK;
+}
+
+int c3_get_column_index(c3_engine* e, int node, int64_t* out) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_REQUIRE(node >= 0 && node < e->n_nodes, "bad node");
+  C3_REQUIRE(e->n_columns >= 0 && !e->d_index.empty() && e->d_index[node] != nullptr,
+             "no column numbering on the device for this node (c3_compress_alignment keeps the root's; "
+             "keep_index=1 keeps all)");
+  C3_CUDA(cudaSetDevice(e->device));
+  std::vector<int32_t> tmp((size_t)e->n_columns);
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->n_columns > 0)
+    C3_CUDA(cudaMemcpy(tmp.data(), e->d_index[node], tmp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < tmp.size(); ++i) out[i] = tmp[i];
+  return C3_OK;
+}
+
+int c3_set_column_index(c3_engine* e, const int64_t* index, int64_t n_columns) {
+  C3_REQUIRE(e && (index || n_columns == 0), "null pointer");
+  C3_REQUIRE(n_columns >= 0 && n_columns < INT32_MAX - 1, "bad column count");
+  C3_CUDA(cudaSetDevice(e->device));
+  const int64_t rows = e->n_rows[e->root];
+  C3_REQUIRE(rows > 0, "set the root's pattern table first");
+  std::vector<int32_t> tmp((size_t)n_columns);
+  for (int64_t i = 0; i < n_columns; ++i) {
+    if (index[i] < 0 || index[i] >= rows) return fail(C3_ERR_INVALID, "column index out of range");
+    tmp[i] = (int32_t)index[i];
+  }
+  if (e->d_index.empty()) e->d_index.assign(e->n_nodes, nullptr);
+  if (e->d_index[e->root]) cudaFree(e->d_index[e->root]);
+  e->d_index[e->root] = nullptr;
+  C3_CUDA(cudaMalloc(&e->d_index[e->root], std::max<size_t>(1, tmp.size()) * sizeof(int32_t)));
+  C3_CUDA(cudaMemcpy(e->d_index[e->root], tmp.data(), tmp.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  e->d_root_index = e->d_index[e->root];
+  e->n_columns = n_columns;
+  return C3_OK;
+}
+
+int c3_get_site_lh(c3_engine* e, int bin, double* out, int64_t n_columns) {
+  C3_REQUIRE(e && (out || n_columns == 0), "null pointer");
+  C3_REQUIRE(e->finalized && e->have_cached, "no evaluation yet");
+  C3_REQUIRE(bin >= 0 && bin < e->K, "bad bin");
+  C3_REQUIRE(e->d_root_index != nullptr, "the column numbering is not on the device (c3_compress_alignment / c3_set_column_index)");
+  C3_REQUIRE(n_columns == e->n_columns, "bad column count");
+  if (n_columns == 0) return C3_OK;
+  C3_CUDA(cudaSetDevice(e->device));
+  double* d_out = nullptr;
+  C3_CUDA(cudaMalloc(&d_out, (size_t)n_columns * sizeof(double)));
+  const int grid = (int)std::min<int64_t>((n_columns + CMP_THREADS - 1) / CMP_THREADS, (int64_t)e->n_sm * 16);
+  site_lh_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(n_columns, e->d_root_index, e->d_lh, e->K, bin, d_out);
+  cudaError_t err = cudaMemcpyAsync(out, d_out, (size_t)n_columns * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(d_out);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("c3_get_site_lh: ") + cudaGetErrorString(err));
   return C3_OK;
 }
 
@@ -678,8 +1000,14 @@ int c3_finalize(c3_engine* e) {
       C3_CUDA(cudaMemsetAsync(e->d_rows[n], 0, (size_t)e->n_rows[n] * K * MP * sizeof(double), e->stream));
     } else {
       e->d_idx[n] = reinterpret_cast<int32_t*>(e->d_pool + o_idx[n]);
-      C3_CUDA(cudaMemcpyAsync(e->d_idx[n], e->idx32[n].data(), e->idx32[n].size() * sizeof(int32_t),
-                              cudaMemcpyHostToDevice, e->stream));
+      if (!e->d_idx_tmp.empty() && e->d_idx_tmp[n] != nullptr) {
+        C3_CUDA(cudaMemcpyAsync(e->d_idx[n], e->d_idx_tmp[n],
+                                e->children[n].size() * (size_t)e->n_rows[n] * sizeof(int32_t),
+                                cudaMemcpyDeviceToDevice, e->stream));
+      } else {
+        C3_CUDA(cudaMemcpyAsync(e->d_idx[n], e->idx32[n].data(), e->idx32[n].size() * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, e->stream));
+      }
     }
   }
   e->d_P = reinterpret_cast<double*>(e->d_pool + o_P);
@@ -743,7 +1071,12 @@ int c3_finalize(c3_engine* e) {
   C3_CUDA(cudaMalloc(&e->d_block, (size_t)b));
   C3_CUDA(cudaStreamSynchronize(e->stream));
 
-  // host copies no longer needed
+  // host / temporary copies no longer needed
+  for (auto& p : e->d_idx_tmp)
+    if (p) {
+      cudaFree(p);
+      p = nullptr;
+    }
   for (auto& v : e->tip_table) std::vector<double>().swap(v);
   for (auto& v : e->idx32) std::vector<int32_t>().swap(v);
   e->stats.device_bytes += off + b;

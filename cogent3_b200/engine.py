@@ -63,11 +63,97 @@ class LikelihoodEngine:
             counts = np.ascontiguousarray(patterns.root.counts, dtype=np.float64)
             _lib.check(self._lib.c3_set_root_counts(self._h, _dptr(counts), counts.shape[0]))
             _lib.check(self._lib.c3_finalize(self._h))
+            self.n_columns = int(len(patterns.root.index))
+            self.set_column_index(patterns.root.index)
         except Exception:
             self.close()
             raise
         self.root_rows = int(patterns.root.n_rows)
         self._dist = np.zeros((self.n_nodes, self.n_bins), np.float64)
+
+    @classmethod
+    def from_alignment(cls, topo, codes, symbol_rows, n_bins=1, device=0, stream=None, keep_index=False):
+        """engine whose pattern tables are built ON THE DEVICE from the raw alignment
+        (c3_compress_alignment): ``codes`` uint8 [n_tips, L], tips in node order
+        (``topo.tips``), ``symbol_rows`` [S, M] the 0/1 row of every code."""
+        from .patterns import DevicePatternTree
+
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        self._h = c_void_p()
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        symbol_rows = np.ascontiguousarray(symbol_rows, dtype=np.float64)
+        assert codes.ndim == 2 and codes.shape[0] == len(topo.tips)
+        self.topo = topo
+        self.n_states = int(symbol_rows.shape[1])
+        self.n_bins = int(n_bins)
+        self.n_nodes = topo.n_nodes
+        self.n_columns = int(codes.shape[1])
+        ptr, idx = topo.child_csr()
+        _lib.check(
+            self._lib.c3_create(
+                device, topo.n_nodes, self.n_states, self.n_bins, _i32ptr(ptr), _i32ptr(idx),
+                byref(self._h),
+            )
+        )  # fmt: skip
+        try:
+            if stream is not None:
+                self.set_stream(stream)
+            _lib.check(
+                self._lib.c3_compress_alignment(
+                    self._h, codes.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), self.n_columns,
+                    _dptr(symbol_rows), symbol_rows.shape[0], int(bool(keep_index)),
+                )
+            )  # fmt: skip
+            _lib.check(self._lib.c3_finalize(self._h))
+        except Exception:
+            self.close()
+            raise
+        self.patterns = DevicePatternTree(topo, self, self.n_states, self.n_columns)
+        self.root_rows = int(self.patterns.rows()[topo.root])
+        self._dist = np.zeros((self.n_nodes, self.n_bins), np.float64)
+        return self
+
+    # -- pattern tables held by the engine ----------------------------------------
+    def fetch_node_rows(self):
+        out = np.zeros(self.n_nodes, np.int64)
+        _lib.check(self._lib.c3_get_node_rows(self._h, _i64ptr(out)))
+        return out
+
+    def fetch_node_indexes(self, node):
+        rows = int(self.fetch_node_rows()[node])
+        out = np.zeros((len(self.topo.children[node]), rows), np.int64)
+        _lib.check(self._lib.c3_get_node_indexes(self._h, int(node), _i64ptr(out)))
+        return out
+
+    def fetch_tip_table(self, node):
+        rows = int(self.fetch_node_rows()[node])
+        out = np.zeros((rows, self.n_states), np.float64)
+        _lib.check(self._lib.c3_get_tip_table(self._h, int(node), _dptr(out)))
+        return out
+
+    def fetch_root_counts(self):
+        out = np.zeros(int(self.fetch_node_rows()[self.topo.root]), np.float64)
+        _lib.check(self._lib.c3_get_root_counts(self._h, _dptr(out)))
+        return out
+
+    def fetch_column_index(self, node):
+        out = np.zeros(self.n_columns, np.int64)
+        _lib.check(self._lib.c3_get_column_index(self._h, int(node), _i64ptr(out)))
+        return out
+
+    def set_column_index(self, index):
+        """the root's ``index`` (column -> pattern) when the tables came from the host;
+        enables :meth:`get_site_lh`"""
+        ix = np.ascontiguousarray(index, dtype=np.int64)
+        _lib.check(self._lib.c3_set_column_index(self._h, _i64ptr(ix), ix.shape[0]))
+        self.n_columns = int(ix.shape[0])
+
+    def get_site_lh(self, bin_=0):
+        """per-column likelihoods lh[root.index], gathered on the device"""
+        out = np.empty(self.n_columns, np.float64)
+        _lib.check(self._lib.c3_get_site_lh(self._h, int(bin_), _dptr(out), out.shape[0]))
+        return out
 
     # -- lifetime ------------------------------------------------------------
     def close(self):

@@ -59,23 +59,51 @@ class LikelihoodFunction:
         self._n_evals = 0
 
     # ------------------------------------------------------------------ data
-    def set_alignment(self, codes_by_tip, symbol_rows=None, patterns: PatternTree | None = None):
+    def set_alignment(self, codes_by_tip, symbol_rows=None, patterns: PatternTree | None = None,
+                      compress="auto"):  # fmt: skip
         """``codes_by_tip``: {tip name: int codes[L]} or array [n_tips, L] in
         ``topo.tip_names`` order; ``symbol_rows[S, M]`` indicator row per code.
-        Runs the per-node pattern compression (a2/a3) and uploads the tables."""
+        Runs the per-node pattern compression (a2/a3) -- on the device for the CUDA engine
+        (``compress="device"``, the default there; c3_compress_alignment), on the host with
+        numpy otherwise (``"host"``) -- and makes the tables resident."""
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+        self._tip_codes = None
         if patterns is None:
             if symbol_rows is None:
                 M = self.model.n_states
                 symbol_rows = (
                     hostmodels.dna_symbol_rows()[1] if M == 4 else hostmodels.codon_symbol_rows()[1]
                 )
-            patterns = compress_alignment(self.topo, codes_by_tip, symbol_rows)
-        self.patterns = patterns
-        if self.engine is not None:
-            self.engine.close()
-        self.engine = self._engine_factory(
-            patterns, self.n_bins, device=self.device, stream=self.stream
-        )
+            symbol_rows = np.asarray(symbol_rows, np.float64)
+            on_device = compress == "device" or (
+                compress == "auto" and self._engine_factory is _default_engine_factory
+                and symbol_rows.shape[0] <= 256
+            )  # fmt: skip
+            if on_device:
+                if isinstance(codes_by_tip, dict):
+                    arr = np.stack([np.asarray(codes_by_tip[nm]) for nm in self.topo.tip_names])
+                else:
+                    arr = np.asarray(codes_by_tip)
+                if arr.size and (arr.min() < 0 or arr.max() >= symbol_rows.shape[0]):
+                    raise ValueError("symbol code out of range")
+                from .engine import LikelihoodEngine
+
+                self._tip_codes = arr.astype(np.uint8, copy=False)
+                self._symbol_rows = symbol_rows
+                self.engine = LikelihoodEngine.from_alignment(
+                    self.topo, self._tip_codes, symbol_rows, n_bins=self.n_bins, device=self.device,
+                    stream=self.stream,
+                )  # fmt: skip
+                self.patterns = self.engine.patterns
+            else:
+                patterns = compress_alignment(self.topo, codes_by_tip, symbol_rows)
+        if self.engine is None:
+            self.patterns = patterns
+            self.engine = self._engine_factory(
+                patterns, self.n_bins, device=self.device, stream=self.stream
+            )
         self._dirty_q = self._dirty_model = True
         self._slot_keys, self._slot_map_sent = [], None
         return self
@@ -86,15 +114,28 @@ class LikelihoodFunction:
         self.mprobs = mprobs
         self._dirty_q = self._dirty_model = True
 
-    def set_motif_probs_from_data(self):
-        """unambiguous-state frequencies over all tips, like
-        ``set_motif_probs_from_data`` (evolve/parameter_controller.py:135-162 with
-        ``count_motifs``, evolve/motif_prob_model.py:48-59, include_ambiguity=False)."""
+    def state_counts(self):
+        """unambiguous-state counts over all tips (``count_motifs``,
+        evolve/motif_prob_model.py:48-59, include_ambiguity=False)."""
         counts = np.zeros(self.model.n_states)
+        if getattr(self, "_tip_codes", None) is not None:
+            # device-compressed alignment: the same sum straight from the symbol codes
+            rows = self._symbol_rows
+            unambig = rows.sum(axis=1) == 1.0
+            for codes in self._tip_codes:
+                per_symbol = np.bincount(codes, minlength=rows.shape[0]).astype(np.float64)
+                counts += (rows[unambig] * per_symbol[unambig, None]).sum(axis=0)
+            return counts
         for n in self.topo.tips:
             nd = self.patterns.nodes[n]
             unambig = nd.ambig == 1.0
             counts += (nd.table[unambig] * nd.counts[unambig, None]).sum(axis=0)
+        return counts
+
+    def set_motif_probs_from_data(self):
+        """unambiguous-state frequencies over all tips, like
+        ``set_motif_probs_from_data`` (evolve/parameter_controller.py:135-162)."""
+        counts = self.state_counts()
         self.set_motif_probs(counts / counts.sum())
 
     # ------------------------------------------------------------ parameters
@@ -249,6 +290,9 @@ class LikelihoodFunction:
     def get_full_length_likelihoods(self, bin=None):  # noqa: A002
         """per-column likelihoods (``get_full_length_likelihoods``,
         evolve/likelihood_tree.py:93-94): lh[root.index]"""
+        if hasattr(self.engine, "get_site_lh"):
+            self.get_log_likelihood()
+            return self.engine.get_site_lh(self._bin_index(bin))  # gathered on the device
         lh = self.get_param_value("lh", bin=bin)
         return lh[self.patterns.root.index]
 
@@ -256,8 +300,11 @@ class LikelihoodFunction:
         """posterior bin probabilities per column (``BinnedLikelihood.get_posterior_probs``,
         evolve/likelihood_calculation.py:247-257)."""
         self.get_log_likelihood()
-        idx = self.patterns.root.index
-        res = np.array([b * self.engine.get_lh(k)[idx] for k, b in enumerate(self.bprobs)])
+        if hasattr(self.engine, "get_site_lh"):
+            res = np.array([b * self.engine.get_site_lh(k) for k, b in enumerate(self.bprobs)])
+        else:
+            idx = self.patterns.root.index
+            res = np.array([b * self.engine.get_lh(k)[idx] for k, b in enumerate(self.bprobs)])
         res /= res.sum(axis=0)
         return res
 

@@ -227,3 +227,73 @@ def from_reference_lht(lht_root):
     topo = Topology(names, children)
     M = nodes[0].table.shape[1] if nodes[0].is_tip else lht_root.shape[1]
     return topo, PatternTree(topo, nodes, int(lht_root.shape[1]), len(lht_root.index))
+
+
+class _DeviceNode:
+    """lazy view of one node's table held by a CUDA engine (fetched on first use)"""
+
+    def __init__(self, tree, n):
+        self._t = tree
+        self._n = n
+        self.name = tree.topo.names[n]
+        self.is_tip = not tree.topo.children[n]
+        self._cache = {}
+
+    @property
+    def n_rows(self):
+        return int(self._t.rows()[self._n])
+
+    def _get(self, key, fn):
+        if key not in self._cache:
+            self._cache[key] = fn()
+        return self._cache[key]
+
+    @property
+    def indexes(self):
+        return self._get("indexes", lambda: self._t.engine.fetch_node_indexes(self._n))
+
+    @property
+    def uniq(self):
+        if self.is_tip:
+            raise AttributeError("tip symbols stay on the host side of the caller")
+        return np.ascontiguousarray(self.indexes.T)
+
+    @property
+    def table(self):
+        return self._get("table", lambda: self._t.engine.fetch_tip_table(self._n))
+
+    @property
+    def ambig(self):
+        if self.is_tip:
+            return self.table.sum(axis=1)
+        raise AttributeError("ambig of internal nodes is not kept on the device")
+
+    @property
+    def index(self):
+        return self._get("index", lambda: self._t.engine.fetch_column_index(self._n))
+
+    @property
+    def counts(self):
+        if self._n == self._t.topo.root:
+            return self._get("counts", self._t.engine.fetch_root_counts)
+        idx = self.index  # raises unless the numbering was kept (keep_index)
+        c = np.bincount(idx, minlength=self.n_rows).astype(np.float64)
+        return c
+
+
+class DevicePatternTree(PatternTree):
+    """the pattern tree of an alignment compressed ON THE DEVICE (c3_compress_alignment):
+    same attributes as PatternTree, tables fetched from the engine only when read."""
+
+    def __init__(self, topo: Topology, engine, n_states, n_columns):
+        self.topo = topo
+        self.engine = engine
+        self.n_states = n_states
+        self.n_columns = n_columns
+        self._rows = None
+        self.nodes = [_DeviceNode(self, n) for n in range(topo.n_nodes)]
+
+    def rows(self):
+        if self._rows is None:
+            self._rows = self.engine.fetch_node_rows()
+        return self._rows

@@ -63,11 +63,7 @@ class ShardedLikelihoodFunction:
     def set_motif_probs_from_data(self):
         """global (all shards) unambiguous-state frequencies: one all-reduce of M counts"""
         lf = self.lf
-        counts = np.zeros(lf.model.n_states)
-        for n in lf.topo.tips:
-            nd = lf.patterns.nodes[n]
-            unambig = nd.ambig == 1.0
-            counts += (nd.table[unambig] * nd.counts[unambig, None]).sum(axis=0)
+        counts = lf.state_counts()
         t = self._torch.as_tensor(counts, dtype=self._torch.float64, device=self._buf.device)
         if self.world > 1:
             self._dist.all_reduce(t, group=self.group)

@@ -89,6 +89,33 @@ C3_API int c3_set_node_patterns(c3_engine* e, int node, const int64_t* indexes, 
 C3_API int c3_set_root_counts(c3_engine* e, const double* counts, int64_t n_rows);
 C3_API int c3_finalize(c3_engine* e);
 
+/* ---- pattern compression on the device -------------
+ * c3_compress_alignment: builds EVERY table above from the raw alignment, on the
+ *             GPU, bit-identical to the reference's: per tip the distinct symbol
+ *             codes in first-seen column order (make_likelihood_tree_leaf,
+ *             evolve/likelihood_tree.py:223-278, `_indexed` :186-203), per internal
+ *             node the distinct tuples of child pattern numbers in first-seen
+ *             order (LikelihoodTreeEdge.__init__ :13-70), root counts (:62), each
+ *             table followed by its all-gap row.  It replaces the c3_set_tip /
+ *             c3_set_node_patterns / c3_set_root_counts calls; c3_finalize follows.
+ *             codes: uint8 [n_tips][n_columns] (host), tips in node order;
+ *             symbol_rows: float64 [n_symbols][M], the 0/1 row of every code
+ *             (get_matched_array, likelihood_tree.py:206-220).  keep_index != 0
+ *             keeps every node's column numbering on the device (tests); the
+ *             root's (LikelihoodTreeEdge.index) is always kept.
+ * c3_get_node_rows / _indexes / c3_get_tip_table / c3_get_root_counts /
+ * c3_get_column_index: read the tables back (uniq = indexes transposed; `index`).
+ * c3_set_column_index: the root's `index` when the tables came from the host
+ *             (enables c3_get_site_lh for the drop-in).                           */
+C3_API int c3_compress_alignment(c3_engine* e, const uint8_t* codes, int64_t n_columns,
+                                 const double* symbol_rows, int n_symbols, int keep_index);
+C3_API int c3_get_node_rows(c3_engine* e, int64_t* n_rows_of_node);
+C3_API int c3_get_node_indexes(c3_engine* e, int node, int64_t* indexes);
+C3_API int c3_get_tip_table(c3_engine* e, int node, double* table);
+C3_API int c3_get_root_counts(c3_engine* e, double* counts);
+C3_API int c3_get_column_index(c3_engine* e, int node, int64_t* index);
+C3_API int c3_set_column_index(c3_engine* e, const int64_t* index, int64_t n_columns);
+
 /* ---- model state -------------------------------------------------------------
  * A "q slot" is one distinct rate matrix (one value of the Q / Qd Defns,
  * evolve/substitution_model.py:636-641).
@@ -145,6 +172,10 @@ C3_API int c3_get_lh(c3_engine* e, int bin, double* out, int64_t n_rows);
 C3_API int c3_get_psub(c3_engine* e, int node, int bin, double* out);
 C3_API int c3_get_partials(c3_engine* e, int node, int bin, double* out, int64_t n_rows);
 C3_API int c3_get_stats(c3_engine* e, c3_stats* out);
+/* c3_get_site_lh: per-COLUMN likelihoods of one bin, lh[root.index] gathered on the
+ *             device (LikelihoodTreeEdge.get_full_length_likelihoods,
+ *             evolve/likelihood_tree.py:93-94; likelihood_function.py:427-431).   */
+C3_API int c3_get_site_lh(c3_engine* e, int bin, double* out, int64_t n_columns);
 
 /* ---- per-launch timing (CUDA events on the engine's stream) ----------------------
  * With profiling on, every kernel launch of a blocking c3_evaluate is bracketed by
