@@ -115,7 +115,7 @@ struct c3_engine {
   int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0, off_small = 0;
   bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
   bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
-  bool use_dmma_pipe = false;
+  bool use_dmma_reg = true;  // warp-private register pipeline for M != 4 (C3_DMMA_REG=0: first version)
   bool use_ring = false;  // C3_RING=1: the cp.async shared-memory ring version of the strip kernel
   // dataflow kernel: consecutive big binary levels in one launch.  Opt-in (C3_FLOW=1): its kernel
   // time is lower than the per-level launches' sum (C2 0.267 vs 0.289 ms, C3 0.435 vs 0.585 ms) but
@@ -180,21 +180,20 @@ int launch_dmma(c3_engine* e, const PruneArgs& a, bool is_root, int grid) {
 }
 
 template <int MP>
-int launch_dmma_pipe(c3_engine* e, const PruneArgs& a, bool is_root) {
-  const size_t smem = DPipeCfg<MP>::SMEM_BYTES;
+int launch_dmma_reg(c3_engine* e, const PruneArgs& a, bool is_root) {
+  const size_t smem = DRegCfg<MP>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
-    int rc = set_max_smem(prune_dmma_pipe_kernel<MP, false>, smem);
+    int rc = set_max_smem(prune_dmma_reg_kernel<MP, false>, smem);
     if (rc) return rc;
-    rc = set_max_smem(prune_dmma_pipe_kernel<MP, true>, smem);
+    rc = set_max_smem(prune_dmma_reg_kernel<MP, true>, smem);
     if (rc) return rc;
     configured = true;
   }
-  const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + sizeof(DSmem) + 1024))));
-  const int grid = std::max(1, std::min(a.total_tiles, e->n_sm * per_sm));
+  const int grid = std::max(1, std::min(a.total_tiles, e->n_sm));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(DMMA_THREADS);
+  cfg.blockDim = dim3(DR_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = e->stream;
   cudaLaunchAttribute attr[1];
@@ -202,9 +201,9 @@ int launch_dmma_pipe(c3_engine* e, const PruneArgs& a, bool is_root) {
   attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune_dmma_pipe_kernel<MP, true>, a)
-                            : cudaLaunchKernelEx(&cfg, prune_dmma_pipe_kernel<MP, false>, a);
-  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("dmma launch: ") + cudaGetErrorString(err));
+  cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune_dmma_reg_kernel<MP, true>, a)
+                            : cudaLaunchKernelEx(&cfg, prune_dmma_reg_kernel<MP, false>, a);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("dmma-reg launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
 
@@ -291,20 +290,20 @@ int launch_flow(c3_engine* e, const PruneArgs& a, const int32_t* d_dep, unsigned
 }
 
 // kind: 0 = generic kernels (prune4_kernel / prune_dmma_kernel); 2, 3 = strip kernel for
-// nodes with that many children (4-state, K in {1,2,4})
+// nodes with that many children (4-state, K in {1,2,4}); 6 = register-pipeline DMMA kernel
 int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
   if (a.total_tiles <= 0) return C3_OK;
-  if (kind == 4) {
+  if (kind == 6) {
     int rc = C3_OK;
     switch (e->MP) {
-      case 8: rc = launch_dmma_pipe<8>(e, a, is_root); break;
-      case 16: rc = launch_dmma_pipe<16>(e, a, is_root); break;
-      case 24: rc = launch_dmma_pipe<24>(e, a, is_root); break;
-      case 32: rc = launch_dmma_pipe<32>(e, a, is_root); break;
-      case 40: rc = launch_dmma_pipe<40>(e, a, is_root); break;
-      case 48: rc = launch_dmma_pipe<48>(e, a, is_root); break;
-      case 56: rc = launch_dmma_pipe<56>(e, a, is_root); break;
-      case 64: rc = launch_dmma_pipe<64>(e, a, is_root); break;
+      case 8: rc = launch_dmma_reg<8>(e, a, is_root); break;
+      case 16: rc = launch_dmma_reg<16>(e, a, is_root); break;
+      case 24: rc = launch_dmma_reg<24>(e, a, is_root); break;
+      case 32: rc = launch_dmma_reg<32>(e, a, is_root); break;
+      case 40: rc = launch_dmma_reg<40>(e, a, is_root); break;
+      case 48: rc = launch_dmma_reg<48>(e, a, is_root); break;
+      case 56: rc = launch_dmma_reg<56>(e, a, is_root); break;
+      case 64: rc = launch_dmma_reg<64>(e, a, is_root); break;
       default: return fail(C3_ERR_INVALID, "unsupported padded state count");
     }
     if (rc) return rc;
@@ -364,10 +363,16 @@ int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
 
 // which kernel family handles node n (see launch_prune)
 int kind_of_node(const c3_engine* e, int n) {
-  // the pipelined DMMA kernel is an experiment that measured SLOWER than the first version
-  // (1.48 vs 1.40 ms on C4: one CTA of 8 warps per SM hides less latency than two CTAs);
-  // it stays selectable (C3_DMMA_PIPE=1) for the next round's tuning
-  if (e->use_dmma) return (e->use_dmma_pipe && (int)e->children[n].size() <= DP_MAXC) ? 4 : 0;
+  if (e->use_dmma) {
+    // register-pipeline DMMA kernel; nodes with more children / contraction children than it
+    // stages fall back to the first version
+    if (e->use_dmma_reg && (int)e->children[n].size() <= DR_MAXC) {
+      int n_contract = 0;
+      for (int c : e->children[n]) n_contract += !e->children[c].empty();
+      if (n_contract <= DR_MAXP) return 6;
+    }
+    return 0;
+  }
   if (!e->use_strip) return 0;
   if (e->K != 1 && e->K != 2 && e->K != 4) return 0;
   const int nc = (int)e->children[n].size();
@@ -375,7 +380,7 @@ int kind_of_node(const c3_engine* e, int n) {
 }
 
 int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
-  if (kind == 4) return (int64_t)e->K * ((e->n_rows[n] + DP_TILE_ROWS - 1) / DP_TILE_ROWS);
+  if (kind == 6) return (int64_t)e->K * ((e->n_rows[n] + DR_TILE_ROWS - 1) / DR_TILE_ROWS);
   if (kind >= 2) {
     const int rows = 128 / e->K;
     return (e->n_rows[n] + rows - 1) / rows;
@@ -472,7 +477,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_STRIP")) e->use_strip = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_SMALL")) e->use_small = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
-  if (const char* env = getenv("C3_DMMA_PIPE")) e->use_dmma_pipe = atoi(env) != 0;
+  if (const char* env = getenv("C3_DMMA_REG")) e->use_dmma_reg = atoi(env) != 0;
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   if (const char* env = getenv("C3_FLOW")) e->use_flow = atoi(env) != 0;
   e->root = n_nodes - 1;
@@ -1498,7 +1503,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     // nodes the dataflow kernel cannot take are launched on their own, BEFORE the group that
     // this level's binary nodes open (later levels of the group may depend on them)
     if (other_kinds || !flow_ok) close_flow();
-    for (int kind : {0, 3, 4, 2}) {
+    for (int kind : {0, 3, 6, 2}) {
       if (kind == 2 && flow_ok) {
         for (int n : order) {
           if (!recompute[n] || kind_of_node(e, n) != 2) continue;
@@ -1531,7 +1536,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       int64_t bytes0 = alg_bytes, flops0 = flops;
       for (int n : e->level_nodes[l]) {
         if (!recompute[n] || kind_of_node(e, n) != kind) continue;
-        if (kind >= 2 && ll.n_work == (kind == 4 ? DP_MAXW : P4S_MAXW)) {
+        if (kind >= 2 && ll.n_work == (kind == 6 ? DR_MAXW : P4S_MAXW)) {
           // the strip kernel stages at most P4S_MAXW descriptors: close this launch, open another
           ll.bytes = alg_bytes - bytes0;
           ll.flops = flops - flops0;

@@ -1153,284 +1153,227 @@ __global__ void __launch_bounds__(DMMA_THREADS) prune_dmma_kernel(const PruneArg
 }
 
 // ---------------------------------------------------------------------------------------
-// DMMA kernel, pipelined version (the production path for M != 4, nodes with <= 4 children).
+// DMMA kernel, warp-private register pipeline ("dmma-reg").
 //
-// ncu on the first version: FP64 tensor pipe 50-63 % active, the rest long-scoreboard stalls:
-// each child's 64 gathered rows were fetched and waited for before its contraction started.
-// Here the CTA walks the sequence of (tile, contraction-child) units with a fetch cursor that
-// runs DP_NBUF-1 units ahead of the compute cursor: the rows of the next units are landing in
-// the other A buffers (cp.async) while the current one feeds the tensor cores.  One block
-// barrier per unit.  Descriptors are staged in shared memory; launched with programmatic
-// dependent launch like the strip kernel.
+// ncu on the first version (C4): FP64 tensor pipe 50 % active -- every (tile, child) unit is
+// "gather 64 rows into shared memory, wait, barrier, contract, barrier", two CTAs per SM taking
+// turns.  Here the gathered rows never touch shared memory: with the k index of the contraction
+// PERMUTED (step s, quad lane q  ->  column 8 (s>>1) + 2 q + (s&1)) the m8n8k4 A fragment of a
+// lane is a run of adjacent column PAIRS of its row, i.e. MP/8 128-bit loads straight from
+// global memory -- the same access pattern as the C fragment that tip children (pre-multiplied
+// rows) and the output use.  P is stored in shared memory with the same permutation applied to
+// its columns, so the B-fragment loads keep the conflict-free pattern of the first version.
+// Each warp owns 8 rows of a 96-row super-tile and runs its own software pipeline: while the
+// tensor core works on unit u, the rows of unit u+1 are in flight into a second register
+// buffer and the gather index of unit u+2 is being fetched.  (Refilling the consumed buffer in
+// place for unit u+2 spills at 168 registers and measured 1.61 vs 1.27 ms on C4: dropped.)  No barrier except when the CTA
+// moves to another (node, rate class) and reloads P; CTAs take contiguous ranges of super-tiles
+// so that happens once or twice per launch.  One CTA of 12 warps per SM (register bound).
+// Summation order over k differs from the first version (permuted), so results differ from it
+// in the last bits; within the kernel they are deterministic.
 // ---------------------------------------------------------------------------------------
-#ifndef DP_NBUF
-#define DP_NBUF 2
-#endif
-#ifndef DP_WM
-#define DP_WM 2  // 8-row blocks per warp: each B fragment feeds DP_WM DMMAs
-#endif
-constexpr int DP_TILE_ROWS = (DMMA_THREADS / 32) * 8 * DP_WM;
-constexpr int DP_MAXC = 4;   // children per node handled here (more: first version)
-constexpr int DP_MAXW = 48;  // work items per launch (the host splits longer lists)
+constexpr int DR_WARPS = 12;
+constexpr int DR_THREADS = DR_WARPS * 32;
+constexpr int DR_TILE_ROWS = DR_WARPS * 8;
+constexpr int DR_MAXP = 4;   // P matrices resident in shared memory (contraction children per node)
+constexpr int DR_MAXC = 4;   // children per node
+constexpr int DR_MAXW = 48;  // work items per launch
 
-struct DWork {
+struct RWork {
   double* out;
   int64_t n_rows;
   int64_t row_tiles;
-  const double* src[DP_MAXC];
-  const int32_t* idx[DP_MAXC];
-  const double* P[DP_MAXC];
+  const double* src[DR_MAXC];
+  const int32_t* idx[DR_MAXC];
+  const double* P[DR_MAXC];
+  int32_t slot[DR_MAXC];  // shared-memory slot of child c's P (contraction children only)
   int32_t nc;
   int32_t fixed_motif;
 };
-struct DSmem {
-  DWork work[DP_MAXW];
-  int32_t prefix[DP_MAXW + 1];
+struct RSmem {
+  RWork work[DR_MAXW];
+  int32_t prefix[DR_MAXW + 1];
+};
+struct RCur {
+  int st;        // super-tile
+  int c;         // child
+  int w;         // work item
+  int b;         // rate class
+  int64_t row0;  // first row of the super-tile
 };
 
 template <int MP>
-struct DPipeCfg {
+struct DRegCfg {
   static constexpr int LDS = MP + 4;
   static constexpr int NI = MP / 8;
   static constexpr int KS = MP / 4;
-  static constexpr int A_DOUBLES = DP_TILE_ROWS * LDS;
   static constexpr int B_DOUBLES = MP * LDS;
-  static constexpr size_t SMEM_BYTES = (size_t)(DP_NBUF * A_DOUBLES + 2 * B_DOUBLES) * sizeof(double);
+  static constexpr size_t SMEM_BYTES = (size_t)DR_MAXP * B_DOUBLES * sizeof(double);
 };
 
-struct DCursor {  // position in the (tile, child) sequence of one CTA
-  int t;          // tile
-  int w;          // work item of tile t
-  int b;          // rate class
-  int64_t row0;   // first row
-  int c;          // child
-};
+__device__ __forceinline__ double2 ld128_nc(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
 
 template <int MP, bool ROOT>
-__global__ void __launch_bounds__(DMMA_THREADS) prune_dmma_pipe_kernel(const PruneArgs a) {
-  using Cfg = DPipeCfg<MP>;
+__global__ void __launch_bounds__(DR_THREADS, 1) prune_dmma_reg_kernel(const PruneArgs a) {
+  using Cfg = DRegCfg<MP>;
   constexpr int LDS = Cfg::LDS, NI = Cfg::NI, KS = Cfg::KS;
-  extern __shared__ __align__(16) double smem[];
-  __shared__ DSmem sd;
-  double* sA = smem;                                // [DP_NBUF][64*LDS]
-  double* sB = smem + DP_NBUF * Cfg::A_DOUBLES;     // [2][MP*LDS]
+  extern __shared__ __align__(16) double smem[];  // [DR_MAXP][MP * LDS], columns permuted
+  __shared__ RSmem sd;
   const int K = a.K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
 
   pdl_trigger();
-  for (int i = tid; i <= a.n_work; i += DMMA_THREADS) sd.prefix[i] = a.tile_prefix[i];
-  for (int i = tid; i < a.n_work; i += DMMA_THREADS) {
+  for (int i = tid; i <= a.n_work; i += DR_THREADS) sd.prefix[i] = a.tile_prefix[i];
+  for (int i = tid; i < a.n_work; i += DR_THREADS) {
     const NodeDesc nd = a.nodes[a.work_node[i]];
-    DWork& wd = sd.work[i];
+    RWork& wd = sd.work[i];
     wd.out = nd.out;
     wd.n_rows = nd.n_rows;
-    wd.row_tiles = (nd.n_rows + DP_TILE_ROWS - 1) / DP_TILE_ROWS;
+    wd.row_tiles = (nd.n_rows + DR_TILE_ROWS - 1) / DR_TILE_ROWS;
     wd.nc = nd.n_children;
     wd.fixed_motif = nd.fixed_motif;
-    for (int c = 0; c < nd.n_children && c < DP_MAXC; ++c) {
+    int slot = 0;
+    for (int c = 0; c < nd.n_children && c < DR_MAXC; ++c) {
       const ChildRef ch = a.childs[nd.child_begin + c];
       wd.src[c] = ch.src;
       wd.idx[c] = ch.idx;
       wd.P[c] = ch.P;
+      wd.slot[c] = (ch.P != nullptr) ? slot++ : -1;
     }
   }
   __syncthreads();
 
-  auto place = [&](DCursor& cur) {  // fill w / b / row0 for cur.t (t < total)
-    while (cur.t >= sd.prefix[cur.w + 1]) ++cur.w;
-    const DWork& wd = sd.work[cur.w];
-    const int local = cur.t - sd.prefix[cur.w];
+  // this CTA's contiguous range of super-tiles
+  const int per_cta = (a.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int st0 = (int)blockIdx.x * per_cta;
+  const int st1 = min(a.total_tiles, st0 + per_cta);
+  auto place = [&](RCur& cur) {
+    while (cur.st >= sd.prefix[cur.w + 1]) ++cur.w;
+    const RWork& wd = sd.work[cur.w];
+    const int local = cur.st - sd.prefix[cur.w];
     cur.b = (int)(local / wd.row_tiles);
-    cur.row0 = (int64_t)(local - cur.b * wd.row_tiles) * DP_TILE_ROWS;
+    cur.row0 = (int64_t)(local - cur.b * wd.row_tiles) * DR_TILE_ROWS;
   };
-  // advance to the next contraction child at or after (t, c); false when the CTA is done
-  auto seek_unit = [&](DCursor& cur) -> bool {
-    while (cur.t < a.total_tiles) {
-      const DWork& wd = sd.work[cur.w];
-      while (cur.c < wd.nc) {
-        if (wd.P[cur.c] != nullptr) return true;
-        ++cur.c;
-      }
-      cur.t += gridDim.x;
+  auto advance = [&](RCur& cur) {
+    if (++cur.c >= sd.work[cur.w].nc) {
       cur.c = 0;
-      if (cur.t < a.total_tiles) place(cur);
+      if (++cur.st < st1) place(cur);
     }
-    return false;
+  };
+  auto my_row = [&](const RCur& cur) -> int64_t {  // clamped: loads of rows past the end repeat the last
+    const int64_t p = cur.row0 + warp * 8 + g;
+    const int64_t last = sd.work[cur.w].n_rows - 1;
+    return p < last ? p : last;
   };
 
-  DCursor fc{(int)blockIdx.x, 0, 0, 0, 0};
-  if (fc.t < a.total_tiles) place(fc);
-  int n_issued = 0;
-  constexpr int CHUNKS = MP / 2;                       // 16-byte chunks per row
-  constexpr int PASSES = DP_TILE_ROWS * CHUNKS / DMMA_THREADS;
-  // gather indexes of the NEXT unit to issue (this thread's chunks), loaded one unit early
-  // so that their latency hides behind the current contraction
-  int32_t nidx[PASSES];
-  bool f_valid = false;
-  auto prefetch_idx = [&]() {
-    f_valid = seek_unit(fc);
-    if (f_valid) {
-      const DWork& wd = sd.work[fc.w];
-      const int32_t* idx = wd.idx[fc.c];
+  RCur cc{st0, 0, 0, 0, 0};
+  if (cc.st < st1) place(cc);
+  RCur dc = cc, ic = cc;
+  int32_t idx_i = 0;
+  double2 vn[NI];
+  auto fetch = [&](const RCur& cur, int32_t r) {
+    const double* src = sd.work[cur.w].src[cur.c] + ((int64_t)r * K + cur.b) * MP + 2 * q;
 #pragma unroll
-      for (int i = 0; i < PASSES; ++i) {
-        const int rr = (tid + i * DMMA_THREADS) / CHUNKS;
-        int64_t p = fc.row0 + rr;
-        if (p >= wd.n_rows) p = wd.n_rows - 1;
-        nidx[i] = __ldg(idx + p);
-      }
-    }
+    for (int ni = 0; ni < NI; ++ni) vn[ni] = ld128_nc(src + 8 * ni);
   };
-  auto issue_next = [&]() {
-    if (f_valid) {
-      const DWork& wd = sd.work[fc.w];
-      double* dstA = sA + (n_issued % DP_NBUF) * Cfg::A_DOUBLES;
-      const double* src = wd.src[fc.c];
-#pragma unroll
-      for (int i = 0; i < PASSES; ++i) {
-        const int o = tid + i * DMMA_THREADS;
-        const int rr = o / CHUNKS, ck = o - rr * CHUNKS;
-        cp_async16(dstA + rr * LDS + 2 * ck, src + ((int64_t)nidx[i] * K + fc.b) * MP + 2 * ck);
-      }
-      ++fc.c;
-    }
-    cp_async_commit();
-    ++n_issued;
-    prefetch_idx();
-  };
-
+  if (ic.st < st1) idx_i = __ldg(sd.work[ic.w].idx[ic.c] + my_row(ic));
   pdl_wait();
-  prefetch_idx();
-#pragma unroll 1
-  for (int i = 0; i < DP_NBUF - 1; ++i) issue_next();
+  if (dc.st < st1) {
+    const int32_t r = idx_i;
+    advance(ic);
+    if (ic.st < st1) idx_i = __ldg(sd.work[ic.w].idx[ic.c] + my_row(ic));
+    fetch(dc, r);
+  }
 
-  int n_consumed = 0;
-  int res_w = -1, res_b = -1;  // (work item, bin) whose first two P matrices are resident
-  DCursor cc{(int)blockIdx.x, 0, 0, 0, 0};
+  int res_w = -1, res_b = -1;
+  double prod[NI][2];
 #pragma unroll 1
-  for (; cc.t < a.total_tiles; cc.t += gridDim.x) {
-    place(cc);
-    const DWork& wd = sd.work[cc.w];
-    const int b = cc.b;
-    const int nc = wd.nc;
-    if (cc.w != res_w || b != res_b) {
+  while (cc.st < st1) {
+    const RWork& wd = sd.work[cc.w];
+    if (cc.c == 0 && (cc.w != res_w || cc.b != res_b)) {
+      // another (node, rate class): every warp is done with the old P matrices
       __syncthreads();
-      int slot = 0;
-      for (int c = 0; c < nc && slot < 2; ++c)
-        if (wd.P[c] != nullptr) {
-          load_P_to_smem<MP>(sB + slot * Cfg::B_DOUBLES, wd.P[c] + (int64_t)b * MP * MP);
-          ++slot;
-        }
-      res_w = cc.w;
-      res_b = b;
-      __syncthreads();
-    }
-    // this thread's C-fragment rows: DP_WM blocks of 8 rows per warp
-    int64_t my_row[DP_WM];
-    bool row_ok[DP_WM];
-    int64_t my_row_c[DP_WM];
-#pragma unroll
-    for (int m = 0; m < DP_WM; ++m) {
-      my_row[m] = cc.row0 + (warp * DP_WM + m) * 8 + g;
-      row_ok[m] = my_row[m] < wd.n_rows;
-      my_row_c[m] = row_ok[m] ? my_row[m] : wd.n_rows - 1;
-    }
-
-    double prod[DP_WM][NI][2];
-    int dmma_seen = 0;
-    for (int c = 0; c < nc; ++c) {
-      double cur[DP_WM][NI][2];
-      if (wd.P[c] == nullptr) {
-#pragma unroll
-        for (int m = 0; m < DP_WM; ++m) {
-          const int32_t r = __ldg(wd.idx[c] + my_row_c[m]);
-          const double* src = wd.src[c] + ((int64_t)r * K + b) * MP + 2 * q;
-#pragma unroll
-          for (int ni = 0; ni < NI; ++ni) {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(src + 8 * ni));
-            cur[m][ni][0] = v.x;
-            cur[m][ni][1] = v.y;
-          }
-        }
-      } else {
-        const double* sBc;
-        if (dmma_seen < 2) {
-          sBc = sB + dmma_seen * Cfg::B_DOUBLES;
-        } else {
-          // third / fourth contraction child: stream its P through slot 0
-          __syncthreads();
-          load_P_to_smem<MP>(sB, wd.P[c] + (int64_t)b * MP * MP);
-          res_w = -1;
-          sBc = sB;
-        }
-        ++dmma_seen;
-        cp_async_wait_group<DP_NBUF - 2>();
-        __syncthreads();  // unit landed; everyone is done with the previous unit's buffer
-        const double* sAc = sA + (n_consumed % DP_NBUF) * Cfg::A_DOUBLES;
-        ++n_consumed;
-        issue_next();     // refill the buffer the previous unit used
-#pragma unroll
-        for (int m = 0; m < DP_WM; ++m)
-#pragma unroll
-          for (int ni = 0; ni < NI; ++ni) cur[m][ni][0] = cur[m][ni][1] = 0.0;
-        const double* aRow = sAc + ((warp * DP_WM) * 8 + g) * LDS + q;
-        const double* bRow = sBc + g * LDS + q;
-#pragma unroll 2
-        for (int ks = 0; ks < KS; ++ks) {
-          double av[DP_WM];
-#pragma unroll
-          for (int m = 0; m < DP_WM; ++m) av[m] = aRow[m * 8 * LDS + 4 * ks];
-#pragma unroll
-          for (int ni = 0; ni < NI; ++ni) {
-            const double bv = bRow[(8 * ni) * LDS + 4 * ks];
-#pragma unroll
-            for (int m = 0; m < DP_WM; ++m) dmma_m8n8k4(cur[m][ni][0], cur[m][ni][1], av[m], bv);
-          }
+      for (int c = 0; c < wd.nc; ++c) {
+        if (wd.P[c] == nullptr) continue;
+        double* sB = smem + wd.slot[c] * Cfg::B_DOUBLES;
+        const double* P = wd.P[c] + (int64_t)cc.b * MP * MP;
+        for (int o = tid; o < MP * MP; o += DR_THREADS) {
+          const int i = o / MP, pos = o - i * MP;
+          const int s = pos >> 2, qq = pos & 3;
+          sB[i * LDS + pos] = P[i * MP + 8 * (s >> 1) + 2 * qq + (s & 1)];
         }
       }
+      res_w = cc.w;
+      res_b = cc.b;
+      __syncthreads();
+    }
+    // take over the rows in flight, request the next unit's
+    double2 v[NI];
 #pragma unroll
-      for (int m = 0; m < DP_WM; ++m)
+    for (int ni = 0; ni < NI; ++ni) v[ni] = vn[ni];
+    advance(dc);
+    if (dc.st < st1) {
+      const int32_t r = idx_i;
+      advance(ic);
+      if (ic.st < st1) idx_i = __ldg(sd.work[ic.w].idx[ic.c] + my_row(ic));
+      fetch(dc, r);
+    }
+
+    double cur[NI][2];
+    if (wd.P[cc.c] == nullptr) {
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) {
-          if (c == 0) {
-            prod[m][ni][0] = cur[m][ni][0];
-            prod[m][ni][1] = cur[m][ni][1];
-          } else {
-            prod[m][ni][0] *= cur[m][ni][0];
-            prod[m][ni][1] *= cur[m][ni][1];
-          }
-        }
+      for (int ni = 0; ni < NI; ++ni) { cur[ni][0] = v[ni].x; cur[ni][1] = v[ni].y; }
+    } else {
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) cur[ni][0] = cur[ni][1] = 0.0;
+      const double* bRow = smem + wd.slot[cc.c] * Cfg::B_DOUBLES + g * LDS + q;
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const double av = (s & 1) ? v[s >> 1].y : v[s >> 1].x;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) dmma_m8n8k4(cur[ni][0], cur[ni][1], av, bRow[(8 * ni) * LDS + 4 * s]);
+      }
     }
 #pragma unroll
-    for (int m = 0; m < DP_WM; ++m) {
+    for (int ni = 0; ni < NI; ++ni) {
+      if (cc.c == 0) { prod[ni][0] = cur[ni][0]; prod[ni][1] = cur[ni][1]; }
+      else { prod[ni][0] *= cur[ni][0]; prod[ni][1] *= cur[ni][1]; }
+    }
+    if (cc.c == wd.nc - 1) {
+      const int64_t p = cc.row0 + warp * 8 + g;
+      const bool row_ok = p < wd.n_rows;
       if (wd.fixed_motif >= 0) {
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) {
-          if (8 * ni + 2 * q != wd.fixed_motif) prod[m][ni][0] = 0.0;
-          if (8 * ni + 2 * q + 1 != wd.fixed_motif) prod[m][ni][1] = 0.0;
+          if (8 * ni + 2 * q != wd.fixed_motif) prod[ni][0] = 0.0;
+          if (8 * ni + 2 * q + 1 != wd.fixed_motif) prod[ni][1] = 0.0;
         }
       }
-      if (row_ok[m]) {
-        double* dst = wd.out + ((int64_t)my_row[m] * K + b) * MP + 2 * q;
+      if (row_ok) {
+        double* dst = wd.out + (p * K + cc.b) * MP + 2 * q;
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni)
-          *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(prod[m][ni][0], prod[m][ni][1]);
+          *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(prod[ni][0], prod[ni][1]);
       }
       if (ROOT) {
         double sdot = 0.0;
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni) {
-          sdot = fma(prod[m][ni][0], a.pi[8 * ni + 2 * q], sdot);
-          sdot = fma(prod[m][ni][1], a.pi[8 * ni + 2 * q + 1], sdot);
+          sdot = fma(prod[ni][0], a.pi[8 * ni + 2 * q], sdot);
+          sdot = fma(prod[ni][1], a.pi[8 * ni + 2 * q + 1], sdot);
         }
         sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
         sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-        if (row_ok[m] && q == 0) a.lh_out[my_row[m] * K + b] = sdot;
+        if (row_ok && q == 0) a.lh_out[p * K + cc.b] = sdot;
       }
     }
+    advance(cc);
   }
-  cp_async_wait_group<0>();
 }
 
 // ---------------------------------------------------------------------------------------

@@ -238,10 +238,11 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
         assert lfs[0].get_log_likelihood() == got[0]
 
 
-def test_dmma_pipelined_variant_matches(monkeypatch):
-    """the (non-default) pipelined DMMA kernel gives the same numbers as the default one"""
-    monkeypatch.setenv("C3_DMMA_PIPE", "1")
-    for case in ("c4_cnfgtr_mid", "c4_cnfgtr_small"):
+def test_dmma_first_version_matches(monkeypatch):
+    """the first (shared-memory tile) DMMA kernel gives the same numbers as the default
+    register-pipeline kernel, to the tolerances (the k order differs)"""
+    monkeypatch.setenv("C3_DMMA_REG", "0")
+    for case in ("c4_cnfgtr_mid", "c4_cnfgtr_small", "kat_codon", "kat_dinucleotide", "kat_protein"):
         g = Golden(case)
         lf = lf_from_golden(g)
         lnL = lf.get_log_likelihood()
@@ -249,9 +250,14 @@ def test_dmma_pipelined_variant_matches(monkeypatch):
         assert np.max(np.abs(lf.engine.get_lh(0) - g.lh[0])) <= ABS_LH
 
 
-def test_polytomy_and_many_bins():
-    """5-way polytomy at the root, K=3 (generic-K kernel path)"""
+@pytest.mark.parametrize("force_dmma", [False, True])
+def test_polytomy_and_many_bins(force_dmma, monkeypatch):
+    """5-way polytomy at the root, K=3 (generic-K kernel path; with the DMMA kernels: more
+    children than the register-pipeline kernel takes -> first version for that node)"""
     from cogent3_b200.tree import Topology
+
+    if force_dmma:
+        monkeypatch.setenv("C3_FORCE_DMMA", "1")
 
     topo, _ = Topology.from_newick("(a:0.1,b:0.2,c:0.15,(d:0.1,e:0.3):0.05,f:0.2);")
     rng = np.random.default_rng(5)
