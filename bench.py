@@ -404,10 +404,16 @@ def run_ours(args):
         from cogent3_b200.engine import measure_dmma_peak
 
         dmma_peak = measure_dmma_peak(local_rank)
-        achieved = prune_flops / (prune_ms * 1e-3) / 1e12
+        # ALGORITHMIC flops (2 M^2 per internal-child row); the kernel executes 2 MP^2 (M padded to
+        # a multiple of 8: 61 -> 64), reported next to it
+        MP = st["padded_states"]
+        alg_flops = prune_flops * (M * M) / (MP * MP)
+        achieved = alg_flops / (prune_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
                     "frac": achieved / dmma_peak, "traffic": None,
                     "peak_source": "FP64 DMMA issue-loop microbenchmark on this GPU (c3_measure_dmma_peak)",
+                    "executed_tflops": prune_flops / (prune_ms * 1e-3) / 1e12,
+                    "executed_frac": prune_flops / (prune_ms * 1e-3) / 1e12 / dmma_peak,
                     "hbm_gbs_achieved": prune_bytes / (prune_ms * 1e-3) / 1e9}  # fmt: skip
     # DRAM traffic of the dominant launch from the committed ncu capture (per launch, like
     # `achieved` is per launch); null when no capture exists for this config
@@ -421,12 +427,14 @@ def run_ours(args):
     except (OSError, ValueError, KeyError):
         pass
     roofline.update({
-        "kernel": "prune4_kernel" if M == 4 else "prune_dmma_kernel",
+        "kernel": "prune4_reg_kernel" if M == 4 else "prune_dmma_reg_kernel",
         "launches_per_step": len(prune[-1]), "kernel_ms_per_step": prune_ms,
         "kernel_share_of_step": prune_ms / step_ms if step_ms else None,
         "alg_bytes_per_step": prune_bytes, "executed_flops_per_step": prune_flops,
         "per_launch": [{"kind": r["kind"], "ms": round(r["ms"], 5), "bytes": r["bytes"],
-                        "GBps": round(r["bytes"] / r["ms"] / 1e6, 1) if r["ms"] > 0 else None} for r in prof],
+                        "GBps": round(r["bytes"] / r["ms"] / 1e6, 1) if r["ms"] > 0 else None,
+                        **({"exec_TFLOPs": round(r["flops"] / r["ms"] / 1e9, 2)} if M != 4 and r["ms"] > 0 else {})}
+                       for r in prof],
     })  # fmt: skip
 
     # ---- partial updates: one branch length at a time (the optimiser's inner loop) --
