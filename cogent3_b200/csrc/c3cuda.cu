@@ -116,6 +116,7 @@ struct c3_engine {
   bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
   bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
   bool use_dmma_reg = true;  // warp-private register pipeline for M != 4 (C3_DMMA_REG=0: first version)
+  bool use_reg2 = true;   // binary nodes: two strips in flight per warp (C3_REG1=1: the one-strip regpipe kernel)
   bool use_ring = false;  // C3_RING=1: the cp.async shared-memory ring version of the strip kernel
   // dataflow kernel: consecutive big binary levels in one launch.  Opt-in (C3_FLOW=1): its kernel
   // time is lower than the per-level launches' sum (C2 0.267 vs 0.289 ms, C3 0.435 vs 0.585 ms) but
@@ -289,6 +290,25 @@ int launch_flow(c3_engine* e, const PruneArgs& a, const int32_t* d_dep, unsigned
   return C3_OK;
 }
 
+template <int K>
+int launch_reg2(c3_engine* e, const PruneArgs& a, bool is_root) {
+  const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + 7) / 8));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune4_reg2_kernel<K, true>, a)
+                            : cudaLaunchKernelEx(&cfg, prune4_reg2_kernel<K, false>, a);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("regpipe2 launch: ") + cudaGetErrorString(err));
+  return C3_OK;
+}
+
 // kind: 0 = generic kernels (prune4_kernel / prune_dmma_kernel); 2, 3 = strip kernel for
 // nodes with that many children (4-state, K in {1,2,4}); 6 = register-pipeline DMMA kernel
 int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
@@ -313,6 +333,8 @@ int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
   case KK:                                                                                        \
     if (e->use_ring)                                                                              \
       rc = (kind == 2) ? launch_strip<KK, 2>(e, a, is_root) : launch_strip<KK, 3>(e, a, is_root); \
+    else if (kind == 2 && e->use_reg2)                                                            \
+      rc = launch_reg2<KK>(e, a, is_root);                                                        \
     else                                                                                          \
       rc = (kind == 2) ? launch_reg<KK, 2>(e, a, is_root) : launch_reg<KK, 3>(e, a, is_root);     \
     break;
@@ -479,6 +501,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
   if (const char* env = getenv("C3_DMMA_REG")) e->use_dmma_reg = atoi(env) != 0;
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
+  if (const char* env = getenv("C3_REG1")) e->use_reg2 = atoi(env) == 0;
   if (const char* env = getenv("C3_FLOW")) e->use_flow = atoi(env) != 0;
   e->root = n_nodes - 1;
   e->children.resize(n_nodes);

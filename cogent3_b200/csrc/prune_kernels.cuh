@@ -500,11 +500,8 @@ __global__ void __launch_bounds__(P4SCfg<K, NC>::WARPS * 32, 1) prune4_strip_ker
 // and ~200 KB of L1 for the child tables.  Same arithmetic (bit-identical results), same
 // strip numbering, same staged descriptors and programmatic dependent launch as the ring
 // version.
-// Measured and dropped: a variant with TWO strips in flight per warp (row buffers refilled in
-// place right after the FMAs that consume them, 244 registers): 0.119 vs 0.109 ms on the largest
-// C2 level, no change for K = 1.  More bytes in flight do not help: the evolved alignments'
-// gathers (rows re-referenced out of order, 128 B each) hold DRAM at ~4.8 TB/s; i.i.d. columns,
-// whose child index is nearly the identity, reach 5.5-5.9 TB/s with the same kernel.
+// Binary nodes now run regpipe2 below (two strips in flight); this kernel remains for nodes with
+// three children (the trifurcating root: its row buffers alone are 96 registers per strip).
 // ---------------------------------------------------------------------------------------
 template <int NC>
 struct RegCfg {
@@ -639,6 +636,167 @@ __global__ void __launch_bounds__(RegCfg<NC>::WARPS * 32, 1) prune4_reg_kernel(c
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 4-state kernel, register pipeline with TWO strips in flight ("regpipe2", binary nodes) -- the
+// production kernel for the bulk of a tree.
+// ncu on regpipe: DRAM 57 %, issue slots 26 %, 8 warps per SM, the stall samples sit on the first
+// use of the gathered rows: with one strip (8 KB per warp, 64 KB per SM) in flight against ~2 us
+// of loaded latency, Little's law gives the 4.8 TB/s it reaches.
+// Each warp keeps two row buffers and two gather-index sets and walks its strips two at a time:
+// while strip s is computed from buffer A, strip s+GW is in flight into B; A is refilled IN
+// PLACE, child by child, with strip s+2GW as soon as the FMAs that consume it are issued, using
+// indexes that were requested two steps earlier (a first attempt kept ONE index set, i.e. one
+// step of lead: with the shorter steps the refill loads then stalled on their own addresses in
+// the middle of the FMA block and the kernel was 9 % slower than regpipe).  Largest C2 level:
+// 4.78 -> 5.29 TB/s; C5 levels 5.7-6.0 TB/s (the measured copy bandwidth is 6.55).  248 registers.
+// ---------------------------------------------------------------------------------------
+template <int K, bool ROOT>
+__global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) {
+  constexpr int NC = 2;
+  constexpr int ROWS = 128 / K;
+  constexpr int WARPS = 8;
+  __shared__ StripSmem<NC> sd;
+  __shared__ __align__(16) double sPall[WARPS][NC * K * P4S_PSTRIDE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sP = sPall[warp];
+
+  pdl_trigger();
+  for (int i = threadIdx.x; i <= a.n_work; i += blockDim.x) sd.prefix[i] = a.tile_prefix[i];
+  for (int i = threadIdx.x; i < a.n_work; i += blockDim.x) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    WorkDesc<NC>& wd = sd.work[i];
+    wd.out = nd.out;
+    wd.n_rows = nd.n_rows;
+    wd.fixed_motif = nd.fixed_motif;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + c];
+      wd.src[c] = ch.src;
+      wd.idx[c] = ch.idx;
+      wd.P[c] = ch.P;
+    }
+  }
+  __syncthreads();
+
+  const int gw = blockIdx.x * WARPS + warp;
+  const int GW = gridDim.x * WARPS;
+  const int total = a.total_tiles;
+  const int b = lane % K;
+  const int slot = lane / K;
+
+  int i_w = 0, g_w = 0, c_w = 0, p_w = -1;
+  auto load_idx = [&](int32_t(&ix)[NC][P4S_U], int s) {
+    while (s >= sd.prefix[i_w + 1]) ++i_w;
+    const WorkDesc<NC>& wd = sd.work[i_w];
+    const int64_t row0 = (int64_t)(s - sd.prefix[i_w]) * ROWS;
+#pragma unroll
+    for (int u = 0; u < P4S_U; ++u) {
+      int64_t p = row0 + u * (32 / K) + slot;
+      if (p >= wd.n_rows) p = wd.n_rows - 1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) ix[c][u] = __ldg(wd.idx[c] + p);
+    }
+  };
+  const double* gsrc[NC];
+  auto gather_seek = [&](int s) {
+    while (s >= sd.prefix[g_w + 1]) ++g_w;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) gsrc[c] = sd.work[g_w].src[c];
+  };
+
+  // compute strip s from x; refill x with strip s + 2 GW (indexes ix, requested two steps ago);
+  // then request the indexes of strip s + 4 GW into ix
+  auto step = [&](d4(&x)[NC][P4S_U], int32_t(&ix)[NC][P4S_U], int s) {
+    while (s >= sd.prefix[c_w + 1]) ++c_w;
+    const WorkDesc<NC>& wd = sd.work[c_w];
+    if (c_w != p_w) {
+      __syncwarp();
+      for (int o = lane; o < NC * K * 16; o += 32) {
+        const int c = o / (K * 16);
+        const int rem = o - c * (K * 16);
+        const double* P = wd.P[c];
+        sP[(c * K + (rem >> 4)) * P4S_PSTRIDE + (rem & 15)] =
+            P ? P[rem] : (((rem & 15) % 5 == 0) ? 1.0 : 0.0);
+      }
+      p_w = c_w;
+      __syncwarp();
+    }
+    const bool refill = s + 2 * GW < total;
+    if (refill) gather_seek(s + 2 * GW);
+    d4 acc[P4S_U];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double* Pc = sP + (c * K + b) * P4S_PSTRIDE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double2 p01 = *reinterpret_cast<const double2*>(Pc + 4 * i);
+        const double2 p23 = *reinterpret_cast<const double2*>(Pc + 4 * i + 2);
+#pragma unroll
+        for (int u = 0; u < P4S_U; ++u) {
+          const double y =
+              fma(x[c][u].w, p23.y, fma(x[c][u].z, p23.x, fma(x[c][u].y, p01.y, x[c][u].x * p01.x)));
+          double& t = (i == 0) ? acc[u].x : (i == 1) ? acc[u].y : (i == 2) ? acc[u].z : acc[u].w;
+          t = (c == 0) ? y : t * y;
+        }
+      }
+      if (refill) {
+#pragma unroll
+        for (int u = 0; u < P4S_U; ++u) x[c][u] = ld256_nc(gsrc[c] + ((int64_t)ix[c][u] * K + b) * 4);
+      }
+    }
+    if (s + 4 * GW < total) load_idx(ix, s + 4 * GW);
+    const int64_t node_row0 = (int64_t)(s - sd.prefix[c_w]) * ROWS;
+    const int c_fixed = wd.fixed_motif;
+#pragma unroll
+    for (int u = 0; u < P4S_U; ++u) {
+      const int64_t p = node_row0 + u * (32 / K) + slot;
+      if (c_fixed >= 0) {
+        if (c_fixed != 0) acc[u].x = 0.0;
+        if (c_fixed != 1) acc[u].y = 0.0;
+        if (c_fixed != 2) acc[u].z = 0.0;
+        if (c_fixed != 3) acc[u].w = 0.0;
+      }
+      if (p < wd.n_rows) {
+        st256(wd.out + (p * K + b) * 4, acc[u]);
+        if (ROOT) {
+          const double lh =
+              fma(acc[u].w, a.pi[3], fma(acc[u].z, a.pi[2], fma(acc[u].y, a.pi[1], acc[u].x * a.pi[0])));
+          a.lh_out[p * K + b] = lh;
+        }
+      }
+    }
+  };
+
+  d4 xa[NC][P4S_U], xb[NC][P4S_U];
+  int32_t ia[NC][P4S_U], ib[NC][P4S_U];
+  // prologue: strips gw, gw+GW into the buffers; indexes of gw+2GW, gw+3GW into the index sets
+  if (gw < total) load_idx(ia, gw);  // static data: may overlap the previous launch
+  if (gw + GW < total) load_idx(ib, gw + GW);
+  pdl_wait();
+  if (gw < total) {
+    gather_seek(gw);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int u = 0; u < P4S_U; ++u) xa[c][u] = ld256_nc(gsrc[c] + ((int64_t)ia[c][u] * K + b) * 4);
+  }
+  if (gw + GW < total) {
+    gather_seek(gw + GW);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int u = 0; u < P4S_U; ++u) xb[c][u] = ld256_nc(gsrc[c] + ((int64_t)ib[c][u] * K + b) * 4);
+  }
+  if (gw + 2 * GW < total) load_idx(ia, gw + 2 * GW);
+  if (gw + 3 * GW < total) load_idx(ib, gw + 3 * GW);
+
+#pragma unroll 1
+  for (int s = gw; s < total; s += 2 * GW) {
+    step(xa, ia, s);
+    if (s + GW < total) step(xb, ib, s + GW);
   }
 }
 

@@ -187,7 +187,7 @@ def test_synthetic_against_oracle(model, n_tips, L, bins, kind):
     ],
 )
 def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, rooted, monkeypatch):
-    """per-level regpipe (default), dataflow, cp.async ring and thread-per-unit kernels do the
+    """regpipe2 (default), regpipe, dataflow, cp.async ring and thread-per-unit kernels do the
     same arithmetic in the same order: every partial row, lh and lnL are bit-identical; so is
     a dirty-path update inside the dataflow launch"""
     from cogent3_b200.tree import Topology
@@ -200,7 +200,7 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
         codes = codes[: int(np.sum(topo.is_tip))]
 
     def build(env):
-        for k in ("C3_FLOW", "C3_RING", "C3_NO_STRIP", "C3_NO_SMALL"):
+        for k in ("C3_FLOW", "C3_RING", "C3_NO_STRIP", "C3_NO_SMALL", "C3_REG1"):
             monkeypatch.delenv(k, raising=False)
         for k in env:
             monkeypatch.setenv(k, "1")
@@ -214,7 +214,7 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
             lf.set_param_rule("rate_shape", value=0.6)
         return lf
 
-    variants = [(), ("C3_FLOW",), ("C3_RING",), ("C3_NO_STRIP",), ("C3_NO_SMALL",), ("C3_FLOW", "C3_NO_SMALL")]
+    variants = [(), ("C3_REG1",), ("C3_FLOW",), ("C3_RING",), ("C3_NO_STRIP",), ("C3_NO_SMALL",), ("C3_FLOW", "C3_NO_SMALL")]
     lfs = [build(v) for v in variants]
     vals = [lf.get_log_likelihood() for lf in lfs]
     assert len(set(vals)) == 1, vals
