@@ -570,6 +570,46 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # ---- many small alignments at once: B independent likelihood functions --
+    many = None
+    if world == 1 and args.config == "c1":
+        from cogent3_b200.engine import evaluate_many as engine_many
+
+        B = 64
+        lfs = [make_lf(problem, device=local_rank)[0] for _ in range(B)]
+        engines = [f.engine for f in lfs]
+        for f in lfs:
+            f.get_log_likelihood()
+
+        def many_step(k):
+            d = np.nan_to_num(step_lengths(base, k))[:, None] * rates[None, :]
+            for e_ in engines:
+                e_.set_distances(d)
+            return engine_many(engines)
+
+        for k in range(3):
+            many_step(k)
+        n_rep = 50
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(n_rep):
+            vals = many_step(k)
+        t_many = (time.perf_counter() - t0) / n_rep
+        t_seq = 0.0
+        for k in range(5):  # the same work, one blocking evaluation after the other
+            d = np.nan_to_num(step_lengths(base, 1000 + k))[:, None] * rates[None, :]
+            for e_ in engines:
+                e_.set_distances(d)
+            t0 = time.perf_counter()
+            one_by_one = [e_.evaluate() for e_ in engines]
+            t_seq += (time.perf_counter() - t0) / 5
+        many = {"engines": B, "evals_per_s": B / t_many, "ms_per_batch": t_many * 1e3,
+                "one_at_a_time_evals_per_s": B / t_seq, "all_equal": bool(len(set(vals)) == 1),
+                "api": "c3_evaluate_many: every engine on its own stream, launched before any is waited for"}
+        del one_by_one
+        for f in lfs:
+            f.engine.close()
+
     cpu_rec = None
     if world == 1 and not args.no_cpu:
         # in a fresh process: torch's OpenMP runtime settings must not throttle the CPU arm
@@ -606,6 +646,7 @@ def run_ours(args):
                   "root_patterns_per_gpu": int(lf.patterns.root.n_rows - 1),
                   "node_rows_per_step": int(st["last_node_rows"])},
         "partial_update": partial,
+        "many_small": many,
         "setup": {**setup_t, "device_bytes": int(st["device_bytes"]),
                   "partial_bytes": int(st["partial_bytes"]), "levels": int(st["n_levels"])},
         "lnL": lnl,

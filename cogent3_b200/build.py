@@ -25,7 +25,7 @@ HEADERS = [
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
-    "-Xcompiler", "-fvisibility=hidden", "--fmad=true",
+    "-Xcompiler", "-fvisibility=hidden", "--fmad=true", *os.environ.get("C3_NVCC_EXTRA", "").split(),
 ]  # fmt: skip
 
 

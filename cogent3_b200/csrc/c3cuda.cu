@@ -140,6 +140,7 @@ struct c3_engine {
   bool have_pi = false, have_dist = false;
   double cached_lnl = NAN;
   bool have_cached = false;
+  bool deferred_pending = false;  // c3_evaluate_many: launched, result not collected yet
 
   c3_stats stats{};
 
@@ -432,7 +433,8 @@ int ensure_slots(c3_engine* e, int n) {
   return C3_OK;
 }
 
-int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out);
+int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out, bool deferred = false);
+int finish_deferred(c3_engine* e, double* host_out);
 
 cudaEvent_t next_event(c3_engine* e) {
   if (e->events_used == e->event_pool.size()) {
@@ -1253,6 +1255,23 @@ int c3_evaluate_device(c3_engine* e, double* device_lnL) {
   return run_evaluation(e, device_lnL, false, nullptr);
 }
 
+int c3_evaluate_many(c3_engine** engines, int n, double* lnL) {
+  C3_REQUIRE(engines && lnL && n >= 0, "null pointer");
+  for (int i = 0; i < n; ++i) C3_REQUIRE(engines[i] != nullptr, "null engine");
+  // launch every engine's evaluation on its own stream, then collect: small problems overlap
+  int rc = C3_OK;
+  int launched = 0;
+  for (; launched < n; ++launched) {
+    rc = run_evaluation(engines[launched], nullptr, false, nullptr, true);
+    if (rc != C3_OK) break;
+  }
+  for (int i = 0; i < launched; ++i) {
+    const int rc2 = finish_deferred(engines[i], lnL + i);
+    if (rc == C3_OK) rc = rc2;
+  }
+  return rc;
+}
+
 int c3_update(c3_engine* e, const double* d, double* lnL) {
   int rc = c3_set_distances(e, d);
   if (rc) return rc;
@@ -1362,8 +1381,11 @@ int c3_measure_dmma_peak(int device, double* tflops) {
 // =========================================================================================
 namespace {
 
-int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out) {
+// deferred: launch everything like a blocking call (the scalar also goes to the mapped host word)
+// but do not wait; finish_deferred() collects it.  Lets many engines run concurrently.
+int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out, bool deferred) {
   C3_REQUIRE(e->finalized, "call c3_finalize first");
+  e->deferred_pending = false;
   C3_REQUIRE(e->have_pi, "root motif probabilities not set");
   C3_CUDA(cudaSetDevice(e->device));
   const int N = e->n_nodes, K = e->K, M = e->M, MP = e->MP;
@@ -1715,7 +1737,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     ProfScope ps(e, 4, rows * (K + 1) * 8, 0);
     lnl_reduce_kernel<<<grid, REDUCE_THREADS, 0, e->stream>>>(
         e->d_lh, reinterpret_cast<const double*>(e->d_block + e->off_bprobs), e->d_counts, rows, K, n_tiles,
-        e->d_tile_sums, e->d_counter, e->d_lnl, device_out, blocking ? e->h_lnl_dev : nullptr);
+        e->d_tile_sums, e->d_counter, e->d_lnl, device_out, (blocking || deferred) ? e->h_lnl_dev : nullptr);
     ++n_launch;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(err));
@@ -1735,6 +1757,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   e->stats.last_flops = flops;
   e->stats.last_h2d_bytes = h2d_bytes;
 
+  if (deferred) {
+    e->deferred_pending = true;
+    return C3_OK;
+  }
   if (blocking) {
     cudaError_t err = cudaStreamSynchronize(e->stream);
     if (err != cudaSuccess) {
@@ -1751,6 +1777,23 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     e->cached_lnl = NAN;
     e->reduce_dirty = true;  // a later blocking call must re-run the reduction for the host value
   }
+  return C3_OK;
+}
+
+int finish_deferred(c3_engine* e, double* host_out) {
+  if (e->deferred_pending) {
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    e->deferred_pending = false;
+    if (err != cudaSuccess) {
+      e->have_cached = false;
+      c3_invalidate(e);
+      return fail(C3_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(err));
+    }
+    for (auto& r : e->prof) cudaEventElapsedTime(&r.ms, r.a, r.b);
+    e->cached_lnl = *e->h_lnl;
+    e->have_cached = true;
+  }
+  if (host_out) *host_out = e->cached_lnl;
   return C3_OK;
 }
 

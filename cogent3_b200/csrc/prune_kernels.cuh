@@ -1327,7 +1327,10 @@ __global__ void __launch_bounds__(DMMA_THREADS) prune_dmma_kernel(const PruneArg
 // place for unit u+2 spills at 168 registers and measured 1.61 vs 1.27 ms on C4: dropped.
 // Taking the tip children (tables of <= 62 rows, L1 / shared-memory resident) out of the
 // pipeline so that they do not displace the next contraction unit's prefetch: 1.55 ms with the
-// tables staged in shared memory, 1.50 ms with the rows loaded at use from L1 -- both dropped.)  No barrier except when the CTA
+// tables staged in shared memory, 1.50 ms with the rows loaded at use from L1 -- both dropped.
+// Two units in flight WITHOUT spills (8 warps per SM, 236 registers, gather indexes four units
+// ahead as in regpipe2): 1.50 ms -- the tensor pipe wants the 12 warps more than the depth.
+// Starting the three warps of a scheduler a third of a unit apart: no change.)  No barrier except when the CTA
 // moves to another (node, rate class) and reloads P; CTAs take contiguous ranges of super-tiles
 // so that happens once or twice per launch.  One CTA of 12 warps per SM (register bound).
 // Summation order over k differs from the first version (permuted), so results differ from it

@@ -290,6 +290,19 @@ class LikelihoodEngine:
         return st.as_dict()
 
 
+def evaluate_many(engines) -> np.ndarray:
+    """evaluate several independent engines concurrently (c3_evaluate_many): every engine's
+    kernels are launched on its own stream before any result is waited for"""
+    n = len(engines)
+    out = np.zeros(n, np.float64)
+    if n == 0:
+        return out
+    handles = (c_void_p * n)(*[e._h.value for e in engines])
+    lib = engines[0]._lib
+    _lib.check(lib.c3_evaluate_many(handles, n, _dptr(out)))
+    return out
+
+
 def measure_dmma_peak(device=0) -> float:
     """sustained FP64 tensor-core TFLOP/s of this GPU (DMMA m8n8k4 issue loop)."""
     out = c_double(0.0)

@@ -382,3 +382,14 @@ class LikelihoodFunction:
         self._apply_vector(spec, np.clip(np.exp(res.x), lo, hi))
         self.last_optimise_evaluations = evals[0]
         return self.get_log_likelihood()
+
+
+def evaluate_many(lfs) -> np.ndarray:
+    """log-likelihoods of several independent likelihood functions, evaluated concurrently on
+    the GPU (many small alignments).  Host-side parameter syncing stays per
+    function; the device work of all of them is in flight at once."""
+    from .engine import evaluate_many as engine_many
+
+    for lf in lfs:
+        lf._sync()
+    return engine_many([lf.engine for lf in lfs])

@@ -162,6 +162,12 @@ C3_API int c3_invalidate(c3_engine* e); /* force a full recomputation next time 
 C3_API int c3_evaluate(c3_engine* e, double* lnL);
 C3_API int c3_evaluate_device(c3_engine* e, double* device_lnL);
 C3_API int c3_update(c3_engine* e, const double* distance_of_edge_bin, double* lnL);
+/* c3_evaluate_many: c3_evaluate for n independent engines (each on its own stream): all are
+ *             launched before any is waited for, so small alignments -- the app layer's
+ *             workload, hundreds of independent likelihood functions (app/evo.py:317-386,
+ *             evolve/bootstrap.py:68) -- overlap on the GPU instead of paying the launch /
+ *             level latency one after the other.                          */
+C3_API int c3_evaluate_many(c3_engine** engines, int n, double* lnL);
 
 /* ---- accessors (what likelihood_function.py reads back) -------------------------
  * c3_get_lh: per-pattern root likelihood of one bin, "lh" Defn

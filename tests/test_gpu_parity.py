@@ -315,3 +315,34 @@ def test_optimise_improves_and_matches_oracle_path():
     ref._dirty_q = ref._dirty_model = True
     want = ref.get_log_likelihood()
     assert abs(after - want) <= REL_LNL * abs(want)
+
+
+def test_evaluate_many_matches_individual_evaluations():
+    """c3_evaluate_many: several independent engines in flight at once give exactly the numbers
+    of one-at-a-time evaluation, for full sweeps and for dirty-path updates"""
+    from cogent3_b200.likelihood import evaluate_many
+
+    cases = ["c1_brca1_hky85_default", "c2_gtr_gamma4_small", "c5_hky85_gamma4_small", "c4_cnfgtr_small",
+             "c3_gn_pade_small", "kat_protein", "c2_gtr_gamma4_mid", "c1_brca1_hky85_point2"]  # fmt: skip
+    goldens = [Golden(c) for c in cases]
+    many = [lf_from_golden(g) for g in goldens]
+    single = [lf_from_golden(g) for g in goldens]
+    got = evaluate_many(many)
+    for g, v, lf in zip(goldens, got, single, strict=True):
+        assert v == lf.get_log_likelihood()
+        assert abs(v - g.lnL) <= REL_LNL * abs(g.lnL)
+    rng = np.random.default_rng(2)
+    for _ in range(3):
+        for g, a, b in zip(goldens, many, single, strict=True):
+            n = int(rng.choice(g.topo.edges))
+            v = float(rng.uniform(0.01, 0.4))
+            for lf in (a, b):
+                lf.set_param_rule("length", edge=g.topo.names[n], value=v)
+        got = evaluate_many(many)
+        for v, lf in zip(got, single, strict=True):
+            assert v == lf.get_log_likelihood()
+    # nothing changed: served from the cached values, no launch
+    again = evaluate_many(many)
+    np.testing.assert_array_equal(again, got)
+    assert all(lf.engine.stats()["last_launches"] == 0 for lf in many)
+    assert len(evaluate_many([])) == 0
