@@ -408,9 +408,15 @@ def run_ours(args):
     rates = lf.rates()
     lnl_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
 
+    fused = False
+    if world > 1:
+        from cogent3_b200.sharded import attach_fused_allreduce
+
+        fused = attach_fused_allreduce(eng)  # the sum over ranks inside the reduction kernel
+
     def device_step(k):
         d = np.nan_to_num(step_lengths(base, k))[:, None] * rates[None, :]
-        if world == 1:
+        if world == 1 or fused:
             return eng.update(d)
         eng.set_distances(d)
         eng.evaluate_device(lnl_dev.data_ptr())
@@ -424,7 +430,7 @@ def run_ours(args):
             p = lf.model.parameter_order[0]
             lf.set_param_rule(p, value=lf.params[p] * (1.0 + 1e-4 * ((k % 3) - 1)))
         v = lf.get_log_likelihood()
-        if world > 1:
+        if world > 1 and not fused:
             lnl_dev.fill_(v)
             dist.all_reduce(lnl_dev)
             v = float(lnl_dev.item())
@@ -565,6 +571,18 @@ def run_ours(args):
         partial = {"evals_per_s": len(sel) / t_part, "updates_per_s": units / t_part,
                    "edges_sampled": len(sel), "mean_units_per_eval": units / len(sel)}  # fmt: skip
 
+    # ---- N > 1: the fused all-reduce against an NCCL all-reduce of the shard values ----------
+    allreduce_check = None
+    if world > 1 and fused:
+        d = np.nan_to_num(step_lengths(base, 3))[:, None] * rates[None, :]
+        total = eng.update(d)
+        eng.comm_detach()
+        eng.invalidate()
+        t = torch.tensor([eng.update(d)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        allreduce_check = {"fused_total": total, "nccl_sum_of_shards": float(t.item()),
+                           "rel_diff": abs(total - float(t.item())) / abs(total)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -647,6 +665,9 @@ def run_ours(args):
                   "node_rows_per_step": int(st["last_node_rows"])},
         "partial_update": partial,
         "many_small": many,
+        "allreduce": ({"kind": "fused into the reduction kernel (peer-memory mailboxes over NVLink)",
+                       "check": allreduce_check} if fused else
+                      ({"kind": "NCCL all-reduce of one double per step"} if world > 1 else None)),
         "setup": {**setup_t, "device_bytes": int(st["device_bytes"]),
                   "partial_bytes": int(st["partial_bytes"]), "levels": int(st["n_levels"])},
         "lnL": lnl,

@@ -65,6 +65,20 @@ struct PruneArgs {
   double* lh_out;    // root only: [rows][K]
 };
 
+// Site-pattern shards on several GPUs of one node: the reduction's last CTA exchanges the shard
+// log-likelihoods through peer memory (NVLink / NVSwitch P2P stores into every rank's mailbox).
+constexpr int C3_MAX_RANKS = 16;
+struct CommSlot {
+  double value;
+  unsigned long long epoch;  // evaluation number the value belongs to (written after the value)
+};
+struct CommArgs {
+  int32_t nranks;  // 0: not sharded
+  int32_t rank;
+  unsigned long long epoch;
+  CommSlot* peer[C3_MAX_RANKS];  // mailbox of every rank: [2 parities][nranks] slots (own included)
+};
+
 // one tree level inside a fused "small levels" launch
 struct SmallLevel {
   int32_t work_off;    // into PruneArgs::work_node

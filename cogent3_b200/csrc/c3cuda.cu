@@ -142,6 +142,12 @@ struct c3_engine {
   bool have_cached = false;
   bool deferred_pending = false;  // c3_evaluate_many: launched, result not collected yet
 
+  // sharded runs: fused all-reduce through peer mailboxes (c3_comm_*)
+  CommArgs comm{};            // nranks == 0: not attached
+  CommSlot* d_mailbox = nullptr;
+  int mailbox_ranks = 0;
+  std::vector<void*> ipc_opened;
+
   c3_stats stats{};
 
   // per-launch profiling
@@ -576,6 +582,8 @@ int c3_destroy(c3_engine* e) {
     if (p) cudaFree(p);
   for (int32_t* p : e->d_idx_tmp)
     if (p) cudaFree(p);
+  for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (e->d_mailbox) cudaFree(e->d_mailbox);
   if (e->d_pool) cudaFree(e->d_pool);
   if (e->d_slots) cudaFree(e->d_slots);
   if (e->d_block) cudaFree(e->d_block);
@@ -1272,6 +1280,80 @@ int c3_evaluate_many(c3_engine** engines, int n, double* lnL) {
   return rc;
 }
 
+int c3_comm_mailbox(c3_engine* e, int nranks, void** device_ptr, unsigned char* ipc_handle) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  C3_REQUIRE(nranks >= 1 && nranks <= C3_MAX_RANKS, "nranks must be in [1, 16]");
+  C3_CUDA(cudaSetDevice(e->device));
+  if (e->d_mailbox == nullptr || e->mailbox_ranks != nranks) {
+    C3_REQUIRE(e->comm.nranks == 0, "detach before resizing the mailbox");
+    if (e->d_mailbox) C3_CUDA(cudaFree(e->d_mailbox));
+    e->d_mailbox = nullptr;
+    const size_t bytes = (size_t)2 * nranks * sizeof(CommSlot);
+    C3_CUDA(cudaMalloc(&e->d_mailbox, bytes));
+    C3_CUDA(cudaMemset(e->d_mailbox, 0, bytes));  // epoch 0 is never used by an evaluation
+    e->mailbox_ranks = nranks;
+  }
+  if (device_ptr) *device_ptr = e->d_mailbox;
+  if (ipc_handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    C3_CUDA(cudaIpcGetMemHandle(&h, e->d_mailbox));
+    std::memcpy(ipc_handle, &h, sizeof h);
+  }
+  return C3_OK;
+}
+
+int c3_comm_attach(c3_engine* e, int nranks, int rank, const unsigned char* ipc_handles, void* const* device_ptrs) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  C3_REQUIRE(nranks >= 1 && nranks <= C3_MAX_RANKS && rank >= 0 && rank < nranks, "bad rank / nranks");
+  C3_REQUIRE(e->d_mailbox != nullptr && e->mailbox_ranks == nranks, "call c3_comm_mailbox(nranks) first");
+  C3_REQUIRE(ipc_handles != nullptr || device_ptrs != nullptr || nranks == 1, "no peer mailboxes given");
+  C3_REQUIRE(e->comm.nranks == 0, "already attached");
+  C3_CUDA(cudaSetDevice(e->device));
+  CommArgs c{};
+  c.nranks = nranks;
+  c.rank = rank;
+  c.epoch = 0;
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      c.peer[r] = e->d_mailbox;
+    } else if (device_ptrs != nullptr) {
+      C3_REQUIRE(device_ptrs[r] != nullptr, "null peer mailbox");
+      c.peer[r] = static_cast<CommSlot*>(device_ptrs[r]);
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, ipc_handles + (size_t)r * sizeof h, sizeof h);
+      void* p = nullptr;
+      cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+      if (err != cudaSuccess) {
+        for (void* q : e->ipc_opened) cudaIpcCloseMemHandle(q);
+        e->ipc_opened.clear();
+        return fail(C3_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer access between the GPUs?): ") +
+                                     cudaGetErrorString(err));
+      }
+      e->ipc_opened.push_back(p);
+      c.peer[r] = static_cast<CommSlot*>(p);
+    }
+  }
+  e->comm = c;
+  // a cached value is a shard value: it must not be served as the total
+  e->have_cached = false;
+  e->reduce_dirty = true;
+  return C3_OK;
+}
+
+int c3_comm_detach(c3_engine* e) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  C3_CUDA(cudaSetDevice(e->device));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
+  e->ipc_opened.clear();
+  e->comm = CommArgs{};
+  e->have_cached = false;
+  e->reduce_dirty = true;
+  return C3_OK;
+}
+
 int c3_update(c3_engine* e, const double* d, double* lnL) {
   int rc = c3_set_distances(e, d);
   if (rc) return rc;
@@ -1731,13 +1813,16 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     ++n_launch;
   }
   {
+    CommArgs comm = e->comm;
+    if (comm.nranks > 1) comm.epoch = ++e->comm.epoch;  // every rank evaluates in lock-step
     const int64_t rows = e->n_rows[e->root];
     const int n_tiles = (int)((rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
     const int grid = std::min(n_tiles, e->n_sm * 8);
     ProfScope ps(e, 4, rows * (K + 1) * 8, 0);
     lnl_reduce_kernel<<<grid, REDUCE_THREADS, 0, e->stream>>>(
         e->d_lh, reinterpret_cast<const double*>(e->d_block + e->off_bprobs), e->d_counts, rows, K, n_tiles,
-        e->d_tile_sums, e->d_counter, e->d_lnl, device_out, (blocking || deferred) ? e->h_lnl_dev : nullptr);
+        e->d_tile_sums, e->d_counter, e->d_lnl, device_out, (blocking || deferred) ? e->h_lnl_dev : nullptr,
+        comm);
     ++n_launch;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(err));

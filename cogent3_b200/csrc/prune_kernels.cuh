@@ -1564,12 +1564,32 @@ __device__ __forceinline__ double block_sum(double v, double* s_warp) {
   return total;  // valid on thread 0
 }
 
+// Sharded runs (CommArgs.nranks > 1): the last CTA then turns the shard's sum into the TOTAL over
+// all ranks of the node without a separate collective -- thread r stores (value, epoch) into
+// rank r's mailbox over NVLink (value, fence.sys, epoch), every rank waits until its own mailbox
+// holds all nranks values of this epoch and adds them in rank order (deterministic and identical
+// on every rank).  Two mailbox parities: a rank can be at most one evaluation ahead of another.
+// A bounded wait (5 s) turns a missing peer into NaN instead of a hung GPU.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(REDUCE_THREADS)
 lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bprobs,
                   const double* __restrict__ counts, int64_t n_rows, int K, int n_tiles,
                   double* __restrict__ tile_sums, unsigned int* __restrict__ counter,
                   double* __restrict__ d_lnl, double* __restrict__ d_lnl2,
-                  volatile double* __restrict__ h_lnl) {
+                  volatile double* __restrict__ h_lnl, const CommArgs comm) {
   __shared__ double s_warp[REDUCE_THREADS / 32];
   __shared__ bool s_last;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -1603,7 +1623,39 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
   __threadfence();
   double acc = 0.0;
   for (int i = threadIdx.x; i < n_tiles; i += REDUCE_THREADS) acc += __ldcg(tile_sums + i);
-  const double total = block_sum(acc, s_warp);
+  double total = block_sum(acc, s_warp);
+  if (comm.nranks > 1) {
+    __shared__ double s_shard[C3_MAX_RANKS];
+    __shared__ double s_local;
+    if (threadIdx.x == 0) s_local = total;
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < comm.nranks) {
+      const int parity = (int)(comm.epoch & 1ull);
+      // my value into rank r's mailbox
+      CommSlot* dst = comm.peer[r] + parity * comm.nranks + comm.rank;
+      *reinterpret_cast<volatile double*>(&dst->value) = s_local;
+      st_release_sys_u64(&dst->epoch, comm.epoch);
+      // rank r's value out of my mailbox
+      const CommSlot* src = comm.peer[comm.rank] + parity * comm.nranks + r;
+      const unsigned long long t0 = globaltimer_ns();
+      double v = __longlong_as_double(0x7ff8000000000000ll);  // NaN unless the peer shows up
+      while (true) {
+        if (ld_acquire_sys_u64(&src->epoch) == comm.epoch) {
+          v = *reinterpret_cast<const volatile double*>(&src->value);
+          break;
+        }
+        if (globaltimer_ns() - t0 > 5000000000ull) break;
+        __nanosleep(200);
+      }
+      s_shard[r] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      total = 0.0;
+      for (int i = 0; i < comm.nranks; ++i) total += s_shard[i];
+    }
+  }
   if (threadIdx.x == 0) {
     *d_lnl = total;
     if (d_lnl2) *d_lnl2 = total;

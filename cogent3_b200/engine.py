@@ -155,6 +155,30 @@ class LikelihoodEngine:
         _lib.check(self._lib.c3_get_site_lh(self._h, int(bin_), _dptr(out), out.shape[0]))
         return out
 
+    # -- sharded runs: the all-reduce fused into the reduction kernel ------------------------
+    def comm_mailbox(self, nranks):
+        """allocate this rank's mailbox; returns (device pointer, 64-byte CUDA IPC handle)"""
+        ptr = c_void_p()
+        handle = (ctypes.c_uint8 * 64)()
+        _lib.check(self._lib.c3_comm_mailbox(self._h, int(nranks), byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def comm_attach(self, nranks, rank, ipc_handles=None, device_ptrs=None):
+        """peers' mailboxes: ``ipc_handles`` = list of 64-byte handles (one per rank, other
+        processes) or ``device_ptrs`` = list of device pointers valid in this process.  From
+        now on ``evaluate`` returns the TOTAL over all ranks."""
+        hbuf = pbuf = None
+        if ipc_handles is not None:
+            raw = b"".join(ipc_handles)
+            assert len(raw) == 64 * nranks
+            hbuf = (ctypes.c_uint8 * len(raw)).from_buffer_copy(raw)
+        if device_ptrs is not None:
+            pbuf = (c_void_p * nranks)(*[int(p) for p in device_ptrs])
+        _lib.check(self._lib.c3_comm_attach(self._h, int(nranks), int(rank), hbuf, pbuf))
+
+    def comm_detach(self):
+        _lib.check(self._lib.c3_comm_detach(self._h))
+
     # -- lifetime ------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -170,6 +194,11 @@ class LikelihoodEngine:
     def set_stream(self, stream):
         """``stream``: a ``torch.cuda.Stream`` / raw cudaStream_t int / None"""
         raw = getattr(stream, "cuda_stream", stream)
+        if stream is not None and not raw:
+            # torch's default stream is handle 0, which the C ABI reads as "create your own":
+            # name the legacy default stream explicitly (cudaStreamLegacy) so that work issued by
+            # torch on its current stream (an NCCL all-reduce of the result) is ordered after ours
+            raw = 1
         _lib.check(self._lib.c3_set_stream(self._h, c_void_p(raw) if raw else None))
 
     # -- model state ---------------------------------------------------------

@@ -72,7 +72,9 @@ C3_API int c3_device_count(int* n);
 C3_API int c3_create(int device, int n_nodes, int n_states, int n_bins,
               const int32_t* child_ptr, const int32_t* child_idx, c3_engine** out);
 C3_API int c3_destroy(c3_engine* e);
-/* run on the caller's CUDA stream (e.g. torch's current stream); NULL = own    */
+/* run on the caller's CUDA stream (e.g. torch's current stream); NULL = a stream of
+ * the engine's own.  The legacy default stream is named by its CUDA handle
+ * cudaStreamLegacy ((void*)1), not by NULL.                                      */
 C3_API int c3_set_stream(c3_engine* e, void* cuda_stream);
 
 /* ---- pattern tables (set once per alignment) -------------------------------
@@ -162,6 +164,24 @@ C3_API int c3_invalidate(c3_engine* e); /* force a full recomputation next time 
 C3_API int c3_evaluate(c3_engine* e, double* lnL);
 C3_API int c3_evaluate_device(c3_engine* e, double* device_lnL);
 C3_API int c3_update(c3_engine* e, const double* distance_of_edge_bin, double* lnL);
+
+/* ---- site-pattern shards on the GPUs of one node ----------------------
+ * Each rank (one process per GPU) holds a column block of the alignment in its own engine
+ * and the log-likelihood is the sum over ranks (the multi-locus / multi-cpu sum of
+ * SumDefn, recalculation/definition.py:672-676; likelihood_calculation.py:140-145).  The
+ * sum is FUSED into the reduction kernel: its last CTA stores the shard value into every
+ * rank's mailbox over NVLink peer memory, waits for the other shards' values and adds them
+ * in rank order, so c3_evaluate returns the TOTAL on every rank without a collective call.
+ * c3_comm_mailbox: allocate this rank's mailbox; returns its device pointer and / or its
+ *             64-byte CUDA IPC handle (to be all-gathered by the host, any transport).
+ * c3_comm_attach: the peers' mailboxes, as IPC handles [nranks][64] (other processes) or as
+ *             device pointers valid in this process (several engines in one process).
+ *             Every rank must then evaluate the same number of times.
+ * c3_comm_detach: back to shard-local values.                                           */
+C3_API int c3_comm_mailbox(c3_engine* e, int nranks, void** device_ptr, unsigned char* ipc_handle);
+C3_API int c3_comm_attach(c3_engine* e, int nranks, int rank, const unsigned char* ipc_handles,
+                          void* const* device_ptrs);
+C3_API int c3_comm_detach(c3_engine* e);
 /* c3_evaluate_many: c3_evaluate for n independent engines (each on its own stream): all are
  *             launched before any is waited for, so small alignments -- the app layer's
  *             workload, hundreds of independent likelihood functions (app/evo.py:317-386,

@@ -346,3 +346,63 @@ def test_evaluate_many_matches_individual_evaluations():
     np.testing.assert_array_equal(again, got)
     assert all(lf.engine.stats()["last_launches"] == 0 for lf in many)
     assert len(evaluate_many([])) == 0
+
+
+def test_fused_allreduce_between_engines_in_one_process():
+    """c3_comm_*: column shards in separate engines; the reduction kernel's last CTA exchanges the
+    shard values through the peers' mailboxes and every engine returns the TOTAL (summed in rank
+    order).  Here the "ranks" are three engines of one process (mailboxes shared by device
+    pointer), evaluated together with c3_evaluate_many; across processes the mailboxes are
+    mapped through CUDA IPC handles (tools/check_fused_allreduce.py, run under torchrun)."""
+    from cogent3_b200.engine import evaluate_many as engine_many
+    from cogent3_b200.sharded import column_block
+
+    m = hostmodels.get_model("HKY85")
+    topo, lengths, codes = make_workload(14, 30_000, 4, kind="evolved", seed=23)
+    world = 3
+
+    def make(cols):
+        lf = LikelihoodFunction(m, topo, bins=4)
+        lf.set_alignment(cols)
+        lf.set_motif_probs(np.array([0.2, 0.3, 0.25, 0.25]))
+        lf.lengths[:-1] = np.asarray(lengths)[:-1]
+        lf.set_param_rule("kappa", value=3.0)
+        lf.set_param_rule("rate_shape", value=0.8)
+        return lf
+
+    shards = [make(codes[:, slice(*column_block(codes.shape[1], world, r))]) for r in range(world)]
+    local = [lf.get_log_likelihood() for lf in shards]
+    want = 0.0
+    for v in local:  # rank order, like the kernel
+        want += v
+    whole = make(codes).get_log_likelihood()
+    assert abs(want - whole) <= 1e-12 * abs(whole)
+
+    ptrs = [lf.engine.comm_mailbox(world)[0] for lf in shards]
+    for r, lf in enumerate(shards):
+        lf.engine.comm_attach(world, r, device_ptrs=ptrs)
+    for lf in shards:
+        lf._sync()
+    got = engine_many([lf.engine for lf in shards])
+    assert list(got) == [want] * world
+    # more evaluations (both mailbox parities), dirty-path updates included
+    rng = np.random.default_rng(4)
+    for _ in range(4):
+        n = int(rng.choice(topo.edges))
+        v = float(rng.uniform(0.02, 0.4))
+        for lf in shards:
+            lf.set_param_rule("length", edge=topo.names[n], value=v)
+            lf._sync()
+        got = engine_many([lf.engine for lf in shards])
+        assert len(set(got)) == 1
+        ref = make(codes)
+        ref.lengths[:] = shards[0].lengths
+        assert abs(got[0] - ref.get_log_likelihood()) <= 1e-12 * abs(got[0])
+    # nothing changed: every rank serves the cached TOTAL, no launch
+    again = engine_many([lf.engine for lf in shards])
+    np.testing.assert_array_equal(again, got)
+    # detached engines give shard values again
+    for lf in shards:
+        lf.engine.comm_detach()
+    back = [lf.engine.evaluate() for lf in shards]
+    assert abs(sum(back) - got[0]) <= 1e-12 * abs(got[0]) and len(set(back)) == world
