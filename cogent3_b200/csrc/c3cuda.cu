@@ -297,12 +297,14 @@ int launch_flow(c3_engine* e, const PruneArgs& a, const int32_t* d_dep, unsigned
   return C3_OK;
 }
 
-template <int K>
+template <int K, int NC>
 int launch_reg2(c3_engine* e, const PruneArgs& a, bool is_root) {
-  const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + 7) / 8));
+  constexpr int U = (NC == 2) ? 4 : 2;
+  constexpr int WARPS = (NC == 2) ? 8 : 12;
+  const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + WARPS - 1) / WARPS));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(WARPS * 32);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = e->stream;
   cudaLaunchAttribute attr[1];
@@ -310,8 +312,8 @@ int launch_reg2(c3_engine* e, const PruneArgs& a, bool is_root) {
   attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune4_reg2_kernel<K, true>, a)
-                            : cudaLaunchKernelEx(&cfg, prune4_reg2_kernel<K, false>, a);
+  cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune4_reg2_kernel<K, NC, U, WARPS, true>, a)
+                            : cudaLaunchKernelEx(&cfg, prune4_reg2_kernel<K, NC, U, WARPS, false>, a);
   if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("regpipe2 launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
@@ -340,8 +342,8 @@ int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
   case KK:                                                                                        \
     if (e->use_ring)                                                                              \
       rc = (kind == 2) ? launch_strip<KK, 2>(e, a, is_root) : launch_strip<KK, 3>(e, a, is_root); \
-    else if (kind == 2 && e->use_reg2)                                                            \
-      rc = launch_reg2<KK>(e, a, is_root);                                                        \
+    else if (e->use_reg2)                                                                         \
+      rc = (kind == 2) ? launch_reg2<KK, 2>(e, a, is_root) : launch_reg2<KK, 3>(e, a, is_root);   \
     else                                                                                          \
       rc = (kind == 2) ? launch_reg<KK, 2>(e, a, is_root) : launch_reg<KK, 3>(e, a, is_root);     \
     break;
@@ -411,7 +413,8 @@ int kind_of_node(const c3_engine* e, int n) {
 int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
   if (kind == 6) return (int64_t)e->K * ((e->n_rows[n] + DR_TILE_ROWS - 1) / DR_TILE_ROWS);
   if (kind >= 2) {
-    const int rows = 128 / e->K;
+    // strips of 128 (row, bin) units; regpipe2 walks three-children nodes in strips of 64
+    const int rows = ((kind == 3 && e->use_reg2 && !e->use_ring) ? 64 : 128) / e->K;
     return (e->n_rows[n] + rows - 1) / rows;
   }
   if (!e->use_dmma) {
@@ -1786,13 +1789,15 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
         small_cfg = true;
       }
       cfg.stream = e->stream;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = ctas;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
       cfg.attrs = attr;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = 2;
       cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel, a, d_small, ll.n_small, ll.n_work,
                                            ll.n_work + ll.n_small);
       if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("small-level launch: ") + cudaGetErrorString(err));
@@ -1819,12 +1824,24 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     const int n_tiles = (int)((rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
     const int grid = std::min(n_tiles, e->n_sm * 8);
     ProfScope ps(e, 4, rows * (K + 1) * 8, 0);
-    lnl_reduce_kernel<<<grid, REDUCE_THREADS, 0, e->stream>>>(
-        e->d_lh, reinterpret_cast<const double*>(e->d_block + e->off_bprobs), e->d_counts, rows, K, n_tiles,
-        e->d_tile_sums, e->d_counter, e->d_lnl, device_out, (blocking || deferred) ? e->h_lnl_dev : nullptr,
-        comm);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(REDUCE_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const double* a_lh = e->d_lh;
+    const double* a_bp = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
+    const double* a_counts = e->d_counts;
+    volatile double* a_host = (blocking || deferred) ? e->h_lnl_dev : nullptr;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, lnl_reduce_kernel, a_lh, a_bp, a_counts, (int64_t)rows, K, n_tiles,
+                                         e->d_tile_sums, e->d_counter, e->d_lnl, device_out, a_host, comm);
     ++n_launch;
-    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(err));
   }
 

@@ -653,11 +653,11 @@ __global__ void __launch_bounds__(RegCfg<NC>::WARPS * 32, 1) prune4_reg_kernel(c
 // the middle of the FMA block and the kernel was 9 % slower than regpipe).  Largest C2 level:
 // 4.78 -> 5.29 TB/s; C5 levels 5.7-6.0 TB/s (the measured copy bandwidth is 6.55).  248 registers.
 // ---------------------------------------------------------------------------------------
-template <int K, bool ROOT>
-__global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) {
-  constexpr int NC = 2;
-  constexpr int ROWS = 128 / K;
-  constexpr int WARPS = 8;
+// Instantiated as <K, 2 children, U = 4 rows per lane, 8 warps> (248 registers) and, for the
+// trifurcating root, <K, 3, 2, 12> (strips of 64 units, 12 warps per SM instead of regpipe's 6).
+template <int K, int NC, int U, int WARPS, bool ROOT>
+__global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneArgs a) {
+  constexpr int ROWS = 32 * U / K;  // pattern rows per strip
   __shared__ StripSmem<NC> sd;
   __shared__ __align__(16) double sPall[WARPS][NC * K * P4S_PSTRIDE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -688,12 +688,12 @@ __global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) 
   const int slot = lane / K;
 
   int i_w = 0, g_w = 0, c_w = 0, p_w = -1;
-  auto load_idx = [&](int32_t(&ix)[NC][P4S_U], int s) {
+  auto load_idx = [&](int32_t(&ix)[NC][U], int s) {
     while (s >= sd.prefix[i_w + 1]) ++i_w;
     const WorkDesc<NC>& wd = sd.work[i_w];
     const int64_t row0 = (int64_t)(s - sd.prefix[i_w]) * ROWS;
 #pragma unroll
-    for (int u = 0; u < P4S_U; ++u) {
+    for (int u = 0; u < U; ++u) {
       int64_t p = row0 + u * (32 / K) + slot;
       if (p >= wd.n_rows) p = wd.n_rows - 1;
 #pragma unroll
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) 
 
   // compute strip s from x; refill x with strip s + 2 GW (indexes ix, requested two steps ago);
   // then request the indexes of strip s + 4 GW into ix
-  auto step = [&](d4(&x)[NC][P4S_U], int32_t(&ix)[NC][P4S_U], int s) {
+  auto step = [&](d4(&x)[NC][U], int32_t(&ix)[NC][U], int s) {
     while (s >= sd.prefix[c_w + 1]) ++c_w;
     const WorkDesc<NC>& wd = sd.work[c_w];
     if (c_w != p_w) {
@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) 
     }
     const bool refill = s + 2 * GW < total;
     if (refill) gather_seek(s + 2 * GW);
-    d4 acc[P4S_U];
+    d4 acc[U];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const double* Pc = sP + (c * K + b) * P4S_PSTRIDE;
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) 
         const double2 p01 = *reinterpret_cast<const double2*>(Pc + 4 * i);
         const double2 p23 = *reinterpret_cast<const double2*>(Pc + 4 * i + 2);
 #pragma unroll
-        for (int u = 0; u < P4S_U; ++u) {
+        for (int u = 0; u < U; ++u) {
           const double y =
               fma(x[c][u].w, p23.y, fma(x[c][u].z, p23.x, fma(x[c][u].y, p01.y, x[c][u].x * p01.x)));
           double& t = (i == 0) ? acc[u].x : (i == 1) ? acc[u].y : (i == 2) ? acc[u].z : acc[u].w;
@@ -744,14 +744,14 @@ __global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) 
       }
       if (refill) {
 #pragma unroll
-        for (int u = 0; u < P4S_U; ++u) x[c][u] = ld256_nc(gsrc[c] + ((int64_t)ix[c][u] * K + b) * 4);
+        for (int u = 0; u < U; ++u) x[c][u] = ld256_nc(gsrc[c] + ((int64_t)ix[c][u] * K + b) * 4);
       }
     }
     if (s + 4 * GW < total) load_idx(ix, s + 4 * GW);
     const int64_t node_row0 = (int64_t)(s - sd.prefix[c_w]) * ROWS;
     const int c_fixed = wd.fixed_motif;
 #pragma unroll
-    for (int u = 0; u < P4S_U; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t p = node_row0 + u * (32 / K) + slot;
       if (c_fixed >= 0) {
         if (c_fixed != 0) acc[u].x = 0.0;
@@ -770,8 +770,8 @@ __global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) 
     }
   };
 
-  d4 xa[NC][P4S_U], xb[NC][P4S_U];
-  int32_t ia[NC][P4S_U], ib[NC][P4S_U];
+  d4 xa[NC][U], xb[NC][U];
+  int32_t ia[NC][U], ib[NC][U];
   // prologue: strips gw, gw+GW into the buffers; indexes of gw+2GW, gw+3GW into the index sets
   if (gw < total) load_idx(ia, gw);  // static data: may overlap the previous launch
   if (gw + GW < total) load_idx(ib, gw + GW);
@@ -781,14 +781,14 @@ __global__ void __launch_bounds__(256, 1) prune4_reg2_kernel(const PruneArgs a) 
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int u = 0; u < P4S_U; ++u) xa[c][u] = ld256_nc(gsrc[c] + ((int64_t)ia[c][u] * K + b) * 4);
+      for (int u = 0; u < U; ++u) xa[c][u] = ld256_nc(gsrc[c] + ((int64_t)ia[c][u] * K + b) * 4);
   }
   if (gw + GW < total) {
     gather_seek(gw + GW);
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int u = 0; u < P4S_U; ++u) xb[c][u] = ld256_nc(gsrc[c] + ((int64_t)ib[c][u] * K + b) * 4);
+      for (int u = 0; u < U; ++u) xb[c][u] = ld256_nc(gsrc[c] + ((int64_t)ib[c][u] * K + b) * 4);
   }
   if (gw + 2 * GW < total) load_idx(ia, gw + 2 * GW);
   if (gw + 3 * GW < total) load_idx(ib, gw + 3 * GW);
@@ -1103,6 +1103,7 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
     }
     __syncthreads();
   }
+  pdl_wait();  // P matrices / tip tables of the expm launch, rows of earlier levels
   for (int li = 0; li < n_levels; ++li) {
     const SmallLevel L = staged ? sm.levels[li] : levels[li];
     const int32_t* prefix = (staged ? sm.prefix : a.tile_prefix) + L.prefix_off;
@@ -1592,6 +1593,7 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
                   volatile double* __restrict__ h_lnl, const CommArgs comm) {
   __shared__ double s_warp[REDUCE_THREADS / 32];
   __shared__ bool s_last;
+  pdl_wait();  // launched early (programmatic dependent launch): lh is the root launch's output
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     double acc = 0.0;
     const int64_t base = (int64_t)tile * REDUCE_ROWS_PER_TILE;
