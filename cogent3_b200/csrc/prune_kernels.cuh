@@ -1467,10 +1467,11 @@ __global__ void __launch_bounds__(DR_THREADS, 1) prune_dmma_reg_kernel(const Pru
         if (wd.P[c] == nullptr) continue;
         double* sB = smem + wd.slot[c] * Cfg::B_DOUBLES;
         const double* P = wd.P[c] + (int64_t)cc.b * MP * MP;
+        // coalesced reads of P; column j = 8a + 2q + b lands at position 4 (2a + b) + q
         for (int o = tid; o < MP * MP; o += DR_THREADS) {
-          const int i = o / MP, pos = o - i * MP;
-          const int s = pos >> 2, qq = pos & 3;
-          sB[i * LDS + pos] = P[i * MP + 8 * (s >> 1) + 2 * qq + (s & 1)];
+          const int i = o / MP, j = o - i * MP;
+          const int pos = (j & ~7) + ((j & 1) << 2) + ((j >> 1) & 3);
+          sB[i * LDS + pos] = P[o];
         }
       }
       res_w = cc.w;
