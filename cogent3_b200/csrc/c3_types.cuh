@@ -27,6 +27,9 @@ struct NodeDesc {
   int32_t n_children;
   int32_t fixed_motif;  // -1: none (PartialLikelihoodProductDefnFixedMotif)
   int32_t is_root;
+  // edge-major engines (M != 4): the node stores its rows already multiplied by the P of the
+  // branch above it; P_own = that P [K][MP][MP], nullptr for the root
+  const double* P_own;
 };
 
 // per edge (node with a branch above it)

@@ -115,6 +115,9 @@ struct c3_engine {
   int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0, off_small = 0;
   bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
   bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
+  // M != 4: every node stores its rows already multiplied by the P of the branch above it, one
+  // contraction per NODE row (prune_dmma_edge_kernel); C3_EDGE_MAJOR=0: the parent-major kernels
+  bool edge_major = false;
   bool use_dmma_reg = true;  // warp-private register pipeline for M != 4 (C3_DMMA_REG=0: first version)
   bool use_reg2 = true;   // binary nodes: two strips in flight per warp (C3_REG1=1: the one-strip regpipe kernel)
   bool use_ring = false;  // C3_RING=1: the cp.async shared-memory ring version of the strip kernel
@@ -212,6 +215,31 @@ int launch_dmma_reg(c3_engine* e, const PruneArgs& a, bool is_root) {
   cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune_dmma_reg_kernel<MP, true>, a)
                             : cudaLaunchKernelEx(&cfg, prune_dmma_reg_kernel<MP, false>, a);
   if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("dmma-reg launch: ") + cudaGetErrorString(err));
+  return C3_OK;
+}
+
+template <int MP>
+int launch_dmma_edge(c3_engine* e, const PruneArgs& a) {
+  const size_t smem = (size_t)MP * (MP + 4) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_max_smem(prune_dmma_edge_kernel<MP>, smem);
+    if (rc) return rc;
+    configured = true;
+  }
+  const int grid = std::max(1, std::min(a.total_tiles, e->n_sm));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(DE_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP>, a);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("dmma-edge launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
 
@@ -322,7 +350,21 @@ int launch_reg2(c3_engine* e, const PruneArgs& a, bool is_root) {
 // nodes with that many children (4-state, K in {1,2,4}); 6 = register-pipeline DMMA kernel
 int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
   if (a.total_tiles <= 0) return C3_OK;
-  if (kind == 6) {
+  if (kind == 8) {
+    int rc = C3_OK;
+    switch (e->MP) {
+      case 8: rc = launch_dmma_edge<8>(e, a); break;
+      case 16: rc = launch_dmma_edge<16>(e, a); break;
+      case 24: rc = launch_dmma_edge<24>(e, a); break;
+      case 32: rc = launch_dmma_edge<32>(e, a); break;
+      case 40: rc = launch_dmma_edge<40>(e, a); break;
+      case 48: rc = launch_dmma_edge<48>(e, a); break;
+      case 56: rc = launch_dmma_edge<56>(e, a); break;
+      case 64: rc = launch_dmma_edge<64>(e, a); break;
+      default: return fail(C3_ERR_INVALID, "unsupported padded state count");
+    }
+    if (rc) return rc;
+  } else if (kind == 6) {
     int rc = C3_OK;
     switch (e->MP) {
       case 8: rc = launch_dmma_reg<8>(e, a, is_root); break;
@@ -394,6 +436,7 @@ int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
 
 // which kernel family handles node n (see launch_prune)
 int kind_of_node(const c3_engine* e, int n) {
+  if (e->use_dmma && e->edge_major) return 8;
   if (e->use_dmma) {
     // register-pipeline DMMA kernel; nodes with more children / contraction children than it
     // stages fall back to the first version
@@ -411,6 +454,7 @@ int kind_of_node(const c3_engine* e, int n) {
 }
 
 int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
+  if (kind == 8) return (int64_t)e->K * ((e->n_rows[n] + DE_TILE_ROWS - 1) / DE_TILE_ROWS);
   if (kind == 6) return (int64_t)e->K * ((e->n_rows[n] + DR_TILE_ROWS - 1) / DR_TILE_ROWS);
   if (kind >= 2) {
     // strips of 128 (row, bin) units; regpipe2 walks three-children nodes in strips of 64
@@ -511,6 +555,8 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_SMALL")) e->use_small = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
   if (const char* env = getenv("C3_DMMA_REG")) e->use_dmma_reg = atoi(env) != 0;
+  e->edge_major = e->use_dmma;
+  if (const char* env = getenv("C3_EDGE_MAJOR")) e->edge_major = e->use_dmma && atoi(env) != 0;
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   if (const char* env = getenv("C3_REG1")) e->use_reg2 = atoi(env) == 0;
   if (const char* env = getenv("C3_FLOW")) e->use_flow = atoi(env) != 0;
@@ -1076,12 +1122,14 @@ int c3_finalize(c3_engine* e) {
     nd.n_children = (int)e->children[n].size();
     nd.fixed_motif = -1;
     nd.is_root = (n == e->root);
+    nd.P_own = (e->edge_major && n != e->root && !e->children[n].empty()) ? e->d_P + (int64_t)n * K * MP * MP : nullptr;
     for (size_t c = 0; c < e->children[n].size(); ++c) {
       const int ch = e->children[n][c];
       ChildRef& cr = h_childs[e->child_begin[n] + c];
       cr.src = e->d_rows[ch];
       cr.idx = e->d_idx[n] + c * e->n_rows[n];
-      cr.P = e->children[ch].empty() ? nullptr : e->d_P + (int64_t)ch * K * MP * MP;
+      // edge-major: every child's rows are already multiplied by its P (like tips always were)
+      cr.P = (e->children[ch].empty() || e->edge_major) ? nullptr : e->d_P + (int64_t)ch * K * MP * MP;
       cr.src_rows = e->n_rows[ch];
     }
     EdgeDesc& ed = h_edges[n];
@@ -1395,6 +1443,20 @@ int c3_get_partials(c3_engine* e, int node, int bin, double* out, int64_t n_rows
   C3_CUDA(cudaSetDevice(e->device));
   C3_CUDA(cudaStreamSynchronize(e->stream));
   const int M = e->M, MP = e->MP;
+  if (e->edge_major && node != e->root && !e->children[node].empty()) {
+    // the stored rows are P . plh; the accessor returns plh = product of the children's rows
+    double* tmp = nullptr;
+    C3_CUDA(cudaMalloc(&tmp, (size_t)n_rows * MP * sizeof(double)));
+    const int grid = (int)std::min<int64_t>((n_rows * MP + 255) / 256, (int64_t)e->n_sm * 8);
+    edge_major_plh_kernel<<<grid, 256, 0, e->stream>>>(e->h_nodes[node], e->d_childs, e->K, MP, bin, tmp);
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    if (err == cudaSuccess)
+      err = cudaMemcpy2D(out, M * sizeof(double), tmp, MP * sizeof(double), M * sizeof(double), (size_t)n_rows,
+                         cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("c3_get_partials: ") + cudaGetErrorString(err));
+    return C3_OK;
+  }
   // rows are [row][bin][MP]; for a tip this returns the P-multiplied tip table
   C3_CUDA(cudaMemcpy2D(out, M * sizeof(double), e->d_rows[node] + (int64_t)bin * MP,
                        (size_t)e->K * MP * sizeof(double), M * sizeof(double), (size_t)n_rows,
@@ -1528,7 +1590,13 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   for (int n = 0; n < N; ++n) {
     if (e->children[n].empty()) continue;
     bool d = e->node_dirty[n] != 0;
-    for (int c : e->children[n]) d = d || edge_touched[c] || recompute[c];
+    if (e->edge_major) {
+      // a node's rows include the P of the branch above it: that branch dirties the node itself
+      for (int c : e->children[n]) d = d || recompute[c] || (edge_touched[c] && e->children[c].empty());
+      d = d || (n != e->root && edge_touched[n]);
+    } else {
+      for (int c : e->children[n]) d = d || edge_touched[c] || recompute[c];
+    }
     if (d) {
       recompute[n] = 1;
       ++n_dirty_nodes;
@@ -1563,8 +1631,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     alg_bytes += rows * K * M * 8;  // write
     for (int c : e->children[n]) {
       alg_bytes += e->n_rows[c] * K * M * 8 + rows * 4;  // child rows once + gather index
-      if (!e->children[c].empty()) flops += rows * K * 2 * (int64_t)(e->use_dmma ? MP * MP : M * M);
+      if (!e->edge_major && !e->children[c].empty())
+        flops += rows * K * 2 * (int64_t)(e->use_dmma ? MP * MP : M * M);
     }
+    if (e->edge_major && n != e->root) flops += rows * K * 2 * (int64_t)MP * MP;  // one contraction per node row
     if (n == e->root) alg_bytes += rows * K * 8;
   };
   int open_small = -1;  // index into launches of the small group being extended
@@ -1633,7 +1703,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     // nodes the dataflow kernel cannot take are launched on their own, BEFORE the group that
     // this level's binary nodes open (later levels of the group may depend on them)
     if (other_kinds || !flow_ok) close_flow();
-    for (int kind : {0, 3, 6, 2}) {
+    for (int kind : {0, 3, 6, 8, 2}) {
       if (kind == 2 && flow_ok) {
         for (int n : order) {
           if (!recompute[n] || kind_of_node(e, n) != 2) continue;
@@ -1666,7 +1736,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       int64_t bytes0 = alg_bytes, flops0 = flops;
       for (int n : e->level_nodes[l]) {
         if (!recompute[n] || kind_of_node(e, n) != kind) continue;
-        if (kind >= 2 && ll.n_work == (kind == 6 ? DR_MAXW : P4S_MAXW)) {
+        if (kind >= 2 && ll.n_work == (kind == 8 ? DE_MAXW : (kind == 6 ? DR_MAXW : P4S_MAXW))) {
           // the strip kernel stages at most P4S_MAXW descriptors: close this launch, open another
           ll.bytes = alg_bytes - bytes0;
           ll.flops = flops - flops0;

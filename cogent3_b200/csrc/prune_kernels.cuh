@@ -1543,6 +1543,254 @@ __global__ void __launch_bounds__(DR_THREADS, 1) prune_dmma_reg_kernel(const Pru
 }
 
 // ---------------------------------------------------------------------------------------
+// DMMA kernel, EDGE-MAJOR ("dmma-edge") -- the production path for M != 4.
+//
+// The kernels above contract per PARENT row and internal child: 2 MP^2 flops for every
+// (parent pattern, internal edge).  cogent3 itself contracts per CHILD row
+// (numpy.inner(child_plh, psub), likelihood_calculation.py:86) and gathers afterwards; with
+// per-node pattern compression a child has far fewer rows than the parent patterns that
+// reference them (C4: 1.66M child rows vs 3.9M parent-row references), so the fused
+// parent-major form executes ~1.9x the reference's flops on the unit that bounds the codon
+// model.  Here every node stores its rows ALREADY multiplied by the P of the branch above it
+// (exactly what tips always did: tip_inner):
+//     inner_n[p, b, :] = P_n,b . ( prod_c inner_c[idx_c[p], b, :] )        (root: no P, + lh)
+// so a tile is: gather the children's rows (C-fragment layout, 128-bit loads), multiply them,
+// ONE contraction with the node's own P, store.  With the permuted k order of dmma-reg the
+// product in C-fragment layout IS the A fragment of the contraction (column pair ni of a lane
+// = k steps 2ni, 2ni+1): no shuffle, no shared-memory round trip.  Flops: 2 MP^2 per NODE row.
+// The numbers are the same as before (the contraction of a child row gives the same bits
+// wherever it is done); what changes is when a node is dirty: a changed branch recomputes the
+// node BELOW it too.  Pipeline: per warp, the two (first) children's rows of the next tile are in
+// flight while the current tile is multiplied and contracted; gather indexes one tile further.
+// ---------------------------------------------------------------------------------------
+constexpr int DE_WARPS = 12;
+constexpr int DE_THREADS = DE_WARPS * 32;
+constexpr int DE_TILE_ROWS = DE_WARPS * 8;
+constexpr int DE_MAXW = 64;  // work items per launch
+constexpr int DE_PRE = 2;    // children whose rows are prefetched (further ones: loaded at use)
+
+struct EWork {
+  double* out;
+  int64_t n_rows;
+  int64_t row_tiles;
+  const double* P_own;
+  const double* src[DE_PRE];
+  const int32_t* idx[DE_PRE];
+  int32_t child_begin;
+  int32_t nc;
+  int32_t fixed_motif;
+  int32_t is_root;
+};
+struct ESmem {
+  EWork work[DE_MAXW];
+  int32_t prefix[DE_MAXW + 1];
+};
+struct ECur {
+  int st;        // super-tile
+  int w;         // work item
+  int b;         // rate class
+  int64_t row0;  // first row of the super-tile
+};
+
+template <int MP>
+__global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const PruneArgs a) {
+  constexpr int LDS = MP + 4, NI = MP / 8, KS = MP / 4;
+  extern __shared__ __align__(16) double smem[];  // [MP * LDS]: the node's own P, columns permuted
+  __shared__ ESmem sd;
+  const int K = a.K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+
+  pdl_trigger();
+  for (int i = tid; i <= a.n_work; i += DE_THREADS) sd.prefix[i] = a.tile_prefix[i];
+  for (int i = tid; i < a.n_work; i += DE_THREADS) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    EWork& wd = sd.work[i];
+    wd.out = nd.out;
+    wd.n_rows = nd.n_rows;
+    wd.row_tiles = (nd.n_rows + DE_TILE_ROWS - 1) / DE_TILE_ROWS;
+    wd.P_own = nd.P_own;
+    wd.child_begin = nd.child_begin;
+    wd.nc = nd.n_children;
+    wd.fixed_motif = nd.fixed_motif;
+    wd.is_root = nd.is_root;
+    for (int c = 0; c < DE_PRE; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + (c < nd.n_children ? c : 0)];
+      wd.src[c] = ch.src;
+      wd.idx[c] = ch.idx;
+    }
+  }
+  __syncthreads();
+
+  const int per_cta = (a.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int st0 = (int)blockIdx.x * per_cta;
+  const int st1 = min(a.total_tiles, st0 + per_cta);
+  auto place = [&](ECur& cur) {
+    while (cur.st >= sd.prefix[cur.w + 1]) ++cur.w;
+    const EWork& wd = sd.work[cur.w];
+    const int local = cur.st - sd.prefix[cur.w];
+    cur.b = (int)(local / wd.row_tiles);
+    cur.row0 = (int64_t)(local - cur.b * wd.row_tiles) * DE_TILE_ROWS;
+  };
+  auto next = [&](ECur& cur) {
+    if (++cur.st < st1) place(cur);
+  };
+  auto my_row = [&](const ECur& cur) -> int64_t {  // clamped: rows past the end repeat the last
+    const int64_t p = cur.row0 + warp * 8 + g;
+    const int64_t last = sd.work[cur.w].n_rows - 1;
+    return p < last ? p : last;
+  };
+
+  ECur cc{st0, 0, 0, 0};
+  if (cc.st < st1) place(cc);
+  ECur fc = cc, ic = cc;
+  int32_t ix[DE_PRE] = {0, 0};
+  auto load_idx = [&]() {
+    if (ic.st < st1) {
+      const EWork& wi = sd.work[ic.w];
+      const int64_t p = my_row(ic);
+#pragma unroll
+      for (int c = 0; c < DE_PRE; ++c) ix[c] = __ldg(wi.idx[c] + p);  // (a single child is read twice)
+    }
+  };
+  double2 vn[DE_PRE][NI];
+  auto fetch = [&]() {  // rows of tile fc (gather rows in ix)
+    const EWork& wf = sd.work[fc.w];
+#pragma unroll
+    for (int c = 0; c < DE_PRE; ++c) {
+      const double* src = wf.src[c] + ((int64_t)ix[c] * K + fc.b) * MP + 2 * q;
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) vn[c][ni] = ld128_nc(src + 8 * ni);
+    }
+  };
+  load_idx();  // static data: may overlap the previous launch
+  pdl_wait();
+  if (fc.st < st1) {
+    fetch();
+    next(ic);
+    load_idx();
+  }
+
+  int res_w = -1, res_b = -1;
+#pragma unroll 1
+  while (cc.st < st1) {
+    const EWork& wd = sd.work[cc.w];
+    if ((cc.w != res_w || cc.b != res_b)) {
+      // another (node, rate class): every warp is done with the old P
+      __syncthreads();
+      if (wd.P_own != nullptr) {
+        const double* P = wd.P_own + (int64_t)cc.b * MP * MP;
+        // coalesced reads; column j = 8a + 2q + b lands at position 4 (2a + b) + q
+        for (int o = tid; o < MP * MP; o += DE_THREADS) {
+          const int i = o / MP, j = o - i * MP;
+          const int pos = (j & ~7) + ((j & 1) << 2) + ((j >> 1) & 3);
+          smem[i * LDS + pos] = P[o];
+        }
+      }
+      res_w = cc.w;
+      res_b = cc.b;
+      __syncthreads();
+    }
+    // product of the children's rows (C-fragment layout); then the next tile's rows are requested
+    double prod[NI][2];
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+      prod[ni][0] = vn[0][ni].x;
+      prod[ni][1] = vn[0][ni].y;
+    }
+    if (wd.nc >= 2) {
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        prod[ni][0] *= vn[1][ni].x;
+        prod[ni][1] *= vn[1][ni].y;
+      }
+    }
+    next(fc);
+    if (fc.st < st1) {
+      fetch();
+      next(ic);
+      load_idx();
+    }
+    const int64_t p = cc.row0 + warp * 8 + g;
+    const bool row_ok = p < wd.n_rows;
+    for (int c = DE_PRE; c < wd.nc; ++c) {  // third, ... child (trifurcating root, polytomies): at use
+      const ChildRef ch = a.childs[wd.child_begin + c];
+      const int32_t r = __ldg(ch.idx + (row_ok ? p : wd.n_rows - 1));
+      const double* src = ch.src + ((int64_t)r * K + cc.b) * MP + 2 * q;
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        const double2 v = ld128_nc(src + 8 * ni);
+        prod[ni][0] *= v.x;
+        prod[ni][1] *= v.y;
+      }
+    }
+    if (wd.fixed_motif >= 0) {
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) {
+        if (8 * ni + 2 * q != wd.fixed_motif) prod[ni][0] = 0.0;
+        if (8 * ni + 2 * q + 1 != wd.fixed_motif) prod[ni][1] = 0.0;
+      }
+    }
+    double* dst = wd.out + (p * K + cc.b) * MP + 2 * q;
+    if (wd.P_own == nullptr) {
+      // the root: plh itself, and lh = inner(plh_root, pi)
+      if (row_ok) {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni)
+          *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(prod[ni][0], prod[ni][1]);
+      }
+      if (wd.is_root) {
+        double sdot = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          sdot = fma(prod[ni][0], a.pi[8 * ni + 2 * q], sdot);
+          sdot = fma(prod[ni][1], a.pi[8 * ni + 2 * q + 1], sdot);
+        }
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+        if (row_ok && q == 0) a.lh_out[p * K + cc.b] = sdot;
+      }
+    } else {
+      double cur[NI][2];
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) cur[ni][0] = cur[ni][1] = 0.0;
+      const double* bRow = smem + g * LDS + q;
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const double av = prod[s >> 1][s & 1];
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) dmma_m8n8k4(cur[ni][0], cur[ni][1], av, bRow[(8 * ni) * LDS + 4 * s]);
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni)
+          *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(cur[ni][0], cur[ni][1]);
+      }
+    }
+    next(cc);
+  }
+}
+
+// plh of an edge-major node for the accessors: prod_c inner_c[idx_c[p]] (masked like the kernel)
+__global__ void __launch_bounds__(256)
+edge_major_plh_kernel(const NodeDesc nd, const ChildRef* __restrict__ childs, int K, int MP, int bin,
+                      double* __restrict__ out) {
+  const int64_t total = nd.n_rows * MP;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = o / MP;
+    const int j = (int)(o - p * MP);
+    double v = 1.0;
+    for (int c = 0; c < nd.n_children; ++c) {
+      const ChildRef ch = childs[nd.child_begin + c];
+      const double x = ch.src[((int64_t)ch.idx[p] * K + bin) * MP + j];
+      v = (c == 0) ? x : v * x;
+    }
+    if (nd.fixed_motif >= 0 && j != nd.fixed_motif) v = 0.0;
+    out[o] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // site-weighted log-likelihood reduction
 //   mix[p] = sum_b bprob_b lh_b[p]     BinnedSiteDistribution.get_weighted_sum_lh
 //                                      (evolve/likelihood_calculation.py:178-185)

@@ -73,7 +73,10 @@ def test_partial_update_equals_full_recompute(case):
         got = lf.get_log_likelihood()
         st = lf.engine.stats()
         assert st["last_expm_jobs"] == g.n_bins  # only that edge was re-exponentiated
-        assert st["last_nodes"] == len(g.topo.ancestors(n))  # only its ancestors re-pruned
+        # only its ancestors re-pruned -- plus, for M != 4 (edge-major: a node's rows include the P
+        # of the branch above it), the internal node below the changed branch
+        below = 1 if (g.n_states != 4 and not g.topo.is_tip[n]) else 0
+        assert st["last_nodes"] == len(g.topo.ancestors(n)) + below
         want = ref.get_log_likelihood()
         assert abs(got - want) <= REL_LNL * abs(want)
         lf.engine.invalidate()
@@ -238,10 +241,13 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
         assert lfs[0].get_log_likelihood() == got[0]
 
 
-def test_dmma_first_version_matches(monkeypatch):
-    """the first (shared-memory tile) DMMA kernel gives the same numbers as the default
-    register-pipeline kernel, to the tolerances (the k order differs)"""
-    monkeypatch.setenv("C3_DMMA_REG", "0")
+@pytest.mark.parametrize("env", [{"C3_EDGE_MAJOR": "0"}, {"C3_EDGE_MAJOR": "0", "C3_DMMA_REG": "0"}])
+def test_dmma_parent_major_kernels_match(env, monkeypatch):
+    """the parent-major DMMA kernels (register pipeline; first shared-memory-tile version) give the
+    same numbers as the default edge-major kernel, to the tolerances (the k order of the first
+    differs)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     for case in ("c4_cnfgtr_mid", "c4_cnfgtr_small", "kat_codon", "kat_dinucleotide", "kat_protein"):
         g = Golden(case)
         lf = lf_from_golden(g)
