@@ -542,7 +542,7 @@ def run_ours(args):
     except (OSError, ValueError, KeyError):
         pass
     roofline.update({
-        "kernel": "prune4_reg2_kernel" if M == 4 else "prune_dmma_reg_kernel",
+        "kernel": "prune4_reg2_kernel" if M == 4 else "prune_dmma_edge_kernel",
         "launches_per_step": len(prune[-1]), "kernel_ms_per_step": prune_ms,
         "kernel_share_of_step": prune_ms / step_ms if step_ms else None,
         "alg_bytes_per_step": prune_bytes, "executed_flops_per_step": prune_flops,

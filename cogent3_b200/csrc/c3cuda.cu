@@ -219,11 +219,13 @@ int launch_dmma_reg(c3_engine* e, const PruneArgs& a, bool is_root) {
 }
 
 template <int MP>
-int launch_dmma_edge(c3_engine* e, const PruneArgs& a) {
-  const size_t smem = (size_t)MP * (MP + 4) * sizeof(double);
+int launch_dmma_edge(c3_engine* e, const PruneArgs& a, bool root_only3) {
+  const size_t smem = (size_t)MP * (MP + 8) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    int rc = set_max_smem(prune_dmma_edge_kernel<MP>, smem);
+    int rc = set_max_smem(prune_dmma_edge_kernel<MP, 2, true>, smem);
+    if (rc) return rc;
+    rc = set_max_smem(prune_dmma_edge_kernel<MP, 3, false>, smem);
     if (rc) return rc;
     configured = true;
   }
@@ -238,7 +240,9 @@ int launch_dmma_edge(c3_engine* e, const PruneArgs& a) {
   attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP>, a);
+  // a launch holding only the trifurcating root: three prefetched children, no contraction
+  cudaError_t err = root_only3 ? cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 3, false>, a)
+                               : cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 2, true>, a);
   if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("dmma-edge launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
@@ -352,15 +356,16 @@ int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
   if (a.total_tiles <= 0) return C3_OK;
   if (kind == 8) {
     int rc = C3_OK;
+    const bool r3 = is_root && a.n_work == 1 && e->children[e->root].size() == 3;
     switch (e->MP) {
-      case 8: rc = launch_dmma_edge<8>(e, a); break;
-      case 16: rc = launch_dmma_edge<16>(e, a); break;
-      case 24: rc = launch_dmma_edge<24>(e, a); break;
-      case 32: rc = launch_dmma_edge<32>(e, a); break;
-      case 40: rc = launch_dmma_edge<40>(e, a); break;
-      case 48: rc = launch_dmma_edge<48>(e, a); break;
-      case 56: rc = launch_dmma_edge<56>(e, a); break;
-      case 64: rc = launch_dmma_edge<64>(e, a); break;
+      case 8: rc = launch_dmma_edge<8>(e, a, r3); break;
+      case 16: rc = launch_dmma_edge<16>(e, a, r3); break;
+      case 24: rc = launch_dmma_edge<24>(e, a, r3); break;
+      case 32: rc = launch_dmma_edge<32>(e, a, r3); break;
+      case 40: rc = launch_dmma_edge<40>(e, a, r3); break;
+      case 48: rc = launch_dmma_edge<48>(e, a, r3); break;
+      case 56: rc = launch_dmma_edge<56>(e, a, r3); break;
+      case 64: rc = launch_dmma_edge<64>(e, a, r3); break;
       default: return fail(C3_ERR_INVALID, "unsupported padded state count");
     }
     if (rc) return rc;

@@ -1567,15 +1567,15 @@ constexpr int DE_WARPS = 12;
 constexpr int DE_THREADS = DE_WARPS * 32;
 constexpr int DE_TILE_ROWS = DE_WARPS * 8;
 constexpr int DE_MAXW = 64;  // work items per launch
-constexpr int DE_PRE = 2;    // children whose rows are prefetched (further ones: loaded at use)
+constexpr int DE_PRE_MAX = 3;  // children whose rows can be prefetched (further ones: loaded at use)
 
 struct EWork {
   double* out;
   int64_t n_rows;
   int64_t row_tiles;
   const double* P_own;
-  const double* src[DE_PRE];
-  const int32_t* idx[DE_PRE];
+  const double* src[DE_PRE_MAX];
+  const int32_t* idx[DE_PRE_MAX];
   int32_t child_begin;
   int32_t nc;
   int32_t fixed_motif;
@@ -1592,10 +1592,15 @@ struct ECur {
   int64_t row0;  // first row of the super-tile
 };
 
-template <int MP>
+// DE_PRE children are prefetched (2; 3 for the launch of a trifurcating root, which is also
+// compiled without the contraction: CONTRACT = false)
+template <int MP, int DE_PRE, bool CONTRACT>
 __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const PruneArgs a) {
-  constexpr int LDS = MP + 4, NI = MP / 8, KS = MP / 4;
-  extern __shared__ __align__(16) double smem[];  // [MP * LDS]: the node's own P, columns permuted
+  // P in its natural layout with row stride MP + 8: the lane (g, q) then reads the B values of k
+  // steps 2a and 2a+1 of column block ni -- P[8 ni + g][8a + 2q], [.. + 1] -- with ONE conflict-free
+  // 128-bit load (quarter-warps: g in {0,1} -> 16-byte bank groups 0-3 and 4-7)
+  constexpr int LDS = MP + 8, NI = MP / 8, KS = MP / 4;
+  extern __shared__ __align__(16) double smem[];  // [MP * LDS]: the node's own P
   __shared__ ESmem sd;
   const int K = a.K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1614,7 +1619,7 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
     wd.nc = nd.n_children;
     wd.fixed_motif = nd.fixed_motif;
     wd.is_root = nd.is_root;
-    for (int c = 0; c < DE_PRE; ++c) {
+    for (int c = 0; c < DE_PRE_MAX; ++c) {
       const ChildRef ch = a.childs[nd.child_begin + (c < nd.n_children ? c : 0)];
       wd.src[c] = ch.src;
       wd.idx[c] = ch.idx;
@@ -1678,13 +1683,11 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
     if ((cc.w != res_w || cc.b != res_b)) {
       // another (node, rate class): every warp is done with the old P
       __syncthreads();
-      if (wd.P_own != nullptr) {
+      if (CONTRACT && wd.P_own != nullptr) {
         const double* P = wd.P_own + (int64_t)cc.b * MP * MP;
-        // coalesced reads; column j = 8a + 2q + b lands at position 4 (2a + b) + q
-        for (int o = tid; o < MP * MP; o += DE_THREADS) {
-          const int i = o / MP, j = o - i * MP;
-          const int pos = (j & ~7) + ((j & 1) << 2) + ((j >> 1) & 3);
-          smem[i * LDS + pos] = P[o];
+        for (int o = tid; o < MP * MP / 2; o += DE_THREADS) {
+          const int i = (2 * o) / MP, j = 2 * o - i * MP;
+          *reinterpret_cast<double2*>(smem + i * LDS + j) = *reinterpret_cast<const double2*>(P + 2 * o);
         }
       }
       res_w = cc.w;
@@ -1698,11 +1701,14 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
       prod[ni][0] = vn[0][ni].x;
       prod[ni][1] = vn[0][ni].y;
     }
-    if (wd.nc >= 2) {
 #pragma unroll
-      for (int ni = 0; ni < NI; ++ni) {
-        prod[ni][0] *= vn[1][ni].x;
-        prod[ni][1] *= vn[1][ni].y;
+    for (int c = 1; c < DE_PRE; ++c) {
+      if (c < wd.nc) {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          prod[ni][0] *= vn[c][ni].x;
+          prod[ni][1] *= vn[c][ni].y;
+        }
       }
     }
     next(fc);
@@ -1732,7 +1738,7 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
       }
     }
     double* dst = wd.out + (p * K + cc.b) * MP + 2 * q;
-    if (wd.P_own == nullptr) {
+    if (!CONTRACT || wd.P_own == nullptr) {
       // the root: plh itself, and lh = inner(plh_root, pi)
       if (row_ok) {
 #pragma unroll
@@ -1754,12 +1760,15 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
       double cur[NI][2];
 #pragma unroll
       for (int ni = 0; ni < NI; ++ni) cur[ni][0] = cur[ni][1] = 0.0;
-      const double* bRow = smem + g * LDS + q;
+      const double* bRow = smem + g * LDS + 2 * q;
 #pragma unroll
-      for (int s = 0; s < KS; ++s) {
-        const double av = prod[s >> 1][s & 1];
+      for (int a2 = 0; a2 < KS / 2; ++a2) {
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) dmma_m8n8k4(cur[ni][0], cur[ni][1], av, bRow[(8 * ni) * LDS + 4 * s]);
+        for (int ni = 0; ni < NI; ++ni) {
+          const double2 bv = *reinterpret_cast<const double2*>(bRow + (8 * ni) * LDS + 8 * a2);
+          dmma_m8n8k4(cur[ni][0], cur[ni][1], prod[a2][0], bv.x);
+          dmma_m8n8k4(cur[ni][0], cur[ni][1], prod[a2][1], bv.y);
+        }
       }
       if (row_ok) {
 #pragma unroll
