@@ -95,14 +95,30 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
         sIi[i * LD + k] = evI[2 * o + 1];
       }
       __syncthreads();
-      for (int o = threadIdx.x; o < MM; o += blockDim.x) {
-        const int i = o / M, j = o - i * M;
-        double acc = 0.0;
-        for (int k = 0; k < M; ++k)
-          acc += sWr[i * LD + k] * sIr[j * LD + k] - sWi[i * LD + k] * sIi[j * LD + k];
-        acc = fmax(acc, 0.0);
-        sP[i * MP + j] = acc;
-        Pout[i * MP + j] = acc;
+      // 2 x 2 register tiles: each shared-memory operand feeds two outputs (the contraction is bound
+      // by its shared-memory loads); every element still sums k = 0..M-1 in order
+      const int T = (M + 1) / 2;
+      for (int o = threadIdx.x; o < T * T; o += blockDim.x) {
+        const int i0 = 2 * (o / T), j0 = 2 * (o % T);
+        const int i1 = min(i0 + 1, M - 1), j1 = min(j0 + 1, M - 1);
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        for (int k = 0; k < M; ++k) {
+          const double w0r = sWr[i0 * LD + k], w0i = sWi[i0 * LD + k];
+          const double w1r = sWr[i1 * LD + k], w1i = sWi[i1 * LD + k];
+          const double v0r = sIr[j0 * LD + k], v0i = sIi[j0 * LD + k];
+          const double v1r = sIr[j1 * LD + k], v1i = sIi[j1 * LD + k];
+          a00 += w0r * v0r - w0i * v0i;
+          a01 += w0r * v1r - w0i * v1i;
+          a10 += w1r * v0r - w1i * v0i;
+          a11 += w1r * v1r - w1i * v1i;
+        }
+        const double r[2][2] = {{fmax(a00, 0.0), fmax(a01, 0.0)}, {fmax(a10, 0.0), fmax(a11, 0.0)}};
+        for (int di = 0; di < 2; ++di)
+          for (int dj = 0; dj < 2; ++dj)
+            if (i0 + di < M && j0 + dj < M) {
+              sP[(i0 + di) * MP + j0 + dj] = r[di][dj];
+              Pout[(i0 + di) * MP + j0 + dj] = r[di][dj];
+            }
       }
     } else {
       for (int o = threadIdx.x; o < MM; o += blockDim.x) {
@@ -137,13 +153,26 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
         sI[i * LD + k] = evI[o];
       }
       __syncthreads();
-      for (int o = threadIdx.x; o < MM; o += blockDim.x) {
-        const int i = o / M, j = o - i * M;
-        double acc = 0.0;
-        for (int k = 0; k < M; ++k) acc += sW[i * LD + k] * sI[j * LD + k];
-        acc = fmax(acc, 0.0);
-        sP[i * MP + j] = acc;
-        Pout[i * MP + j] = acc;
+      const int T = (M + 1) / 2;  // 2 x 2 register tiles, see the complex branch
+      for (int o = threadIdx.x; o < T * T; o += blockDim.x) {
+        const int i0 = 2 * (o / T), j0 = 2 * (o % T);
+        const int i1 = min(i0 + 1, M - 1), j1 = min(j0 + 1, M - 1);
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        for (int k = 0; k < M; ++k) {
+          const double w0 = sW[i0 * LD + k], w1 = sW[i1 * LD + k];
+          const double v0 = sI[j0 * LD + k], v1 = sI[j1 * LD + k];
+          a00 += w0 * v0;
+          a01 += w0 * v1;
+          a10 += w1 * v0;
+          a11 += w1 * v1;
+        }
+        const double r[2][2] = {{fmax(a00, 0.0), fmax(a01, 0.0)}, {fmax(a10, 0.0), fmax(a11, 0.0)}};
+        for (int di = 0; di < 2; ++di)
+          for (int dj = 0; dj < 2; ++dj)
+            if (i0 + di < M && j0 + dj < M) {
+              sP[(i0 + di) * MP + j0 + dj] = r[di][dj];
+              Pout[(i0 + di) * MP + j0 + dj] = r[di][dj];
+            }
       }
     } else {
       for (int o = threadIdx.x; o < MM; o += blockDim.x) {
