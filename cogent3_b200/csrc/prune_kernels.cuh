@@ -1828,7 +1828,7 @@ __device__ __forceinline__ double block_sum(double v, double* s_warp) {
 // rank r's mailbox over NVLink (value, fence.sys, epoch), every rank waits until its own mailbox
 // holds all nranks values of this epoch and adds them in rank order (deterministic and identical
 // on every rank).  Two mailbox parities: a rank can be at most one evaluation ahead of another.
-// A bounded wait (5 s) turns a missing peer into NaN instead of a hung GPU.
+// A bounded wait (30 s) turns a missing peer into NaN instead of a hung GPU.
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1905,7 +1905,7 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
           v = *reinterpret_cast<const volatile double*>(&src->value);
           break;
         }
-        if (globaltimer_ns() - t0 > 5000000000ull) break;
+        if (globaltimer_ns() - t0 > 30000000000ull) break;
         __nanosleep(200);
       }
       s_shard[r] = v;
