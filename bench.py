@@ -373,7 +373,7 @@ def workload_config(args, problem):
     model_name, topo, _, codes, _, bins, setup = problem
     return {
         "workload": f"{args.config}: {CONFIGS[args.config][4]}",
-        "model": model_name, "taxa": len(topo.tips), "columns_per_gpu": int(codes.shape[1]),
+        "substitution_model": model_name, "taxa": len(topo.tips), "columns_per_gpu": int(codes.shape[1]),
         "rate_classes": bins, "alignment": args.kind, "expm": setup.get("expm", "either"),
         "l2_policy": "working set (resident partials + gather tables) larger than the 126 MB L2",
         "step": "full evaluation: all branch lengths changed",
