@@ -269,7 +269,9 @@ class LikelihoodFunction:
             self.engine.set_root_mprobs(self.mprobs)
             if self.n_bins > 1:
                 self.engine.set_bin_probs(self.bprobs)
-            dist = np.nan_to_num(self.lengths)[:, None] * self.rates()[None, :]
+            lengths = self.lengths.copy()
+            lengths[self.topo.root] = 0.0  # the root has no branch (NaN placeholder)
+            dist = lengths[:, None] * self.rates()[None, :]
             self.engine.set_distances(dist)
             self._dirty_model = False
 
