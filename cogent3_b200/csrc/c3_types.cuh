@@ -93,7 +93,7 @@ struct SmallLevel {
 constexpr int SMALL_THREADS = 1024;
 constexpr int SMALL_CLUSTER = 8;            // CTAs (SMs) cooperating on the small levels
 constexpr int SMALL_LEVEL_UNITS = SMALL_THREADS * SMALL_CLUSTER;  // one unit per thread and level
-constexpr int SMALL_MAX_WORK = 384;  // work items whose descriptors are staged in shared memory
+constexpr int SMALL_MAX_WORK = 192;  // work items whose descriptors are staged in shared memory
 constexpr int SMALL_MAX_LEVELS = 64;
 constexpr int SMALL_STAGED_CHILDREN = 3;
 

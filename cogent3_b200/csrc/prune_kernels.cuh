@@ -1071,12 +1071,53 @@ __device__ __forceinline__ unsigned cluster_nctarank() {
   return r;
 }
 
+constexpr int SMALL_MAX_P = 192;  // P matrices (work item x staged child x bin) kept in shared memory (the whole
+                                  // struct stays near 52 KB: a larger carve-out costs the overlap with the neighbouring launches)
 struct SmallSmem {
   SmallLevel levels[SMALL_MAX_LEVELS];
   int32_t prefix[SMALL_MAX_WORK + SMALL_MAX_LEVELS];
   NodeDesc nodes[SMALL_MAX_WORK];
   ChildRef childs[SMALL_MAX_WORK * SMALL_STAGED_CHILDREN];
+  double P[SMALL_MAX_P * 16];
 };
+
+// One (row, bin) unit of a small level with everything staged: the gather indexes of ALL children
+// are requested first, then all their rows, then the arithmetic with P from shared memory -- the
+// dependent chain per unit is two global latencies, not three per child.  Same arithmetic
+// (matvec4, children multiplied in order) as every other 4-state kernel: bit-identical.
+__device__ __forceinline__ void small_unit_staged(const PruneArgs& a, const NodeDesc& nd,
+                                                  const ChildRef* __restrict__ ch, const double* __restrict__ sP,
+                                                  int64_t p, int b, int K) {
+  const int nc = nd.n_children;  // <= SMALL_STAGED_CHILDREN (checked by the caller)
+  // the first two children together (1024 threads per CTA leave 64 registers: a third row would spill)
+  const int32_t r0 = ch[0].idx[p];
+  const int32_t r1 = (nc > 1) ? ch[1].idx[p] : 0;
+  const d4 x0 = ld256(ch[0].src + ((int64_t)r0 * K + b) * 4);
+  d4 x1 = x0;
+  if (nc > 1) x1 = ld256(ch[1].src + ((int64_t)r1 * K + b) * 4);  // in flight together with x0
+  d4 acc = (ch[0].P != nullptr) ? matvec4(sP + (0 * K + b) * 16, x0) : x0;
+  if (nc > 1) {
+    const d4 y = (ch[1].P != nullptr) ? matvec4(sP + (1 * K + b) * 16, x1) : x1;
+    acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w;
+  }
+  for (int c = 2; c < nc; ++c) {
+    const int32_t r = ch[c].idx[p];
+    const d4 x = ld256(ch[c].src + ((int64_t)r * K + b) * 4);
+    const d4 y = (ch[c].P != nullptr) ? matvec4(sP + (c * K + b) * 16, x) : x;
+    acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w;
+  }
+  if (nd.fixed_motif >= 0) {
+    if (nd.fixed_motif != 0) acc.x = 0.0;
+    if (nd.fixed_motif != 1) acc.y = 0.0;
+    if (nd.fixed_motif != 2) acc.z = 0.0;
+    if (nd.fixed_motif != 3) acc.w = 0.0;
+  }
+  st256(nd.out + (p * K + b) * 4, acc);
+  if (nd.is_root) {
+    const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
+    a.lh_out[p * K + b] = lh;
+  }
+}
 
 // n_work_total / n_prefix_total: sizes of the launch's work and prefix arrays.  When they
 // fit, every descriptor the units need is staged in shared memory first, so the
@@ -1104,6 +1145,18 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
     __syncthreads();
   }
   pdl_wait();  // P matrices / tip tables of the expm launch, rows of earlier levels
+  // the P matrices of every staged child, per bin, into shared memory
+  const bool p_staged = staged && (int64_t)n_work_total * SMALL_STAGED_CHILDREN * K <= SMALL_MAX_P;
+  if (p_staged) {
+    const int per_item = SMALL_STAGED_CHILDREN * K * 16;
+    for (int o = threadIdx.x; o < n_work_total * per_item; o += SMALL_THREADS) {
+      const int i = o / per_item, rem = o - i * per_item;
+      const int c = rem / (K * 16), e16 = rem - c * (K * 16);  // e16 = bin * 16 + element
+      const double* P = (c < sm.nodes[i].n_children) ? sm.childs[i * SMALL_STAGED_CHILDREN + c].P : nullptr;
+      if (P != nullptr) sm.P[o] = P[e16];
+    }
+    __syncthreads();
+  }
   for (int li = 0; li < n_levels; ++li) {
     const SmallLevel L = staged ? sm.levels[li] : levels[li];
     const int32_t* prefix = (staged ? sm.prefix : a.tile_prefix) + L.prefix_off;
@@ -1114,6 +1167,11 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
       const int local = u - prefix[w];
       const int64_t p = local / K;
       const int b = local - (int)p * K;
+      if (p_staged && nd.n_children <= SMALL_STAGED_CHILDREN) {
+        small_unit_staged(a, nd, sm.childs + wi * SMALL_STAGED_CHILDREN,
+                          sm.P + (int64_t)wi * SMALL_STAGED_CHILDREN * K * 16, p, b, K);
+        continue;
+      }
       d4 acc;
       for (int c = 0; c < nd.n_children; ++c) {
         const ChildRef ch = (staged && c < SMALL_STAGED_CHILDREN) ? sm.childs[wi * SMALL_STAGED_CHILDREN + c]
