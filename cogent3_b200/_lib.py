@@ -78,6 +78,10 @@ SIGNATURES = {
     "c3_set_bin_probs": (c_int, [c_void_p, _pd]),
     "c3_set_fixed_motifs": (c_int, [c_void_p, _pi32]),
     "c3_invalidate": (c_int, [c_void_p]),
+    "c3_set_rescaling": (c_int, [c_void_p, c_int, c_int]),
+    "c3_get_rescaling": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "c3_get_root_exponents": (c_int, [c_void_p, _pi32, c_int64]),
+    "c3_get_scaled_lh": (c_int, [c_void_p, c_int, _pd, c_int64]),
     "c3_evaluate": (c_int, [c_void_p, _pd]),
     "c3_evaluate_device": (c_int, [c_void_p, c_void_p]),
     "c3_update": (c_int, [c_void_p, _pd, _pd]),

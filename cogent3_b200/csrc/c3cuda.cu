@@ -151,6 +151,17 @@ struct c3_engine {
   int mailbox_ranks = 0;
   std::vector<void*> ipc_opened;
 
+  // per-pattern underflow rescaling (c3_set_rescaling; kernels in prune_kernels.cuh)
+  int rescale_mode = C3_RESCALE_AUTO;
+  int rescale_threshold = 16;  // a subtree becomes a scaled node once it holds this many unscaled tips
+  bool rescale_active = false;
+  char* d_scale_pool = nullptr;
+  int64_t scale_pool_bytes = 0;
+  std::vector<char> is_scaled;  // [n_nodes]
+  struct ScaleRec { int32_t* d_exps = nullptr; const ScaleSrc* d_src = nullptr; int n_src = 0; };
+  std::vector<ScaleRec> scale_rec;  // [n_nodes]; the root's d_exps are the per-pattern exponents of lh
+  int n_scaled = 0;
+
   c3_stats stats{};
 
   // per-launch profiling
@@ -493,6 +504,9 @@ int ensure_slots(c3_engine* e, int n) {
 
 int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out, bool deferred = false);
 int finish_deferred(c3_engine* e, double* host_out);
+int activate_rescaling(c3_engine* e);
+void deactivate_rescaling(c3_engine* e);
+int launch_rescale(c3_engine* e, int node);
 
 cudaEvent_t next_event(c3_engine* e) {
   if (e->events_used == e->event_pool.size()) {
@@ -565,6 +579,8 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   if (const char* env = getenv("C3_REG1")) e->use_reg2 = atoi(env) == 0;
   if (const char* env = getenv("C3_FLOW")) e->use_flow = atoi(env) != 0;
+  if (const char* env = getenv("C3_RESCALE")) e->rescale_mode = std::max(0, std::min(2, atoi(env)));
+  if (const char* env = getenv("C3_RESCALE_TIPS")) e->rescale_threshold = std::max(2, atoi(env));
   e->root = n_nodes - 1;
   e->children.resize(n_nodes);
   e->parent.assign(n_nodes, -1);
@@ -639,6 +655,7 @@ int c3_destroy(c3_engine* e) {
   for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->d_mailbox) cudaFree(e->d_mailbox);
   if (e->d_pool) cudaFree(e->d_pool);
+  if (e->d_scale_pool) cudaFree(e->d_scale_pool);
   if (e->d_slots) cudaFree(e->d_slots);
   if (e->d_block) cudaFree(e->d_block);
   if (e->h_block) cudaFreeHost(e->h_block);
@@ -1013,7 +1030,8 @@ int c3_get_site_lh(c3_engine* e, int bin, double* out, int64_t n_columns) {
   double* d_out = nullptr;
   C3_CUDA(cudaMalloc(&d_out, (size_t)n_columns * sizeof(double)));
   const int grid = (int)std::min<int64_t>((n_columns + CMP_THREADS - 1) / CMP_THREADS, (int64_t)e->n_sm * 16);
-  site_lh_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(n_columns, e->d_root_index, e->d_lh, e->K, bin, d_out);
+  site_lh_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(n_columns, e->d_root_index, e->d_lh, e->K, bin, d_out,
+                                                      e->rescale_active ? e->scale_rec[e->root].d_exps : nullptr);
   cudaError_t err = cudaMemcpyAsync(out, d_out, (size_t)n_columns * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
   cudaFree(d_out);
@@ -1309,6 +1327,59 @@ int c3_invalidate(c3_engine* e) {
   return C3_OK;
 }
 
+int c3_set_rescaling(c3_engine* e, int mode, int tip_threshold) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  C3_REQUIRE(mode >= C3_RESCALE_OFF && mode <= C3_RESCALE_AUTO, "bad rescaling mode");
+  if (tip_threshold > 0 && std::max(2, tip_threshold) != e->rescale_threshold) {
+    e->rescale_threshold = std::max(2, tip_threshold);
+    if (e->rescale_active) {
+      // a different set of scaled nodes: rebuild the tables at the next evaluation
+      C3_CUDA(cudaSetDevice(e->device));
+      deactivate_rescaling(e);
+      if (mode == C3_RESCALE_AUTO) mode = C3_RESCALE_ON;
+    }
+  }
+  e->rescale_mode = mode;  // ON / OFF take effect at the next evaluation
+  if (mode != C3_RESCALE_AUTO && (mode == C3_RESCALE_ON) != e->rescale_active) {
+    e->reduce_dirty = true;
+    e->have_cached = false;
+  }
+  return C3_OK;
+}
+
+int c3_get_rescaling(c3_engine* e, int* active, int* n_scaled_nodes) {
+  C3_REQUIRE(e != nullptr, "null engine");
+  if (active) *active = e->rescale_active ? 1 : 0;
+  if (n_scaled_nodes) *n_scaled_nodes = e->rescale_active ? e->n_scaled : 0;
+  return C3_OK;
+}
+
+int c3_get_root_exponents(c3_engine* e, int32_t* out, int64_t n_rows) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_REQUIRE(e->finalized && e->have_cached, "no evaluation yet");
+  C3_REQUIRE(n_rows == e->n_rows[e->root], "bad row count");
+  if (!e->rescale_active) {
+    std::fill(out, out + n_rows, 0);
+    return C3_OK;
+  }
+  C3_CUDA(cudaSetDevice(e->device));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  C3_CUDA(cudaMemcpy(out, e->scale_rec[e->root].d_exps, (size_t)n_rows * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return C3_OK;
+}
+
+int c3_get_scaled_lh(c3_engine* e, int bin, double* out, int64_t n_rows) {
+  C3_REQUIRE(e && out, "null pointer");
+  C3_REQUIRE(e->finalized && e->have_cached, "no evaluation yet");
+  C3_REQUIRE(bin >= 0 && bin < e->K, "bad bin");
+  C3_REQUIRE(n_rows == e->n_rows[e->root], "bad row count");
+  C3_CUDA(cudaSetDevice(e->device));
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  C3_CUDA(cudaMemcpy2D(out, sizeof(double), e->d_lh + bin, e->K * sizeof(double), sizeof(double),
+                       (size_t)n_rows, cudaMemcpyDeviceToHost));
+  return C3_OK;
+}
+
 int c3_evaluate(c3_engine* e, double* lnL) {
   C3_REQUIRE(e && lnL, "null pointer");
   return run_evaluation(e, nullptr, true, lnL);
@@ -1425,6 +1496,13 @@ int c3_get_lh(c3_engine* e, int bin, double* out, int64_t n_rows) {
   C3_CUDA(cudaStreamSynchronize(e->stream));
   C3_CUDA(cudaMemcpy2D(out, sizeof(double), e->d_lh + bin, e->K * sizeof(double), sizeof(double),
                        (size_t)n_rows, cudaMemcpyDeviceToHost));
+  if (e->rescale_active) {
+    // fold the per-pattern exponents back: exact unless the true value leaves the FP64 range
+    std::vector<int32_t> ex((size_t)n_rows);
+    C3_CUDA(cudaMemcpy(ex.data(), e->scale_rec[e->root].d_exps, (size_t)n_rows * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < n_rows; ++p) out[p] = std::ldexp(out[p], ex[p]);
+  }
   return C3_OK;
 }
 
@@ -1541,6 +1619,12 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   C3_REQUIRE(e->have_pi, "root motif probabilities not set");
   C3_CUDA(cudaSetDevice(e->device));
   const int N = e->n_nodes, K = e->K, M = e->M, MP = e->MP;
+  if (e->rescale_mode == C3_RESCALE_ON && !e->rescale_active) {
+    int rc = activate_rescaling(e);
+    if (rc) return rc;
+  } else if (e->rescale_mode == C3_RESCALE_OFF && e->rescale_active) {
+    deactivate_rescaling(e);
+  }
 
   // slots whose contents changed dirty every (edge, bin) that uses them
   bool any_slot_dirty = false;
@@ -1657,7 +1741,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     for (int i = 0; i < g.n_work; ++i) flow_item[work[g.work_off + i]] = -1;
     open_flow = -1;
   };
-  const bool flow_ok = e->use_flow && !e->use_dmma && e->use_strip && !e->use_ring && (K == 1 || K == 2 || K == 4);
+  const bool flow_ok = e->use_flow && !e->use_dmma && e->use_strip && !e->use_ring && (K == 1 || K == 2 || K == 4) &&
+                       !e->rescale_active;  // rescaling runs between levels
   for (int l = 1; l <= e->n_levels; ++l) {
     int64_t units = 0;
     int n_dirty = 0;
@@ -1701,6 +1786,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       g.total_tiles += (int)u;
       g.bytes += alg_bytes - bytes0;
       g.flops += flops - flops0;
+      // a scaled node is rescaled right after its launch: it must be in the group's LAST level
+      if (e->rescale_active)
+        for (int n : e->level_nodes[l])
+          if (recompute[n] && e->is_scaled[n]) open_small = -1;
       continue;
     }
     open_small = -1;
@@ -1891,6 +1980,16 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       if (rc) return rc;
     }
     ++n_launch;
+    if (e->rescale_active) {
+      // scaled nodes of this launch: normalise their rows before the next level reads them
+      for (int i = 0; i < ll.n_work; ++i) {
+        const int n = work[ll.work_off + i];
+        if (!e->is_scaled[n] && n != e->root) continue;
+        int rc = launch_rescale(e, n);
+        if (rc) return rc;
+        ++n_launch;
+      }
+    }
   }
   {
     CommArgs comm = e->comm;
@@ -1914,7 +2013,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     const double* a_counts = e->d_counts;
     volatile double* a_host = (blocking || deferred) ? e->h_lnl_dev : nullptr;
     cudaError_t err = cudaLaunchKernelEx(&cfg, lnl_reduce_kernel, a_lh, a_bp, a_counts, (int64_t)rows, K, n_tiles,
-                                         e->d_tile_sums, e->d_counter, e->d_lnl, device_out, a_host, comm);
+                                         e->d_tile_sums, e->d_counter, e->d_lnl, device_out, a_host, comm,
+                                         (const int32_t*)(e->rescale_active ? e->scale_rec[e->root].d_exps : nullptr));
     ++n_launch;
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(err));
@@ -1948,6 +2048,14 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     for (auto& r : e->prof) cudaEventElapsedTime(&r.ms, r.a, r.b);
     e->cached_lnl = *e->h_lnl;
     e->have_cached = true;
+    if (!std::isfinite(e->cached_lnl) && e->rescale_mode == C3_RESCALE_AUTO && !e->rescale_active) {
+      // some pattern's likelihood left the FP64 range (the reference returns -inf here,
+      // evolve/likelihood_tree.py:10): switch to rescaled rows for good and evaluate again.
+      // Sharded runs: every rank sees the same total, so every rank takes this branch.
+      int rc = activate_rescaling(e);
+      if (rc) return rc;
+      return run_evaluation(e, device_out, blocking, host_out, deferred);
+    }
     if (host_out) *host_out = e->cached_lnl;
   } else {
     e->have_cached = true;  // value lives in d_lnl; the host copy is refreshed lazily
@@ -1969,8 +2077,149 @@ int finish_deferred(c3_engine* e, double* host_out) {
     for (auto& r : e->prof) cudaEventElapsedTime(&r.ms, r.a, r.b);
     e->cached_lnl = *e->h_lnl;
     e->have_cached = true;
+    if (!std::isfinite(e->cached_lnl) && e->rescale_mode == C3_RESCALE_AUTO && !e->rescale_active) {
+      int rc = activate_rescaling(e);
+      if (rc) return rc;
+      return run_evaluation(e, nullptr, true, host_out);
+    }
   }
   if (host_out) *host_out = e->cached_lnl;
+  return C3_OK;
+}
+
+// ---- per-pattern underflow rescaling: set-up -------------------------------------------------
+void deactivate_rescaling(c3_engine* e) {
+  if (!e->rescale_active) return;
+  cudaStreamSynchronize(e->stream);
+  if (e->d_scale_pool) cudaFree(e->d_scale_pool);
+  e->d_scale_pool = nullptr;
+  e->stats.device_bytes -= e->scale_pool_bytes;
+  e->scale_pool_bytes = 0;
+  e->rescale_active = false;
+  e->n_scaled = 0;
+  std::fill(e->node_dirty.begin(), e->node_dirty.end(), 1);  // stored rows carry the old scaling
+  e->reduce_dirty = true;
+  e->have_cached = false;
+}
+
+int activate_rescaling(c3_engine* e) {
+  if (e->rescale_active) return C3_OK;
+  C3_REQUIRE(e->finalized, "call c3_finalize first");
+  const int N = e->n_nodes, root = e->root;
+  // scaled nodes: post-order, a subtree is cut off once it has gathered `threshold` unscaled tips
+  e->is_scaled.assign(N, 0);
+  std::vector<int> unscaled(N, 0);
+  int n_scaled = 0;
+  for (int n = 0; n < N; ++n) {
+    if (e->children[n].empty()) { unscaled[n] = 1; continue; }
+    int u = 0;
+    for (int c : e->children[n]) u += e->is_scaled[c] ? 0 : unscaled[c];
+    unscaled[n] = u;
+    if (n != root && u >= e->rescale_threshold) { e->is_scaled[n] = 1; ++n_scaled; }
+  }
+  // nearest scaled descendants of every scaled node and of the root
+  std::vector<std::vector<int>> near(N);
+  int64_t bytes = 0, tmp_rows = 0;
+  auto carve = [&](int64_t b) { const int64_t o = bytes; bytes += align_up(b, 256); return o; };
+  std::vector<int64_t> o_exps(N, -1), o_src(N, -1);
+  std::vector<std::vector<int64_t>> o_map(N);
+  for (int x = 0; x < N; ++x) {
+    if (!e->is_scaled[x] && x != root) continue;
+    std::vector<int> stack(e->children[x].begin(), e->children[x].end());
+    while (!stack.empty()) {
+      const int c = stack.back();
+      stack.pop_back();
+      if (e->is_scaled[c]) near[x].push_back(c);
+      else for (int g : e->children[c]) stack.push_back(g);
+    }
+    std::sort(near[x].begin(), near[x].end());
+    o_exps[x] = carve(e->n_rows[x] * (int64_t)sizeof(int32_t));
+    o_src[x] = carve((int64_t)std::max<size_t>(1, near[x].size()) * sizeof(ScaleSrc));
+    for (size_t i = 0; i < near[x].size(); ++i) o_map[x].push_back(carve(e->n_rows[x] * (int64_t)sizeof(int32_t)));
+    if (!near[x].empty()) tmp_rows = std::max(tmp_rows, e->n_rows[x]);
+  }
+  const int64_t o_tmp = carve(std::max<int64_t>(1, tmp_rows) * sizeof(int32_t));
+  C3_CUDA(cudaSetDevice(e->device));
+  size_t free_b = 0, total_b = 0;
+  C3_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  if ((size_t)bytes > free_b) return fail(C3_ERR_MEMORY, "not enough device memory for the rescaling tables");
+  C3_CUDA(cudaMalloc(&e->d_scale_pool, (size_t)bytes));
+  e->scale_pool_bytes = bytes;
+  e->stats.device_bytes += bytes;
+  e->scale_rec.assign(N, c3_engine::ScaleRec{});
+  int32_t* d_tmp = reinterpret_cast<int32_t*>(e->d_scale_pool + o_tmp);
+  for (int x = 0; x < N; ++x) {
+    if (o_exps[x] < 0) continue;
+    c3_engine::ScaleRec& rec = e->scale_rec[x];
+    rec.d_exps = reinterpret_cast<int32_t*>(e->d_scale_pool + o_exps[x]);
+    rec.d_src = reinterpret_cast<const ScaleSrc*>(e->d_scale_pool + o_src[x]);
+    rec.n_src = (int)near[x].size();
+    std::vector<ScaleSrc> h_src(near[x].size());
+    const int64_t rows = e->n_rows[x];
+    const int grid = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)e->n_sm * 16);
+    for (size_t i = 0; i < near[x].size(); ++i) {
+      const int d = near[x][i];
+      // the path x -> ... -> d: compose the gather tables on the way down
+      std::vector<int> path;  // nodes from d up to (excluding) x
+      for (int a = d; a != x; a = e->parent[a]) path.push_back(a);
+      int32_t* final_map = reinterpret_cast<int32_t*>(e->d_scale_pool + o_map[x][i]);
+      const int32_t* cur = nullptr;
+      int a = x;
+      for (int s = (int)path.size() - 1; s >= 0; --s) {
+        const int c = path[s];
+        int ci = 0;
+        while (e->children[a][ci] != c) ++ci;
+        // rows of `a` index rows of `c`; alternate buffers so that the last step lands in final_map
+        int32_t* out = (s % 2 == 0) ? final_map : d_tmp;
+        compose_map_kernel<<<grid, 256, 0, e->stream>>>(out, cur, e->d_idx[a] + (int64_t)ci * e->n_rows[a], rows);
+        cur = out;
+        a = c;
+      }
+      h_src[i].map = final_map;
+      h_src[i].exps = reinterpret_cast<const int32_t*>(e->d_scale_pool + o_exps[d]);
+    }
+    if (!h_src.empty())
+      C3_CUDA(cudaMemcpyAsync(e->d_scale_pool + o_src[x], h_src.data(), h_src.size() * sizeof(ScaleSrc),
+                              cudaMemcpyHostToDevice, e->stream));
+    C3_CUDA(cudaStreamSynchronize(e->stream));  // h_src goes out of scope
+  }
+  {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("rescaling set-up: ") + cudaGetErrorString(err));
+  }
+  e->rescale_active = true;
+  e->n_scaled = n_scaled;
+  std::fill(e->node_dirty.begin(), e->node_dirty.end(), 1);
+  e->reduce_dirty = true;
+  e->have_cached = false;
+  return C3_OK;
+}
+
+// after the launch that computed `node`: scale its rows (a scaled node) / sum the exponents (the root)
+int launch_rescale(c3_engine* e, int node) {
+  const c3_engine::ScaleRec& rec = e->scale_rec[node];
+  const int64_t rows = e->n_rows[node];
+  if (node == e->root) {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (int64_t)e->n_sm * 16));
+    root_exp_kernel<<<grid, 256, 0, e->stream>>>(rec.d_exps, rows, rec.d_src, rec.n_src);
+  } else {
+    const int row_len = e->K * e->MP, chunks = row_len / 4;
+    int lpr = 1;
+    while (lpr < chunks && lpr < 32) lpr *= 2;
+    const int64_t warps = (rows + (32 / lpr) - 1) / (32 / lpr);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)e->n_sm * 8));
+    double* r = e->d_rows[node];
+    switch (lpr) {
+      case 1: rescale_rows_kernel<1><<<grid, 256, 0, e->stream>>>(r, rows, row_len, rec.d_exps, rec.d_src, rec.n_src); break;
+      case 2: rescale_rows_kernel<2><<<grid, 256, 0, e->stream>>>(r, rows, row_len, rec.d_exps, rec.d_src, rec.n_src); break;
+      case 4: rescale_rows_kernel<4><<<grid, 256, 0, e->stream>>>(r, rows, row_len, rec.d_exps, rec.d_src, rec.n_src); break;
+      case 8: rescale_rows_kernel<8><<<grid, 256, 0, e->stream>>>(r, rows, row_len, rec.d_exps, rec.d_src, rec.n_src); break;
+      case 16: rescale_rows_kernel<16><<<grid, 256, 0, e->stream>>>(r, rows, row_len, rec.d_exps, rec.d_src, rec.n_src); break;
+      default: rescale_rows_kernel<32><<<grid, 256, 0, e->stream>>>(r, rows, row_len, rec.d_exps, rec.d_src, rec.n_src); break;
+    }
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("rescale launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
 

@@ -227,10 +227,13 @@ cmp_counts_to_double_kernel(long long n, const unsigned* __restrict__ counts, do
 // evolve/likelihood_tree.py:93-94)
 __global__ void __launch_bounds__(CMP_THREADS)
 site_lh_kernel(long long n_cols, const int32_t* __restrict__ index, const double* __restrict__ lh, int K, int bin,
-               double* __restrict__ out) {
+               double* __restrict__ out, const int32_t* __restrict__ root_exp) {
   for (long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x; col < n_cols;
-       col += (long long)gridDim.x * blockDim.x)
-    out[col] = lh[(long long)index[col] * K + bin];
+       col += (long long)gridDim.x * blockDim.x) {
+    const int32_t p = index[col];
+    const double v = lh[(long long)p * K + bin];
+    out[col] = root_exp ? scalbn(v, root_exp[p]) : v;  // rescaled rows: fold the exponent back
+  }
 }
 
 }  // namespace c3

@@ -1906,7 +1906,8 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
                   const double* __restrict__ counts, int64_t n_rows, int K, int n_tiles,
                   double* __restrict__ tile_sums, unsigned int* __restrict__ counter,
                   double* __restrict__ d_lnl, double* __restrict__ d_lnl2,
-                  volatile double* __restrict__ h_lnl, const CommArgs comm) {
+                  volatile double* __restrict__ h_lnl, const CommArgs comm,
+                  const int32_t* __restrict__ root_exp) {
   __shared__ double s_warp[REDUCE_THREADS / 32];
   __shared__ bool s_last;
   pdl_wait();  // launched early (programmatic dependent launch): lh is the root launch's output
@@ -1924,7 +1925,9 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
           mix = 0.0;
           for (int b = 0; b < K; ++b) mix = __dadd_rn(mix, __dmul_rn(lh[p * K + b], bprobs[b]));
         }
-        acc += log(mix) * counts[p];
+        // rescaled rows: lh = mix * 2^root_exp[p]  (exact powers of two carried as integers)
+        const double lg = (root_exp != nullptr) ? fma((double)root_exp[p], 0.6931471805599453094, log(mix)) : log(mix);
+        acc += lg * counts[p];
       }
     }
     const double total = block_sum(acc, s_warp);
@@ -1980,6 +1983,77 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
     if (h_lnl) *h_lnl = total;
     *counter = 0u;
     __threadfence_system();
+  }
+}
+
+// ---- per-pattern underflow rescaling --------------------------------------------------------
+// The reference multiplies plain FP64 partials and has no rescaling on this path
+// (evolve/likelihood_tree.py:10,151-153): beyond a few hundred divergent taxa lh underflows to 0
+// and lnL is -inf.  When rescaling is active the host picks "scaled" nodes (every subtree that has
+// gathered >= threshold unscaled tips); after such a node's rows are computed, every row (all K
+// bins together) is divided by 2^e, e = ilogb(largest element), and e is kept as an integer.
+// Multiplying by a power of two is exact, so whenever the reference does not underflow
+// lh_scaled * 2^E == lh bit for bit.  A scaled node's exponent is cumulative: it adds the
+// exponents of its nearest scaled descendants, gathered through index maps composed at set-up
+// (compose_map_kernel), so the root only has to gather from its own nearest scaled descendants.
+struct ScaleSrc {
+  const int32_t* map;   // row of the descendant for every row of this node
+  const int32_t* exps;  // the descendant's cumulative exponents
+};
+
+// out[p] = idx[cur[p]]   (cur == nullptr: identity) -- one step of composing gather tables down a path
+__global__ void __launch_bounds__(256)
+compose_map_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ cur, const int32_t* __restrict__ idx,
+                   int64_t n) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    out[p] = idx[cur ? cur[p] : p];
+}
+
+// rows: [n_rows][row_len] doubles, row_len a multiple of 4; LPR lanes share a row
+template <int LPR>
+__global__ void __launch_bounds__(256)
+rescale_rows_kernel(double* __restrict__ rows, int64_t n_rows, int row_len, int32_t* __restrict__ exps,
+                    const ScaleSrc* __restrict__ src, int n_src) {
+  constexpr int ROWS_PER_WARP = 32 / LPR;
+  const int lane = threadIdx.x & 31, g = lane % LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int chunks = row_len >> 2;
+  for (int64_t base = warp * ROWS_PER_WARP; base < n_rows; base += n_warps * ROWS_PER_WARP) {
+    const int64_t row = base + lane / LPR;
+    const bool valid = row < n_rows;
+    double* r = rows + row * row_len;
+    double m = 0.0;
+    if (valid)
+      for (int c = g; c < chunks; c += LPR) {
+        const d4 v = ld256(r + c * 4);
+        m = fmax(m, fmax(fmax(v.x, v.y), fmax(v.z, v.w)));
+      }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    int ex = 0;
+    if (m > 0.0 && m < __longlong_as_double(0x7ff0000000000000ll)) ex = ilogb(m);
+    if (valid && ex != 0)
+      for (int c = g; c < chunks; c += LPR) {
+        d4 v = ld256(r + c * 4);
+        v.x = scalbn(v.x, -ex); v.y = scalbn(v.y, -ex); v.z = scalbn(v.z, -ex); v.w = scalbn(v.w, -ex);
+        st256(r + c * 4, v);
+      }
+    if (valid && g == 0) {
+      int tot = ex;
+      for (int s = 0; s < n_src; ++s) tot += src[s].exps[src[s].map[row]];
+      exps[row] = tot;
+    }
+  }
+}
+
+// the root is never scaled itself: its exponent is the sum over its nearest scaled descendants
+__global__ void __launch_bounds__(256)
+root_exp_kernel(int32_t* __restrict__ exps, int64_t n_rows, const ScaleSrc* __restrict__ src, int n_src) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_rows; p += (int64_t)gridDim.x * blockDim.x) {
+    int tot = 0;
+    for (int s = 0; s < n_src; ++s) tot += src[s].exps[src[s].map[p]];
+    exps[p] = tot;
   }
 }
 

@@ -9,7 +9,7 @@ whole post-order sweep behind one call.
 from __future__ import annotations
 
 import ctypes
-from ctypes import byref, c_double, c_void_p
+from ctypes import byref, c_double, c_int, c_void_p
 
 import numpy as np
 
@@ -254,6 +254,35 @@ class LikelihoodEngine:
 
     def invalidate(self):
         _lib.check(self._lib.c3_invalidate(self._h))
+
+    # -- per-pattern underflow rescaling ------------------------------------------
+    RESCALE_OFF, RESCALE_ON, RESCALE_AUTO = 0, 1, 2
+
+    def set_rescaling(self, mode="auto", tip_threshold=0):
+        """``"off"``: the reference's plain FP64 products (-inf once a pattern underflows,
+        evolve/likelihood_tree.py:10); ``"on"``: per-pattern power-of-two exponents carried up
+        the tree; ``"auto"`` (default): switch on when a blocking evaluation is not finite."""
+        m = {"off": 0, "on": 1, "auto": 2, False: 0, True: 1}.get(mode, mode)
+        _lib.check(self._lib.c3_set_rescaling(self._h, int(m), int(tip_threshold)))
+
+    def rescaling(self):
+        """(active, number of scaled nodes)"""
+        a, n = c_int(0), c_int(0)
+        _lib.check(self._lib.c3_get_rescaling(self._h, byref(a), byref(n)))
+        return bool(a.value), n.value
+
+    def get_root_exponents(self):
+        """E[p]: the true per-pattern likelihood is lh[p] * 2**E[p] (zeros when rescaling is off)"""
+        out = np.empty(self.root_rows, np.int32)
+        _lib.check(self._lib.c3_get_root_exponents(self._h, _i32ptr(out), out.shape[0]))
+        return out
+
+    def get_scaled_lh(self):
+        """[K, root rows] root likelihoods as stored: the true value is ``out[b, p] * 2**E[p]``"""
+        out = np.empty((self.n_bins, self.root_rows), np.float64)
+        for b in range(self.n_bins):
+            _lib.check(self._lib.c3_get_scaled_lh(self._h, b, _dptr(out[b]), out.shape[1]))
+        return out
 
     # -- evaluation ----------------------------------------------------------
     def evaluate(self) -> float:

@@ -110,6 +110,8 @@ class ShardedLikelihoodFunction:
             return getattr(self.lf, name)
         raise AttributeError(name)
 
+    _rescale_tried = False
+
     def get_log_likelihood(self) -> float:
         lf = self.lf
         lf._sync()
@@ -121,4 +123,12 @@ class ShardedLikelihoodFunction:
             self._buf[0] = lf.engine.evaluate()
         if self.world > 1:
             self._dist.all_reduce(self._buf, group=self.group)
-        return float(self._buf.item())
+        total = float(self._buf.item())
+        if self.on_gpu and not np.isfinite(total) and not lf.engine.rescaling()[0] and not self._rescale_tried:
+            # c3_evaluate_device is asynchronous, so the engine's automatic switch to per-pattern
+            # rescaling (c3_set_rescaling) cannot see the value: every rank sees the same total
+            # and switches here, then the evaluation is repeated once
+            self._rescale_tried = True
+            lf.engine.set_rescaling("on")
+            return self.get_log_likelihood()
+        return total

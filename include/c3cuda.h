@@ -150,6 +150,40 @@ C3_API int c3_set_bin_probs(c3_engine* e, const double* bprobs);
 C3_API int c3_set_fixed_motifs(c3_engine* e, const int32_t* fixed_motif_of_node);
 C3_API int c3_invalidate(c3_engine* e); /* force a full recomputation next time        */
 
+/* ---- per-pattern underflow rescaling ----------------------------------------------
+ * The reference multiplies plain FP64 partials on this path and has no rescaling
+ * (evolve/likelihood_tree.py:10,151-153; its only scaling, BASE = 2**100, is in the
+ * phylo-HMM reducer :168-176): past a few hundred divergent taxa a pattern's
+ * likelihood underflows to 0 and lnL is -inf.  The engine can carry a per-pattern
+ * power-of-two exponent instead: the rows of "scaled" nodes (every subtree that has
+ * gathered tip_threshold unscaled tips) are divided by 2^ilogb(largest element)
+ * and the integer exponents are summed up the tree and folded back in the
+ * reduction (log(mix) + E ln 2) and in c3_get_lh / c3_get_site_lh (ldexp).  Powers
+ * of two are exact, so wherever the reference does not underflow the per-pattern
+ * values are bit-identical with and without rescaling.
+ *   C3_RESCALE_OFF   never (the reference's arithmetic, -inf included)
+ *   C3_RESCALE_ON    always
+ *   C3_RESCALE_AUTO  (default) plain products until a blocking c3_evaluate / c3_update /
+ *                    c3_evaluate_many returns a non-finite lnL; the engine then switches
+ *                    rescaling on for good and repeats that evaluation.  The
+ *                    asynchronous c3_evaluate_device cannot look at the value: callers
+ *                    that use it switch modes themselves.
+ * tip_threshold <= 0 keeps the current value (default 16).  While rescaling is active,
+ * c3_get_partials returns the stored (scaled) rows.
+ * c3_get_rescaling: whether rescaling is active, and the number of scaled nodes.
+ * c3_get_root_exponents: E[p] of every root pattern (all zero when inactive).
+ * c3_get_scaled_lh: like c3_get_lh but WITHOUT folding the exponent back: the true value is
+ *             out[p] * 2^E[p], the same E for every bin of a pattern -- what a caller needs
+ *             for ratios (posterior bin probabilities, likelihood_calculation.py:247-257)
+ *             and logs of patterns whose likelihood is below the FP64 range.             */
+#define C3_RESCALE_OFF 0
+#define C3_RESCALE_ON 1
+#define C3_RESCALE_AUTO 2
+C3_API int c3_set_rescaling(c3_engine* e, int mode, int tip_threshold);
+C3_API int c3_get_rescaling(c3_engine* e, int* active, int* n_scaled_nodes);
+C3_API int c3_get_root_exponents(c3_engine* e, int32_t* out, int64_t n_rows);
+C3_API int c3_get_scaled_lh(c3_engine* e, int bin, double* out, int64_t n_rows);
+
 /* ---- evaluation ----------------------------------------------------------------
  * c3_evaluate: batched expm for the dirty (edge, bin)s, level-by-level pruning of
  *             the dirty nodes, site-weighted reduction; blocks for the scalar
