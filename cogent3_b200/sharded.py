@@ -132,3 +132,111 @@ class ShardedLikelihoodFunction:
             lf.engine.set_rescaling("on")
             return self.get_log_likelihood()
         return total
+
+
+def loci_of_rank(n_loci: int, world_size: int, rank: int):
+    """whole loci are dealt round-robin: locus i lives on rank i % world_size"""
+    return list(range(rank, n_loci, world_size))
+
+
+class MultiLocusLikelihoodFunction:
+    """Several alignments ("loci") on one tree, whole loci dealt to the ranks.
+
+    The reference builds one likelihood tree per locus and sums the per-locus log-likelihoods
+    (``make_likelihood_function(tree, loci=[...])``; ``SumDefn`` over the locus dimension,
+    evolve/likelihood_calculation.py:161-163, recalculation/definition.py:672-676).  Loci are a
+    second independent axis next to the columns: every rank owns the engines of its
+    loci, launches them together (``c3_evaluate_many``: each on its own stream), adds its values in
+    locus order and the ranks' sums meet in ONE all-reduce of a double per evaluation (NCCL on
+    GPUs, gloo in the CPU tests).  Parameters are global unless a ``locus`` is named
+    (cogent3's ``set_param_rule(..., locus=...)`` / ``is_independent`` over loci)."""
+
+    def __init__(self, model, topo, loci, bins=1, group=None, device=None, engine_factory=None, **kw):
+        import torch
+        import torch.distributed as dist
+
+        self._torch, self._dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.locus_names = list(loci)
+        self.local = loci_of_rank(len(self.locus_names), self.world, self.rank)
+        self.on_gpu = engine_factory is None
+        self.lfs = {}
+        for i in self.local:
+            if self.on_gpu:
+                dev = torch.cuda.current_device() if device is None else device
+                # stream=None: every engine creates its own stream, so the loci of a rank overlap
+                self.lfs[i] = LikelihoodFunction(model, topo, bins=bins, device=dev, stream=None, **kw)
+            else:
+                self.lfs[i] = LikelihoodFunction(model, topo, bins=bins, engine_factory=engine_factory, **kw)
+        if self.on_gpu:
+            dev = torch.cuda.current_device() if device is None else device
+            self._buf = torch.zeros(1, dtype=torch.float64, device=f"cuda:{dev}")
+        else:
+            self._buf = torch.zeros(1, dtype=torch.float64)
+
+    def _index(self, locus):
+        return self.locus_names.index(locus) if not isinstance(locus, int) else locus
+
+    def set_alignment(self, alignments, symbol_rows=None):
+        """``alignments``: one ``codes[n_tips, L_i]`` per locus, in ``loci`` order (entries of
+        loci that live on other ranks may be None)"""
+        assert len(alignments) == len(self.locus_names)
+        for i in self.local:
+            self.lfs[i].set_alignment(np.asarray(alignments[i]), symbol_rows)
+        return self
+
+    def set_motif_probs_from_data(self, pooled=True):
+        """``pooled``: one set of motif probabilities from all loci (an all-reduce of M counts);
+        otherwise every locus uses its own"""
+        if not pooled:
+            for lf in self.lfs.values():
+                lf.set_motif_probs_from_data()
+            return
+        M = next(iter(self.lfs.values())).model.n_states if self.lfs else None
+        counts = np.zeros(M if M else 0)
+        for lf in self.lfs.values():
+            counts = counts + lf.state_counts()
+        t = self._torch.as_tensor(counts, dtype=self._torch.float64, device=self._buf.device)
+        if self.world > 1:
+            self._dist.all_reduce(t, group=self.group)
+        counts = t.cpu().numpy()
+        for lf in self.lfs.values():
+            lf.set_motif_probs(counts / counts.sum())
+
+    def set_param_rule(self, par_name, value=None, edge=None, edges=None, locus=None, **kw):
+        """every rank makes the same calls; a rank ignores loci it does not own"""
+        targets = self.local if locus is None else [self._index(locus)]
+        for i in targets:
+            if i in self.lfs:
+                self.lfs[i].set_param_rule(par_name, value=value, edge=edge, edges=edges, **kw)
+
+    def set_lengths(self, lengths, locus=None):
+        targets = self.local if locus is None else [self._index(locus)]
+        for i in targets:
+            if i in self.lfs:
+                self.lfs[i].lengths[:-1] = np.asarray(lengths)[:-1]
+                self.lfs[i]._dirty_model = True
+
+    def locus_log_likelihoods(self):
+        """{locus index: lnL} of this rank's loci, evaluated together"""
+        lfs = [self.lfs[i] for i in self.local]
+        for lf in lfs:
+            lf._sync()
+        if self.on_gpu and len(lfs) > 1:
+            from .engine import evaluate_many
+
+            vals = evaluate_many([lf.engine for lf in lfs])
+        else:
+            vals = [lf.engine.evaluate() for lf in lfs]
+        return {i: float(v) for i, v in zip(self.local, vals, strict=True)}
+
+    def get_log_likelihood(self) -> float:
+        local = 0.0
+        for _i, v in sorted(self.locus_log_likelihoods().items()):
+            local += v  # locus order: the same bits on every run
+        self._buf[0] = local
+        if self.world > 1:
+            self._dist.all_reduce(self._buf, group=self.group)
+        return float(self._buf.item())

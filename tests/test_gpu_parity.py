@@ -412,3 +412,32 @@ def test_fused_allreduce_between_engines_in_one_process():
         lf.engine.comm_detach()
     back = [lf.engine.evaluate() for lf in shards]
     assert abs(sum(back) - got[0]) <= 1e-12 * abs(got[0]) and len(set(back)) == world
+
+
+def test_multi_locus_on_one_gpu_matches_the_oracle_sum():
+    """whole loci as a second axis (SumDefn over loci, likelihood_calculation.py:161-163): the
+    engines of a rank's loci are launched together (c3_evaluate_many) and summed in locus order"""
+    from cogent3_b200.sharded import MultiLocusLikelihoodFunction
+
+    topo, lengths, _ = make_workload(12, 10, 4, seed=31)
+    alns = [make_workload(12, L, 4, seed=31, shard=k)[2].astype(np.int64) for k, L in enumerate((4000, 911, 20_000))]
+    names = ["a", "b", "c"]
+    got_lf = MultiLocusLikelihoodFunction("GTR", topo, names, bins=4)
+    want_lf = MultiLocusLikelihoodFunction("GTR", topo, names, bins=4, engine_factory=OracleEngine)
+    for lf in (got_lf, want_lf):
+        lf.set_alignment(alns, np.eye(4))
+        lf.set_motif_probs_from_data()
+        lf.set_lengths(lengths)
+        for k, p in enumerate(hostmodels.get_model("GTR").parameter_order):
+            lf.set_param_rule(p, value=0.6 + 0.3 * k)
+        lf.set_param_rule("rate_shape", value=0.7)
+        lf.set_param_rule("rate_shape", value=1.4, locus="b")
+    got, want = got_lf.get_log_likelihood(), want_lf.get_log_likelihood()
+    assert abs(got - want) <= REL_LNL * abs(want)
+    per_g, per_w = got_lf.locus_log_likelihoods(), want_lf.locus_log_likelihoods()
+    for i in range(3):
+        assert abs(per_g[i] - per_w[i]) <= REL_LNL * abs(per_w[i])
+    got_lf.set_param_rule("length", edge=topo.names[2], value=0.4, locus="c")
+    want_lf.set_param_rule("length", edge=topo.names[2], value=0.4, locus="c")
+    got, want = got_lf.get_log_likelihood(), want_lf.get_log_likelihood()
+    assert abs(got - want) <= REL_LNL * abs(want)

@@ -89,3 +89,90 @@ def test_column_blocks_partition():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- whole loci dealt to the ranks (second axis) -----------------------------------
+def _loci_problem():
+    from cogent3_b200.synthetic import make_workload
+
+    topo, lengths, _ = make_workload(7, 10, 4, seed=21)
+    alns = [make_workload(7, L, 4, seed=21, shard=k)[2].astype(np.int64) for k, L in enumerate((300, 511, 77, 1200, 64))]
+    return topo, lengths, alns
+
+
+def _configure_loci(lf, lengths):
+    lf.set_motif_probs_from_data()
+    lf.set_lengths(lengths)
+    lf.set_param_rule("kappa", value=2.5)
+    lf.set_param_rule("kappa", value=5.0, locus="l3")  # one locus with its own kappa
+    lf.set_param_rule("rate_shape", value=0.8)
+
+
+def _loci_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from cogent3_b200.sharded import MultiLocusLikelihoodFunction
+    from oracle.engine import OracleEngine
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        topo, lengths, alns = _loci_problem()
+        names = [f"l{i}" for i in range(len(alns))]
+        lf = MultiLocusLikelihoodFunction("HKY85", topo, names, bins=2,
+                                          engine_factory=functools.partial(OracleEngine, mode="port"))
+        # a rank only needs the alignments of its own loci
+        lf.set_alignment([a if i % world == rank else None for i, a in enumerate(alns)], np.eye(4))
+        _configure_loci(lf, lengths)
+        v1 = lf.get_log_likelihood()
+        lf.set_param_rule("length", edge=topo.names[1], value=0.27)
+        v2 = lf.get_log_likelihood()
+        out.put((rank, v1, v2, sorted(lf.local)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_loci_dealt_to_ranks_equal_the_sum_of_single_locus_functions(world):
+    import torch.multiprocessing as mp
+
+    from cogent3_b200.likelihood import LikelihoodFunction
+    from oracle.engine import OracleEngine
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loci_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+    topo, lengths, alns = _loci_problem()
+    singles = []
+    for a in alns:
+        lf = LikelihoodFunction("HKY85", topo, bins=2, engine_factory=OracleEngine)
+        lf.set_alignment(a, np.eye(4))
+        singles.append(lf)
+    counts = sum(lf.state_counts() for lf in singles)
+    want = []
+    for step in range(2):
+        tot = 0.0
+        for i, lf in enumerate(singles):
+            lf.set_motif_probs(counts / counts.sum())
+            lf.lengths[:-1] = lengths[:-1]
+            lf.set_param_rule("kappa", value=5.0 if i == 3 else 2.5)
+            lf.set_param_rule("rate_shape", value=0.8)
+            if step == 1:
+                lf.set_param_rule("length", edge=topo.names[1], value=0.27)
+            tot += lf.get_log_likelihood()
+        want.append(tot)
+    owned = sorted(i for r in results for i in r[3])
+    assert owned == list(range(len(alns)))  # every locus on exactly one rank
+    for _rank, v1, v2, _loc in results:
+        assert v1 == results[0][1] and v2 == results[0][2]
+        assert abs(v1 - want[0]) <= 1e-12 * abs(want[0])
+        assert abs(v2 - want[1]) <= 1e-12 * abs(want[1])
