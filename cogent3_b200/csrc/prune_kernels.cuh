@@ -1912,23 +1912,42 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
   __shared__ bool s_last;
   pdl_wait();  // launched early (programmatic dependent launch): lh is the root launch's output
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    double acc = 0.0;
+    constexpr int U = REDUCE_ROWS_PER_TILE / REDUCE_THREADS;
     const int64_t base = (int64_t)tile * REDUCE_ROWS_PER_TILE;
+    // all loads of the thread's rows first (one 256-bit / 128-bit load per row for K = 4 / 2), then the logs
+    double mix[U], cnt[U];
+    int32_t ex[U];
 #pragma unroll
-    for (int u = 0; u < REDUCE_ROWS_PER_TILE / REDUCE_THREADS; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t p = base + u * REDUCE_THREADS + threadIdx.x;
+      mix[u] = 1.0;
+      cnt[u] = 0.0;
+      ex[u] = 0;
       if (p < n_rows) {
-        double mix;
         if (K == 1) {
-          mix = lh[p];
+          mix[u] = lh[p];
+        } else if (K == 4) {
+          const d4 v = ld256(lh + p * 4);
+          mix[u] = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(v.x, bprobs[0])), __dmul_rn(v.y, bprobs[1])),
+                                       __dmul_rn(v.z, bprobs[2])), __dmul_rn(v.w, bprobs[3]));
+        } else if (K == 2) {
+          const double2 v = *reinterpret_cast<const double2*>(lh + p * 2);
+          mix[u] = __dadd_rn(__dadd_rn(0.0, __dmul_rn(v.x, bprobs[0])), __dmul_rn(v.y, bprobs[1]));
         } else {
-          mix = 0.0;
-          for (int b = 0; b < K; ++b) mix = __dadd_rn(mix, __dmul_rn(lh[p * K + b], bprobs[b]));
+          double m = 0.0;
+          for (int b = 0; b < K; ++b) m = __dadd_rn(m, __dmul_rn(lh[p * K + b], bprobs[b]));
+          mix[u] = m;
         }
-        // rescaled rows: lh = mix * 2^root_exp[p]  (exact powers of two carried as integers)
-        const double lg = (root_exp != nullptr) ? fma((double)root_exp[p], 0.6931471805599453094, log(mix)) : log(mix);
-        acc += lg * counts[p];
+        cnt[u] = counts[p];
+        if (root_exp != nullptr) ex[u] = root_exp[p];
       }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // rescaled rows: lh = mix * 2^root_exp[p]  (exact powers of two carried as integers)
+      const double lg = (root_exp != nullptr) ? fma((double)ex[u], 0.6931471805599453094, log(mix[u])) : log(mix[u]);
+      acc += lg * cnt[u];
     }
     const double total = block_sum(acc, s_warp);
     if (threadIdx.x == 0) tile_sums[tile] = total;
