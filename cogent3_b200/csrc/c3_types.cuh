@@ -37,6 +37,7 @@ struct EdgeDesc {
   double* P;                // [K][MP][MP]
   const double* tip_table;  // [tip_rows][MP] indicator rows, nullptr for internal
   double* tip_inner;        // [tip_rows][K][MP]
+  const int32_t* tip_state; // [tip_rows] the state of a one-hot row, -1 for ambiguity codes / the gap row
   int64_t tip_rows;
 };
 

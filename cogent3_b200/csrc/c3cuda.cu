@@ -1054,13 +1054,14 @@ int c3_finalize(c3_engine* e) {
     off += align_up(bytes, 256);
     return o;
   };
-  std::vector<int64_t> o_rows(N), o_tab(N, -1), o_idx(N, -1);
+  std::vector<int64_t> o_rows(N), o_tab(N, -1), o_idx(N, -1), o_state(N, -1);
   int64_t n_child_total = 0, partial_bytes = 0;
   for (int n = 0; n < N; ++n) {
     const int64_t bytes = e->n_rows[n] * K * MP * (int64_t)sizeof(double);
     o_rows[n] = carve(bytes);
     if (e->children[n].empty()) {
       o_tab[n] = carve(e->n_rows[n] * MP * (int64_t)sizeof(double));
+      o_state[n] = carve(e->n_rows[n] * (int64_t)sizeof(int32_t));
     } else {
       partial_bytes += bytes;
       o_idx[n] = carve((int64_t)e->children[n].size() * e->n_rows[n] * (int64_t)sizeof(int32_t));
@@ -1106,6 +1107,18 @@ int c3_finalize(c3_engine* e) {
       e->d_tip_table[n] = reinterpret_cast<double*>(e->d_pool + o_tab[n]);
       C3_CUDA(cudaMemcpyAsync(e->d_tip_table[n], e->tip_table[n].data(),
                               e->tip_table[n].size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+      // which rows are plain indicators (one entry 1.0, the rest 0.0): their inner product with P is a column
+      std::vector<int32_t> state((size_t)e->n_rows[n], -1);
+      for (int64_t u = 0; u < e->n_rows[n]; ++u) {
+        const double* row = e->tip_table[n].data() + u * MP;
+        int hot = -1, nonzero = 0;
+        for (int j = 0; j < MP; ++j)
+          if (row[j] != 0.0) { ++nonzero; hot = j; }
+        if (nonzero == 1 && row[hot] == 1.0 && hot < e->M) state[(size_t)u] = hot;
+      }
+      C3_CUDA(cudaMemcpyAsync(e->d_pool + o_state[n], state.data(), state.size() * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, e->stream));
+      C3_CUDA(cudaStreamSynchronize(e->stream));  // `state` goes out of scope
       // padded tip_inner columns must be zero
       C3_CUDA(cudaMemsetAsync(e->d_rows[n], 0, (size_t)e->n_rows[n] * K * MP * sizeof(double), e->stream));
     } else {
@@ -1158,6 +1171,7 @@ int c3_finalize(c3_engine* e) {
     EdgeDesc& ed = h_edges[n];
     ed.P = e->d_P + (int64_t)n * K * MP * MP;
     ed.tip_table = e->d_tip_table[n];
+    ed.tip_state = o_state[n] >= 0 ? reinterpret_cast<const int32_t*>(e->d_pool + o_state[n]) : nullptr;
     ed.tip_inner = e->children[n].empty() ? e->d_rows[n] : nullptr;
     ed.tip_rows = e->children[n].empty() ? e->n_rows[n] : 0;
   }

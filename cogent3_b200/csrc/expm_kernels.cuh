@@ -18,6 +18,10 @@
 
 namespace c3 {
 
+// tip_state[u] >= 0: row u is the indicator of that one state (an unambiguous symbol), so its inner
+// product with the rows of P is just a column of P -- the same bits as the sum (every other term is
+// fma(0, x, s) = s).  Only ambiguity codes and the gap row run the sum.  (ncu on the 61-state
+// launch: the sums over all rows were more than half of the kernel's instructions.)
 __device__ __forceinline__ void tip_inner_update(const EdgeDesc& ed, const double* sP, int bin,
                                                  int M, int MP, int K) {
   if (ed.tip_table == nullptr) return;
@@ -25,15 +29,21 @@ __device__ __forceinline__ void tip_inner_update(const EdgeDesc& ed, const doubl
   for (int64_t o = threadIdx.x; o < total; o += blockDim.x) {
     const int64_t u = o / M;
     const int i = (int)(o - u * M);
-    const double* row = ed.tip_table + u * MP;
-    // the j loop starts at i: consecutive lanes (consecutive i) then read different shared
-    // memory banks of sP (row stride MP is a multiple of the bank count); the rows are 0/1
-    // indicators, so the rotated summation order only matters for ambiguity codes (~1 ulp)
-    double s = 0.0;
-    int j = (MP > 8) ? i : 0;
-    for (int n = 0; n < M; ++n) {
-      s = fma(row[j], sP[i * MP + j], s);
-      j = (j + 1 == M) ? 0 : j + 1;
+    const int state = ed.tip_state[u];
+    double s;
+    if (state >= 0) {
+      s = sP[i * MP + state];
+    } else {
+      const double* row = ed.tip_table + u * MP;
+      // the j loop starts at i: consecutive lanes (consecutive i) then read different shared
+      // memory banks of sP (row stride MP is a multiple of the bank count); the rows are 0/1
+      // indicators, so the rotated summation order only matters for ambiguity codes (~1 ulp)
+      s = 0.0;
+      int j = (MP > 8) ? i : 0;
+      for (int n = 0; n < M; ++n) {
+        s = fma(row[j], sP[i * MP + j], s);
+        j = (j + 1 == M) ? 0 : j + 1;
+      }
     }
     ed.tip_inner[(u * K + bin) * MP + i] = s;
   }
@@ -158,6 +168,7 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
         const int i0 = 2 * (o / T), j0 = 2 * (o % T);
         const int i1 = min(i0 + 1, M - 1), j1 = min(j0 + 1, M - 1);
         double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll 4
         for (int k = 0; k < M; ++k) {
           const double w0 = sW[i0 * LD + k], w1 = sW[i1 * LD + k];
           const double v0 = sI[j0 * LD + k], v1 = sI[j1 * LD + k];
