@@ -109,8 +109,10 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
       // by its shared-memory loads); every element still sums k = 0..M-1 in order
       const int T = (M + 1) / 2;
       for (int o = threadIdx.x; o < T * T; o += blockDim.x) {
-        const int i0 = 2 * (o / T), j0 = 2 * (o % T);
-        const int i1 = min(i0 + 1, M - 1), j1 = min(j0 + 1, M - 1);
+        // rows (i0, i0 + T) x columns (j0, j0 + T): consecutive lanes read consecutive rows of evI,
+        // LD (odd) doubles apart -- conflict free; adjacent pairs (stride 2 LD) were 2-way conflicts
+        const int i0 = o / T, j0 = o % T;
+        const int i1 = min(i0 + T, M - 1), j1 = min(j0 + T, M - 1);
         double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
         for (int k = 0; k < M; ++k) {
           const double w0r = sWr[i0 * LD + k], w0i = sWi[i0 * LD + k];
@@ -125,9 +127,9 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
         const double r[2][2] = {{fmax(a00, 0.0), fmax(a01, 0.0)}, {fmax(a10, 0.0), fmax(a11, 0.0)}};
         for (int di = 0; di < 2; ++di)
           for (int dj = 0; dj < 2; ++dj)
-            if (i0 + di < M && j0 + dj < M) {
-              sP[(i0 + di) * MP + j0 + dj] = r[di][dj];
-              Pout[(i0 + di) * MP + j0 + dj] = r[di][dj];
+            if (i0 + di * T < M && j0 + dj * T < M) {
+              sP[(i0 + di * T) * MP + j0 + dj * T] = r[di][dj];
+              Pout[(i0 + di * T) * MP + j0 + dj * T] = r[di][dj];
             }
       }
     } else {
@@ -165,8 +167,10 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
       __syncthreads();
       const int T = (M + 1) / 2;  // 2 x 2 register tiles, see the complex branch
       for (int o = threadIdx.x; o < T * T; o += blockDim.x) {
-        const int i0 = 2 * (o / T), j0 = 2 * (o % T);
-        const int i1 = min(i0 + 1, M - 1), j1 = min(j0 + 1, M - 1);
+        // rows (i0, i0 + T) x columns (j0, j0 + T): consecutive lanes read consecutive rows of evI,
+        // LD (odd) doubles apart -- conflict free; adjacent pairs (stride 2 LD) were 2-way conflicts
+        const int i0 = o / T, j0 = o % T;
+        const int i1 = min(i0 + T, M - 1), j1 = min(j0 + T, M - 1);
         double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
 #pragma unroll 4
         for (int k = 0; k < M; ++k) {
@@ -180,9 +184,9 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
         const double r[2][2] = {{fmax(a00, 0.0), fmax(a01, 0.0)}, {fmax(a10, 0.0), fmax(a11, 0.0)}};
         for (int di = 0; di < 2; ++di)
           for (int dj = 0; dj < 2; ++dj)
-            if (i0 + di < M && j0 + dj < M) {
-              sP[(i0 + di) * MP + j0 + dj] = r[di][dj];
-              Pout[(i0 + di) * MP + j0 + dj] = r[di][dj];
+            if (i0 + di * T < M && j0 + dj * T < M) {
+              sP[(i0 + di * T) * MP + j0 + dj * T] = r[di][dj];
+              Pout[(i0 + di * T) * MP + j0 + dj * T] = r[di][dj];
             }
       }
     } else {
