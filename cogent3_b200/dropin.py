@@ -72,10 +72,110 @@ class LazyPsub:
         return self.materialise().copy()
 
 
+# ---------------------------------------------------------------------------------------
+# cogent3's per-node pattern compression, vectorised
+#
+# ``lf.set_alignment`` spends its time in ``_indexed`` (evolve/likelihood_tree.py:186-203): a Python
+# dict loop over every column of every node -- ~7 s per 64 taxa x 100k columns, and it runs three
+# times per set_alignment + make_calculator.  The two functions below build the SAME
+# objects (real ``LikelihoodTreeLeaf`` / ``LikelihoodTreeEdge`` instances with identical ``uniq``,
+# ``index``, ``counts``, ``indexes``, ``ambig``, ``shape``) from numpy's first-occurrence ranking
+# (``patterns.first_seen_unique``, checked bit-exact against the dict loop in
+# tests/test_host_logic.py and against the live reference here in tests/test_dropin.py).
+# ---------------------------------------------------------------------------------------
+def fast_likelihood_tree_leaf(likelihood_tree, sequence, alphabet, seq_name):
+    """``make_likelihood_tree_leaf`` (evolve/likelihood_tree.py:223-278) without the per-column loop"""
+    from .patterns import first_seen_unique
+
+    motif_len = alphabet.motif_len
+    try:
+        seq = str(sequence)
+        raw = np.frombuffer(seq.encode("ascii"), np.uint8)
+        n = len(raw) // motif_len
+        if motif_len > 7 or n == 0:
+            raise ValueError("use the reference loop")
+        words = raw[: n * motif_len].reshape(n, motif_len).astype(np.int64)
+        key = words[:, 0].copy()
+        for k in range(1, motif_len):
+            key = key * 256 + words[:, k]
+        first, counts, index = first_seen_unique(key)
+        uniq_motifs = [seq[int(c) * motif_len : (int(c) + 1) * motif_len] for c in first]
+        uniq_motifs.append("?" * motif_len)  # extra column for gap
+        counts = np.append(counts, 0.0).astype(float)
+        moltype = getattr(sequence, "moltype", None) or alphabet.moltype
+        likelihoods = likelihood_tree.get_matched_array(alphabet, moltype, uniq_motifs, dtype=float)
+        return likelihood_tree.LikelihoodTreeLeaf(
+            uniq_motifs, likelihoods, counts, index.astype(int), seq_name, alphabet, sequence
+        )
+    except Exception:  # noqa: BLE001 - anything unusual: the reference's own code and its error messages
+        return likelihood_tree.make_likelihood_tree_leaf(sequence, alphabet, seq_name)
+
+
+def fast_likelihood_tree_edge(likelihood_tree, children, edge_name):
+    """``LikelihoodTreeEdge(children, edge_name)`` (evolve/likelihood_tree.py:13-70, pre-aligned
+    children) without the per-column zip + dict loop"""
+    from .patterns import _combine_keys, first_seen_unique
+
+    e = likelihood_tree.LikelihoodTreeEdge.__new__(likelihood_tree.LikelihoodTreeEdge)
+    e.edge_name = edge_name
+    e.alphabet = children[0].alphabet
+    M = children[0].shape[-1]
+    for child in children:
+        assert child.shape[-1] == M
+    assignments = [np.asarray(c.index, np.int64) for c in children]
+    sizes = [len(c.uniq) for c in children]
+    first, counts, index = first_seen_unique(_combine_keys(assignments, sizes))
+    uniq = np.stack([a[first] for a in assignments], axis=1).reshape(len(first), len(children))
+    gap = np.array([[s - 1 for s in sizes]], np.int64)  # extra column for gap
+    e.uniq = np.concatenate([uniq, gap]).astype(int)
+    e.index = index.astype(int)
+    e.indexes = np.ascontiguousarray(e.uniq.T)
+    e.counts = np.append(counts, 0.0).astype(float)
+    e._indexed_children = list(zip(e.indexes, children, strict=False))
+    e.shape = [len(e.uniq), M]
+    ambigs = [child.ambig[ix] for (ix, child) in e._indexed_children]
+    e.ambig = np.prod(ambigs, axis=0)
+    return e
+
+
 def _build(cogent3_modules):
     """create the Defn / LF classes lazily so that importing this module does not
     require cogent3"""
     (likelihood_calculation, parameter_controller, definition, matrix_exponentiation) = cogent3_modules
+    from cogent3.evolve import likelihood_tree, substitution_calculation
+
+    class FastAlignmentAdaptDefn(substitution_calculation.AlignmentAdaptDefn):
+        """``leaf_likelihoods``: ``model.convert_alignment`` (evolve/substitution_model.py:393-404) with
+        the vectorised leaf builder"""
+
+        def calc(self, model, alignment):
+            if type(model).convert_sequence is not _reference_convert_sequence(model):
+                return model.convert_alignment(alignment)  # a model with its own conversion
+            alphabet = model.get_alphabet()
+            return {
+                name: fast_likelihood_tree_leaf(
+                    likelihood_tree, alignment.get_gapped_seq(name, model.recode_gaps), alphabet, name
+                )
+                for name in alignment.names
+            }
+
+    def _reference_convert_sequence(model):
+        from cogent3.evolve.substitution_model import _SubstitutionModel
+
+        return _SubstitutionModel.convert_sequence
+
+    class FastLikelihoodTreeDefn(likelihood_calculation.LikelihoodTreeDefn):
+        """``lht``: ``recursive_lht_build`` (evolve/likelihood_calculation.py:103-122) with the
+        vectorised edge builder"""
+
+        def calc(self, leaves):
+            def build(edge):
+                if edge.istip():
+                    return leaves[edge.name]
+                kids = [build(child) for child in edge.children]
+                return fast_likelihood_tree_edge(likelihood_tree, kids, edge.name)
+
+            return build(self.tree)
     CalculationDefn = definition.CalculationDefn
     NonParamDefn = definition.NonParamDefn
     SumDefn = definition.SumDefn
@@ -235,7 +335,7 @@ def _build(cogent3_modules):
                 "the phylo-HMM (sites_independent=False) is out of scope (SURVEY §8a)"
             )
         fixed_motifs = NonParamDefn("fixed_motif", ["edge"])
-        lht = likelihood_calculation.LikelihoodTreeDefn(leaves, tree=tree)
+        lht = FastLikelihoodTreeDefn(leaves, tree=tree)
         root = likelihood_calculation.LhtEdgeLookupDefn(lht, edge_name="root")
         edges = [e for e in tree.postorder() if e.name != "root"]
         internal = [e.name for e in tree.postorder() if not e.istip()]
@@ -287,11 +387,51 @@ def _build(cogent3_modules):
                     if original in arg.clients:
                         arg.clients.remove(original)
             self._gpu_defn_factory = None
+            leaves = defns["align"]
+            if type(leaves) is substitution_calculation.AlignmentAdaptDefn:
+                # same inputs (model, alignment), vectorised conversion; the Defn the model built is
+                # detached like the psubs CallDefn above
+                original = leaves
+                leaves = FastAlignmentAdaptDefn(*original.args)
+                for arg in original.args:
+                    if original in arg.clients:
+                        arg.clients.remove(original)
             return make_total_loglikelihood_defn(
-                self.tree, defns["align"], psubs, defns["word_probs"], defns["bprobs"],
+                self.tree, leaves, psubs, defns["word_probs"], defns["bprobs"],
                 self.bin_names, self.locus_names, sites_independent,
                 engine_factory or _default_engine_factory, device,
             )  # fmt: skip
+
+        def set_motif_probs_from_data(self, align, locus=None, is_constant=None, include_ambiguity=False,
+                                      is_independent=None, auto=False, warn=False, pseudocount=None,
+                                      **kwargs):  # fmt: skip
+            """the reference method (evolve/parameter_controller.py:135-162) with the motif counts
+            (``MotifProbModel.count_motifs``, evolve/motif_prob_model.py:48-59: one
+            ``make_likelihood_tree_leaf`` dict loop per sequence -- most of what is left of
+            ``set_alignment`` once the tables are built with numpy) taken from the vectorised leaves"""
+            from cogent3.evolve import motif_prob_model, substitution_model
+
+            mm = self.model.mprob_model
+            if (type(self.model).count_motifs is not substitution_model._SubstitutionModel.count_motifs
+                    or type(mm).count_motifs is not motif_prob_model.MotifProbModel.count_motifs):  # fmt: skip
+                return super().set_motif_probs_from_data(
+                    align, locus=locus, is_constant=is_constant, include_ambiguity=include_ambiguity,
+                    is_independent=is_independent, auto=auto, warn=warn, pseudocount=pseudocount, **kwargs,
+                )  # fmt: skip
+            alpha = mm.get_counted_alphabet()
+            counts = None
+            for seq_name in align.names:
+                sequence = align.get_gapped_seq(seq_name, self.model.recode_gaps)
+                leaf = fast_likelihood_tree_leaf(likelihood_tree, sequence, alpha, seq_name)
+                count = leaf.get_motif_counts(include_ambiguity=include_ambiguity)
+                counts = count.copy() if counts is None else counts + count
+            if is_constant is None:
+                is_constant = not self.optimise_motif_probs
+            pseudocount = 0.0 if is_constant or (counts != 0).all() else pseudocount or 0.5
+            counts += pseudocount
+            mprobs = counts / (1.0 * sum(counts))
+            self.set_motif_probs(mprobs, locus=locus, is_constant=is_constant, is_independent=is_independent,
+                                 auto=auto, warn=warn, **kwargs)  # fmt: skip
 
         # -- values the rest of cogent3 looks up by name (SURVEY §8b) -------------------
         def _gpu_defn(self):

@@ -162,3 +162,76 @@ def test_product_default_engine_has_no_cpu_fallback():
     lf = make_likelihood_function(get_model("HKY85"), tree)  # default engine = CUDA
     with pytest.raises((_lib.C3Error, RuntimeError)):
         lf.set_alignment(aln)
+
+
+# ---- the vectorised pattern compression behind lf.set_alignment ----------------
+def _same_lht(a, b):
+    """recursively: every table of the reference's lht and of the drop-in's, bit for bit"""
+    assert type(a) is type(b) and a.edge_name == b.edge_name
+    assert np.array_equal(np.asarray(a.index), np.asarray(b.index))
+    assert np.asarray(a.index).dtype == np.asarray(b.index).dtype
+    assert np.array_equal(a.counts, b.counts) and a.counts.dtype == b.counts.dtype
+    assert np.array_equal(a.ambig, b.ambig)
+    assert list(a.shape) == list(b.shape)
+    if hasattr(a, "input_likelihoods"):  # a leaf
+        assert list(a.uniq) == list(b.uniq)
+        assert np.array_equal(a.input_likelihoods, b.input_likelihoods)
+        return 1
+    assert np.array_equal(a.uniq, b.uniq) and a.uniq.dtype == b.uniq.dtype
+    assert np.array_equal(a.indexes, b.indexes) and a.indexes.dtype == b.indexes.dtype
+    assert b.indexes.flags["C_CONTIGUOUS"]
+    n = 1
+    for (ia, ca), (ib, cb) in zip(a._indexed_children, b._indexed_children, strict=True):
+        assert np.array_equal(ia, ib)
+        n += _same_lht(ca, cb)
+    return n
+
+
+@pytest.mark.parametrize(
+    "model,data",
+    [("HKY85", "brca1"), ("GTR", "ambiguous"), ("CNFGTR", "codon"), ("GN", "small"), ("dinuc", "small")],
+)
+def test_fast_compression_builds_the_reference_tables(model, data):
+    from cogent3.evolve import substitution_model
+
+    if data == "brca1":
+        aln, tree = get_dataset("brca1"), get_dataset("mammal-tree")
+        tree = tree.get_sub_tree(aln.names)
+    elif data == "codon":
+        tree, aln = small_problem(n_tips=6, L=120, n_states=61)
+    elif data == "ambiguous":
+        tree = make_tree("((a,b),c,(d,e));")
+        aln = make_aligned_seqs(
+            {"a": "ACGTACGTAAGTNNRY-A", "b": "ACGTACGGAAGT-RYYCA", "c": "ACCTACGGTAGCAAGG-A",
+             "d": "ACCTATGGTAGCAAGGTA", "e": "NCCTATGG--GCAWGGTA"}, moltype="dna")  # fmt: skip
+    else:
+        tree, aln = small_problem(n_tips=9, L=400)
+
+    def factory():
+        if model == "dinuc":
+            return substitution_model.TimeReversibleDinucleotide(equal_motif_probs=True)
+        return get_model(model)
+
+    ref, lf = pair(factory, tree, aln)
+    a, b = ref.get_param_value("lht"), lf.get_param_value("lht")
+    assert _same_lht(a, b) == len(tree.get_edge_vector())
+    assert_same(ref, lf)
+    np.testing.assert_array_equal(ref.get_motif_probs().to_array(), lf.get_motif_probs().to_array())
+
+
+def test_fast_compression_is_what_set_alignment_runs():
+    """a 40-taxon x 30k-column alignment: the reference's dict loops take seconds per pass"""
+    import time
+
+    tree, aln = small_problem(n_tips=40, L=30_000, seed=9)
+    t0 = time.perf_counter()
+    ref = get_model("HKY85").make_likelihood_function(tree)
+    ref.set_alignment(aln)
+    t_ref = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lf = make_likelihood_function(get_model("HKY85"), tree, engine_factory=FACTORY)
+    lf.set_alignment(aln)
+    t_fast = time.perf_counter() - t0
+    assert _same_lht(ref.get_param_value("lht"), lf.get_param_value("lht")) == 2 * 40 - 2
+    assert t_fast < t_ref, (t_fast, t_ref)
+    print(f"set_alignment 40 x 30k: reference {t_ref:.2f} s, drop-in {t_fast:.2f} s")
