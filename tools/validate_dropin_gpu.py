@@ -86,4 +86,46 @@ lf.set_alignment(aln)
 for f in (ref, lf):
     f.set_param_rule("omega", value=0.4)
 report("C4-like CNFGTR 10x900 codons", ref, lf)
+# ---- set_alignment / make_calculator wall time at a size where the reference's Python loops hurt ----
+tree, aln = small_problem(n_tips=64, L=100_000, seed=13)
+times = {}
+for tag, make in (("reference", lambda: mk().make_likelihood_function(tree, bins=4)),
+                  ("drop-in", lambda: make_likelihood_function(mk(), tree, bins=4))):
+    t0 = time.perf_counter()
+    f = make()
+    f.set_alignment(aln)
+    t1 = time.perf_counter()
+    f.set_param_rule("bprobs", is_constant=True)
+    calc = f.make_calculator()
+    t2 = time.perf_counter()
+    x = calc.get_value_array()
+    calc(x)
+    n, t3 = 0, time.perf_counter()
+    while time.perf_counter() - t3 < 2.0:
+        calc([v * (1 + 1e-3 * ((n % 5) + 1)) for v in x])
+        n += 1
+    t4 = time.perf_counter()
+    times[tag] = (t1 - t0, t2 - t1, (t4 - t3) / n, f.get_log_likelihood())
+    print(f"64 x 100k GTR+G4, {tag}: set_alignment {t1 - t0:.2f} s, make_calculator {t2 - t1:.2f} s, "
+          f"full evaluation through Calculator {1e3 * (t4 - t3) / n:.2f} ms, lnL {times[tag][3]!r}")
+a, b = times["reference"][3], times["drop-in"][3]
+assert abs(a - b) <= 1e-9 * abs(a)
+
+# ---- a tree deep enough to underflow FP64: the reference returns -inf, the engine rescales ------
+from cogent3_b200.synthetic import dense_alignment  # noqa: E402
+from cogent3_b200.tree import random_join_tree  # noqa: E402
+
+rng = np.random.default_rng(11)
+topo, lengths = random_join_tree(700, rng)
+codes = dense_alignment(topo, 300, 4, rng)
+data = {n: "".join("TCAG"[c] for c in row) for n, row in zip(topo.tip_names, codes, strict=True)}
+tree, aln = make_tree(topo.to_newick(np.asarray(lengths) * 4.0)), make_aligned_seqs(data, moltype="dna")
+ref = get_model("HKY85").make_likelihood_function(tree)
+ref.set_alignment(aln)
+lf = make_likelihood_function(get_model("HKY85"), tree)
+lf.set_alignment(aln)
+a, b = ref.get_log_likelihood(), lf.get_log_likelihood()
+print(f"700 taxa x 300 i.i.d. columns, HKY85: reference lnL {a!r}, drop-in lnL {b!r} "
+      f"(per-pattern rescaling switched on automatically: {lf._engine().rescaling()})")
+assert not np.isfinite(a) and np.isfinite(b)
 print("drop-in + CUDA engine + real cogent3: OK")
