@@ -121,6 +121,11 @@ struct c3_engine {
   bool use_dmma_reg = true;  // warp-private register pipeline for M != 4 (C3_DMMA_REG=0: first version)
   bool use_reg2 = true;   // binary nodes: two strips in flight per warp (C3_REG1=1: the one-strip regpipe kernel)
   bool use_ring = false;  // C3_RING=1: the cp.async shared-memory ring version of the strip kernel
+  // Nothing on the path reads the ROOT's partial rows (only lh = inner(plh_root, pi) goes on, and the
+  // root is recomputed whenever anything changed), so by default they are neither allocated nor written
+  // -- a quarter of the root launch's traffic at 4 states; c3_get_partials(root) recomputes them.
+  // C3_STORE_ROOT=1, or a kernel family without the check, keeps them.
+  bool store_root = false;
   // dataflow kernel: consecutive big binary levels in one launch.  Opt-in (C3_FLOW=1): its kernel
   // time is lower than the per-level launches' sum (C2 0.267 vs 0.289 ms, C3 0.435 vs 0.585 ms) but
   // the per-level launches overlap through programmatic dependent launch, so the STEP is not faster
@@ -579,6 +584,9 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   if (const char* env = getenv("C3_REG1")) e->use_reg2 = atoi(env) == 0;
   if (const char* env = getenv("C3_FLOW")) e->use_flow = atoi(env) != 0;
+  e->store_root = !(e->use_dmma ? e->edge_major
+                                : (e->use_strip && e->use_reg2 && !e->use_ring && !e->use_flow));
+  if (const char* env = getenv("C3_STORE_ROOT")) e->store_root = e->store_root || atoi(env) != 0;
   if (const char* env = getenv("C3_RESCALE")) e->rescale_mode = std::max(0, std::min(2, atoi(env)));
   if (const char* env = getenv("C3_RESCALE_TIPS")) e->rescale_threshold = std::max(2, atoi(env));
   e->root = n_nodes - 1;
@@ -1057,7 +1065,7 @@ int c3_finalize(c3_engine* e) {
   std::vector<int64_t> o_rows(N), o_tab(N, -1), o_idx(N, -1), o_state(N, -1);
   int64_t n_child_total = 0, partial_bytes = 0;
   for (int n = 0; n < N; ++n) {
-    const int64_t bytes = e->n_rows[n] * K * MP * (int64_t)sizeof(double);
+    const int64_t bytes = (n == e->root && !e->store_root) ? 0 : e->n_rows[n] * K * MP * (int64_t)sizeof(double);
     o_rows[n] = carve(bytes);
     if (e->children[n].empty()) {
       o_tab[n] = carve(e->n_rows[n] * MP * (int64_t)sizeof(double));
@@ -1102,7 +1110,7 @@ int c3_finalize(c3_engine* e) {
   e->d_tip_table.assign(N, nullptr);
   e->d_idx.assign(N, nullptr);
   for (int n = 0; n < N; ++n) {
-    e->d_rows[n] = reinterpret_cast<double*>(e->d_pool + o_rows[n]);
+    e->d_rows[n] = (n == e->root && !e->store_root) ? nullptr : reinterpret_cast<double*>(e->d_pool + o_rows[n]);
     if (o_tab[n] >= 0) {
       e->d_tip_table[n] = reinterpret_cast<double*>(e->d_pool + o_tab[n]);
       C3_CUDA(cudaMemcpyAsync(e->d_tip_table[n], e->tip_table[n].data(),
@@ -1540,12 +1548,13 @@ int c3_get_partials(c3_engine* e, int node, int bin, double* out, int64_t n_rows
   C3_CUDA(cudaSetDevice(e->device));
   C3_CUDA(cudaStreamSynchronize(e->stream));
   const int M = e->M, MP = e->MP;
-  if (e->edge_major && node != e->root && !e->children[node].empty()) {
-    // the stored rows are P . plh; the accessor returns plh = product of the children's rows
+  if ((e->edge_major && node != e->root && !e->children[node].empty()) || (node == e->root && !e->store_root)) {
+    // the stored rows are P . plh (edge-major) or not stored at all (the root); the accessor returns
+    // plh = product of the children's (P-multiplied) rows
     double* tmp = nullptr;
     C3_CUDA(cudaMalloc(&tmp, (size_t)n_rows * MP * sizeof(double)));
     const int grid = (int)std::min<int64_t>((n_rows * MP + 255) / 256, (int64_t)e->n_sm * 8);
-    edge_major_plh_kernel<<<grid, 256, 0, e->stream>>>(e->h_nodes[node], e->d_childs, e->K, MP, bin, tmp);
+    edge_major_plh_kernel<<<grid, 256, 0, e->stream>>>(e->h_nodes[node], e->d_childs, e->K, M, MP, bin, tmp);
     cudaError_t err = cudaStreamSynchronize(e->stream);
     if (err == cudaSuccess)
       err = cudaMemcpy2D(out, M * sizeof(double), tmp, MP * sizeof(double), M * sizeof(double), (size_t)n_rows,
@@ -1731,7 +1740,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   auto account = [&](int n) {
     const int64_t rows = e->n_rows[n];
     node_rows += rows;
-    alg_bytes += rows * K * M * 8;  // write
+    if (n != e->root || e->store_root) alg_bytes += rows * K * M * 8;  // write
     for (int c : e->children[n]) {
       alg_bytes += e->n_rows[c] * K * M * 8 + rows * 4;  // child rows once + gather index
       if (!e->edge_major && !e->children[c].empty())

@@ -122,7 +122,7 @@ __device__ __forceinline__ void prune4_tile(const PruneArgs& a, const NodeDesc& 
       if (nd.fixed_motif != 3) acc.w = 0.0;
     }
     if (ok[u]) {
-      st256(nd.out + (p[u] * K + b) * 4, acc);
+      if (!ROOT || nd.out != nullptr) st256(nd.out + (p[u] * K + b) * 4, acc);  // (root rows: see c3_engine::store_root)
       if (ROOT) {
         // lh = numpy.inner(plh_root, pi)
         const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
@@ -165,7 +165,7 @@ __device__ __forceinline__ void prune4_tile_generic(const PruneArgs& a, const No
       if (nd.fixed_motif != 2) acc.z = 0.0;
       if (nd.fixed_motif != 3) acc.w = 0.0;
     }
-    st256(nd.out + (p * K + b) * 4, acc);
+    if (!ROOT || nd.out != nullptr) st256(nd.out + (p * K + b) * 4, acc);
     if (ROOT) {
       const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
       a.lh_out[p * K + b] = lh;
@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
         if (c_fixed != 3) acc[u].w = 0.0;
       }
       if (p < wd.n_rows) {
-        st256(wd.out + (p * K + b) * 4, acc[u]);
+        if (!ROOT || wd.out != nullptr) st256(wd.out + (p * K + b) * 4, acc[u]);
         if (ROOT) {
           const double lh =
               fma(acc[u].w, a.pi[3], fma(acc[u].z, a.pi[2], fma(acc[u].y, a.pi[1], acc[u].x * a.pi[0])));
@@ -1112,7 +1112,7 @@ __device__ __forceinline__ void small_unit_staged(const PruneArgs& a, const Node
     if (nd.fixed_motif != 2) acc.z = 0.0;
     if (nd.fixed_motif != 3) acc.w = 0.0;
   }
-  st256(nd.out + (p * K + b) * 4, acc);
+  if (nd.out != nullptr) st256(nd.out + (p * K + b) * 4, acc);
   if (nd.is_root) {
     const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
     a.lh_out[p * K + b] = lh;
@@ -1193,7 +1193,7 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
         if (nd.fixed_motif != 2) acc.z = 0.0;
         if (nd.fixed_motif != 3) acc.w = 0.0;
       }
-      st256(nd.out + (p * K + b) * 4, acc);
+      if (nd.out != nullptr) st256(nd.out + (p * K + b) * 4, acc);
       if (nd.is_root) {
         const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
         a.lh_out[p * K + b] = lh;
@@ -1797,8 +1797,8 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
     }
     double* dst = wd.out + (p * K + cc.b) * MP + 2 * q;
     if (!CONTRACT || wd.P_own == nullptr) {
-      // the root: plh itself, and lh = inner(plh_root, pi)
-      if (row_ok) {
+      // the root: plh itself (when it is stored at all), and lh = inner(plh_root, pi)
+      if (row_ok && wd.out != nullptr) {
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni)
           *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(prod[ni][0], prod[ni][1]);
@@ -1838,9 +1838,11 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
   }
 }
 
-// plh of an edge-major node for the accessors: prod_c inner_c[idx_c[p]] (masked like the kernel)
+// plh of a node recomputed for the accessors: prod_c (P_c .) rows_c[idx_c[p]] (masked like the kernels).
+// Used for edge-major nodes (stored rows are P . plh) and for a root whose rows are not stored.
+// The contraction sums k = 0..M-1 in order with FMAs, like matvec4 and the DMMA accumulation.
 __global__ void __launch_bounds__(256)
-edge_major_plh_kernel(const NodeDesc nd, const ChildRef* __restrict__ childs, int K, int MP, int bin,
+edge_major_plh_kernel(const NodeDesc nd, const ChildRef* __restrict__ childs, int K, int M, int MP, int bin,
                       double* __restrict__ out) {
   const int64_t total = nd.n_rows * MP;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
@@ -1849,10 +1851,18 @@ edge_major_plh_kernel(const NodeDesc nd, const ChildRef* __restrict__ childs, in
     double v = 1.0;
     for (int c = 0; c < nd.n_children; ++c) {
       const ChildRef ch = childs[nd.child_begin + c];
-      const double x = ch.src[((int64_t)ch.idx[p] * K + bin) * MP + j];
+      const double* row = ch.src + ((int64_t)ch.idx[p] * K + bin) * MP;
+      double x;
+      if (ch.P != nullptr) {
+        const double* Pj = ch.P + ((int64_t)bin * MP + j) * MP;
+        x = row[0] * Pj[0];
+        for (int k = 1; k < M; ++k) x = fma(row[k], Pj[k], x);
+      } else {
+        x = row[j];
+      }
       v = (c == 0) ? x : v * x;
     }
-    if (nd.fixed_motif >= 0 && j != nd.fixed_motif) v = 0.0;
+    if (j >= M || (nd.fixed_motif >= 0 && j != nd.fixed_motif)) v = 0.0;
     out[o] = v;
   }
 }
