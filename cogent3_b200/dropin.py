@@ -326,8 +326,93 @@ def _build(cogent3_modules):
             st = self._engines.get(id(lht))
             return None if st is None or st["lht"] is not lht else st["engine"]
 
+    class GpuFactoredLogLikelihoodDefn(GpuLogLikelihoodDefn):
+        """The same terminal Defn fed with the FACTORS of the psubs instead of the psubs:
+
+            psubs[edge, bin] = Qd[edge, bin](length[edge] * rate[bin])
+                (``CallDefn(Qd, distance)``, ``distance = ProductDefn(length, rate)``,
+                evolve/substitution_model.py:684-710)
+
+        args: lht, root, root mprobs, [bprobs], one fixed_motif per internal node, one Qd
+        (exponentiator) per (edge, bin), one length per edge, [one rate per bin].  The K*E
+        ``distance`` and K*E ``psubs`` cells disappear from the Calculator's sweep (each costs
+        cogent3 ~1.5 us of Python per evaluation: 1.5 ms of a 2.1 ms full evaluation at 64 taxa x 4
+        bins, and 2 K cells plus a K*E-long Python loop here for every single-branch update); the
+        product is formed here with one numpy outer product -- the same IEEE multiplication
+        ``ProductDefn.calc`` does (``numpy.prod((length, rate))``,
+        recalculation/definition.py:679-683)."""
+
+        name = "gpu_lnL"
+
+        def setup(self, has_rate, **kw):
+            super().setup(**kw)
+            self.has_rate = has_rate
+
+        def calc(self, lht, root, mprobs, *rest):
+            K, E = self.n_bins, len(self.edge_names)
+            if K > 1:
+                bprobs, rest = rest[0], rest[1:]
+            else:
+                bprobs = None
+            n_int = len(self.internal_names)
+            fixed, rest = rest[:n_int], rest[n_int:]
+            qds, lengths, rates = rest[: E * K], rest[E * K : E * K + E], rest[E * K + E :]
+            st = self._state_for(lht)
+            eng = st["engine"]
+            qslots, dist = st["qslots"], st["dist"]
+            edge_ids = st["edge_ids"]
+            last = st.get("last_qds")
+            try:
+                # tuple comparison short-cuts on identity in C; exponentiators compare by identity
+                same_qds = last is not None and bool(qds == last)
+            except Exception:  # noqa: BLE001 - an exotic exponentiator with an array-valued __eq__
+                same_qds = last is not None and all(a is b for a, b in zip(qds, last, strict=True))
+            if not same_qds:
+                # (re)assign exponentiators to q slots; rare: only when a rate-matrix parameter moved
+                live, host = set(), {}
+                k = 0
+                for node in edge_ids:
+                    for b in range(K):
+                        ex = qds[k]
+                        k += 1
+                        slot = self._slot_for(st, ex)
+                        if slot is None:
+                            host[(node, b)] = ex  # not an eigen / Pade exponentiator: P on the host
+                            qslots[node, b] = -1
+                        else:
+                            live.add(slot)
+                            st["psub_obj"].pop((node, b), None)
+                            qslots[node, b] = slot
+                eng.set_edge_qslots(qslots)  # negative entries are left alone by the engine
+                for slot in [s for s in st["slot_obj"] if s not in live]:
+                    ex = st["slot_obj"].pop(slot)
+                    st["slot_of"].pop(id(ex), None)
+                st["last_qds"] = qds
+                st["host_ex"] = host
+            d = np.array(lengths, np.float64)[:, None]
+            if self.has_rate:
+                d = d * np.array(rates, np.float64)[None, :]
+            dist[edge_ids, :] = d
+            for (node, b), ex in st["host_ex"].items():
+                key = (ex, float(dist[node, b]))
+                prev = st["psub_obj"].get((node, b))
+                if prev is None or prev[0] is not key[0] or prev[1] != key[1]:
+                    eng.set_psub(node, b, np.asarray(ex(key[1]), float))
+                    st["psub_obj"][(node, b)] = key
+            eng.set_distances(dist)
+            eng.set_root_mprobs(np.asarray(mprobs, float))
+            if bprobs is not None:
+                eng.set_bin_probs(np.asarray(bprobs, float))
+            if st.get("last_fixed") != fixed:
+                fm = np.full(st["topo"].n_nodes, -1, np.int32)
+                for node, f in zip(st["internal_ids"], fixed, strict=True):
+                    fm[node] = -1 if f in (None, -1) else int(f)
+                eng.set_fixed_motifs(fm)
+                st["last_fixed"] = fixed
+            return eng.evaluate()
+
     def make_total_loglikelihood_defn(tree, leaves, psubs, mprobs, bprobs, bin_names, locus_names,
-                                      sites_independent, engine_factory, device):  # fmt: skip
+                                      sites_independent, engine_factory, device, factors=None):  # fmt: skip
         """same signature and role as the reference function of this name
         (evolve/likelihood_calculation.py:125-134), plus the engine selection"""
         if not sites_independent:
@@ -345,16 +430,33 @@ def _build(cogent3_modules):
         if multi_bin:
             args.append(bprobs)
         args.extend(fixed_motifs.select_from_dimension("edge", name) for name in internal)
-        for name in edge_names:
-            p_e = psubs.select_from_dimension("edge", name)
-            if multi_bin:
-                args.extend(p_e.across_dimension("bin", bin_names))
-            else:
-                args.append(p_e.select_from_dimension("bin", bin_names[0]))
-        tll = GpuLogLikelihoodDefn(
-            *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
-            engine_factory=engine_factory, device=device,
-        )  # fmt: skip
+        def select(defn, dimension, cat):
+            # (a Defn that does not have the dimension is the same for every category)
+            return defn.select_from_dimension(dimension, cat) if dimension in defn.valid_dimensions else defn
+
+        if factors is not None:
+            Qd, length, rate = factors
+            for name in edge_names:
+                q_e = select(Qd, "edge", name)
+                args.extend(select(q_e, "bin", b) for b in bin_names)
+            args.extend(select(length, "edge", name) for name in edge_names)
+            if rate is not None:
+                args.extend(select(rate, "bin", b) for b in bin_names)
+            tll = GpuFactoredLogLikelihoodDefn(
+                *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
+                engine_factory=engine_factory, device=device, has_rate=rate is not None,
+            )  # fmt: skip
+        else:
+            for name in edge_names:
+                p_e = psubs.select_from_dimension("edge", name)
+                if multi_bin:
+                    args.extend(p_e.across_dimension("bin", bin_names))
+                else:
+                    args.append(p_e.select_from_dimension("bin", bin_names[0]))
+            tll = GpuLogLikelihoodDefn(
+                *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
+                engine_factory=engine_factory, device=device,
+            )  # fmt: skip
         if len(locus_names) > 1:
             tll = SumDefn(*tll.across_dimension("locus", locus_names))
         else:
@@ -367,10 +469,12 @@ def _build(cogent3_modules):
         ``engine_factory`` (test seam) and ``device``."""
 
         def make_likelihood_defn(self, sites_independent=True, discrete_edges=None,
-                                 engine_factory=None, device=0):  # fmt: skip
+                                 engine_factory=None, device=0, factored=True):  # fmt: skip
             # constructor kwargs land in _serialisable (parameter_controller.py:62-66);
             # a callable cannot be serialised, so it is dropped from there
             self._serialisable.pop("engine_factory", None)
+            self._serialisable.pop("factored", None)
+            factors = None
             defns = self.model.make_param_controller_defns(bin_names=self.bin_names)
             psubs = defns["psubs"]
             if discrete_edges is not None:
@@ -378,14 +482,30 @@ def _build(cogent3_modules):
 
                 psubs = PartialyDiscretePsubsDefn(self.motifs, psubs, discrete_edges)
             elif type(psubs) is definition.CallDefn and len(psubs.args) == 2:
-                # psubs = CallDefn(Qd, distance): keep (exponentiator, distance) symbolic.
-                # The CallDefn the model built is detached from its inputs so that the
-                # controller does not see a value that is never used (scope.py:148-162).
+                # psubs = CallDefn(Qd, distance).  The CallDefn the model built is detached from its
+                # inputs so that the controller does not see a value that is never used
+                # (scope.py:148-162).
                 original = psubs
-                psubs = LazyPsubDefn(*original.args)
-                for arg in original.args:
-                    if original in arg.clients:
-                        arg.clients.remove(original)
+
+                def detach(defn):
+                    for arg in defn.args:
+                        if defn in arg.clients:
+                            arg.clients.remove(defn)
+
+                detach(original)
+                Qd, distance = original.args
+                if (type(distance) is definition.ProductDefn and len(distance.args) == 2
+                        and distance.args[0].name == "length" and not distance.clients
+                        and factored):  # fmt: skip
+                    # distance = ProductDefn(length, rate): hand the FACTORS to the engine Defn
+                    detach(distance)
+                    factors = (Qd, distance.args[0], distance.args[1])
+                elif distance.name == "length" and factored:
+                    factors = (Qd, distance, None)  # no rate heterogeneity: distance is the length
+                else:
+                    # keep (exponentiator, distance) symbolic, one LazyPsub cell per (edge, bin)
+                    psubs = LazyPsubDefn(*original.args)
+            self._factors = factors
             self._gpu_defn_factory = None
             leaves = defns["align"]
             if type(leaves) is substitution_calculation.AlignmentAdaptDefn:
@@ -399,7 +519,7 @@ def _build(cogent3_modules):
             return make_total_loglikelihood_defn(
                 self.tree, leaves, psubs, defns["word_probs"], defns["bprobs"],
                 self.bin_names, self.locus_names, sites_independent,
-                engine_factory or _default_engine_factory, device,
+                engine_factory or _default_engine_factory, device, factors=factors,
             )  # fmt: skip
 
         def set_motif_probs_from_data(self, align, locus=None, is_constant=None, include_ambiguity=False,
@@ -449,7 +569,55 @@ def _build(cogent3_modules):
                 raise RuntimeError("no engine for this locus: set_alignment first")
             return eng
 
+        # -- psubs when the engine Defn is fed with their factors: there is no "psubs" Defn in the
+        # graph any more, so the three ways cogent3 reads them (get_param_value("psubs", ...),
+        # get_psub_for_edge -> get_param_value, get_all_psubs; evolve/likelihood_function.py:272-320)
+        # compute Qd(length * rate) from the Defns that are there -- the reference's own arithmetic
+        def _factored_psub(self, edge, bin=None, locus=None):  # noqa: A002
+            Qd, length, rate = self._factors
+            given = {"edge": edge, "bin": bin, "locus": locus}
+
+            def value(defn):
+                scope = {d: given[d] for d in defn.valid_dimensions if given.get(d) is not None}
+                return super(CudaAlignmentLikelihoodFunction, self).get_param_value(defn.name, **scope)
+
+            t = value(length)
+            if rate is not None:
+                t = np.prod((t, value(rate)))  # ProductDefn.calc
+            return value(Qd)(t)
+
+        def get_all_psubs(self):
+            if getattr(self, "_factors", None) is None:
+                return self._lazy_get_all_psubs()
+            from cogent3.util.dict_array import DictArrayTemplate
+
+            Qd, length, rate = self._factors
+            # the key of the reference's dict: the used dimensions of psubs in valid-dimension
+            # (alphabetical) order = those used by any of its factors
+            used = set()
+            for defn in (Qd, length, rate):
+                if defn is not None:
+                    used.update(d for d in defn.used_dimensions() if d in ("bin", "edge", "locus"))
+            used.add("edge")
+            dims = [d for d in ("bin", "edge", "locus") if d in used]
+            cats = {"bin": list(self.bin_names), "locus": list(self.locus_names),
+                    "edge": [e.name for e in self.tree.postorder(include_self=False)]}  # fmt: skip
+            template = DictArrayTemplate(self._motifs, self._motifs)
+            result = {}
+            import itertools
+
+            for combo in itertools.product(*(cats[d] for d in dims)):
+                scope = dict(zip(dims, combo, strict=True))
+                # a dimension that is not used takes its first category, like the last scope the
+                # reference's loop happens to see: the values are the same by definition
+                full = {d: scope.get(d, cats[d][0]) for d in ("bin", "edge", "locus")}
+                key = combo[0] if len(combo) == 1 else tuple(combo)
+                result[key] = template.wrap(self._factored_psub(full["edge"], full["bin"], full["locus"]))
+            return result
+
         def get_param_value(self, par_name, *args, **kw):
+            if par_name == "psubs" and getattr(self, "_factors", None) is not None and not args:
+                return self._factored_psub(kw.get("edge"), kw.get("bin"), kw.get("locus"))
             if par_name == "lh":
                 # per-pattern root likelihoods of one bin, straight from the device
                 bin_ = kw.get("bin")
@@ -467,7 +635,7 @@ def _build(cogent3_modules):
                 value = value.materialise()
             return value
 
-        def get_all_psubs(self):
+        def _lazy_get_all_psubs(self):
             defn = self.defn_for["psubs"]
             saved = list(defn.values)
             try:

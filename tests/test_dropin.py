@@ -235,3 +235,82 @@ def test_fast_compression_is_what_set_alignment_runs():
     assert _same_lht(ref.get_param_value("lht"), lf.get_param_value("lht")) == 2 * 40 - 2
     assert t_fast < t_ref, (t_fast, t_ref)
     print(f"set_alignment 40 x 30k: reference {t_ref:.2f} s, drop-in {t_fast:.2f} s")
+
+
+# ---- the engine Defn fed with the factors of the psubs (Qd, length, rate) -----------------------
+def _psub_cases():
+    tree, aln = small_problem(n_tips=8, L=300, seed=3)
+    yield "HKY85", (lambda: get_model("HKY85")), tree, aln, {}, None
+    yield "GTR+G4", (lambda: get_model("GTR", ordered_param="rate", distribution="gamma")), tree, aln, {"bins": 4}, None
+    yield "GN het", (lambda: get_model("GN")), tree, aln, {"expm": "pade"}, "het"
+
+
+@pytest.mark.parametrize("factored", [True, False])
+def test_psub_accessors_match_the_reference(factored):
+    for tag, mk, tree, aln, kw, extra in _psub_cases():
+        ref = mk().make_likelihood_function(tree, **kw)
+        ref.set_alignment(aln)
+        lf = make_likelihood_function(mk(), tree, engine_factory=FACTORY, factored=factored, **kw)
+        lf.set_alignment(aln)
+        assert (lf._factors is not None) == factored, tag
+        for f in (ref, lf):
+            if "bins" in kw:
+                f.set_param_rule("bprobs", is_constant=True)
+                f.set_param_rule("rate_shape", value=0.7)
+            if extra == "het":
+                f.set_time_heterogeneity(is_independent=True, upper=50)
+            f.set_param_rule("length", edge=tree.get_tip_names()[0], value=0.37)
+        assert_same(ref, lf)
+        a, b = ref.get_all_psubs(), lf.get_all_psubs()
+        assert list(a) == list(b) or set(a) == set(b), (tag, list(a)[:3], list(b)[:3])
+        for key in a:
+            np.testing.assert_array_equal(a[key].to_array(), b[key].to_array())
+        name = tree.get_tip_names()[1]
+        scope = {"bin": "bin2"} if "bins" in kw else {}
+        np.testing.assert_array_equal(
+            ref.get_psub_for_edge(name, **scope).to_array(), lf.get_psub_for_edge(name, **scope).to_array()
+        )
+        np.testing.assert_array_equal(
+            np.asarray(ref.get_param_value("psubs", edge=name, **scope)),
+            np.asarray(lf.get_param_value("psubs", edge=name, **scope)),
+        )
+        assert ref.all_psubs_DLC() == lf.all_psubs_DLC()
+        np.testing.assert_allclose(
+            ref.get_lengths_as_ens()[name], lf.get_lengths_as_ens()[name], rtol=1e-12
+        )
+
+
+def test_factored_defn_has_no_distance_or_psub_cells():
+    tree, aln = small_problem(n_tips=12, L=200, seed=4)
+    mk = lambda: get_model("GTR", ordered_param="rate", distribution="gamma")  # noqa: E731
+    counts = {}
+    for factored in (True, False):
+        lf = make_likelihood_function(mk(), tree, bins=4, engine_factory=FACTORY, factored=factored)
+        lf.set_alignment(aln)
+        calc = lf.make_calculator()
+        counts[factored] = len(calc._cells)
+        names = {d.name for d in lf.defns}
+        assert ("psubs" in names) == (not factored)
+    n_edges = len(tree.get_edge_vector()) - 1
+    # K*E distance cells and K*E psubs cells are gone
+    assert counts[False] - counts[True] >= 2 * 4 * n_edges - 8, counts
+
+
+def test_factored_optimise_and_partial_updates():
+    aln, tree = get_dataset("brca1"), get_dataset("mammal-tree")
+    tree = tree.get_sub_tree(aln.names)
+    ref = get_model("HKY85").make_likelihood_function(tree)
+    ref.set_alignment(aln)
+    lf = make_likelihood_function(get_model("HKY85"), tree, engine_factory=FACTORY)
+    lf.set_alignment(aln)
+    assert lf._factors is not None
+    assert_same(ref, lf)
+    rc, lc = ref.make_calculator(), lf.make_calculator()
+    x = np.array(rc.get_value_array())
+    assert np.array_equal(x, lc.get_value_array())
+    rng = np.random.default_rng(0)
+    for _ in range(25):  # one parameter at a time, like Powell's line searches
+        i = int(rng.integers(len(x)))
+        x[i] *= 1.0 + 0.05 * rng.standard_normal()
+        a, b = rc(x), lc(x)
+        assert abs(a - b) <= 1e-12 * abs(a)
