@@ -1,0 +1,46 @@
+"""pytest plugin: run the REFERENCE's own test files with the drop-in class swapped in.
+
+``_SubstitutionModel.make_likelihood_function`` (evolve/substitution_model.py:313-391) is replaced
+by ``cogent3_b200.dropin.make_likelihood_function``; the engine behind it is the CPU oracle port
+(build container, no GPU) or, with C3_REFRUN_CUDA=1, the CUDA engine.  Unaligned / phylo-HMM
+likelihood functions (out of scope) stay with the reference.  Used by
+tests/test_reference_suite_dropin.py:
+
+    cd /root/reference/tests && PYTHONPATH=<repo>/tests:<repo>:<repo>/tests/_shims:/root/reference/src \
+        python -m pytest -p no:cacheprovider -p refrun_plugin test_evolve/test_likelihood_function.py
+"""
+import functools
+import os
+import sys
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests", "_shims"), "/root/reference/src"]
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+from cogent3.evolve import substitution_model  # noqa: E402
+
+from cogent3_b200 import dropin  # noqa: E402
+from oracle.engine import OracleEngine  # noqa: E402
+
+FACTORY = None if os.environ.get("C3_REFRUN_CUDA") else functools.partial(OracleEngine, mode="port")
+_orig = substitution_model._SubstitutionModel.make_likelihood_function
+STATS = {"dropin": 0, "reference": 0}
+
+
+def patched(self, tree, motif_probs_from_align=None, optimise_motif_probs=None, aligned=True, expm=None,
+            digits=None, space=None, **kw):
+    if not aligned or kw.get("sites_independent", True) is False:
+        STATS["reference"] += 1
+        return _orig(self, tree, motif_probs_from_align=motif_probs_from_align,
+                     optimise_motif_probs=optimise_motif_probs, aligned=aligned, expm=expm, digits=digits,
+                     space=space, **kw)
+    STATS["dropin"] += 1
+    return dropin.make_likelihood_function(self, tree, motif_probs_from_align=motif_probs_from_align,
+                                           optimise_motif_probs=optimise_motif_probs, expm=expm, digits=digits,
+                                           space=space, engine_factory=FACTORY, **kw)
+
+
+substitution_model._SubstitutionModel.make_likelihood_function = patched
+
+
+def pytest_sessionfinish(session, exitstatus):
+    print("\nmake_likelihood_function calls:", STATS)
