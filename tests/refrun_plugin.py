@@ -14,7 +14,8 @@ import os
 import sys
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests", "_shims"), "/root/reference/src"]
+_REF = "/root/reference/src" if os.path.isdir("/root/reference/src") else os.path.join(_ROOT, "baseline", "_ref")
+sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests", "_shims"), _REF]
 os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
 from cogent3.evolve import substitution_model  # noqa: E402
 
