@@ -569,6 +569,16 @@ def _build(cogent3_modules):
                 raise RuntimeError("no engine for this locus: set_alignment first")
             return eng
 
+        def to_rich_dict(self):
+            """serialised results stay interchangeable with stock cogent3 (and deserialise without a
+            GPU): the recorded type is the reference class (evolve/likelihood_function.py:968-1030,
+            util/deserialise.py:118-140); the engine seams are not construction arguments"""
+            data = super().to_rich_dict()
+            data["type"] = "cogent3.evolve.parameter_controller.AlignmentLikelihoodFunction"
+            for key in ("engine_factory", "device", "factored"):
+                data.get("likelihood_construction", {}).pop(key, None)
+            return data
+
         # -- psubs when the engine Defn is fed with their factors: there is no "psubs" Defn in the
         # graph any more, so the three ways cogent3 reads them (get_param_value("psubs", ...),
         # get_psub_for_edge -> get_param_value, get_all_psubs; evolve/likelihood_function.py:272-320)
@@ -644,7 +654,14 @@ def _build(cogent3_modules):
             finally:
                 defn.values = saved
 
-    return CudaAlignmentLikelihoodFunction, GpuLogLikelihoodDefn, LazyPsubDefn
+    # picklable by reference (process-parallel apps, app/evo.py bootstrap with parallel=True, pickle
+    # likelihood functions): the classes are reachable as attributes of this module
+    exported = (CudaAlignmentLikelihoodFunction, GpuLogLikelihoodDefn, LazyPsubDefn,
+                GpuFactoredLogLikelihoodDefn, FastAlignmentAdaptDefn, FastLikelihoodTreeDefn)  # fmt: skip
+    for cls in exported:
+        cls.__module__ = __name__
+        cls.__qualname__ = cls.__name__
+    return exported
 
 
 _CLASSES = None
@@ -663,9 +680,13 @@ def _classes():
     return _CLASSES
 
 
+_CLASS_NAMES = ("CudaAlignmentLikelihoodFunction", "GpuLogLikelihoodDefn", "LazyPsubDefn",
+                "GpuFactoredLogLikelihoodDefn", "FastAlignmentAdaptDefn", "FastLikelihoodTreeDefn")  # fmt: skip
+
+
 def __getattr__(name):
-    if name == "CudaAlignmentLikelihoodFunction":
-        return _classes()[0]
+    if name in _CLASS_NAMES:
+        return _classes()[_CLASS_NAMES.index(name)]
     raise AttributeError(name)
 
 

@@ -17,6 +17,10 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _REF = "/root/reference/src" if os.path.isdir("/root/reference/src") else os.path.join(_ROOT, "baseline", "_ref")
 sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests", "_shims"), _REF]
 os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+# import order decides the reference's global numpy error state: maths/util.py:14 sets divide="raise",
+# evolve/likelihood_tree.py:10 sets all="ignore", the last one imported wins.  Keep the order of a plain
+# run of the reference's tests (likelihood_tree last).
+import cogent3.maths.util  # noqa: E402, F401
 from cogent3.evolve import substitution_model  # noqa: E402
 
 from cogent3_b200 import dropin  # noqa: E402
@@ -45,3 +49,9 @@ substitution_model._SubstitutionModel.make_likelihood_function = patched
 
 def pytest_sessionfinish(session, exitstatus):
     print("\nmake_likelihood_function calls:", STATS)
+    out = os.environ.get("C3_REFRUN_STATS")  # a directory: one file per (xdist worker) process
+    if out:
+        import json
+
+        with open(os.path.join(out, f"{os.getpid()}.json"), "w") as f:
+            json.dump(STATS, f)

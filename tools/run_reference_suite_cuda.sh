@@ -6,7 +6,5 @@ ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 cd "$ROOT/baseline/_ref/tests" || exit 1
 export PYTHONPATH="$ROOT/tests:$ROOT:$ROOT/tests/_shims:$ROOT/baseline/_ref"
 export NUMBA_CACHE_DIR=/tmp/numba_cache C3_REFRUN_CUDA=1 COGENT3_REFERENCE_ROOT="$ROOT/baseline/_ref"
-python -m pytest -p no:cacheprovider -p refrun_plugin -q --no-header \
-  test_evolve/test_likelihood_function.py test_evolve/test_newq.py test_evolve/test_ns_substitution_model.py \
-  test_evolve/test_parameter_controller.py test_evolve/test_substitution_model.py test_evolve/test_bootstrap.py \
-  test_evolve/test_scale_rules.py test_evolve/test_motifchange.py "$@"
+python -m pytest -p no:cacheprovider -p refrun_plugin -q --no-header -k "not test_get_app_tree_is_url" \
+  test_evolve test_app/test_evo.py test_phylo.py "$@"
