@@ -399,7 +399,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     problem = build_problem(args.config, args.columns, args.kind, shard=rank)
-    stream = torch.cuda.current_stream()
+    # a stream of our own (torch's legacy default stream cannot be captured into the engine's CUDA graphs);
+    # it is torch's current stream from here on, so NCCL orders after the engine's kernels
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     lf, setup_t = make_lf(problem, device=local_rank, stream=stream)
     eng = lf.engine
     bins = lf.n_bins
@@ -610,9 +613,9 @@ def run_ours(args):
                 e_.set_distances(d)
             return engine_many(engines)
 
-        for k in range(3):
+        for k in range(20):  # (past the engines' graph-capture threshold: steady state)
             many_step(k)
-        n_rep = 50
+        n_rep = 100
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for k in range(n_rep):

@@ -37,6 +37,7 @@ class C3Stats(ctypes.Structure):
         ("last_h2d_bytes", c_int64),
         ("device_bytes", c_int64),
         ("partial_bytes", c_int64),
+        ("graph_replays", c_int64),
         ("n_levels", c_int32),
         ("padded_states", c_int32),
     ]

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/c3cuda.h"
@@ -155,6 +156,20 @@ struct c3_engine {
   CommSlot* d_mailbox = nullptr;
   int mailbox_ranks = 0;
   std::vector<void*> ipc_opened;
+
+  // CUDA graphs: the stream operations of an evaluation (parameter-block copy, expm, one launch per
+  // dirty level, reduction) depend only on its STRUCTURE -- which nodes are dirty, how many expm jobs --
+  // while the numbers travel in the parameter block.  An optimiser revisits the same structures over
+  // and over (Powell: every parameter, every iteration; a full sweep for every rate-matrix
+  // parameter; bootstraps and batches of small alignments: always the full sweep), so a structure
+  // that has come up `graph_after` times is captured once and from then on replayed with ONE
+  // cudaGraphLaunch instead of 4-15 launch calls.  C3_GRAPH=0 disables.
+  bool use_graphs = true;
+  struct GraphEntry { std::vector<int32_t> sig; cudaGraphExec_t exec = nullptr; int64_t n_launch = 0; uint64_t last_use = 0; };
+  std::unordered_map<uint64_t, GraphEntry> graphs;
+  std::unordered_map<uint64_t, int> graph_seen;  // structure hash -> times seen before its capture
+  int graph_after = 16;                          // sightings before a structure is captured (C3_GRAPH_AFTER)
+  uint64_t graph_clock = 0;
 
   // per-pattern underflow rescaling (c3_set_rescaling; kernels in prune_kernels.cuh)
   int rescale_mode = C3_RESCALE_AUTO;
@@ -489,12 +504,21 @@ int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
   return (int64_t)e->K * ((e->n_rows[n] + DMMA_TILE_ROWS - 1) / DMMA_TILE_ROWS);
 }
 
+// captured graphs hold device pointers: drop them whenever an allocation they name is replaced
+void clear_graphs(c3_engine* e) {
+  for (auto& g : e->graphs)
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  e->graphs.clear();
+  e->graph_seen.clear();
+}
+
 int ensure_slots(c3_engine* e, int n) {
   if ((int)e->slots.size() < n) e->slots.resize(n);
   if (n <= e->n_slots_alloc) return C3_OK;
   const int new_n = std::max(n, std::max(4, 2 * e->n_slots_alloc));
   double* fresh = nullptr;
   C3_CUDA(cudaMalloc(&fresh, (size_t)new_n * e->slot_stride * sizeof(double)));
+  clear_graphs(e);  // the expm launches name d_slots
   if (e->d_slots) {
     C3_CUDA(cudaStreamSynchronize(e->stream));
     C3_CUDA(cudaMemcpy(fresh, e->d_slots, (size_t)e->n_slots_alloc * e->slot_stride * sizeof(double),
@@ -587,6 +611,8 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   e->store_root = !(e->use_dmma ? e->edge_major
                                 : (e->use_strip && e->use_reg2 && !e->use_ring && !e->use_flow));
   if (const char* env = getenv("C3_STORE_ROOT")) e->store_root = e->store_root || atoi(env) != 0;
+  if (const char* env = getenv("C3_GRAPH")) e->use_graphs = atoi(env) != 0;
+  if (const char* env = getenv("C3_GRAPH_AFTER")) e->graph_after = std::max(1, atoi(env));
   if (const char* env = getenv("C3_RESCALE")) e->rescale_mode = std::max(0, std::min(2, atoi(env)));
   if (const char* env = getenv("C3_RESCALE_TIPS")) e->rescale_threshold = std::max(2, atoi(env));
   e->root = n_nodes - 1;
@@ -664,6 +690,8 @@ int c3_destroy(c3_engine* e) {
   if (e->d_mailbox) cudaFree(e->d_mailbox);
   if (e->d_pool) cudaFree(e->d_pool);
   if (e->d_scale_pool) cudaFree(e->d_scale_pool);
+  for (auto& g : e->graphs)
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   if (e->d_slots) cudaFree(e->d_slots);
   if (e->d_block) cudaFree(e->d_block);
   if (e->h_block) cudaFreeHost(e->h_block);
@@ -1908,15 +1936,20 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   std::memcpy(e->h_block + e->off_bprobs, e->bprobs.data(), K * sizeof(double));
   // one contiguous copy of the used part of the block
   const int64_t used = e->off_jobs + (int64_t)(n_eigen + n_pade) * sizeof(ExpmJob);
-  C3_CUDA(cudaMemcpyAsync(e->d_block, e->h_block, (size_t)std::min(used, e->block_bytes),
-                          cudaMemcpyHostToDevice, e->stream));
-  C3_CUDA(cudaEventRecord(e->block_copied, e->stream));
   h2d_bytes += std::min(used, e->block_bytes);
-
-  if (any_flow) C3_CUDA(cudaMemsetAsync(e->d_done, 0, (size_t)w_off * sizeof(unsigned int), e->stream));
   int64_t n_launch = 0;
   e->prof.clear();
   e->events_used = 0;
+  CommArgs comm = e->comm;
+  if (comm.nranks > 1) comm.epoch = ++e->comm.epoch;  // every rank evaluates in lock-step
+
+  // every stream operation of the evaluation (issued directly, or into a graph capture)
+  bool capturing = false;
+  auto issue = [&]() -> int {
+  C3_CUDA(cudaMemcpyAsync(e->d_block, e->h_block, (size_t)std::min(used, e->block_bytes),
+                          cudaMemcpyHostToDevice, e->stream));
+  if (!capturing) C3_CUDA(cudaEventRecord(e->block_copied, e->stream));  // the staging buffer is free again
+  if (any_flow) C3_CUDA(cudaMemsetAsync(e->d_done, 0, (size_t)w_off * sizeof(unsigned int), e->stream));
   const ExpmJob* d_jobs = reinterpret_cast<const ExpmJob*>(e->d_block + e->off_jobs);
   if (n_eigen > 0) {
     const int threads = (M <= 4) ? 32 : (M <= 16 ? 64 : (M <= 32 ? 256 : 1024));
@@ -2015,8 +2048,6 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     }
   }
   {
-    CommArgs comm = e->comm;
-    if (comm.nranks > 1) comm.epoch = ++e->comm.epoch;  // every rank evaluates in lock-step
     const int64_t rows = e->n_rows[e->root];
     const int n_tiles = (int)((rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
     const int grid = std::min(n_tiles, e->n_sm * 8);
@@ -2042,6 +2073,88 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(err));
   }
+  return C3_OK;
+  };  // issue
+
+  // ---- direct launches, or capture / replay of this structure's graph ---------------------------
+  bool graphed = false;
+  if (e->use_graphs && !e->profiling && comm.nranks <= 1 && !any_flow) {
+    std::vector<int32_t> sig;
+    sig.reserve(16 + 8 * launches.size() + w_off);
+    sig.push_back(n_eigen); sig.push_back(n_pade); sig.push_back((int32_t)std::min(used, e->block_bytes));
+    sig.push_back(e->rescale_active ? 1 : 0);
+    sig.push_back((int32_t)((uintptr_t)device_out & 0xffffffffu)); sig.push_back((int32_t)((uintptr_t)device_out >> 32));
+    sig.push_back((blocking || deferred) ? 1 : 0);
+    sig.push_back((int32_t)((uintptr_t)e->stream & 0xffffffffu)); sig.push_back((int32_t)((uintptr_t)e->stream >> 32));
+    for (const LevelLaunch& ll : launches) {
+      sig.push_back(ll.kind); sig.push_back(ll.work_off); sig.push_back(ll.prefix_off); sig.push_back(ll.n_work);
+      sig.push_back(ll.total_tiles); sig.push_back(ll.is_root ? 1 : 0); sig.push_back(ll.small_off); sig.push_back(ll.n_small);
+    }
+    for (int i = 0; i < w_off; ++i) sig.push_back(work[i]);  // (rescale launches name their nodes)
+    uint64_t h = 1469598103934665603ull;
+    for (int32_t v : sig) { h ^= (uint32_t)v; h *= 1099511628211ull; }
+    ++e->graph_clock;
+    auto it = e->graphs.find(h);
+    if (it != e->graphs.end() && it->second.sig == sig) {
+      C3_CUDA(cudaGraphLaunch(it->second.exec, e->stream));
+      it->second.last_use = e->graph_clock;
+      n_launch = it->second.n_launch;
+      graphed = true;
+    } else if (it == e->graphs.end() && ++e->graph_seen[h] >= e->graph_after) {
+      // this structure keeps coming up: capture it (capture + instantiation cost ~100 launches'
+      // worth of host time, a replay saves a few microseconds: only frequent structures pay)
+      cudaGraph_t graph = nullptr;
+      cudaError_t err = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+      if (err == cudaSuccess) {
+        capturing = true;
+        const int rc = issue();
+        capturing = false;
+        err = cudaStreamEndCapture(e->stream, &graph);
+        if (rc != C3_OK || err != cudaSuccess || graph == nullptr) {
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          e->use_graphs = false;  // not capturable here (e.g. a stream that is already being captured): plain launches
+          graph = nullptr;
+          n_launch = 0;
+        }
+      } else {
+        cudaGetLastError();
+        e->use_graphs = false;
+      }
+      if (graph != nullptr) {
+        c3_engine::GraphEntry entry;
+        err = cudaGraphInstantiate(&entry.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (err == cudaSuccess) {
+          if (e->graphs.size() >= 512) {  // evict the least recently used structure
+            auto victim = e->graphs.begin();
+            for (auto g = e->graphs.begin(); g != e->graphs.end(); ++g)
+              if (g->second.last_use < victim->second.last_use) victim = g;
+            cudaGraphExecDestroy(victim->second.exec);
+            e->graphs.erase(victim);
+          }
+          entry.sig = sig;
+          entry.n_launch = n_launch;
+          entry.last_use = e->graph_clock;
+          C3_CUDA(cudaGraphLaunch(entry.exec, e->stream));
+          e->graphs.emplace(h, std::move(entry));
+          graphed = true;
+        } else {
+          cudaGetLastError();
+          e->use_graphs = false;
+          n_launch = 0;
+        }
+      }
+    } else if (e->graph_seen.size() > 4096) {
+      e->graph_seen.clear();
+    }
+  }
+  if (!graphed) {
+    int rc = issue();
+    if (rc) return rc;
+  } else {
+    C3_CUDA(cudaEventRecord(e->block_copied, e->stream));  // (a replay frees the staging buffer when it is through)
+  }
 
   // bookkeeping: everything launched is now clean
   std::fill(e->pdirty.begin(), e->pdirty.end(), 0);
@@ -2056,6 +2169,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   e->stats.last_alg_bytes = alg_bytes;
   e->stats.last_flops = flops;
   e->stats.last_h2d_bytes = h2d_bytes;
+  if (graphed) e->stats.graph_replays += 1;
 
   if (deferred) {
     e->deferred_pending = true;
@@ -2114,6 +2228,7 @@ int finish_deferred(c3_engine* e, double* host_out) {
 void deactivate_rescaling(c3_engine* e) {
   if (!e->rescale_active) return;
   cudaStreamSynchronize(e->stream);
+  clear_graphs(e);
   if (e->d_scale_pool) cudaFree(e->d_scale_pool);
   e->d_scale_pool = nullptr;
   e->stats.device_bytes -= e->scale_pool_bytes;
@@ -2210,6 +2325,7 @@ int activate_rescaling(c3_engine* e) {
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("rescaling set-up: ") + cudaGetErrorString(err));
   }
+  clear_graphs(e);
   e->rescale_active = true;
   e->n_scaled = n_scaled;
   std::fill(e->node_dirty.begin(), e->node_dirty.end(), 1);

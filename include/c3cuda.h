@@ -56,6 +56,7 @@ typedef struct c3_stats {
   int64_t last_h2d_bytes;     /* host->device bytes copied by the last evaluation */
   int64_t device_bytes;       /* device memory owned by the engine              */
   int64_t partial_bytes;      /* ... of which resident partial likelihoods      */
+  int64_t graph_replays;      /* evaluations issued as ONE cudaGraphLaunch      */
   int32_t n_levels;           /* tree levels (kernel launches of a full sweep)  */
   int32_t padded_states;      /* row stride of a partial row, in doubles        */
 } c3_stats;

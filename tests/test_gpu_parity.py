@@ -441,3 +441,38 @@ def test_multi_locus_on_one_gpu_matches_the_oracle_sum():
     want_lf.set_param_rule("length", edge=topo.names[2], value=0.4, locus="c")
     got, want = got_lf.get_log_likelihood(), want_lf.get_log_likelihood()
     assert abs(got - want) <= REL_LNL * abs(want)
+
+
+@pytest.mark.parametrize("case", ["c1_brca1_hky85_default", "c2_gtr_gamma4_mid", "c4_cnfgtr_small"])
+def test_graph_replay_is_bit_identical(case, monkeypatch):
+    """an evaluation structure (dirty nodes, expm jobs) seen twice is captured into a CUDA graph and
+    replayed; the numbers travel in the parameter block, so replays must return the bits of plain launches"""
+    g = Golden(case)
+
+    def run(graphs):
+        monkeypatch.setenv("C3_GRAPH", "1" if graphs else "0")
+        monkeypatch.setenv("C3_GRAPH_AFTER", "2")  # (default 16: only structures that keep coming up)
+        lf = lf_from_golden(g)
+        out = []
+        rng = np.random.default_rng(8)
+        edges = [g.topo.names[int(n)] for n in rng.choice(g.topo.edges, size=3, replace=False)]
+        for rep in range(5):
+            # full sweeps: every length moves
+            lf.lengths[:-1] = g.lengths[:-1] * (1.0 + 0.01 * (rep + 1))
+            lf._dirty_model = True
+            out.append(lf.get_log_likelihood())
+            # the same three single-branch updates every round: three structures, revisited
+            for k, name in enumerate(edges):
+                lf.set_param_rule("length", edge=name, value=0.05 + 0.03 * k + 0.01 * rep)
+                out.append(lf.get_log_likelihood())
+        out.append(np.array(lf.engine.get_lh(0)))
+        return out, lf.engine.stats()
+
+    plain, st0 = run(False)
+    graphed, st1 = run(True)
+    assert st0["graph_replays"] == 0
+    assert st1["graph_replays"] >= 12  # 4 structures x 5 rounds: launched plainly, captured, then replayed 3 times
+    assert st0["kernel_launches"] == st1["kernel_launches"]
+    for a, b in zip(plain[:-1], graphed[:-1], strict=True):
+        assert a == b
+    assert np.array_equal(plain[-1], graphed[-1])

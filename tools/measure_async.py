@@ -24,19 +24,19 @@ eng = lf.engine
 base, rates = lf.lengths.copy(), lf.rates()
 lf.get_log_likelihood()
 buf = torch.zeros(1, dtype=torch.float64, device="cuda")
-ds = [np.nan_to_num(bench.step_lengths(base, k))[:, None] * rates[None, :] for k in range(8)]
+ds = [np.nan_to_num(bench.step_lengths(base, k))[:, None] * rates[None, :] for k in range(7)]
 for mode in ("blocking", "queued", "blocking", "queued"):
     for k in range(5):
-        eng.update(ds[k % 8])
+        eng.update(ds[k % 7])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
     for k in range(a.steps):
         if mode == "blocking":
-            eng.update(ds[k % 8])
+            eng.update(ds[k % 7])
         else:
-            eng.set_distances(ds[k % 8])
+            eng.set_distances(ds[k % 7])
             eng.evaluate_device(buf.data_ptr())
     e1.record(stream)
     t_host = time.perf_counter() - t0
