@@ -599,7 +599,7 @@ def run_ours(args):
     # ---- many small alignments at once: B independent likelihood functions --
     many = None
     if world == 1 and args.config == "c1":
-        from cogent3_b200.engine import evaluate_many as engine_many
+        from cogent3_b200.engine import update_many as engine_update_many
 
         B = 64
         lfs = [make_lf(problem, device=local_rank)[0] for _ in range(B)]
@@ -608,10 +608,7 @@ def run_ours(args):
             f.get_log_likelihood()
 
         def many_step(k):
-            d = np.nan_to_num(step_lengths(base, k))[:, None] * rates[None, :]
-            for e_ in engines:
-                e_.set_distances(d)
-            return engine_many(engines)
+            return engine_update_many(engines, step_dist[k % 7])
 
         for k in range(20):  # (past the engines' graph-capture threshold: steady state)
             many_step(k)
@@ -631,7 +628,7 @@ def run_ours(args):
             t_seq += (time.perf_counter() - t0) / 5
         many = {"engines": B, "evals_per_s": B / t_many, "ms_per_batch": t_many * 1e3,
                 "one_at_a_time_evals_per_s": B / t_seq, "all_equal": bool(len(set(vals)) == 1),
-                "api": "c3_evaluate_many: every engine on its own stream, launched before any is waited for"}
+                "api": "c3_update_many: every engine on its own stream; a batch that keeps coming up is ONE CUDA graph"}
         del one_by_one
         for f in lfs:
             f.engine.close()

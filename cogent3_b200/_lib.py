@@ -87,6 +87,7 @@ SIGNATURES = {
     "c3_evaluate_device": (c_int, [c_void_p, c_void_p]),
     "c3_update": (c_int, [c_void_p, _pd, _pd]),
     "c3_evaluate_many": (c_int, [POINTER(c_void_p), c_int, _pd]),
+    "c3_update_many": (c_int, [POINTER(c_void_p), c_int, _pd, c_int64, _pd]),
     "c3_comm_mailbox": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_uint8)]),
     "c3_comm_attach": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint8), POINTER(c_void_p)]),
     "c3_comm_detach": (c_int, [c_void_p]),

@@ -167,6 +167,13 @@ struct c3_engine {
   bool use_graphs = true;
   struct GraphEntry { std::vector<int32_t> sig; cudaGraphExec_t exec = nullptr; int64_t n_launch = 0; uint64_t last_use = 0; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
+  // c3_evaluate_many batches: 0 = normal; 1 = issue into the caller's capture (no graph of its own);
+  // 2 = dry plan: fill the parameter block, report the structure hash, launch nothing, mark nothing
+  int batch_mode = 0;
+  uint64_t last_sig_hash = 0;
+  bool last_skipped = false;  // nothing was dirty: the evaluation returned the cached value
+  struct PlanStats { int64_t expm_jobs = 0, nodes = 0, node_rows = 0, alg_bytes = 0, flops = 0, h2d_bytes = 0; };
+  PlanStats plan;
   std::unordered_map<uint64_t, int> graph_seen;  // structure hash -> times seen before its capture
   int graph_after = 16;                          // sightings before a structure is captured (C3_GRAPH_AFTER)
   uint64_t graph_clock = 0;
@@ -504,12 +511,49 @@ int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
   return (int64_t)e->K * ((e->n_rows[n] + DMMA_TILE_ROWS - 1) / DMMA_TILE_ROWS);
 }
 
+// bookkeeping after the stream operations of a planned evaluation were issued (or replayed): everything is clean
+void commit_evaluation(c3_engine* e, int64_t n_launch, bool replayed) {
+  std::fill(e->pdirty.begin(), e->pdirty.end(), 0);
+  std::fill(e->node_dirty.begin(), e->node_dirty.end(), 0);
+  e->reduce_dirty = false;
+  e->stats.evaluations += 1;
+  e->stats.kernel_launches += n_launch;
+  e->stats.last_launches = n_launch;
+  e->stats.last_expm_jobs = e->plan.expm_jobs;
+  e->stats.last_nodes = e->plan.nodes;
+  e->stats.last_node_rows = e->plan.node_rows;
+  e->stats.last_alg_bytes = e->plan.alg_bytes;
+  e->stats.last_flops = e->plan.flops;
+  e->stats.last_h2d_bytes = e->plan.h2d_bytes;
+  if (replayed) e->stats.graph_replays += 1;
+}
+
+// c3_evaluate_many: ONE graph over all engines of a batch (each engine's operations on its own
+// stream, forked from / joined to the first engine's stream inside the capture)
+struct BatchGraph {
+  std::vector<c3_engine*> engines;
+  std::vector<uint64_t> hashes;  // structure hash of every engine's evaluation
+  std::vector<int64_t> n_launch;
+  cudaGraphExec_t exec = nullptr;
+  int seen = 0;
+};
+std::unordered_map<uint64_t, BatchGraph> g_batches;  // (single-threaded use, like the engines themselves)
+cudaEvent_t g_fork = nullptr;
+std::vector<cudaEvent_t> g_joins;
+
+void clear_batches() {
+  for (auto& b : g_batches)
+    if (b.second.exec) cudaGraphExecDestroy(b.second.exec);
+  g_batches.clear();
+}
+
 // captured graphs hold device pointers: drop them whenever an allocation they name is replaced
 void clear_graphs(c3_engine* e) {
   for (auto& g : e->graphs)
     if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   e->graphs.clear();
   e->graph_seen.clear();
+  clear_batches();
 }
 
 int ensure_slots(c3_engine* e, int n) {
@@ -533,6 +577,7 @@ int ensure_slots(c3_engine* e, int n) {
 
 int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out, bool deferred = false);
 int finish_deferred(c3_engine* e, double* host_out);
+int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used);
 int activate_rescaling(c3_engine* e);
 void deactivate_rescaling(c3_engine* e);
 int launch_rescale(c3_engine* e, int node);
@@ -690,8 +735,7 @@ int c3_destroy(c3_engine* e) {
   if (e->d_mailbox) cudaFree(e->d_mailbox);
   if (e->d_pool) cudaFree(e->d_pool);
   if (e->d_scale_pool) cudaFree(e->d_scale_pool);
-  for (auto& g : e->graphs)
-    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  clear_graphs(e);
   if (e->d_slots) cudaFree(e->d_slots);
   if (e->d_block) cudaFree(e->d_block);
   if (e->h_block) cudaFreeHost(e->h_block);
@@ -1443,6 +1487,12 @@ int c3_evaluate_device(c3_engine* e, double* device_lnL) {
 int c3_evaluate_many(c3_engine** engines, int n, double* lnL) {
   C3_REQUIRE(engines && lnL && n >= 0, "null pointer");
   for (int i = 0; i < n; ++i) C3_REQUIRE(engines[i] != nullptr, "null engine");
+  {
+    int used_batch = 0;
+    const int brc = evaluate_many_batched(engines, n, lnL, &used_batch);
+    if (brc != C3_OK) return brc;
+    if (used_batch) return C3_OK;
+  }
   // launch every engine's evaluation on its own stream, then collect: small problems overlap
   int rc = C3_OK;
   int launched = 0;
@@ -1455,6 +1505,17 @@ int c3_evaluate_many(c3_engine** engines, int n, double* lnL) {
     if (rc == C3_OK) rc = rc2;
   }
   return rc;
+}
+
+int c3_update_many(c3_engine** engines, int n, const double* distances, int64_t stride, double* lnL) {
+  C3_REQUIRE(engines && distances && lnL && n >= 0, "null pointer");
+  for (int i = 0; i < n; ++i) {
+    C3_REQUIRE(engines[i] != nullptr, "null engine");
+    C3_REQUIRE(stride == 0 || stride >= (int64_t)engines[i]->n_nodes * engines[i]->K, "stride shorter than an engine's distance table");
+    const int rc = c3_set_distances(engines[i], distances + (int64_t)i * stride);
+    if (rc != C3_OK) return rc;
+  }
+  return c3_evaluate_many(engines, n, lnL);
 }
 
 int c3_comm_mailbox(c3_engine* e, int nranks, void** device_ptr, unsigned char* ipc_handle) {
@@ -1742,7 +1803,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       ++n_dirty_nodes;
     }
   }
+  e->last_skipped = false;
   if (n_dirty_nodes == 0 && n_eigen + n_pade == 0 && !e->reduce_dirty && e->have_cached) {
+    e->last_skipped = true;
+    if (e->batch_mode == 2) return C3_OK;
     if (host_out) *host_out = e->cached_lnl;
     if (device_out)
       C3_CUDA(cudaMemcpyAsync(device_out, e->d_lnl, sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
@@ -2078,7 +2142,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
 
   // ---- direct launches, or capture / replay of this structure's graph ---------------------------
   bool graphed = false;
-  if (e->use_graphs && !e->profiling && comm.nranks <= 1 && !any_flow) {
+  e->plan = c3_engine::PlanStats{n_eigen + n_pade, n_dirty_nodes, node_rows, alg_bytes, flops, h2d_bytes};
+  const bool graph_ok = e->use_graphs && !e->profiling && comm.nranks <= 1 && !any_flow;
+  if (e->batch_mode != 0 && !graph_ok) return fail(C3_ERR_INVALID, "engine cannot take part in a batch graph");
+  if (graph_ok) {
     std::vector<int32_t> sig;
     sig.reserve(16 + 8 * launches.size() + w_off);
     sig.push_back(n_eigen); sig.push_back(n_pade); sig.push_back((int32_t)std::min(used, e->block_bytes));
@@ -2093,9 +2160,18 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     for (int i = 0; i < w_off; ++i) sig.push_back(work[i]);  // (rescale launches name their nodes)
     uint64_t h = 1469598103934665603ull;
     for (int32_t v : sig) { h ^= (uint32_t)v; h *= 1099511628211ull; }
+    e->last_sig_hash = h;
+    if (e->batch_mode == 2) return C3_OK;  // dry plan: the parameter block is filled, nothing else happened
     ++e->graph_clock;
     auto it = e->graphs.find(h);
-    if (it != e->graphs.end() && it->second.sig == sig) {
+    if (e->batch_mode == 1) {
+      // the caller is capturing a batch graph over several engines' streams: issue into it
+      capturing = true;
+      const int rc = issue();
+      capturing = false;
+      if (rc) return rc;
+      graphed = true;
+    } else if (it != e->graphs.end() && it->second.sig == sig) {
       C3_CUDA(cudaGraphLaunch(it->second.exec, e->stream));
       it->second.last_use = e->graph_clock;
       n_launch = it->second.n_launch;
@@ -2152,24 +2228,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   if (!graphed) {
     int rc = issue();
     if (rc) return rc;
-  } else {
+  } else if (e->batch_mode == 0) {
     C3_CUDA(cudaEventRecord(e->block_copied, e->stream));  // (a replay frees the staging buffer when it is through)
   }
-
-  // bookkeeping: everything launched is now clean
-  std::fill(e->pdirty.begin(), e->pdirty.end(), 0);
-  std::fill(e->node_dirty.begin(), e->node_dirty.end(), 0);
-  e->reduce_dirty = false;
-  e->stats.evaluations += 1;
-  e->stats.kernel_launches += n_launch;
-  e->stats.last_launches = n_launch;
-  e->stats.last_expm_jobs = n_eigen + n_pade;
-  e->stats.last_nodes = n_dirty_nodes;
-  e->stats.last_node_rows = node_rows;
-  e->stats.last_alg_bytes = alg_bytes;
-  e->stats.last_flops = flops;
-  e->stats.last_h2d_bytes = h2d_bytes;
-  if (graphed) e->stats.graph_replays += 1;
+  commit_evaluation(e, n_launch, graphed && e->batch_mode == 0);
 
   if (deferred) {
     e->deferred_pending = true;
@@ -2222,6 +2284,143 @@ int finish_deferred(c3_engine* e, double* host_out) {
   }
   if (host_out) *host_out = e->cached_lnl;
   return C3_OK;
+}
+
+// ---- c3_evaluate_many as ONE graph ---------------------------------------------------------------
+// Small alignments are bound by the host's launch calls (~14 us per engine even with per-engine
+// graphs).  When the same set of engines keeps being evaluated with the same structures (bootstraps,
+// batches of genes: always the full sweep), the whole batch is captured once -- every engine's
+// operations on its own stream, forked from and joined to the first engine's stream -- and replayed
+// with one cudaGraphLaunch; per evaluation the host only plans (fills every engine's parameter block).
+// *used = 0: not applicable this time, the caller takes the one-launch-sequence-per-engine path.
+int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
+  *used = 0;
+  if (n < 2) return C3_OK;
+  uint64_t key = 1469598103934665603ull;
+  for (int i = 0; i < n; ++i) {
+    c3_engine* e = engines[i];
+    if (!e->finalized || !e->use_graphs || e->profiling || e->comm.nranks > 1 || e->use_flow || !e->own_stream ||
+        e->device != engines[0]->device || e->nodes_dirty || !e->have_pi)
+      return C3_OK;
+    for (const Slot& s : e->slots)
+      if (s.dirty) return C3_OK;  // rate matrices changed: their upload is not part of the graph
+    if (e->rescale_mode == C3_RESCALE_ON && !e->rescale_active) return C3_OK;
+    for (int j = 0; j < i; ++j)
+      if (engines[j] == e) return C3_OK;
+    key ^= (uint64_t)(uintptr_t)e;
+    key *= 1099511628211ull;
+  }
+  BatchGraph& bg = g_batches[key];
+  if (bg.engines.empty()) bg.engines.assign(engines, engines + n);
+  if (bg.engines.size() != (size_t)n || !std::equal(engines, engines + n, bg.engines.begin())) return C3_OK;  // (hash collision)
+  C3_CUDA(cudaSetDevice(engines[0]->device));
+  if (bg.exec == nullptr) {
+    if (++bg.seen < engines[0]->graph_after) return C3_OK;
+    // capture: every engine issues into the capture on its own stream
+    if (g_fork == nullptr) C3_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+    while ((int)g_joins.size() < n) {
+      cudaEvent_t ev;
+      C3_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      g_joins.push_back(ev);
+    }
+    cudaStream_t s0 = engines[0]->stream;
+    if (cudaStreamBeginCapture(s0, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      bg.seen = -(1 << 30);  // never again for this set of engines
+      return C3_OK;
+    }
+    int rc = C3_OK;
+    bool skipped = false;
+    cudaError_t err = cudaEventRecord(g_fork, s0);
+    std::vector<uint64_t> hashes(n);
+    std::vector<int64_t> n_launch(n);
+    for (int i = 0; i < n && rc == C3_OK && err == cudaSuccess; ++i) {
+      c3_engine* e = engines[i];
+      if (e->stream != s0) err = cudaStreamWaitEvent(e->stream, g_fork, 0);
+      if (err != cudaSuccess) break;
+      e->batch_mode = 1;
+      rc = run_evaluation(e, nullptr, false, nullptr, true);
+      e->batch_mode = 0;
+      skipped = skipped || e->last_skipped;
+      hashes[i] = e->last_sig_hash;
+      n_launch[i] = e->stats.last_launches;
+      if (e->stream != s0 && rc == C3_OK) {
+        err = cudaEventRecord(g_joins[i], e->stream);
+        if (err == cudaSuccess) err = cudaStreamWaitEvent(s0, g_joins[i], 0);
+      }
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end_err = cudaStreamEndCapture(s0, &graph);
+    if (rc != C3_OK || err != cudaSuccess || end_err != cudaSuccess || graph == nullptr || skipped) {
+      // not capturable (or an engine had nothing to do): everything is evaluated again from scratch, plainly
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      bg.seen = skipped ? 0 : -(1 << 30);
+      for (int i = 0; i < n; ++i) {
+        engines[i]->deferred_pending = false;
+        c3_invalidate(engines[i]);
+      }
+      return C3_OK;
+    }
+    err = cudaGraphInstantiate(&bg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      bg.exec = nullptr;
+      bg.seen = -(1 << 30);
+      for (int i = 0; i < n; ++i) {
+        engines[i]->deferred_pending = false;
+        c3_invalidate(engines[i]);
+      }
+      return C3_OK;
+    }
+    bg.hashes = hashes;
+    bg.n_launch = n_launch;
+  } else {
+    // replay: plan every engine (fills its parameter block), check that the structures are the captured ones
+    bool same = true;
+    for (int i = 0; i < n && same; ++i) {
+      c3_engine* e = engines[i];
+      e->batch_mode = 2;
+      const int rc = run_evaluation(e, nullptr, false, nullptr, true);
+      e->batch_mode = 0;
+      if (rc != C3_OK) return rc;
+      same = !e->last_skipped && e->last_sig_hash == bg.hashes[i];
+    }
+    if (!same) return C3_OK;  // e.g. a single-branch update this time: the per-engine path plans again
+    for (int i = 0; i < n; ++i) {
+      commit_evaluation(engines[i], bg.n_launch[i], true);
+      engines[i]->deferred_pending = true;
+    }
+  }
+  cudaStream_t s0 = engines[0]->stream;
+  C3_CUDA(cudaGraphLaunch(bg.exec, s0));
+  for (int i = 0; i < n; ++i) C3_CUDA(cudaEventRecord(engines[i]->block_copied, s0));
+  cudaError_t err = cudaStreamSynchronize(s0);
+  if (err != cudaSuccess) {
+    for (int i = 0; i < n; ++i) {
+      engines[i]->deferred_pending = false;
+      engines[i]->have_cached = false;
+      c3_invalidate(engines[i]);
+    }
+    return fail(C3_ERR_CUDA, std::string("batched evaluation failed: ") + cudaGetErrorString(err));
+  }
+  int rc = C3_OK;
+  for (int i = 0; i < n; ++i) {
+    c3_engine* e = engines[i];
+    e->deferred_pending = false;
+    e->cached_lnl = *e->h_lnl;
+    e->have_cached = true;
+    lnL[i] = e->cached_lnl;
+    if (!std::isfinite(e->cached_lnl) && e->rescale_mode == C3_RESCALE_AUTO && !e->rescale_active) {
+      int rc2 = activate_rescaling(e);  // (drops the batch graphs: the structures change)
+      if (rc2 == C3_OK) rc2 = run_evaluation(e, nullptr, true, lnL + i);
+      if (rc == C3_OK) rc = rc2;
+      if (rc2 != C3_OK) break;
+    }
+  }
+  *used = 1;
+  return rc;
 }
 
 // ---- per-pattern underflow rescaling: set-up -------------------------------------------------

@@ -361,6 +361,23 @@ def evaluate_many(engines) -> np.ndarray:
     return out
 
 
+def update_many(engines, distances) -> np.ndarray:
+    """new distances for every engine, then ``evaluate_many`` -- one FFI crossing per batch
+    (c3_update_many).  ``distances``: one table [n_nodes, n_bins] shared by all engines, or an array
+    [n_engines, n_nodes, n_bins]."""
+    n = len(engines)
+    out = np.zeros(n, np.float64)
+    if n == 0:
+        return out
+    d = np.ascontiguousarray(distances, np.float64)
+    per = engines[0].n_nodes * engines[0].n_bins
+    stride = 0 if d.size == per else per
+    assert d.size in (per, n * per) and all(e.n_nodes * e.n_bins == per for e in engines)
+    handles = (c_void_p * n)(*[e._h.value for e in engines])
+    _lib.check(engines[0]._lib.c3_update_many(handles, n, _dptr(d), stride, _dptr(out)))
+    return out
+
+
 def measure_dmma_peak(device=0) -> float:
     """sustained FP64 tensor-core TFLOP/s of this GPU (DMMA m8n8k4 issue loop)."""
     out = c_double(0.0)

@@ -223,6 +223,11 @@ C3_API int c3_comm_detach(c3_engine* e);
  *             evolve/bootstrap.py:68) -- overlap on the GPU instead of paying the launch /
  *             level latency one after the other.                          */
 C3_API int c3_evaluate_many(c3_engine** engines, int n, double* lnL);
+/* c3_update_many: c3_set_distances for every engine (engine i reads distances + i * stride;
+ *             stride 0: the same table for all), then c3_evaluate_many -- one FFI crossing per
+ *             batch.  Engines that keep being evaluated together with the same structure are
+ *             captured into ONE CUDA graph (every engine on its own stream inside it).        */
+C3_API int c3_update_many(c3_engine** engines, int n, const double* distances, int64_t stride, double* lnL);
 
 /* ---- accessors (what likelihood_function.py reads back) -------------------------
  * c3_get_lh: per-pattern root likelihood of one bin, "lh" Defn

@@ -476,3 +476,37 @@ def test_graph_replay_is_bit_identical(case, monkeypatch):
     for a, b in zip(plain[:-1], graphed[:-1], strict=True):
         assert a == b
     assert np.array_equal(plain[-1], graphed[-1])
+
+
+def test_batched_graph_of_many_engines_matches_individual_evaluations(monkeypatch):
+    """c3_update_many: a set of engines that keeps being evaluated together is captured into ONE graph
+    (every engine on its own stream inside it); results are the bits of one-at-a-time evaluations,
+    and a batch with a different structure (one branch only) falls back without harm"""
+    from cogent3_b200.engine import update_many
+
+    monkeypatch.setenv("C3_GRAPH_AFTER", "3")
+    g = Golden("c1_brca1_hky85_default")
+    lfs = [lf_from_golden(g) for _ in range(6)]
+    solo = lf_from_golden(g)
+    for f in [*lfs, solo]:
+        f.get_log_likelihood()
+    engines = [f.engine for f in lfs]
+    rates = solo.rates()
+    base = np.nan_to_num(g.lengths)
+    rng = np.random.default_rng(2)
+    for step in range(12):
+        if step == 8:  # a different structure in the middle: only two branches move
+            d = np.array(last)
+            d[int(g.topo.edges[3])] *= 1.1
+            d[int(g.topo.edges[9])] *= 0.9
+        else:
+            d = (base * (1.0 + 0.01 * (step + 1)))[:, None] * rates[None, :]
+        # every engine its own table on odd steps, one shared table on even ones
+        tables = np.stack([d * (1.0 + 1e-3 * i) for i in range(len(engines))]) if step % 2 else d
+        got = update_many(engines, tables)
+        for i in range(len(engines)):
+            want = solo.engine.update(tables[i] if step % 2 else d)
+            assert got[i] == want, (step, i)
+        last = tables[0] if step % 2 else d
+    replays = [e.stats()["graph_replays"] for e in engines]
+    assert min(replays) >= 5, replays  # captured at the third batch, replayed for the full sweeps after it
