@@ -115,6 +115,7 @@ struct c3_engine {
   int64_t block_bytes = 0;
   int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0, off_small = 0;
   bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
+  bool use_small_reduce = true;  // ... which also reduces when the root is in it (C3_NO_SMALL_REDUCE=1 disables)
   bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
   // M != 4: every node stores its rows already multiplied by the P of the branch above it, one
   // contraction per NODE row (prune_dmma_edge_kernel); C3_EDGE_MAJOR=0: the parent-major kernels
@@ -647,6 +648,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_STRIP")) e->use_strip = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_SMALL")) e->use_small = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
+  if (const char* env = getenv("C3_NO_SMALL_REDUCE")) e->use_small_reduce = atoi(env) == 0;
   if (const char* env = getenv("C3_DMMA_REG")) e->use_dmma_reg = atoi(env) != 0;
   e->edge_major = e->use_dmma;
   if (const char* env = getenv("C3_EDGE_MAJOR")) e->edge_major = e->use_dmma && atoi(env) != 0;
@@ -2007,6 +2009,12 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   CommArgs comm = e->comm;
   if (comm.nranks > 1) comm.epoch = ++e->comm.epoch;  // every rank evaluates in lock-step
 
+  // small problems whose root sits in the (last) small-levels launch: that launch also reduces
+  // (prune4_small_kernel's tail: the same tiles and summation trees, one launch fewer)
+  const bool fuse_reduce = e->use_small_reduce && !launches.empty() && launches.back().kind == 1 &&
+                           launches.back().is_root && !e->rescale_active && comm.nranks <= 1 &&
+                           e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE;
+
   // every stream operation of the evaluation (issued directly, or into a graph capture)
   bool capturing = false;
   auto issue = [&]() -> int {
@@ -2082,8 +2090,18 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       attr[1].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
       cfg.attrs = attr;
       cfg.numAttrs = 2;
+      ReduceTail tail{};
+      if (fuse_reduce && li + 1 == launches.size()) {
+        tail.bprobs = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
+        tail.counts = e->d_counts;
+        tail.n_rows = e->n_rows[e->root];
+        tail.n_tiles = (int)((tail.n_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
+        tail.d_lnl = e->d_lnl;
+        tail.d_lnl2 = device_out;
+        tail.h_lnl = (blocking || deferred) ? e->h_lnl_dev : nullptr;
+      }
       cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel, a, d_small, ll.n_small, ll.n_work,
-                                           ll.n_work + ll.n_small);
+                                           ll.n_work + ll.n_small, tail);
       if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("small-level launch: ") + cudaGetErrorString(err));
     } else if (ll.kind == 5) {
       const int32_t* d_dep = reinterpret_cast<const int32_t*>(e->d_block + e->off_dep) + 2 * ll.work_off;
@@ -2111,7 +2129,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       }
     }
   }
-  {
+  if (!fuse_reduce) {
     const int64_t rows = e->n_rows[e->root];
     const int n_tiles = (int)((rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
     const int grid = std::min(n_tiles, e->n_sm * 8);
@@ -2149,7 +2167,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     std::vector<int32_t> sig;
     sig.reserve(16 + 8 * launches.size() + w_off);
     sig.push_back(n_eigen); sig.push_back(n_pade); sig.push_back((int32_t)std::min(used, e->block_bytes));
-    sig.push_back(e->rescale_active ? 1 : 0);
+    sig.push_back((e->rescale_active ? 1 : 0) | (fuse_reduce ? 2 : 0));
     sig.push_back((int32_t)((uintptr_t)device_out & 0xffffffffu)); sig.push_back((int32_t)((uintptr_t)device_out >> 32));
     sig.push_back((blocking || deferred) ? 1 : 0);
     sig.push_back((int32_t)((uintptr_t)e->stream & 0xffffffffu)); sig.push_back((int32_t)((uintptr_t)e->stream >> 32));

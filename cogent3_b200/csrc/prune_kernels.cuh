@@ -1119,13 +1119,85 @@ __device__ __forceinline__ void small_unit_staged(const PruneArgs& a, const Node
   }
 }
 
+// ---- pieces of the site-weighted reduction shared by lnl_reduce_kernel and the small-levels kernel ----
+__device__ __forceinline__ double block_sum(double v, double* s_warp) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  double total = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) total += s_warp[i];
+  }
+  return total;  // valid on thread 0
+}
+
+// one thread's share of a reduction tile: rows base + u * REDUCE_THREADS + t  (t < REDUCE_THREADS)
+__device__ __forceinline__ double reduce_tile_partial(const double* __restrict__ lh, const double* __restrict__ bprobs,
+                                                      const double* __restrict__ counts, int64_t n_rows, int K,
+                                                      int tile, int t, const int32_t* __restrict__ root_exp) {
+  constexpr int U = REDUCE_ROWS_PER_TILE / REDUCE_THREADS;
+  const int64_t base = (int64_t)tile * REDUCE_ROWS_PER_TILE;
+  // all loads of the thread's rows first (one 256-bit / 128-bit load per row for K = 4 / 2), then the logs
+  double mix[U], cnt[U];
+  int32_t ex[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t p = base + u * REDUCE_THREADS + t;
+    mix[u] = 1.0;
+    cnt[u] = 0.0;
+    ex[u] = 0;
+    if (p < n_rows) {
+      if (K == 1) {
+        mix[u] = lh[p];
+      } else if (K == 4) {
+        const d4 v = ld256(lh + p * 4);
+        mix[u] = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(v.x, bprobs[0])), __dmul_rn(v.y, bprobs[1])),
+                                     __dmul_rn(v.z, bprobs[2])), __dmul_rn(v.w, bprobs[3]));
+      } else if (K == 2) {
+        const double2 v = *reinterpret_cast<const double2*>(lh + p * 2);
+        mix[u] = __dadd_rn(__dadd_rn(0.0, __dmul_rn(v.x, bprobs[0])), __dmul_rn(v.y, bprobs[1]));
+      } else {
+        double m = 0.0;
+        for (int b = 0; b < K; ++b) m = __dadd_rn(m, __dmul_rn(lh[p * K + b], bprobs[b]));
+        mix[u] = m;
+      }
+      cnt[u] = counts[p];
+      if (root_exp != nullptr) ex[u] = root_exp[p];
+    }
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    // rescaled rows: lh = mix * 2^root_exp[p]  (exact powers of two carried as integers)
+    const double lg = (root_exp != nullptr) ? fma((double)ex[u], 0.6931471805599453094, log(mix[u])) : log(mix[u]);
+    acc += lg * cnt[u];
+  }
+  return acc;
+}
+
+// the reduction of a small problem done by the small-levels kernel itself (no separate launch)
+constexpr int SMALL_REDUCE_MAX_TILES = 8;
+struct ReduceTail {
+  const double* bprobs;
+  const double* counts;
+  int64_t n_rows;
+  int n_tiles;  // 0: no fused reduction
+  double* d_lnl;
+  double* d_lnl2;
+  volatile double* h_lnl;
+};
+
 // n_work_total / n_prefix_total: sizes of the launch's work and prefix arrays.  When they
 // fit, every descriptor the units need is staged in shared memory first, so the
 // dependent-load chain per level is just  gather index -> child row  (P and the
 // descriptors no longer sit on it).
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
 prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, int n_levels,
-                    int n_work_total, int n_prefix_total) {
+                    int n_work_total, int n_prefix_total, const ReduceTail tail) {
   extern __shared__ __align__(16) unsigned char small_raw[];
   SmallSmem& sm = *reinterpret_cast<SmallSmem*>(small_raw);
   pdl_trigger();
@@ -1200,6 +1272,34 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
       }
     }
     if (li + 1 < n_levels) cluster_barrier();
+  }
+  if (tail.n_tiles > 0) {
+    // the root was in this launch and the problem is small: the site-weighted reduction right here
+    // (same tiles, same per-thread rows, same summation trees as lnl_reduce_kernel: same bits), by
+    // the cluster's first CTA once every CTA's lh values are there
+    cluster_barrier();
+    if (cluster_ctarank() != 0) return;
+    __shared__ double s_warp[SMALL_THREADS / 32];
+    __shared__ double s_tiles[SMALL_REDUCE_MAX_TILES];
+    const int t = (int)threadIdx.x;
+    for (int tile = 0; tile < tail.n_tiles; ++tile) {
+      const double acc = (t < REDUCE_THREADS)
+                             ? reduce_tile_partial(a.lh_out, tail.bprobs, tail.counts, tail.n_rows, K, tile, t, nullptr)
+                             : 0.0;
+      const double total = block_sum(acc, s_warp);  // (the warps past REDUCE_THREADS add +0.0)
+      if (t == 0) s_tiles[tile] = total;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    if (t < REDUCE_THREADS)
+      for (int i = t; i < tail.n_tiles; i += REDUCE_THREADS) acc += s_tiles[i];
+    const double total = block_sum(acc, s_warp);
+    if (t == 0) {
+      *tail.d_lnl = total;
+      if (tail.d_lnl2) *tail.d_lnl2 = total;
+      if (tail.h_lnl) *tail.h_lnl = total;
+      __threadfence_system();
+    }
   }
 }
 
@@ -1876,20 +1976,6 @@ edge_major_plh_kernel(const NodeDesc nd, const ChildRef* __restrict__ childs, in
 // Deterministic: fixed tile size, fixed in-tile tree, tiles summed in index order by the
 // last CTA to finish -- the result does not depend on the grid or on timing.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double* s_warp) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) s_warp[warp] = v;
-  __syncthreads();
-  double total = 0.0;
-  if (threadIdx.x == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    for (int i = 0; i < nw; ++i) total += s_warp[i];
-  }
-  return total;  // valid on thread 0
-}
 
 // Sharded runs (CommArgs.nranks > 1): the last CTA then turns the shard's sum into the TOTAL over
 // all ranks of the node without a separate collective -- thread r stores (value, epoch) into
@@ -1922,43 +2008,7 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
   __shared__ bool s_last;
   pdl_wait();  // launched early (programmatic dependent launch): lh is the root launch's output
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    constexpr int U = REDUCE_ROWS_PER_TILE / REDUCE_THREADS;
-    const int64_t base = (int64_t)tile * REDUCE_ROWS_PER_TILE;
-    // all loads of the thread's rows first (one 256-bit / 128-bit load per row for K = 4 / 2), then the logs
-    double mix[U], cnt[U];
-    int32_t ex[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = base + u * REDUCE_THREADS + threadIdx.x;
-      mix[u] = 1.0;
-      cnt[u] = 0.0;
-      ex[u] = 0;
-      if (p < n_rows) {
-        if (K == 1) {
-          mix[u] = lh[p];
-        } else if (K == 4) {
-          const d4 v = ld256(lh + p * 4);
-          mix[u] = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(v.x, bprobs[0])), __dmul_rn(v.y, bprobs[1])),
-                                       __dmul_rn(v.z, bprobs[2])), __dmul_rn(v.w, bprobs[3]));
-        } else if (K == 2) {
-          const double2 v = *reinterpret_cast<const double2*>(lh + p * 2);
-          mix[u] = __dadd_rn(__dadd_rn(0.0, __dmul_rn(v.x, bprobs[0])), __dmul_rn(v.y, bprobs[1]));
-        } else {
-          double m = 0.0;
-          for (int b = 0; b < K; ++b) m = __dadd_rn(m, __dmul_rn(lh[p * K + b], bprobs[b]));
-          mix[u] = m;
-        }
-        cnt[u] = counts[p];
-        if (root_exp != nullptr) ex[u] = root_exp[p];
-      }
-    }
-    double acc = 0.0;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      // rescaled rows: lh = mix * 2^root_exp[p]  (exact powers of two carried as integers)
-      const double lg = (root_exp != nullptr) ? fma((double)ex[u], 0.6931471805599453094, log(mix[u])) : log(mix[u]);
-      acc += lg * cnt[u];
-    }
+    const double acc = reduce_tile_partial(lh, bprobs, counts, n_rows, K, tile, (int)threadIdx.x, root_exp);
     const double total = block_sum(acc, s_warp);
     if (threadIdx.x == 0) tile_sums[tile] = total;
   }

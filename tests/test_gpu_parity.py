@@ -35,7 +35,7 @@ def test_golden_lnL_lh_psubs(case):
     if "pinned_lnL" in g.meta:
         np.testing.assert_allclose(lnL, g.meta["pinned_lnL"], rtol=1e-7)
     st = lf.engine.stats()
-    assert st["last_launches"] >= 3  # expm + >=1 level + reduction: the CUDA path ran
+    assert st["last_launches"] >= 2  # expm + >=1 level launch (+ reduction unless the small-levels launch did it): the CUDA path ran
 
 
 @pytest.mark.parametrize("case", ["c2_gtr_gamma4_small", "c4_cnfgtr_small", "c3_gn_pade_small"])
