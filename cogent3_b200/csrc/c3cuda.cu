@@ -257,21 +257,23 @@ int launch_dmma_reg(c3_engine* e, const PruneArgs& a, bool is_root) {
   return C3_OK;
 }
 
+constexpr int DE_RA = 1;  // row groups per warp of the contraction instance (2: 8 warps x 16 rows, measured slower, DESIGN lesson 13)
+
 template <int MP>
 int launch_dmma_edge(c3_engine* e, const PruneArgs& a, bool root_only3) {
   const size_t smem = (size_t)MP * (MP + 8) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    int rc = set_max_smem(prune_dmma_edge_kernel<MP, 2, true>, smem);
+    int rc = set_max_smem(prune_dmma_edge_kernel<MP, 2, true, DE_RA>, smem);
     if (rc) return rc;
-    rc = set_max_smem(prune_dmma_edge_kernel<MP, 3, false>, smem);
+    rc = set_max_smem(prune_dmma_edge_kernel<MP, 3, false, 1>, smem);
     if (rc) return rc;
     configured = true;
   }
   const int grid = std::max(1, std::min(a.total_tiles, e->n_sm));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(DE_THREADS);
+  cfg.blockDim = dim3(root_only3 ? DECfg<1>::THREADS : DECfg<DE_RA>::THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = e->stream;
   cudaLaunchAttribute attr[1];
@@ -280,8 +282,8 @@ int launch_dmma_edge(c3_engine* e, const PruneArgs& a, bool root_only3) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // a launch holding only the trifurcating root: three prefetched children, no contraction
-  cudaError_t err = root_only3 ? cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 3, false>, a)
-                               : cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 2, true>, a);
+  cudaError_t err = root_only3 ? cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 3, false, 1>, a)
+                               : cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 2, true, DE_RA>, a);
   if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("dmma-edge launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
@@ -498,7 +500,11 @@ int kind_of_node(const c3_engine* e, int n) {
 }
 
 int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
-  if (kind == 8) return (int64_t)e->K * ((e->n_rows[n] + DE_TILE_ROWS - 1) / DE_TILE_ROWS);
+  if (kind == 8) {
+    // the trifurcating root is always alone in its launch and runs the 3-children instance (12 warps x 8 rows)
+    const int tile_rows = (n == e->root && e->children[n].size() == 3) ? DECfg<1>::TILE_ROWS : DECfg<DE_RA>::TILE_ROWS;
+    return (int64_t)e->K * ((e->n_rows[n] + tile_rows - 1) / tile_rows);
+  }
   if (kind == 6) return (int64_t)e->K * ((e->n_rows[n] + DR_TILE_ROWS - 1) / DR_TILE_ROWS);
   if (kind >= 2) {
     // strips of 128 (row, bin) units; regpipe2 walks three-children nodes in strips of 64

@@ -1751,13 +1751,25 @@ struct ECur {
 };
 
 // DE_PRE children are prefetched (2; 3 for the launch of a trifurcating root, which is also
-// compiled without the contraction: CONTRACT = false)
-template <int MP, int DE_PRE, bool CONTRACT>
-__global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const PruneArgs a) {
+// compiled without the contraction: CONTRACT = false).
+// RA row groups of 8 per warp: with RA = 2 (the contraction instance: 8 warps x 16 rows) every
+// 128-bit B-fragment load from shared memory feeds FOUR DMMAs instead of two -- the shared-memory
+// pipe was ~50 % busy with B loads at one row group per warp -- and the accumulators are produced
+// in two column halves so that rows in flight + products + accumulators fit the register file.
+template <int RA>
+struct DECfg {
+  static constexpr int WARPS = (RA == 2) ? 8 : DE_WARPS;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int TILE_ROWS = WARPS * 8 * RA;
+};
+
+template <int MP, int DE_PRE, bool CONTRACT, int RA>
+__global__ void __launch_bounds__(DECfg<RA>::THREADS, 1) prune_dmma_edge_kernel(const PruneArgs a) {
   // P in its natural layout with row stride MP + 8: the lane (g, q) then reads the B values of k
   // steps 2a and 2a+1 of column block ni -- P[8 ni + g][8a + 2q], [.. + 1] -- with ONE conflict-free
   // 128-bit load (quarter-warps: g in {0,1} -> 16-byte bank groups 0-3 and 4-7)
   constexpr int LDS = MP + 8, NI = MP / 8, KS = MP / 4;
+  constexpr int THREADS = DECfg<RA>::THREADS, TILE_ROWS = DECfg<RA>::TILE_ROWS;
   extern __shared__ __align__(16) double smem[];  // [MP * LDS]: the node's own P
   __shared__ ESmem sd;
   const int K = a.K;
@@ -1765,13 +1777,13 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
   const int g = lane >> 2, q = lane & 3;
 
   pdl_trigger();
-  for (int i = tid; i <= a.n_work; i += DE_THREADS) sd.prefix[i] = a.tile_prefix[i];
-  for (int i = tid; i < a.n_work; i += DE_THREADS) {
+  for (int i = tid; i <= a.n_work; i += THREADS) sd.prefix[i] = a.tile_prefix[i];
+  for (int i = tid; i < a.n_work; i += THREADS) {
     const NodeDesc nd = a.nodes[a.work_node[i]];
     EWork& wd = sd.work[i];
     wd.out = nd.out;
     wd.n_rows = nd.n_rows;
-    wd.row_tiles = (nd.n_rows + DE_TILE_ROWS - 1) / DE_TILE_ROWS;
+    wd.row_tiles = (nd.n_rows + TILE_ROWS - 1) / TILE_ROWS;
     wd.P_own = nd.P_own;
     wd.child_begin = nd.child_begin;
     wd.nc = nd.n_children;
@@ -1793,13 +1805,13 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
     const EWork& wd = sd.work[cur.w];
     const int local = cur.st - sd.prefix[cur.w];
     cur.b = (int)(local / wd.row_tiles);
-    cur.row0 = (int64_t)(local - cur.b * wd.row_tiles) * DE_TILE_ROWS;
+    cur.row0 = (int64_t)(local - cur.b * wd.row_tiles) * TILE_ROWS;
   };
   auto next = [&](ECur& cur) {
     if (++cur.st < st1) place(cur);
   };
-  auto my_row = [&](const ECur& cur) -> int64_t {  // clamped: rows past the end repeat the last
-    const int64_t p = cur.row0 + warp * 8 + g;
+  auto my_row = [&](const ECur& cur, int ra) -> int64_t {  // clamped: rows past the end repeat the last
+    const int64_t p = cur.row0 + (warp * RA + ra) * 8 + g;
     const int64_t last = sd.work[cur.w].n_rows - 1;
     return p < last ? p : last;
   };
@@ -1807,24 +1819,33 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
   ECur cc{st0, 0, 0, 0};
   if (cc.st < st1) place(cc);
   ECur fc = cc, ic = cc;
-  int32_t ix[DE_PRE] = {0, 0};
+  int32_t ix[RA][DE_PRE];
+#pragma unroll
+  for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+    for (int c = 0; c < DE_PRE; ++c) ix[ra][c] = 0;
   auto load_idx = [&]() {
     if (ic.st < st1) {
       const EWork& wi = sd.work[ic.w];
-      const int64_t p = my_row(ic);
 #pragma unroll
-      for (int c = 0; c < DE_PRE; ++c) ix[c] = __ldg(wi.idx[c] + p);  // (a single child is read twice)
+      for (int ra = 0; ra < RA; ++ra) {
+        const int64_t p = my_row(ic, ra);
+#pragma unroll
+        for (int c = 0; c < DE_PRE; ++c) ix[ra][c] = __ldg(wi.idx[c] + p);  // (a single child is read twice)
+      }
     }
   };
-  double2 vn[DE_PRE][NI];
+  double2 vn[RA][DE_PRE][NI];
   auto fetch = [&]() {  // rows of tile fc (gather rows in ix)
     const EWork& wf = sd.work[fc.w];
 #pragma unroll
-    for (int c = 0; c < DE_PRE; ++c) {
-      const double* src = wf.src[c] + ((int64_t)ix[c] * K + fc.b) * MP + 2 * q;
+    for (int ra = 0; ra < RA; ++ra)
 #pragma unroll
-      for (int ni = 0; ni < NI; ++ni) vn[c][ni] = ld128_nc(src + 8 * ni);
-    }
+      for (int c = 0; c < DE_PRE; ++c) {
+        const double* src = wf.src[c] + ((int64_t)ix[ra][c] * K + fc.b) * MP + 2 * q;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) vn[ra][c][ni] = ld128_nc(src + 8 * ni);
+      }
   };
   load_idx();  // static data: may overlap the previous launch
   pdl_wait();
@@ -1843,7 +1864,7 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
       __syncthreads();
       if (CONTRACT && wd.P_own != nullptr) {
         const double* P = wd.P_own + (int64_t)cc.b * MP * MP;
-        for (int o = tid; o < MP * MP / 2; o += DE_THREADS) {
+        for (int o = tid; o < MP * MP / 2; o += THREADS) {
           const int i = (2 * o) / MP, j = 2 * o - i * MP;
           *reinterpret_cast<double2*>(smem + i * LDS + j) = *reinterpret_cast<const double2*>(P + 2 * o);
         }
@@ -1853,19 +1874,22 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
       __syncthreads();
     }
     // product of the children's rows (C-fragment layout); then the next tile's rows are requested
-    double prod[NI][2];
+    double prod[RA][NI][2];
 #pragma unroll
-    for (int ni = 0; ni < NI; ++ni) {
-      prod[ni][0] = vn[0][ni].x;
-      prod[ni][1] = vn[0][ni].y;
-    }
+    for (int ra = 0; ra < RA; ++ra) {
 #pragma unroll
-    for (int c = 1; c < DE_PRE; ++c) {
-      if (c < wd.nc) {
+      for (int ni = 0; ni < NI; ++ni) {
+        prod[ra][ni][0] = vn[ra][0][ni].x;
+        prod[ra][ni][1] = vn[ra][0][ni].y;
+      }
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) {
-          prod[ni][0] *= vn[c][ni].x;
-          prod[ni][1] *= vn[c][ni].y;
+      for (int c = 1; c < DE_PRE; ++c) {
+        if (c < wd.nc) {
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) {
+            prod[ra][ni][0] *= vn[ra][c][ni].x;
+            prod[ra][ni][1] *= vn[ra][c][ni].y;
+          }
         }
       }
     }
@@ -1875,63 +1899,90 @@ __global__ void __launch_bounds__(DE_THREADS, 1) prune_dmma_edge_kernel(const Pr
       next(ic);
       load_idx();
     }
-    const int64_t p = cc.row0 + warp * 8 + g;
-    const bool row_ok = p < wd.n_rows;
+    int64_t prow[RA];
+    bool row_ok[RA];
+#pragma unroll
+    for (int ra = 0; ra < RA; ++ra) {
+      prow[ra] = cc.row0 + (warp * RA + ra) * 8 + g;
+      row_ok[ra] = prow[ra] < wd.n_rows;
+    }
     for (int c = DE_PRE; c < wd.nc; ++c) {  // third, ... child (trifurcating root, polytomies): at use
       const ChildRef ch = a.childs[wd.child_begin + c];
-      const int32_t r = __ldg(ch.idx + (row_ok ? p : wd.n_rows - 1));
-      const double* src = ch.src + ((int64_t)r * K + cc.b) * MP + 2 * q;
 #pragma unroll
-      for (int ni = 0; ni < NI; ++ni) {
-        const double2 v = ld128_nc(src + 8 * ni);
-        prod[ni][0] *= v.x;
-        prod[ni][1] *= v.y;
+      for (int ra = 0; ra < RA; ++ra) {
+        const int32_t r = __ldg(ch.idx + (row_ok[ra] ? prow[ra] : wd.n_rows - 1));
+        const double* src = ch.src + ((int64_t)r * K + cc.b) * MP + 2 * q;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          const double2 v = ld128_nc(src + 8 * ni);
+          prod[ra][ni][0] *= v.x;
+          prod[ra][ni][1] *= v.y;
+        }
       }
     }
     if (wd.fixed_motif >= 0) {
 #pragma unroll
-      for (int ni = 0; ni < NI; ++ni) {
-        if (8 * ni + 2 * q != wd.fixed_motif) prod[ni][0] = 0.0;
-        if (8 * ni + 2 * q + 1 != wd.fixed_motif) prod[ni][1] = 0.0;
-      }
+      for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          if (8 * ni + 2 * q != wd.fixed_motif) prod[ra][ni][0] = 0.0;
+          if (8 * ni + 2 * q + 1 != wd.fixed_motif) prod[ra][ni][1] = 0.0;
+        }
     }
-    double* dst = wd.out + (p * K + cc.b) * MP + 2 * q;
     if (!CONTRACT || wd.P_own == nullptr) {
       // the root: plh itself (when it is stored at all), and lh = inner(plh_root, pi)
-      if (row_ok && wd.out != nullptr) {
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni)
-          *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(prod[ni][0], prod[ni][1]);
-      }
-      if (wd.is_root) {
-        double sdot = 0.0;
+      for (int ra = 0; ra < RA; ++ra) {
+        double* dst = wd.out + (prow[ra] * K + cc.b) * MP + 2 * q;
+        if (row_ok[ra] && wd.out != nullptr) {
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) {
-          sdot = fma(prod[ni][0], a.pi[8 * ni + 2 * q], sdot);
-          sdot = fma(prod[ni][1], a.pi[8 * ni + 2 * q + 1], sdot);
+          for (int ni = 0; ni < NI; ++ni)
+            *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(prod[ra][ni][0], prod[ra][ni][1]);
         }
-        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-        if (row_ok && q == 0) a.lh_out[p * K + cc.b] = sdot;
+        if (wd.is_root) {
+          double sdot = 0.0;
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) {
+            sdot = fma(prod[ra][ni][0], a.pi[8 * ni + 2 * q], sdot);
+            sdot = fma(prod[ra][ni][1], a.pi[8 * ni + 2 * q + 1], sdot);
+          }
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+          if (row_ok[ra] && q == 0) a.lh_out[prow[ra] * K + cc.b] = sdot;
+        }
       }
     } else {
-      double cur[NI][2];
-#pragma unroll
-      for (int ni = 0; ni < NI; ++ni) cur[ni][0] = cur[ni][1] = 0.0;
       const double* bRow = smem + g * LDS + 2 * q;
+      constexpr int NH = (RA == 2 && NI % 2 == 0) ? 2 : 1;  // column halves (RA = 2: accumulators of one half at a time)
+      constexpr int NIH = NI / NH;
 #pragma unroll
-      for (int a2 = 0; a2 < KS / 2; ++a2) {
+      for (int h = 0; h < NH; ++h) {
+        double cur[RA][NIH][2];
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) {
-          const double2 bv = *reinterpret_cast<const double2*>(bRow + (8 * ni) * LDS + 8 * a2);
-          dmma_m8n8k4(cur[ni][0], cur[ni][1], prod[a2][0], bv.x);
-          dmma_m8n8k4(cur[ni][0], cur[ni][1], prod[a2][1], bv.y);
+        for (int ra = 0; ra < RA; ++ra)
+#pragma unroll
+          for (int ni = 0; ni < NIH; ++ni) cur[ra][ni][0] = cur[ra][ni][1] = 0.0;
+#pragma unroll
+        for (int a2 = 0; a2 < KS / 2; ++a2) {
+#pragma unroll
+          for (int ni = 0; ni < NIH; ++ni) {
+            const double2 bv = *reinterpret_cast<const double2*>(bRow + (8 * (h * NIH + ni)) * LDS + 8 * a2);
+#pragma unroll
+            for (int ra = 0; ra < RA; ++ra) {
+              dmma_m8n8k4(cur[ra][ni][0], cur[ra][ni][1], prod[ra][a2][0], bv.x);
+              dmma_m8n8k4(cur[ra][ni][0], cur[ra][ni][1], prod[ra][a2][1], bv.y);
+            }
+          }
         }
-      }
-      if (row_ok) {
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni)
-          *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(cur[ni][0], cur[ni][1]);
+        for (int ra = 0; ra < RA; ++ra) {
+          if (row_ok[ra]) {
+            double* dst = wd.out + (prow[ra] * K + cc.b) * MP + 2 * q;
+#pragma unroll
+            for (int ni = 0; ni < NIH; ++ni)
+              *reinterpret_cast<double2*>(dst + 8 * (h * NIH + ni)) = make_double2(cur[ra][ni][0], cur[ra][ni][1]);
+          }
+        }
       }
     }
     next(cc);
