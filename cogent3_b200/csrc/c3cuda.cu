@@ -258,23 +258,26 @@ int launch_dmma_reg(c3_engine* e, const PruneArgs& a, bool is_root) {
 }
 
 constexpr int DE_RA = 1;  // row groups per warp of the contraction instance (2: 8 warps x 16 rows, measured slower, DESIGN lesson 13)
+constexpr bool DE_STG = false;  // the next tile's rows staged in shared memory (cp.async), 16 warps instead of 12: measured slower (DESIGN lesson 13)
 
 template <int MP>
 int launch_dmma_edge(c3_engine* e, const PruneArgs& a, bool root_only3) {
-  const size_t smem = (size_t)MP * (MP + 8) * sizeof(double);
+  using Cfg = DECfg<DE_RA, DE_STG>;
+  const size_t smem_p = (size_t)MP * (MP + 8) * sizeof(double);
+  const size_t smem = smem_p + (DE_STG ? (size_t)Cfg::WARPS * 2 * 8 * (MP + 8) * sizeof(double) : 0);
   static bool configured = false;
   if (!configured) {
-    int rc = set_max_smem(prune_dmma_edge_kernel<MP, 2, true, DE_RA>, smem);
+    int rc = set_max_smem(prune_dmma_edge_kernel<MP, 2, true, DE_RA, DE_STG>, smem);
     if (rc) return rc;
-    rc = set_max_smem(prune_dmma_edge_kernel<MP, 3, false, 1>, smem);
+    rc = set_max_smem(prune_dmma_edge_kernel<MP, 3, false, 1>, smem_p);
     if (rc) return rc;
     configured = true;
   }
   const int grid = std::max(1, std::min(a.total_tiles, e->n_sm));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(root_only3 ? DECfg<1>::THREADS : DECfg<DE_RA>::THREADS);
-  cfg.dynamicSmemBytes = smem;
+  cfg.blockDim = dim3(root_only3 ? DECfg<1>::THREADS : Cfg::THREADS);
+  cfg.dynamicSmemBytes = root_only3 ? smem_p : smem;
   cfg.stream = e->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -283,7 +286,7 @@ int launch_dmma_edge(c3_engine* e, const PruneArgs& a, bool root_only3) {
   cfg.numAttrs = 1;
   // a launch holding only the trifurcating root: three prefetched children, no contraction
   cudaError_t err = root_only3 ? cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 3, false, 1>, a)
-                               : cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 2, true, DE_RA>, a);
+                               : cudaLaunchKernelEx(&cfg, prune_dmma_edge_kernel<MP, 2, true, DE_RA, DE_STG>, a);
   if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("dmma-edge launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
@@ -502,7 +505,7 @@ int kind_of_node(const c3_engine* e, int n) {
 int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
   if (kind == 8) {
     // the trifurcating root is always alone in its launch and runs the 3-children instance (12 warps x 8 rows)
-    const int tile_rows = (n == e->root && e->children[n].size() == 3) ? DECfg<1>::TILE_ROWS : DECfg<DE_RA>::TILE_ROWS;
+    const int tile_rows = (n == e->root && e->children[n].size() == 3) ? DECfg<1>::TILE_ROWS : DECfg<DE_RA, DE_STG>::TILE_ROWS;
     return (int64_t)e->K * ((e->n_rows[n] + tile_rows - 1) / tile_rows);
   }
   if (kind == 6) return (int64_t)e->K * ((e->n_rows[n] + DR_TILE_ROWS - 1) / DR_TILE_ROWS);

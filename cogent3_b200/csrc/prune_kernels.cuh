@@ -1756,21 +1756,25 @@ struct ECur {
 // 128-bit B-fragment load from shared memory feeds FOUR DMMAs instead of two -- the shared-memory
 // pipe was ~50 % busy with B loads at one row group per warp -- and the accumulators are produced
 // in two column halves so that rows in flight + products + accumulators fit the register file.
-template <int RA>
+// STG: the rows of the next tile are staged in shared memory with cp.async (every lane into slots it alone
+// reads back: no barrier) instead of 64 registers per lane, which buys more warps per scheduler.
+constexpr int DE_STG_WARPS = 16;
+template <int RA, bool STG = false>
 struct DECfg {
-  static constexpr int WARPS = (RA == 2) ? 8 : DE_WARPS;
+  static constexpr int WARPS = STG ? DE_STG_WARPS : ((RA == 2) ? 8 : DE_WARPS);
   static constexpr int THREADS = WARPS * 32;
   static constexpr int TILE_ROWS = WARPS * 8 * RA;
 };
 
-template <int MP, int DE_PRE, bool CONTRACT, int RA>
-__global__ void __launch_bounds__(DECfg<RA>::THREADS, 1) prune_dmma_edge_kernel(const PruneArgs a) {
+template <int MP, int DE_PRE, bool CONTRACT, int RA, bool STG = false>
+__global__ void __launch_bounds__(DECfg<RA, STG>::THREADS, 1) prune_dmma_edge_kernel(const PruneArgs a) {
+  static_assert(!STG || RA == 1, "staged rows: one row group per warp");
   // P in its natural layout with row stride MP + 8: the lane (g, q) then reads the B values of k
   // steps 2a and 2a+1 of column block ni -- P[8 ni + g][8a + 2q], [.. + 1] -- with ONE conflict-free
   // 128-bit load (quarter-warps: g in {0,1} -> 16-byte bank groups 0-3 and 4-7)
   constexpr int LDS = MP + 8, NI = MP / 8, KS = MP / 4;
-  constexpr int THREADS = DECfg<RA>::THREADS, TILE_ROWS = DECfg<RA>::TILE_ROWS;
-  extern __shared__ __align__(16) double smem[];  // [MP * LDS]: the node's own P
+  constexpr int THREADS = DECfg<RA, STG>::THREADS, TILE_ROWS = DECfg<RA, STG>::TILE_ROWS;
+  extern __shared__ __align__(16) double smem[];  // [MP * LDS]: the node's own P; STG: + [WARPS][DE_PRE][8][LDS] rows
   __shared__ ESmem sd;
   const int K = a.K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1835,7 +1839,9 @@ __global__ void __launch_bounds__(DECfg<RA>::THREADS, 1) prune_dmma_edge_kernel(
       }
     }
   };
-  double2 vn[RA][DE_PRE][NI];
+  double2 vn[STG ? 1 : RA][STG ? 1 : DE_PRE][STG ? 1 : NI];
+  // STG: this lane's slots: child c, row g, the 16-byte pieces 8 ni + 2 q (row stride LDS: conflict free)
+  double* stage = smem + MP * LDS + ((warp * DE_PRE) * 8 + g) * LDS + 2 * q;
   auto fetch = [&]() {  // rows of tile fc (gather rows in ix)
     const EWork& wf = sd.work[fc.w];
 #pragma unroll
@@ -1843,9 +1849,16 @@ __global__ void __launch_bounds__(DECfg<RA>::THREADS, 1) prune_dmma_edge_kernel(
 #pragma unroll
       for (int c = 0; c < DE_PRE; ++c) {
         const double* src = wf.src[c] + ((int64_t)ix[ra][c] * K + fc.b) * MP + 2 * q;
+        if (STG) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + c * 8 * LDS);
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) vn[ra][c][ni] = ld128_nc(src + 8 * ni);
+          for (int ni = 0; ni < NI; ++ni) cp_async16_ca(dst + 64 * ni, src + 8 * ni);
+        } else {
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) vn[ra][c][ni] = ld128_nc(src + 8 * ni);
+        }
       }
+    if (STG) cp_async_commit();
   };
   load_idx();  // static data: may overlap the previous launch
   pdl_wait();
@@ -1875,20 +1888,24 @@ __global__ void __launch_bounds__(DECfg<RA>::THREADS, 1) prune_dmma_edge_kernel(
     }
     // product of the children's rows (C-fragment layout); then the next tile's rows are requested
     double prod[RA][NI][2];
+    if (STG) cp_async_wait_group<0>();  // this lane's own copies: nobody else reads these slots
 #pragma unroll
     for (int ra = 0; ra < RA; ++ra) {
 #pragma unroll
       for (int ni = 0; ni < NI; ++ni) {
-        prod[ra][ni][0] = vn[ra][0][ni].x;
-        prod[ra][ni][1] = vn[ra][0][ni].y;
+        const double2 v = STG ? *reinterpret_cast<const double2*>(stage + 8 * ni) : vn[STG ? 0 : ra][0][STG ? 0 : ni];
+        prod[ra][ni][0] = v.x;
+        prod[ra][ni][1] = v.y;
       }
 #pragma unroll
       for (int c = 1; c < DE_PRE; ++c) {
         if (c < wd.nc) {
 #pragma unroll
           for (int ni = 0; ni < NI; ++ni) {
-            prod[ra][ni][0] *= vn[ra][c][ni].x;
-            prod[ra][ni][1] *= vn[ra][c][ni].y;
+            const double2 v = STG ? *reinterpret_cast<const double2*>(stage + c * 8 * LDS + 8 * ni)
+                                  : vn[STG ? 0 : ra][STG ? 0 : c][STG ? 0 : ni];
+            prod[ra][ni][0] *= v.x;
+            prod[ra][ni][1] *= v.y;
           }
         }
       }
