@@ -2422,7 +2422,8 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
   }
   cudaStream_t s0 = engines[0]->stream;
   C3_CUDA(cudaGraphLaunch(bg.exec, s0));
-  for (int i = 0; i < n; ++i) C3_CUDA(cudaEventRecord(engines[i]->block_copied, s0));
+  // (no block_copied records: the call waits for the whole graph below, so every staging buffer is free again
+  // by the time anybody plans the next evaluation)
   cudaError_t err = cudaStreamSynchronize(s0);
   if (err != cudaSuccess) {
     for (int i = 0; i < n; ++i) {
