@@ -2073,7 +2073,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     a.M = M;
     a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
     a.lh_out = e->d_lh;
-    ProfScope ps(e, ll.is_root ? 3 : 2, ll.bytes, ll.flops);
+    ProfScope ps(e, ll.kind == 1 ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
     if (ll.kind == 1) {
       const SmallLevel* d_small = reinterpret_cast<const SmallLevel*>(e->d_block + e->off_small) + ll.small_off;
       // one cluster; fewer CTAs when there is little work (cluster size must divide the grid)

@@ -321,7 +321,7 @@ class LikelihoodEngine:
     def set_profiling(self, on=True):
         _lib.check(self._lib.c3_set_profiling(self._h, int(bool(on))))
 
-    KIND_NAMES = ("expm_eigen", "expm_pade", "prune", "prune_root", "reduce")
+    KIND_NAMES = ("expm_eigen", "expm_pade", "prune", "prune_root", "reduce", "prune_small")
 
     def launch_profile(self):
         """per-launch (kind, ms, algorithmic bytes, executed flops) of the last evaluation"""

@@ -246,7 +246,8 @@ C3_API int c3_get_site_lh(c3_engine* e, int bin, double* out, int64_t n_columns)
 /* ---- per-launch timing (CUDA events on the engine's stream) ----------------------
  * With profiling on, every kernel launch of a blocking c3_evaluate is bracketed by
  * events.  c3_get_launch_profile returns, for the last evaluation and per launch:
- * kind (0 expm-eigen, 1 expm-pade, 2 prune level, 3 prune root level, 4 reduction),
+ * kind (0 expm-eigen, 1 expm-pade, 2 prune level, 3 prune root level, 4 reduction, 5 the fused
+ * small-levels launch, which may hold the root and the reduction too),
  * duration in ms, algorithmic bytes and executed flops of that launch.            */
 C3_API int c3_set_profiling(c3_engine* e, int on);
 C3_API int c3_get_launch_profile(c3_engine* e, int max_n, int32_t* kind, double* ms,
