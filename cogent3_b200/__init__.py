@@ -8,3 +8,17 @@ host-side mirror of the reference interface plus a ctypes binding.
 """
 
 __version__ = "0.1.0"
+
+
+def install(*args, **kw):
+    """route cogent3's own ``sm.make_likelihood_function(tree)`` to the CUDA engine
+    (see :func:`cogent3_b200.dropin.install`)"""
+    from .dropin import install as _install
+
+    return _install(*args, **kw)
+
+
+def uninstall():
+    from .dropin import uninstall as _uninstall
+
+    return _uninstall()

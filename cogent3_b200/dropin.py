@@ -28,11 +28,13 @@ buffers are owned by the engine object cached on the Defn, never by cell values.
 
 from __future__ import annotations
 
+from collections import OrderedDict
+
 import numpy as np
 
 from .patterns import from_reference_lht
 
-__all__ = ["CudaAlignmentLikelihoodFunction", "make_likelihood_function"]
+__all__ = ["CudaAlignmentLikelihoodFunction", "make_likelihood_function", "install", "uninstall", "installed"]
 
 
 def _default_engine_factory(patterns, n_bins, device=0, stream=None):
@@ -138,6 +140,32 @@ def fast_likelihood_tree_edge(likelihood_tree, children, edge_name):
     return e
 
 
+# identity-keyed memo of a Defn's last few results (one per locus + undo); strong references, so
+# ids cannot be recycled.  Never pickled.
+_MEMO_MAX = 2
+
+
+def _memo_get(defn, key):
+    for k, v in defn.__dict__.get("_memo", ()):
+        if len(k) == len(key) and all(a is b for a, b in zip(k, key, strict=True)):
+            return v
+    return None
+
+
+def _memo_put(defn, key, value):
+    memo = defn.__dict__.setdefault("_memo", [])
+    memo.append((key, value))
+    cap = max(_MEMO_MAX, defn.__dict__.get("_memo_cap", 0))
+    del memo[: max(0, len(memo) - cap)]
+    return value
+
+
+def _memo_free_state(self):
+    d = dict(self.__dict__)
+    d.pop("_memo", None)
+    return d
+
+
 def _build(cogent3_modules):
     """create the Defn / LF classes lazily so that importing this module does not
     require cogent3"""
@@ -149,15 +177,25 @@ def _build(cogent3_modules):
         the vectorised leaf builder"""
 
         def calc(self, model, alignment):
+            # cogent3 evaluates this cell up to three times for one alignment (set_alignment, the
+            # eager Defn update, Calculator construction: SURVEY §3.2); the tables depend only on
+            # (model, alignment), both immutable here, so the same objects are handed out again --
+            # which also keeps the identity of ``lht`` and with it the engine and its device tables
+            hit = _memo_get(self, (model, alignment))
+            if hit is not None:
+                return hit
             if type(model).convert_sequence is not _reference_convert_sequence(model):
                 return model.convert_alignment(alignment)  # a model with its own conversion
             alphabet = model.get_alphabet()
-            return {
+            leaves = {
                 name: fast_likelihood_tree_leaf(
                     likelihood_tree, alignment.get_gapped_seq(name, model.recode_gaps), alphabet, name
                 )
                 for name in alignment.names
             }
+            return _memo_put(self, (model, alignment), leaves)
+
+        __getstate__ = _memo_free_state
 
     def _reference_convert_sequence(model):
         from cogent3.evolve.substitution_model import _SubstitutionModel
@@ -169,13 +207,20 @@ def _build(cogent3_modules):
         vectorised edge builder"""
 
         def calc(self, leaves):
+            hit = _memo_get(self, (leaves,))
+            if hit is not None:
+                return hit
+
             def build(edge):
                 if edge.istip():
                     return leaves[edge.name]
                 kids = [build(child) for child in edge.children]
                 return fast_likelihood_tree_edge(likelihood_tree, kids, edge.name)
 
-            return build(self.tree)
+            return _memo_put(self, (leaves,), build(self.tree))
+
+        __getstate__ = _memo_free_state
+
     CalculationDefn = definition.CalculationDefn
     NonParamDefn = definition.NonParamDefn
     SumDefn = definition.SumDefn
@@ -200,18 +245,24 @@ def _build(cogent3_modules):
 
         name = "gpu_lnL"
 
-        def setup(self, edge_names, internal_names, n_bins, engine_factory, device):
+        def setup(self, edge_names, internal_names, n_bins, engine_factory, device, n_loci=1):
             self.edge_names = list(edge_names)
             self.internal_names = list(internal_names)
             self.n_bins = n_bins
             self.engine_factory = engine_factory
             self.device = device
-            self._engines = {}  # id(lht) -> state
+            # id(lht) -> state, least recently used first.  The Defn instance (and so this cache) is
+            # shared by every locus cell behind SumDefn(*tll.across_dimension("locus", ...)): it must
+            # hold one engine per locus plus one for the Calculator's 1-deep undo
+            # (calculation.py:409-439), or every evaluation of a 3-locus function rebuilds engines
+            self._engines = OrderedDict()
+            self.max_engines = max(2, int(n_loci) + 1)
+            self.engines_created = 0
 
         # engines hold device memory and ctypes handles: never pickled / deep-copied
         def __getstate__(self):
             d = dict(self.__dict__)
-            d["_engines"] = {}
+            d["_engines"] = OrderedDict()
             return d
 
         def __deepcopy__(self, memo):
@@ -221,12 +272,13 @@ def _build(cogent3_modules):
             new = cls.__new__(cls)
             memo[id(self)] = new
             for k, v in self.__dict__.items():
-                new.__dict__[k] = {} if k == "_engines" else copy.deepcopy(v, memo)
+                new.__dict__[k] = OrderedDict() if k == "_engines" else copy.deepcopy(v, memo)
             return new
 
         def _state_for(self, lht):
             st = self._engines.get(id(lht))
             if st is not None and st["lht"] is lht:
+                self._engines.move_to_end(id(lht))
                 return st
             # a new alignment (or locus): flatten cogent3's own pattern tables -- they stay
             # the source of truth -- and make the tables resident on the device
@@ -245,12 +297,14 @@ def _build(cogent3_modules):
                 "qslots": np.full((topo.n_nodes, self.n_bins), -1, np.int32),
                 "dist": np.zeros((topo.n_nodes, self.n_bins), np.float64),
             }
-            # keep at most two alignments' worth of device memory per Defn (Calculator
-            # keeps a 1-deep undo, calculation.py:409-439)
-            while len(self._engines) >= 2:
-                _, old = self._engines.popitem()
+            # device memory per Defn: one engine per locus + one (the Calculator keeps a 1-deep undo,
+            # calculation.py:409-439); the OLDEST entry goes first
+            self._engines.pop(id(lht), None)  # (a recycled id: the old lht object is gone)
+            while len(self._engines) >= self.max_engines:
+                _, old = self._engines.popitem(last=False)
                 old["engine"].close()
             self._engines[id(lht)] = st
+            self.engines_created += 1
             return st
 
         def _slot_for(self, st, ex):
@@ -421,6 +475,7 @@ def _build(cogent3_modules):
             )
         fixed_motifs = NonParamDefn("fixed_motif", ["edge"])
         lht = FastLikelihoodTreeDefn(leaves, tree=tree)
+        leaves.__dict__["_memo_cap"] = lht.__dict__["_memo_cap"] = len(locus_names) + 1
         root = likelihood_calculation.LhtEdgeLookupDefn(lht, edge_name="root")
         edges = [e for e in tree.postorder() if e.name != "root"]
         internal = [e.name for e in tree.postorder() if not e.istip()]
@@ -445,6 +500,7 @@ def _build(cogent3_modules):
             tll = GpuFactoredLogLikelihoodDefn(
                 *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
                 engine_factory=engine_factory, device=device, has_rate=rate is not None,
+                n_loci=len(locus_names),
             )  # fmt: skip
         else:
             for name in edge_names:
@@ -455,7 +511,7 @@ def _build(cogent3_modules):
                     args.append(p_e.select_from_dimension("bin", bin_names[0]))
             tll = GpuLogLikelihoodDefn(
                 *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
-                engine_factory=engine_factory, device=device,
+                engine_factory=engine_factory, device=device, n_loci=len(locus_names),
             )  # fmt: skip
         if len(locus_names) > 1:
             tll = SumDefn(*tll.across_dimension("locus", locus_names))
@@ -713,3 +769,85 @@ def make_likelihood_function(model, tree, motif_probs_from_align=None, optimise_
     if digits or space:
         result.set_tables_format(digits=digits, space=space)
     return result
+
+
+# ---------------------------------------------------------------------------------------
+# product hook: cogent3's stock entry point reaches the GPU
+#
+# ``_SubstitutionModel.make_likelihood_function`` picks the likelihood-function class
+# (evolve/substitution_model.py:367-374: AlignmentLikelihoodFunction when ``aligned``).  cogent3 has
+# no plugin group for that choice, so ``install()`` replaces the method -- the one-line
+# change a maintainer would make there is shown in INTEGRATION.md -- and from then on
+#
+#     import cogent3_b200; cogent3_b200.install()
+#     lf = get_model("GTR").make_likelihood_function(tree, bins=4)      # CUDA engine
+#     lf = get_model("GTR").make_likelihood_function(tree, backend="cpu")   # the reference class
+#
+# every stock caller (apps, bootstrap, hypothesis tests, tree search) builds the CUDA class.  What the
+# engine does not cover stays with the reference class: unaligned sequences (pair-HMM alignment) and
+# the phylo-HMM (``sites_independent=False``).
+# ---------------------------------------------------------------------------------------
+_STOCK_MAKE_LF = None
+INSTALL_STATS = {"cuda": 0, "reference": 0}
+
+
+def installed():
+    return _STOCK_MAKE_LF is not None
+
+
+def install(default_backend="cuda", device=0, devices=None, engine_factory=None):
+    """make ``sm.make_likelihood_function(tree, ...)`` return the CUDA likelihood function.
+
+    ``default_backend``: "cuda" or "cpu" -- what a call without ``backend=`` gets; ``device`` /
+    ``devices``: the GPU(s) a call without ``device=`` / ``devices=`` uses (``devices=[0, ..., 7]``
+    shards the site patterns over several GPUs in one process); ``engine_factory``: test seam.
+    Idempotent; ``uninstall()`` restores the reference method."""
+    global _STOCK_MAKE_LF
+    from cogent3.evolve import substitution_model
+
+    cls = substitution_model._SubstitutionModel
+    if _STOCK_MAKE_LF is None:
+        _STOCK_MAKE_LF = cls.make_likelihood_function
+    stock = _STOCK_MAKE_LF
+    if default_backend not in ("cuda", "cpu"):
+        raise ValueError(f"unknown backend {default_backend!r}")
+
+    def make_likelihood_function_with_backend(self, tree, motif_probs_from_align=None,
+                                              optimise_motif_probs=None, aligned=True, expm=None,
+                                              digits=None, space=None, default_length=1.0, warn=False,
+                                              backend=None, **kw):  # fmt: skip
+        backend = backend or default_backend
+        if backend not in ("cuda", "cpu"):
+            raise ValueError(f"unknown backend {backend!r}")
+        if backend == "cpu" or not aligned or kw.get("sites_independent", True) is False:
+            INSTALL_STATS["reference"] += 1
+            for key in ("device", "devices", "engine_factory", "factored"):
+                kw.pop(key, None)
+            return stock(self, tree, motif_probs_from_align=motif_probs_from_align,
+                         optimise_motif_probs=optimise_motif_probs, aligned=aligned, expm=expm,
+                         digits=digits, space=space, default_length=default_length, warn=warn, **kw)  # fmt: skip
+        INSTALL_STATS["cuda"] += 1
+        if devices is not None and "devices" not in kw and "device" not in kw:
+            kw["devices"] = list(devices)
+        elif "device" not in kw and "devices" not in kw and device != 0:
+            kw["device"] = device
+        if engine_factory is not None:
+            kw.setdefault("engine_factory", engine_factory)
+        return make_likelihood_function(self, tree, motif_probs_from_align=motif_probs_from_align,
+                                        optimise_motif_probs=optimise_motif_probs, expm=expm, digits=digits,
+                                        space=space, default_length=default_length, warn=warn, **kw)  # fmt: skip
+
+    make_likelihood_function_with_backend.__doc__ = stock.__doc__
+    make_likelihood_function_with_backend.__name__ = "make_likelihood_function"
+    cls.make_likelihood_function = make_likelihood_function_with_backend
+    return make_likelihood_function_with_backend
+
+
+def uninstall():
+    global _STOCK_MAKE_LF
+    if _STOCK_MAKE_LF is None:
+        return
+    from cogent3.evolve import substitution_model
+
+    substitution_model._SubstitutionModel.make_likelihood_function = _STOCK_MAKE_LF
+    _STOCK_MAKE_LF = None

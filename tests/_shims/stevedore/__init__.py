@@ -12,11 +12,16 @@ _REF = os.environ.get("COGENT3_REFERENCE_ROOT", "/root/reference")
 
 
 def _entry_points(namespace):
-    path = os.path.join(_REF, "pyproject.toml")
-    try:
-        with open(path, "rb") as f:
-            table = tomllib.load(f)
-    except OSError:
+    table = None
+    # <root>/pyproject.toml (baseline/_ref) or <root>/../pyproject.toml (root = /root/reference/src)
+    for path in (os.path.join(_REF, "pyproject.toml"), os.path.join(os.path.dirname(_REF.rstrip("/")), "pyproject.toml")):
+        try:
+            with open(path, "rb") as f:
+                table = tomllib.load(f)
+            break
+        except OSError:
+            continue
+    if table is None:
         return {}
     return table.get("project", {}).get("entry-points", {}).get(namespace, {})
 

@@ -1,25 +1,64 @@
-"""The drop-in glue under the REAL cogent3 objects (build container only: needs
-/root/reference).  The engine is the CPU oracle test double here (no GPU), so what is
-tested is the host logic of cogent3_b200/dropin.py: the replaced Defn sub-graph, slot /
-distance / fixed-motif plumbing, accessors, optimiser protocol.  The same tests run with
-the CUDA engine when a GPU and the reference are both present (never on the GPU box)."""
+"""The drop-in glue under the REAL cogent3 objects.
 
+* build container (no GPU): cogent3 comes from /root/reference/src and the engine is the CPU oracle
+  test double, so what is tested is the host logic of cogent3_b200/dropin.py: the replaced Defn
+  sub-graph, slot / distance / fixed-motif plumbing, accessors, optimiser protocol, the product
+  hook ``cogent3_b200.install()``;
+* GPU box: tests/test_gpu_dropin.py re-exports every test of this module under the ``gpu`` marker;
+  cogent3 then comes from ``baseline/_ref`` (unmodified copy) and FACTORY is None,
+  i.e. the product's own default engine -- libc3cuda.  Same bodies, same tolerances: the composite
+  real cogent3 + drop-in + CUDA engine against the stock class in the same process and against the
+  reference's own known answers."""
+
+import contextlib
 import functools
+import json
+import os
+import pickle
 
 import numpy as np
 import pytest
-from refutil import import_reference, reference_available
+from refutil import import_reference, reference_available, reference_tests_dir
 
-pytestmark = pytest.mark.skipif(not reference_available(), reason="needs /root/reference")
+pytestmark = pytest.mark.skipif(not reference_available(), reason="needs the reference package")
+
+
+def _gpu_present():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        return False
+
+
+ON_GPU = _gpu_present()
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 if reference_available():
     cogent3 = import_reference()
-    from cogent3 import get_dataset, get_model, make_aligned_seqs, make_tree
+    from cogent3 import get_dataset, get_model, load_aligned_seqs, load_tree, make_aligned_seqs, make_tree
 
+    import cogent3_b200
     from cogent3_b200.dropin import make_likelihood_function
-    from oracle.engine import OracleEngine
 
-    FACTORY = functools.partial(OracleEngine, mode="port")
+    if ON_GPU:
+        FACTORY = None  # the product default: LikelihoodEngine over libc3cuda (no CPU fallback)
+    else:
+        from oracle.engine import OracleEngine
+
+        FACTORY = functools.partial(OracleEngine, mode="port")
+    DATA = os.path.join(reference_tests_dir() or "", "data")
+
+
+@contextlib.contextmanager
+def installed(**kw):
+    """the product hook: inside, ``sm.make_likelihood_function(tree)`` itself builds the CUDA class"""
+    cogent3_b200.install(engine_factory=FACTORY, **kw)
+    try:
+        yield
+    finally:
+        cogent3_b200.uninstall()
 
 
 def small_problem(n_tips=7, L=240, n_states=4, seed=5):
@@ -314,3 +353,272 @@ def test_factored_optimise_and_partial_updates():
         x[i] *= 1.0 + 0.05 * rng.standard_normal()
         a, b = rc(x), lc(x)
         assert abs(a - b) <= 1e-12 * abs(a)
+
+
+# ---- the reference's own known answers, through the PRODUCT hook ---------------------------------
+# (constants and set-ups: /root/reference/tests/test_evolve/test_likelihood_function.py; the stock entry
+# point sm.make_likelihood_function(tree) is what builds the CUDA class here)
+def _kat_rules(name):
+    with open(os.path.join(HERE, "golden", "kat_rules.json")) as f:
+        return json.load(f)[name]
+
+
+def test_install_routes_the_stock_entry_point():
+    from cogent3.evolve.parameter_controller import AlignmentLikelihoodFunction
+
+    tree, aln = small_problem(n_tips=5, L=80, seed=12)
+    stock_before = get_model("HKY85").make_likelihood_function(tree)
+    with installed():
+        lf = get_model("HKY85").make_likelihood_function(tree)
+        cpu = get_model("HKY85").make_likelihood_function(tree, backend="cpu")
+        assert type(lf).__name__ == "CudaAlignmentLikelihoodFunction"
+        assert isinstance(lf, AlignmentLikelihoodFunction)
+        assert type(cpu) is AlignmentLikelihoodFunction is type(stock_before)
+        with pytest.raises(ValueError):
+            get_model("HKY85").make_likelihood_function(tree, backend="tpu")
+        # out of the engine's scope: stays with the reference class (pair-HMM alignment)
+        unaligned = get_model("HKY85").make_likelihood_function(make_tree(tip_names=["a", "b"]), aligned=False)
+        assert type(unaligned).__name__ == "SequenceLikelihoodFunction"
+        lf.set_alignment(aln)
+        cpu.set_alignment(aln)
+        assert_same(cpu, lf)
+    after = get_model("HKY85").make_likelihood_function(tree)
+    assert type(after) is AlignmentLikelihoodFunction
+
+
+def test_kat_nucleotide_and_codon():
+    """LikelihoodCalcs.test_nucleotide / test_codon (:245-270)"""
+    from cogent3.evolve import substitution_model
+
+    aln = load_aligned_seqs(os.path.join(DATA, "brca1.fasta"), moltype="dna")
+    names = ["Human", "Mouse", "HowlerMon"]
+    aln = aln.take_seqs(names)[0:42]
+    tree = make_tree(tip_names=names)
+    with installed():
+        sm = substitution_model.TimeReversibleNucleotide(
+            equal_motif_probs=True, motif_probs=None, predicates={"kappa": "transition"}
+        )
+        lf = sm.make_likelihood_function(tree)
+        lf.set_alignment(aln)
+        lf.set_param_rule("length", value=1.0, is_constant=True)
+        lf.set_param_rule("kappa", value=3.0, is_constant=True)
+        assert lf.get_num_free_params() == 0
+        assert lf.get_log_likelihood() == pytest.approx(-148.6455087258624, rel=1e-12)
+        sm = substitution_model.TimeReversibleCodon(
+            equal_motif_probs=True, motif_probs=None,
+            predicates={"kappa": "transition", "omega": "replacement"}, mprob_model="tuple",
+        )  # fmt: skip
+        lf = sm.make_likelihood_function(tree)
+        lf.set_alignment(aln)
+        lf.set_param_rule("length", value=1.0, is_constant=True)
+        lf.set_param_rule("kappa", value=3.0, is_constant=True)
+        lf.set_param_rule("omega", value=0.5, is_constant=True)
+        assert lf.get_log_likelihood() == pytest.approx(-103.05742415448259, rel=1e-12)
+
+
+def test_kat_calclikelihood_g_statistic_ancestral():
+    """LikelihoodFunctionTests.test_calclikelihood / test_g_statistic / test_ancestralsequences (:411-439)"""
+    from cogent3.evolve import substitution_model
+
+    sm = substitution_model.TimeReversibleNucleotide(equal_motif_probs=True, predicates={"beta": "transition"})
+    aln = load_aligned_seqs(os.path.join(DATA, "brca1_5.paml"), moltype=sm.moltype)
+    tree = load_tree(os.path.join(DATA, "brca1_5.tree"))
+    with installed():
+        lf = sm.make_likelihood_function(tree)
+        lf.set_param_rule("beta", is_independent=True)
+        lf.set_alignment(aln)
+        for species, length in [("DogFaced", 0.1), ("NineBande", 0.2), ("Human", 0.3), ("HowlerMon", 0.4), ("Mouse", 0.5)]:
+            lf.set_param_rule("length", value=length, edge=species, is_constant=True)
+        for s1, s2, length in [("Human", "HowlerMon", 0.7), ("Human", "Mouse", 0.6)]:
+            lca = tree.get_connecting_node(s1, s2).name
+            lf.set_param_rule("length", value=length, edge=lca, is_constant=True)
+        lf.set_param_rule("beta", value=4.0, is_constant=True)
+        assert type(lf).__name__ == "CudaAlignmentLikelihoodFunction"
+        assert lf.get_log_likelihood() == pytest.approx(-250.686745262, abs=1e-9)
+        assert lf.get_G_statistic() == pytest.approx(230.77670557, abs=1e-6)
+        result = lf.reconstruct_ancestral_seqs()["edge.0"]
+        assert result[-1][2] == pytest.approx(2.28460181711e-05, abs=1e-8)
+
+
+def test_kat_cnfgtr_rate_het_and_time_rate_het():
+    """ComparisonTests.test_codon_rate_het (-6755.451985437475, nfp 19, posterior bin probabilities,
+    :1522-1772) and test_time_rate_het (-6753.45662012937, rtol 1e-5, nfp 21, :1774-2044)"""
+    aln = load_aligned_seqs(os.path.join(DATA, "primate_brca1.fasta"), moltype="dna")
+    tree = load_tree(os.path.join(DATA, "primate_brca1.tree"))
+    with installed():
+        lf = get_model("CNFGTR").make_likelihood_function(tree, bins=["neutral", "adaptive"], digits=2, space=3)
+        lf.set_alignment(aln)
+        lf.apply_param_rules(_kat_rules("test_codon_rate_het"))
+        assert type(lf).__name__ == "CudaAlignmentLikelihoodFunction"
+        assert lf.lnL == pytest.approx(-6755.451985437475, rel=1e-9)
+        assert lf.nfp == 19
+        got = lf.get_bin_probs()
+        np.testing.assert_allclose(
+            got["adaptive"][:3], [0.8138636520270726, 0.8723917957174725, 0.9922405018465282], rtol=5e-6
+        )
+        assert got.shape == (2, len(aln) // 3)
+
+        lf = get_model("CNFGTR").make_likelihood_function(tree, bins=["0", "1", "2a", "2b"], digits=2, space=3)
+        lf.set_alignment(aln)
+        epsilon = 1e-6
+        lf.set_param_rule("omega", bins=["0", "2a"], upper=1.0, init=1 - epsilon)
+        lf.set_param_rule("omega", bins=["1", "2b"], is_constant=True, value=1.0)
+        lf.set_param_rule("omega", bins=["2a", "2b"], edges=["Chimpanzee", "Human"], init=99, lower=1.0,
+                          upper=100.0, is_constant=False)  # fmt: skip
+        lf.apply_param_rules(_kat_rules("test_time_rate_het"))
+        assert lf.lnL == pytest.approx(-6753.45662012937, rel=1e-5)
+        assert lf.nfp == 21
+        # and against the stock class in the same process, to the product tolerance
+        ref = get_model("CNFGTR").make_likelihood_function(tree, bins=["0", "1", "2a", "2b"], backend="cpu")
+        ref.set_alignment(aln)
+        ref.set_param_rule("omega", bins=["0", "2a"], upper=1.0, init=1 - epsilon)
+        ref.set_param_rule("omega", bins=["1", "2b"], is_constant=True, value=1.0)
+        ref.set_param_rule("omega", bins=["2a", "2b"], edges=["Chimpanzee", "Human"], init=99, lower=1.0,
+                           upper=100.0, is_constant=False)  # fmt: skip
+        ref.apply_param_rules(_kat_rules("test_time_rate_het"))
+        assert_same(ref, lf, rel=1e-9)
+
+
+def _three_loci(tree_names, aln):
+    third = len(aln) // 3
+    return [aln[:third], aln[third : 2 * third], aln[2 * third :]]
+
+
+def test_kat_loci_and_engine_cache():
+    """ComparisonTests.test_loci (-9168.333116203343, nfp 2, :2046-2188); and with THREE loci the engines are
+    built once, not once per evaluation (the per-Defn engine cache holds one engine per locus)"""
+    from cogent3.recalculation.scope import ALL
+
+    aln = load_aligned_seqs(os.path.join(DATA, "long_testseqs.fasta"), moltype="dna")
+    half = len(aln) // 2
+    tree = make_tree(tip_names=aln.names)
+    with installed():
+        lf = get_model("HKY85").make_likelihood_function(tree, loci=["1st-half", "2nd-half"], digits=2, space=3)
+        lf.set_param_rule("length", is_independent=False)
+        lf.set_param_rule("kappa", loci=ALL)
+        lf.set_alignment([aln[:half], aln[half:]])
+        lf.apply_param_rules(_kat_rules("test_loci"))
+        assert lf.lnL == pytest.approx(-9168.333116203343, rel=1e-10)
+        assert lf.nfp == 2
+
+        names = ["a", "b", "c"]
+        loci = _three_loci(aln.names, aln)
+        lf = get_model("HKY85").make_likelihood_function(tree, loci=names)
+        ref = get_model("HKY85").make_likelihood_function(tree, loci=names, backend="cpu")
+        for f in (ref, lf):
+            f.set_param_rule("length", is_independent=False)
+            f.set_alignment(loci)
+        assert_same(ref, lf)
+        defn = lf._gpu_defn()
+        created = defn.engines_created
+        assert created == 3
+        for k in range(4):
+            for f in (ref, lf):
+                f.set_param_rule("kappa", value=2.0 + 0.3 * k)
+                f.set_param_rule("length", value=0.1 + 0.01 * k, is_independent=False)
+            assert_same(ref, lf)
+        calc, rcalc = lf.make_calculator(), ref.make_calculator()
+        x = np.array(calc.get_value_array())
+        for k in range(4):
+            xk = x * (1.0 + 0.01 * (k + 1))
+            a, b = rcalc(xk), calc(xk)
+            assert abs(a - b) <= 1e-12 * abs(a)
+        assert defn.engines_created == created, "engines were rebuilt between evaluations"
+
+
+def test_brca1_optimise_and_per_pattern_values():
+    """SURVEY §8c smoke vectors: C1 initial lnL -193293.46430542142, optimised -57533.56733281018; per-pattern
+    root likelihoods against the stock class in the same process (<= 1e-12 absolute)"""
+    aln, tree = get_dataset("brca1"), get_dataset("mammal-tree")
+    tree = tree.get_sub_tree(aln.names)
+    with installed():
+        lf = get_model("HKY85").make_likelihood_function(tree)
+        ref = get_model("HKY85").make_likelihood_function(tree, backend="cpu")
+        for f in (ref, lf):
+            f.set_alignment(aln)
+        assert lf.get_log_likelihood() == pytest.approx(-193293.46430542142, rel=1e-12)
+        lh, lh_ref = np.asarray(lf.get_param_value("lh")), np.asarray(ref.get_param_value("lh"))
+        assert lh.shape == lh_ref.shape
+        np.testing.assert_allclose(lh, lh_ref, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(lf.get_full_length_likelihoods(), ref.get_full_length_likelihoods(), rtol=0, atol=1e-12)
+        lf.optimise(local=True, show_progress=False)
+        assert lf.get_log_likelihood() == pytest.approx(-57533.56733281018, rel=1e-9)
+        # the same point on the stock class
+        ref.apply_param_rules(lf.get_param_rules())
+        assert_same(ref, lf, rel=1e-10)
+        # relative error of every per-pattern value at the optimum (values ~1e-20 .. 1e-2)
+        a, b = np.asarray(lf.get_param_value("lh")), np.asarray(ref.get_param_value("lh"))
+        assert np.max(np.abs(a - b) / np.maximum(b, 1e-300)) < 1e-10
+
+
+def test_calculator_undo_after_a_rejected_step():
+    """Calculator.change's 1-deep undo (recalculation/calculation.py:409-439): revisiting the previous point
+    presents the previous objects again; the engine's identity diffing must return the previous value"""
+    tree, aln = small_problem(n_tips=9, L=500, seed=21)
+    mk = lambda: get_model("GTR", ordered_param="rate", distribution="gamma")  # noqa: E731
+    ref, lf = pair(mk, tree, aln, bins=4)
+    for f in (ref, lf):
+        f.set_param_rule("bprobs", is_constant=True)
+    rc, lc = ref.make_calculator(), lf.make_calculator()
+    # the two Defn graphs list their optimisable parameters in different orders
+    where = {(p.name, repr(p.scope)): i for i, p in enumerate(rc.opt_pars)}
+    perm = np.array([where[(p.name, repr(p.scope))] for p in lc.opt_pars])
+    x0 = np.array(rc.get_value_array())
+    assert np.array_equal(x0[perm], lc.get_value_array())
+    rng = np.random.default_rng(3)
+    f0 = lc(x0[perm])
+    assert abs(rc(x0) - f0) <= 1e-12 * abs(f0)
+    for _ in range(12):
+        i = int(rng.integers(len(x0)))
+        x1 = x0.copy()
+        x1[i] = x1[i] * (1.0 + 0.2 * rng.standard_normal()) + 0.01
+        a, b = rc(x1), lc(x1[perm])
+        assert abs(a - b) <= 1e-12 * abs(a)
+        if rng.random() < 0.5:
+            # "rejected": back to the previous point -- bit-identical to what it returned before
+            assert lc(x0[perm]) == f0
+            assert abs(rc(x0) - f0) <= 1e-12 * abs(f0)
+        else:
+            x0, f0 = x1, b
+
+
+def test_pickle_and_rich_dict_round_trip():
+    from cogent3.util.deserialise import deserialise_object
+
+    tree, aln = small_problem(n_tips=6, L=200, seed=13)
+    with installed():
+        lf = get_model("HKY85").make_likelihood_function(tree)
+        lf.set_alignment(aln)
+        lf.set_param_rule("kappa", value=2.7)
+        lnl = lf.get_log_likelihood()
+        # serialised results stay interchangeable with stock cogent3 (no GPU needed to read them)
+        data = lf.to_rich_dict()
+        assert data["type"].endswith("parameter_controller.AlignmentLikelihoodFunction")
+        json.dumps(data)
+    back = deserialise_object(data)
+    assert type(back).__name__ == "AlignmentLikelihoodFunction"
+    assert back.get_log_likelihood() == pytest.approx(lnl, rel=1e-12)
+    # pickle: the engine (device memory, ctypes handles) is rebuilt on demand in the new object
+    clone = pickle.loads(pickle.dumps(lf))
+    assert type(clone).__name__ == "CudaAlignmentLikelihoodFunction"
+    assert clone.get_log_likelihood() == pytest.approx(lnl, rel=1e-13)
+    clone.set_param_rule("kappa", value=3.1)
+    lf.set_param_rule("kappa", value=3.1)
+    assert clone.get_log_likelihood() == pytest.approx(lf.get_log_likelihood(), rel=1e-13)
+
+
+def test_solved_models_and_measure_evals_per_second():
+    """a9: ``rate_matrix_required=False`` models (closed-form calc_TN93_P, evolve/solved_models.py:43-49);
+    and the reference's own throughput probe runs through the drop-in (recalculation/calculation.py:547-583)"""
+    tree, aln = small_problem(n_tips=8, L=400, seed=17)
+    for name in ("F81", "HKY85", "TN93"):
+        ref, lf = pair(lambda: get_model(name, rate_matrix_required=False), tree, aln)  # noqa: B023
+        for f in (ref, lf):
+            if name != "F81":
+                f.set_param_rule("kappa" if name == "HKY85" else "kappa_r", value=2.3)
+            f.set_param_rule("length", edge=tree.get_tip_names()[2], value=0.21)
+        assert_same(ref, lf, rel=1e-12)
+        np.testing.assert_allclose(lf.get_full_length_likelihoods(), ref.get_full_length_likelihoods(), rtol=1e-12, atol=1e-300)
+    calc = lf.make_calculator()
+    rate = calc.measure_evals_per_second(time_limit=0.2, wall=True)
+    assert rate > 0
