@@ -244,36 +244,43 @@ def cpu_arm(problem, budget_s=20.0, sample_columns=None, steps=20, warmup=1):
     return best
 
 
-def cogent3_arm(problem, cfg, budget_s=120.0, sample_columns=None, steps=20, warmup=1):
-    """time the UNMODIFIED cogent3 (baseline/_ref, a plain copy of the reference package; it is
-    pure Python + numba) on a bounded sample of the workload: build the likelihood function
-    through cogent3's own public API, ``calc = lf.make_calculator()``, then full evaluations
-    ``calc(x * (1 + eps_k))`` (every parameter changes: SURVEY §8d).  Returns None when the
-    package is not importable on this machine (then the oracle port is the CPU arm)."""
+def import_cogent3():
+    """the UNMODIFIED cogent3 from baseline/_ref (a plain copy of the reference package) with the
+    three import shims of tests/_shims; None when it is not on this machine"""
     ref_root = os.environ.get("COGENT3_REFERENCE_ROOT", os.path.join(ROOT, "baseline", "_ref"))
     if not os.path.isdir(os.path.join(ref_root, "cogent3")):
         return None
     os.environ["COGENT3_REFERENCE_ROOT"] = ref_root
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
-    sys.path[:0] = [os.path.join(ROOT, "tests", "_shims"), ref_root]
+    for pth in (os.path.join(ROOT, "tests", "_shims"), ref_root):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
     try:
-        from cogent3 import get_model, make_aligned_seqs, make_tree
-    except Exception:  # noqa: BLE001 - fall back to the port
+        import cogent3
+        import cogent3.maths.util  # noqa: F401  (import order fixes the reference's numpy error state)
+        from cogent3.evolve import substitution_model  # noqa: F401
+    except Exception:  # noqa: BLE001
         return None
-    from threadpoolctl import threadpool_limits
+    return cogent3
 
-    from cogent3_b200.patterns import from_reference_lht
+
+def build_cogent3_lf(problem, cfg, columns=None, backend="cpu", device=0):
+    """the likelihood function of `problem` through cogent3's OWN public API: get_model(...)
+    .make_likelihood_function(tree), lf.set_alignment(aln), parameter rules.  backend "cuda": the same calls
+    with cogent3_b200.install() active, i.e. sm.make_likelihood_function itself returns the CUDA class."""
+    from cogent3 import get_model, make_aligned_seqs, make_tree
 
     model_name, topo, lengths, codes, rows, bins, setup = problem
     L = codes.shape[1]
     M = rows.shape[1]
-    Ls = min(L, sample_columns or (50_000 if M <= 4 else 5_000))
-    if cfg == "c1":
-        symbols = hostmodels.dna_symbol_rows()[0]
-    else:
-        symbols = hostmodels.dna_symbol_rows()[0] if M == 4 else hostmodels.codon_symbol_rows()[0]
+    Ls = min(L, columns or L)
+    symbols = np.array(hostmodels.dna_symbol_rows()[0] if (cfg == "c1" or M == 4) else hostmodels.codon_symbol_rows()[0])
     t0 = time.perf_counter()
-    data = {n: "".join(symbols[c] for c in row[:Ls]) for n, row in zip(topo.tip_names, codes, strict=True)}
+    if symbols.dtype.itemsize == np.dtype("U1").itemsize:  # single characters: vectorised
+        table = np.frombuffer("".join(symbols).encode("ascii"), np.uint8)
+        data = {n: table[row[:Ls]].tobytes().decode("ascii") for n, row in zip(topo.tip_names, codes, strict=True)}
+    else:
+        data = {n: "".join(symbols[row[:Ls]]) for n, row in zip(topo.tip_names, codes, strict=True)}
     aln = make_aligned_seqs(data, moltype="dna")
     tree = make_tree(topo.to_newick(np.nan_to_num(lengths)))
     kw = {}
@@ -284,9 +291,20 @@ def cogent3_arm(problem, cfg, budget_s=120.0, sample_columns=None, steps=20, war
         sm = get_model(model_name)
     if setup.get("expm"):
         kw["expm"] = setup["expm"]
-    lf = sm.make_likelihood_function(tree, **kw)
+    if backend == "cuda":
+        import cogent3_b200
+
+        cogent3_b200.install(device=device)
+        try:
+            lf = sm.make_likelihood_function(tree, device=device, **kw)
+        finally:
+            cogent3_b200.uninstall()
+        assert type(lf).__name__ == "CudaAlignmentLikelihoodFunction"
+    else:
+        lf = sm.make_likelihood_function(tree, **kw)
+    t1 = time.perf_counter()
     lf.set_alignment(aln)
-    t_aln = time.perf_counter() - t0
+    t_aln = time.perf_counter() - t1
     if bins > 1:
         lf.set_param_rule("bprobs", is_constant=True)
         lf.set_param_rule("rate_shape", value=setup.get("rate_shape", 0.5))
@@ -298,6 +316,47 @@ def cogent3_arm(problem, cfg, budget_s=120.0, sample_columns=None, steps=20, war
                     lf.set_param_rule(pname, edge=topo.names[n], value=v)
     for pname, v in setup.get("params", {}).items():
         lf.set_param_rule(pname, value=v)
+    if "mprobs" in setup:
+        lf.set_motif_probs(dict(zip(symbols[:4], setup["mprobs"], strict=True)))
+    return lf, {"columns": Ls, "make_objects_s": t1 - t0, "set_alignment_s": t_aln}
+
+
+def calculator_points(x, k):
+    """the parameter vector of timed step k: EVERY optimisable parameter moves (a full evaluation), never the
+    previous point (nothing is cached) -- the same sequence for the reference and for the drop-in"""
+    return x * (1.0 + 1e-4 * (1 + k % 97))
+
+
+def single_parameter_rate(calc, x, budget_s=1.0, max_evals=4000):
+    """evaluations / s of an each-parameter-in-turn optimiser making REAL changes through
+    Calculator.change (what measure_evals_per_second, recalculation/calculation.py:547-583, probes with
+    not-a-real-change updates, which an engine that diffs its inputs answers from its cache)"""
+    n, t0, k = 0, time.perf_counter(), 0
+    while True:
+        for i in range(len(x)):
+            k += 1
+            calc.change([(i, x[i] * (1.0 + 1e-6 * (1 + k % 89)))])
+            n += 1
+            if n >= max_evals or time.perf_counter() - t0 > budget_s:
+                return n / (time.perf_counter() - t0)
+
+
+def cogent3_arm(problem, cfg, budget_s=120.0, sample_columns=None, steps=20, warmup=1):
+    """time the UNMODIFIED cogent3 (baseline/_ref) on the workload, or on a bounded sample of its columns:
+    build the likelihood function through cogent3's own public API, ``calc = lf.make_calculator()``, then full
+    evaluations ``calc(x * (1 + eps_k))`` (every parameter changes: SURVEY §8d).  Returns None when the
+    package is not importable on this machine (then the oracle port is the CPU arm)."""
+    if import_cogent3() is None:
+        return None
+    from threadpoolctl import threadpool_limits
+
+    from cogent3_b200.patterns import from_reference_lht
+
+    model_name, topo, lengths, codes, rows, bins, setup = problem
+    L = codes.shape[1]
+    M = rows.shape[1]
+    Ls = min(L, sample_columns or (50_000 if M <= 4 else 5_000))
+    lf, t_setup = build_cogent3_lf(problem, cfg, columns=Ls)
     lnl0 = float(lf.get_log_likelihood())
     _, pt = from_reference_lht(lf.get_param_value("lht"))
     _, u_gp = pt.work_units(bins)
@@ -312,24 +371,38 @@ def cogent3_arm(problem, cfg, budget_s=120.0, sample_columns=None, steps=20, war
                 calc(x * (1.0 - 1e-4 * (1 + w)))
             times, k, t_start = [], 0, time.perf_counter()
             while True:
-                xk = x * (1.0 + 1e-4 * (1 + k % 97))  # never the previous point: nothing is cached
+                xk = calculator_points(x, k)
                 t1 = time.perf_counter()
                 lnl = calc(xk)
                 times.append(time.perf_counter() - t1)
                 k += 1
                 if k >= steps or (k >= 3 and time.perf_counter() - t_start > budget_s / 2):
                     break
+            calc(x)
+            evals = {"measure_evals_per_second": float(calc.measure_evals_per_second(time_limit=0.5, wall=True)),
+                     "single_parameter_real_changes_per_s": single_parameter_rate(calc, x, budget_s=1.0)} if Ls <= 60_000 else None  # fmt: skip
         t = float(np.mean(times))
         rec = {"value": u_gp / t, "unit": UNIT, "cores": 1 if limit == 1 else os.cpu_count(),
                "kind": "reference", "mode": f"cogent3 Calculator, {label}",
                "steps_timed": k, "ms_per_step": t * 1e3, "best_ms": float(np.min(times)) * 1e3,
-               "sample": f"{Ls} of {L} columns, same tree/model/parameters; mean of {k} full evaluations "
-                         f"calc(x*(1+eps)) ({t * 1e3:.2f} ms each, U_gp={u_gp}); set_alignment {t_aln:.1f} s, "
-                         f"make_calculator {t_calc:.1f} s",
-               "lnL_sample": lnl0, "lnL_last": float(lnl)}  # fmt: skip
+               "sample": (f"{Ls} of {L} columns" if Ls < L else f"all {L} columns") +
+                         f", same tree/model/parameters; mean of {k} full evaluations "
+                         f"calc(x*(1+eps)) ({t * 1e3:.2f} ms each, U_gp={u_gp}); set_alignment "
+                         f"{t_setup['set_alignment_s']:.1f} s, make_calculator {t_calc:.1f} s",
+               "columns": Ls, "set_alignment_s": t_setup["set_alignment_s"], "make_calculator_s": t_calc,
+               "lf_evals": evals, "lnL_sample": lnl0, "lnL_last": float(lnl)}  # fmt: skip
         if best is None or rec["value"] > best["value"]:
             best = rec
     return best
+
+
+def host_memory_available_gb():
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available / 1e9
+    except Exception:  # noqa: BLE001
+        return 0.0
 
 
 def run_reference_arm(args):
@@ -337,15 +410,28 @@ def run_reference_arm(args):
     if rank != 0:
         return
     problem = build_problem(args.config, args.columns, args.kind, 0)
-    # bounded sample: steps+warmup evaluations must finish within a few minutes
-    # (both CPU modes get half of a 4-minute budget; `steps` reports what was actually timed)
-    rec = None
+    # the headline for C2 is the reference on the FULL workload (all 1M columns: ~2 min of set_alignment +
+    # make_calculator in stock cogent3, ~30 GB of host memory); the bounded 50k-column sample of round 1 is
+    # timed next to it.  Other configs / small hosts: the sample only (and the line says so).
+    rec = sample = None
+    L, M = problem[3].shape[1], problem[4].shape[1]
+    full_ok = (args.config == "c2" and args.cpu_sample is None and not args.port_only and args.full_reference
+               and host_memory_available_gb() > 24.0)  # fmt: skip
     if not args.port_only:
         try:
-            rec = cogent3_arm(problem, args.config, budget_s=120.0, sample_columns=args.cpu_sample,
-                              steps=args.steps, warmup=args.warmup)  # fmt: skip
+            sample = cogent3_arm(problem, args.config, budget_s=60.0 if full_ok else 120.0,
+                                 sample_columns=args.cpu_sample, steps=args.steps, warmup=args.warmup)  # fmt: skip
         except Exception as err:  # noqa: BLE001 - the port below always works
             print(f"cogent3 arm failed ({err!r}); timing the oracle port", file=sys.stderr)
+        if sample is not None and full_ok:
+            try:
+                rec = cogent3_arm(problem, args.config, budget_s=240.0, sample_columns=L,
+                                  steps=args.steps, warmup=args.warmup)  # fmt: skip
+                rec["sampled_run"] = sample
+            except Exception as err:  # noqa: BLE001
+                print(f"full-size cogent3 run failed ({err!r}); reporting the sample", file=sys.stderr)
+        if rec is None:
+            rec = sample
     port = cpu_arm(problem, budget_s=60.0 if rec else 240.0, sample_columns=args.cpu_sample,
                    steps=args.steps, warmup=args.warmup)  # fmt: skip
     if rec is None:
@@ -361,7 +447,7 @@ def run_reference_arm(args):
         "cpu_baseline": rec,
         "e2e": {"value": rec["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": ("unmodified cogent3 from baseline/_ref through its own public API"
+        "note": ("unmodified cogent3 from baseline/_ref through its own public API (Calculator.__call__)"
                  if rec["kind"] == "reference" else
                  "cogent3's CPU algorithm restated (oracle/, parity pinned to the live reference); "
                  "baseline/_ref (a copy of the reference package) was not importable here"),
@@ -383,27 +469,234 @@ def workload_config(args, problem):
 # ----------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
+class Ctx:
+    """process-wide handles of the GPU arm"""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the likelihood engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+    def __init__(self):
+        import torch
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the likelihood engine has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
 
-    problem = build_problem(args.config, args.columns, args.kind, shard=rank)
-    # a stream of our own (torch's legacy default stream cannot be captured into the engine's CUDA graphs);
-    # it is torch's current stream from here on, so NCCL orders after the engine's kernels
-    stream = torch.cuda.Stream(device=local_rank)
-    torch.cuda.set_stream(stream)
-    lf, setup_t = make_lf(problem, device=local_rank, stream=stream)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        # a stream of our own (torch's legacy default stream cannot be captured into the engine's CUDA graphs);
+        # it is torch's current stream from here on, so NCCL orders after the engine's kernels
+        self.stream = torch.cuda.Stream(device=self.local_rank)
+        torch.cuda.set_stream(self.stream)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, x, op=None):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if op is None:
+            self.dist.all_reduce(t)
+        else:
+            self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.world > 1 else x
+
+    def sum_over_ranks(self, x):
+        return self._reduce(x)
+
+
+def dgemm_peak_tflops(ctx, n=8192, reps=3):
+    """FP64 calibration SURVEY §8d asks for: a cuBLAS DGEMM n^3 on this GPU (2 n^3 flop, best of `reps`)"""
+    torch = ctx.torch
+    try:
+        a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        torch.matmul(a, b)
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n**3 / (best * 1e-3) / 1e12
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def roofline_of(ctx, lf, eng, base, rates, cfg, kind, columns):
+    """per-launch CUDA events of full evaluations (c3_get_launch_profile) -> the roofline object"""
+    eng.set_profiling(True)
+    prof_rows = []
+    for k in range(6):
+        # alternate two length vectors so that every profiled step is a full evaluation
+        eng.update(np.nan_to_num(base * (1.0 + 1e-3 * (1 + k % 2)))[:, None] * rates[None, :])
+        rows = eng.launch_profile()
+        if rows and k >= 1:
+            prof_rows.append(rows)
+    eng.set_profiling(False)
+    prof = prof_rows[-1]
+    prune = [[r for r in rows if r["kind"].startswith("prune")] for rows in prof_rows]
+    all_ms = float(np.median([sum(r["ms"] for r in rows) for rows in prune]))
+    all_bytes = sum(r["bytes"] for r in prune[-1])
+    all_flops = sum(r["flops"] for r in prune[-1])
+    # the roofline is that of the DOMINANT kernel: the launches of the 4-state streaming kernel (levels and
+    # root instantiations), of the contraction instance of prune_dmma_edge_kernel otherwise; the aggregate
+    # over every pruning launch (small-levels launch, codon root) is reported next to it
+    M = lf.model.n_states
+    dom_kinds = ("prune", "prune_root") if M == 4 else ("prune",)
+    dom = [[r for r in rows if r["kind"] in dom_kinds] for rows in prune]
+    dom_name = eng.stats().get("kernel_name", "prune4_reg2_kernel") if M == 4 else "prune_dmma_edge_kernel"
+    if not dom[-1]:
+        dom, dom_name = prune, "prune4_small_kernel"
+    prune_ms = float(np.median([sum(r["ms"] for r in rows) for rows in dom]))
+    prune_bytes = sum(r["bytes"] for r in dom[-1])
+    prune_flops = sum(r["flops"] for r in dom[-1])
+    step_ms = float(np.median([sum(r["ms"] for r in rows) for rows in prof_rows]))
+    hbm_peak, peak_src = peaks()
+    st = eng.stats()
+    if M == 4:
+        achieved = prune_bytes / (prune_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src}  # fmt: skip
+    else:
+        from cogent3_b200.engine import measure_dmma_peak
+
+        dmma_peak = measure_dmma_peak(ctx.local_rank)
+        dgemm = dgemm_peak_tflops(ctx)
+        # ALGORITHMIC flops (2 M^2 per contraction row); the kernel executes 2 MP^2 (M padded to a multiple
+        # of 8: 61 -> 64), reported next to it.  Denominator: the higher of the two FP64 tensor calibrations.
+        MP = st["padded_states"]
+        alg_flops = prune_flops * (M * M) / (MP * MP)
+        achieved = alg_flops / (prune_ms * 1e-3) / 1e12
+        peak = max(dmma_peak, dgemm or 0.0)
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "max(FP64 DMMA issue-loop microbenchmark c3_measure_dmma_peak, cuBLAS DGEMM 8192^3), "
+                                   "both measured in this run on this GPU",
+                    "dmma_issue_loop_tflops": dmma_peak, "cublas_dgemm_8192_tflops": dgemm,
+                    "executed_tflops": prune_flops / (prune_ms * 1e-3) / 1e12,
+                    "executed_frac": prune_flops / (prune_ms * 1e-3) / 1e12 / peak,
+                    "hbm_gbs_achieved": prune_bytes / (prune_ms * 1e-3) / 1e9}  # fmt: skip
+    # DRAM traffic of the dominant launch from the committed ncu capture (per launch, like `achieved` is
+    # per launch); null when no capture exists for this config
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f).get(cfg)
+            if tr and kind == "evolved" and not columns:
+                roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                roofline["traffic_note"] = (f"{tr['kernel']}: algorithmic {tr['algorithmic_bytes']} B per launch; "
+                                            f"{tr.get('profile', 'profiles/')}")
+                break
+        except (OSError, ValueError, KeyError):
+            pass
+    if M == 4:
+        agg = all_bytes / (all_ms * 1e-3) / 1e9
+    else:
+        agg = all_flops * (M * M) / (st["padded_states"] ** 2) / (all_ms * 1e-3) / 1e12
+    roofline["all_pruning_launches"] = {"achieved": agg, "frac": agg / roofline["peak"], "launches": len(prune[-1]),
+                                        "ms_per_step": all_ms}  # fmt: skip
+    roofline.update({
+        "kernel": dom_name,
+        "launches_per_step": len(dom[-1]), "kernel_ms_per_step": prune_ms,
+        "kernel_share_of_step": prune_ms / step_ms if step_ms else None,
+        "alg_bytes_per_step": prune_bytes, "executed_flops_per_step": prune_flops,
+        "per_launch": [{"kind": r["kind"], "ms": round(r["ms"], 5), "bytes": r["bytes"],
+                        "GBps": round(r["bytes"] / r["ms"] / 1e6, 1) if r["ms"] > 0 else None,
+                        **({"exec_TFLOPs": round(r["flops"] / r["ms"] / 1e9, 2)} if M != 4 and r["ms"] > 0 else {})}
+                       for r in prof],
+    })  # fmt: skip
+    return roofline
+
+
+def dropin_leg(ctx, problem, cfg, steps, warmup, expect_units):
+    """END TO END through the product: unmodified cogent3 (baseline/_ref) + cogent3_b200.install() + libc3cuda.
+    `calc = lf.make_calculator(); calc(x_k)` -- the very call the reference arm times (cogent3_arm) -- with
+    every optimisable parameter changed each step: cogent3's own Q build, eigendecomposition and Calculator
+    sweep on the host, c3_set_eigen / c3_update from host buffers, all kernels, the scalar back through mapped
+    pinned memory.  With N ranks every rank drives its own column shard and the sum over ranks is fused into
+    the reduction kernel, so every rank's calc(x) returns the total.  None when cogent3 is not on this box."""
+    if import_cogent3() is None:
+        return None
+    torch = ctx.torch
+    from cogent3_b200.patterns import from_reference_lht
+
+    bins = problem[5]
+    lf, t_setup = build_cogent3_lf(problem, cfg, backend="cuda", device=ctx.local_rank)
+    t0 = time.perf_counter()
+    lnl0 = float(lf.get_log_likelihood())
+    t_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    calc = lf.make_calculator()
+    t_calc = time.perf_counter() - t0
+    x = np.array(calc.get_value_array(), float)
+    eng = lf._engine()
+    _, pt = from_reference_lht(lf.get_param_value("lht"))
+    _, u_gp = pt.work_units(bins)
+    assert int(u_gp) == int(expect_units), (u_gp, expect_units)  # the same tables as the device compression
+    calc(x)
+    fused = None
+    if ctx.world > 1:
+        from cogent3_b200.sharded import attach_fused_allreduce
+
+        fused = bool(attach_fused_allreduce(eng))
+        buf = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def step(xk):
+        v = calc(xk)
+        if ctx.world > 1 and not fused:
+            buf.fill_(v)
+            ctx.dist.all_reduce(buf)
+            v = float(buf.item())
+        return v
+
+    for w in range(max(2, warmup)):
+        step(x * (1.0 - 1e-4 * (1 + w)))
+    h2d = 0
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        lnl = step(calculator_points(x, k))
+        h2d += eng.stats()["last_h2d_bytes"]
+    ctx.barrier()
+    wall = time.perf_counter() - t0
+    evals = None
+    if ctx.world == 1:
+        calc(x)
+        evals = {"measure_evals_per_second": float(calc.measure_evals_per_second(time_limit=0.5, wall=True)),
+                 "single_parameter_real_changes_per_s": single_parameter_rate(calc, x, budget_s=1.0),
+                 "note": "measure_evals_per_second (recalculation/calculation.py:547-583) re-presents UNCHANGED "
+                         "values, which the engine answers from its input diff (no kernel runs); the second "
+                         "figure makes a real one-parameter change per evaluation, for both arms"}  # fmt: skip
+    if fused:
+        eng.comm_detach()
+    st = eng.stats()
+    return {"wall_s": wall, "h2d": h2d, "lnL0": lnl0, "lnL_last": float(lnl), "fused": fused, "lf_evals": evals,
+            "graph_replays": int(st["graph_replays"]), "n_parameters": int(len(x)),
+            "setup": {**t_setup, "first_evaluation_s": t_first, "make_calculator_s": t_calc}}  # fmt: skip
+
+
+def measure_workload(ctx, args, cfg, columns, kind, steps, warmup, shard, clocks=None, with_dropin=True,
+                     with_partial=True):  # fmt: skip
+    """device-timed value, end-to-end legs, roofline, partial updates of ONE config on this rank's shard"""
+    torch, dist, world, rank = ctx.torch, ctx.dist, ctx.world, ctx.rank
+    problem = build_problem(cfg, columns, kind, shard=shard)
+    lf, setup_t = make_lf(problem, device=ctx.local_rank, stream=ctx.stream)
     eng = lf.engine
     bins = lf.n_bins
     u_mv, u_gp = lf.patterns.work_units(bins)
@@ -444,143 +737,52 @@ def run_ours(args):
             v = float(lnl_dev.item())
         return v
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     lf.get_log_likelihood()
-    for k in range(max(args.warmup, 3)):
+    for k in range(max(warmup, 3)):
         device_step(k)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if clocks is not None:
         clocks.start()
     launches0 = eng.stats()["kernel_launches"]
+    replays0 = eng.stats()["graph_replays"]
 
     # ---- device-timed steps ------------------------------------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for k in range(args.steps):
+    ctx.barrier()
+    ev0.record(ctx.stream)
+    for k in range(steps):
         lnl = device_step(k)
-    ev1.record(stream)
-    barrier()
+    ev1.record(ctx.stream)
+    ctx.barrier()
     dev_s = ev0.elapsed_time(ev1) * 1e-3
     launches = eng.stats()["kernel_launches"] - launches0
+    replays = eng.stats()["graph_replays"] - replays0
 
-    # ---- end-to-end steps through the public API --------------------------------------
+    # ---- end-to-end steps through the mirror API (no cogent3 needed) ------------------
     for k in range(2):
         api_step(k)
     h2d = 0
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         api_step(k)
         h2d += eng.stats()["last_h2d_bytes"]
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clock_rec = clocks.stop() if rank == 0 else None
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t)
-        return float(t.item())
-
-    dev_s = max_over_ranks(dev_s)
-    e2e_s = max_over_ranks(e2e_s)
-    total_units = sum_over_ranks(float(u_gp))
-    total_umv = sum_over_ranks(float(u_mv))
-
-    # ---- roofline of the pruning kernels (per-launch CUDA events) -------------------
-    eng.set_profiling(True)
-    prof_rows = []
-    for k in range(6):
-        # alternate two length vectors so that every profiled step is a full evaluation
-        eng.update(np.nan_to_num(base * (1.0 + 1e-3 * (1 + k % 2)))[:, None] * rates[None, :])
-        rows = eng.launch_profile()
-        if rows and k >= 1:
-            prof_rows.append(rows)
-    eng.set_profiling(False)
-    prof = prof_rows[-1]
-    prune = [[r for r in rows if r["kind"].startswith("prune")] for rows in prof_rows]
-    all_ms = float(np.median([sum(r["ms"] for r in rows) for rows in prune]))
-    all_bytes = sum(r["bytes"] for r in prune[-1])
-    all_flops = sum(r["flops"] for r in prune[-1])
-    # the roofline is that of the DOMINANT kernel: the launches of prune4_reg2_kernel (levels and root
-    # instantiations) for 4 states, of the contraction instance of prune_dmma_edge_kernel otherwise;
-    # the aggregate over every pruning launch (small-levels launch, codon root) is reported next to it
-    M_states = lf.model.n_states
-    dom_kinds = ("prune", "prune_root") if M_states == 4 else ("prune",)
-    dom = [[r for r in rows if r["kind"] in dom_kinds] for rows in prune]
-    dom_name = "prune4_reg2_kernel" if M_states == 4 else "prune_dmma_edge_kernel"
-    if not dom[-1]:
-        dom, dom_name = prune, "prune4_small_kernel"
-    prune_ms = float(np.median([sum(r["ms"] for r in rows) for rows in dom]))
-    prune_bytes = sum(r["bytes"] for r in dom[-1])
-    prune_flops = sum(r["flops"] for r in dom[-1])
-    step_ms = float(np.median([sum(r["ms"] for r in rows) for rows in prof_rows]))
-    hbm_peak, peak_src = peaks()
-    st = eng.stats()
-    M = lf.model.n_states
-    if M == 4:
-        achieved = prune_bytes / (prune_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src}  # fmt: skip
+    ctx.barrier()
+    mirror_s = time.perf_counter() - t0
+    if clocks is not None:
+        clock_rec = clocks.stop()
     else:
-        from cogent3_b200.engine import measure_dmma_peak
+        clock_rec = None
 
-        dmma_peak = measure_dmma_peak(local_rank)
-        # ALGORITHMIC flops (2 M^2 per internal-child row); the kernel executes 2 MP^2 (M padded to
-        # a multiple of 8: 61 -> 64), reported next to it
-        MP = st["padded_states"]
-        alg_flops = prune_flops * (M * M) / (MP * MP)
-        achieved = alg_flops / (prune_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-                    "frac": achieved / dmma_peak, "traffic": None,
-                    "peak_source": "FP64 DMMA issue-loop microbenchmark on this GPU (c3_measure_dmma_peak)",
-                    "executed_tflops": prune_flops / (prune_ms * 1e-3) / 1e12,
-                    "executed_frac": prune_flops / (prune_ms * 1e-3) / 1e12 / dmma_peak,
-                    "hbm_gbs_achieved": prune_bytes / (prune_ms * 1e-3) / 1e9}  # fmt: skip
-    # DRAM traffic of the dominant launch from the committed ncu capture (per launch, like
-    # `achieved` is per launch); null when no capture exists for this config
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tr = json.load(f).get(args.config)
-        if tr and args.kind == "evolved" and not args.columns:
-            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-            roofline["traffic_note"] = (f"{tr['kernel']}: algorithmic {tr['algorithmic_bytes']} B per launch; "
-                                        f"{tr.get('profile', 'profiles/')}")
-    except (OSError, ValueError, KeyError):
-        pass
-    if M == 4:
-        agg = all_bytes / (all_ms * 1e-3) / 1e9
-    else:
-        agg = all_flops * (M * M) / (st["padded_states"] ** 2) / (all_ms * 1e-3) / 1e12
-    roofline["all_pruning_launches"] = {"achieved": agg, "frac": agg / roofline["peak"], "launches": len(prune[-1]),
-                                        "ms_per_step": all_ms}  # fmt: skip
-    roofline.update({
-        "kernel": dom_name,
-        "launches_per_step": len(dom[-1]), "kernel_ms_per_step": prune_ms,
-        "kernel_share_of_step": prune_ms / step_ms if step_ms else None,
-        "alg_bytes_per_step": prune_bytes, "executed_flops_per_step": prune_flops,
-        "per_launch": [{"kind": r["kind"], "ms": round(r["ms"], 5), "bytes": r["bytes"],
-                        "GBps": round(r["bytes"] / r["ms"] / 1e6, 1) if r["ms"] > 0 else None,
-                        **({"exec_TFLOPs": round(r["flops"] / r["ms"] / 1e9, 2)} if M != 4 and r["ms"] > 0 else {})}
-                       for r in prof],
-    })  # fmt: skip
+    dev_s = ctx.max_over_ranks(dev_s)
+    mirror_s = ctx.max_over_ranks(mirror_s)
+    total_units = ctx.sum_over_ranks(float(u_gp))
+    total_umv = ctx.sum_over_ranks(float(u_mv))
+
+    roofline = roofline_of(ctx, lf, eng, base, rates, cfg, kind, columns)
 
     # ---- partial updates: one branch length at a time (the optimiser's inner loop) --
     partial = None
-    if world == 1:
+    if world == 1 and with_partial:
         edges = lf.topo.edges
         sel = edges if len(edges) <= 128 else list(np.random.default_rng(0).choice(edges, 128, replace=False))
         d = np.nan_to_num(base)[:, None] * rates[None, :]
@@ -609,10 +811,183 @@ def run_ours(args):
         allreduce_check = {"fused_total": total, "nccl_sum_of_shards": float(t.item()),
                            "rel_diff": abs(total - float(t.item())) / abs(total)}
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    st = eng.stats()
+    root_patterns = int(lf.patterns.root.n_rows - 1)
+    out = {
+        "problem": problem, "lf": lf,
+        "value": total_units * steps / dev_s, "ms_per_step": dev_s / steps * 1e3, "steps": steps,
+        "gpu_launches": int(launches), "graph_replays": int(replays),
+        "clocks": clock_rec, "roofline": roofline, "partial_update": partial,
+        "units": {"U_gp_per_step": total_units, "U_mv_per_step": total_umv, "lf_evals_per_s": steps / dev_s,
+                  "root_patterns_per_gpu": root_patterns, "node_rows_per_step": int(st["last_node_rows"])},
+        "allreduce": ({"kind": "fused into the reduction kernel (peer-memory mailboxes over NVLink); the sharded "
+                               "evaluation replays from a CUDA graph (evaluation number in device memory)",
+                       "check": allreduce_check} if fused else
+                      ({"kind": "NCCL all-reduce of one double per step"} if world > 1 else None)),
+        "setup": {**setup_t, "device_bytes": int(st["device_bytes"]),
+                  "partial_bytes": int(st["partial_bytes"]), "levels": int(st["n_levels"])},
+        "lnL": lnl,
+        "e2e_mirror": {"value": total_units * steps / mirror_s, "unit": UNIT, "ms_per_step": mirror_s / steps * 1e3,
+                       "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": 16,
+                       "api": "cogent3_b200.likelihood.LikelihoodFunction.set_param_rule + get_log_likelihood "
+                              "(host Q/eig, c3_set_eigen, c3_set_distances, c3_evaluate)"},
+    }  # fmt: skip
+
+    # ---- end to end through the PRODUCT: real cogent3 + install() + CUDA engine ----------------------
+    dropin = None
+    if with_dropin:
+        eng_keep = eng  # (both engines stay resident: the drop-in builds its own from cogent3's tables)
+        try:
+            dropin = dropin_leg(ctx, problem, cfg, steps=min(steps, 400), warmup=warmup, expect_units=u_gp)
+        except Exception as err:  # noqa: BLE001 - the line is still printed, with the reason
+            dropin = {"error": repr(err)}
+        del eng_keep
+    have = ctx.sum_over_ranks(1.0 if (dropin and "wall_s" in dropin) else 0.0)
+    if dropin and "wall_s" in dropin and have == world:
+        n = min(steps, 400)
+        wall = ctx.max_over_ranks(dropin["wall_s"])
+        out["e2e"] = {"value": total_units * n / wall, "unit": UNIT, "ms_per_step": wall / n * 1e3, "steps": n,
+                      "h2d_bytes_per_step": dropin["h2d"] / n, "d2h_bytes_per_step": 16,
+                      "api": "cogent3 Calculator.__call__ of sm.make_likelihood_function(tree) with "
+                             "cogent3_b200.install(): calc(x_k), every optimisable parameter changed (the call the "
+                             "reference arm times); unmodified cogent3 from baseline/_ref on the host, libc3cuda on "
+                             "the device",
+                      "n_parameters": dropin["n_parameters"], "lf_evals": dropin["lf_evals"],
+                      "fused_allreduce": dropin["fused"], "graph_replays": dropin["graph_replays"],
+                      "setup": dropin["setup"], "lnL_first": dropin["lnL0"]}  # fmt: skip
+    else:
+        why = (dropin or {}).get("error", "cogent3 (baseline/_ref) is not on this machine")
+        out["e2e"] = dict(out["e2e_mirror"], note=f"drop-in leg unavailable ({why}): the mirror API instead")
+    return out
+
+
+def c5_strong_block(ctx, steps, warmup):
+    """C5 as `north_star` states it: ONE 256-taxon x 10M-column HKY85+Gamma4 alignment, its columns split over the
+    N ranks (strong scaling).  The alignment is the concatenation of 8 blocks of 1.25M columns (block j = the
+    synthetic generator's shard j), rank r holds blocks [8r/N, 8(r+1)/N): the same 10M columns at every N; at
+    N = 1 one GPU holds them all (35.9 GB resident)."""
+    torch, dist, world, rank = ctx.torch, ctx.dist, ctx.world, ctx.rank
+    model_name, n_tips, L, bins, _ = CONFIGS["c5"]
+    n_blocks = 8
+    if n_blocks % world != 0:
+        return {"skipped": f"{world} ranks do not divide the {n_blocks} column blocks"}
+    per = n_blocks // world
+    m = hostmodels.get_model(model_name)
+    t0 = time.perf_counter()
+    parts = []
+    topo = lengths = None
+    for j in range(rank * per, (rank + 1) * per):
+        topo, lengths, codes = make_workload(n_tips, L // n_blocks, m.n_states, kind="evolved", seed=SEED, shard=j)
+        parts.append(codes)
+    codes = np.concatenate(parts, axis=1) if len(parts) > 1 else parts[0]
+    del parts
+    t_gen = time.perf_counter() - t0
+    problem = (model_name, topo, lengths, codes, np.eye(m.n_states), bins,
+               {"params": {"kappa": 4.0}, "rate_shape": 0.5})  # fmt: skip
+    try:
+        lf, setup_t = make_lf(problem, device=ctx.local_rank, stream=ctx.stream)
+    except MemoryError as err:
+        return {"skipped": f"does not fit: {err}"}
+    eng = lf.engine
+    u_mv, u_gp = lf.patterns.work_units(bins)
+    base, rates = lf.lengths.copy(), lf.rates()
+    fused = False
+    if world > 1:
+        from cogent3_b200.sharded import attach_fused_allreduce
+
+        fused = attach_fused_allreduce(eng)
+    lnl_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
+    step_dist = [np.ascontiguousarray(np.nan_to_num(step_lengths(base, k))[:, None] * rates[None, :])
+                 for k in range(7)]  # fmt: skip
+
+    def device_step(k):
+        d = step_dist[k % 7]
+        if world == 1 or fused:
+            return eng.update(d)
+        eng.set_distances(d)
+        eng.evaluate_device(lnl_dev.data_ptr())
+        dist.all_reduce(lnl_dev)
+        return float(lnl_dev.item())
+
+    lf.get_log_likelihood()
+    for k in range(max(3, warmup)):
+        device_step(k)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    ev0.record(ctx.stream)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        lnl = device_step(k)
+    ev1.record(ctx.stream)
+    ctx.barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ctx.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    wall = ctx.max_over_ranks(wall)
+    total_units = ctx.sum_over_ranks(float(u_gp))
+    rows = ctx.sum_over_ranks(float(lf.patterns.root.n_rows - 1))
+    check = None
+    if fused:
+        d = step_dist[3]
+        total = eng.update(d)
+        eng.comm_detach()
+        eng.invalidate()
+        t = torch.tensor([eng.update(d)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        check = {"fused_total": total, "nccl_sum_of_shards": float(t.item()),
+                 "rel_diff": abs(total - float(t.item())) / abs(total)}
+    st = eng.stats()
+    hbm_peak, _ = peaks()
+    alg_bytes = ctx.sum_over_ranks(float(st["last_alg_bytes"]))
+    out = {
+        "workload": "c5: HKY85+Gamma4 256 taxa x 10M columns, ONE alignment, columns split over the ranks",
+        "scaling": "strong", "n_gpus": world, "columns_total": int(L), "columns_per_gpu": int(codes.shape[1]),
+        "value": total_units * steps / dev_s, "unit": UNIT, "ms_per_step": dev_s / steps * 1e3, "steps": steps,
+        "wall_ms_per_step": wall / steps * 1e3,
+        "lnL": lnl, "U_gp_per_step_all_ranks": total_units, "root_pattern_rows_all_ranks": rows,
+        "pattern_note": "per-shard compression: every rank compresses its own columns, so the N-rank total of "
+                        "pattern rows / updates is >= the 1-rank (global compression) figure",
+        "hbm_gbs_algorithmic_all_ranks": alg_bytes / (dev_s / steps) / 1e9,
+        "hbm_frac_per_gpu": alg_bytes / (dev_s / steps) / 1e9 / world / hbm_peak,
+        "allreduce": {"fused": bool(fused), "check": check} if world > 1 else None,
+        "setup": {**setup_t, "generate_s": t_gen, "device_bytes": int(st["device_bytes"])},
+    }  # fmt: skip
+    eng.close()
+    return out
+
+
+def slim(block):
+    """what of a measure_workload record goes into a secondary block of the JSON line"""
+    keep = ("value", "ms_per_step", "steps", "gpu_launches", "graph_replays", "roofline", "units", "e2e", "e2e_mirror",
+            "partial_update", "setup", "lnL", "cpu_baseline")  # fmt: skip
+    return {k: block[k] for k in keep if k in block}
+
+
+def cpu_baseline_subprocess(args, cfg, columns=None, kind="evolved", cpu_sample=None):
+    # in a fresh process: torch's OpenMP runtime settings must not throttle the CPU arm
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", cfg,
+           "--kind", kind, "--steps", "20", "--warmup", "1", "--no-full-reference"]  # fmt: skip  (bounded: ~10-30 s)
+    if columns:
+        cmd += ["--columns", str(columns)]
+    if cpu_sample:
+        cmd += ["--cpu-sample", str(cpu_sample)]
+    env = {k: v for k, v in os.environ.items() if not k.startswith("OMP_")}
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        return json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception as err:  # noqa: BLE001 - the GPU line must still be printed
+        return {"error": f"cpu baseline failed: {err!r}"}
+
+
+def run_ours(args):
+    ctx = Ctx()
+    torch, dist, world, rank = ctx.torch, ctx.dist, ctx.world, ctx.rank
+    clocks = ClockSampler(ctx.local_rank) if rank == 0 else None
+    main_rec = measure_workload(ctx, args, args.config, args.columns, args.kind, steps=args.steps,
+                                warmup=max(args.warmup, 3), shard=rank, clocks=clocks,
+                                with_dropin=not args.no_dropin and (args.columns or CONFIGS[args.config][2]) <= 2_500_000)  # fmt: skip
+    problem, lf = main_rec.pop("problem"), main_rec.pop("lf")
 
     # ---- many small alignments at once (SURVEY §8f-3): B independent likelihood functions --
     many = None
@@ -620,7 +995,10 @@ def run_ours(args):
         from cogent3_b200.engine import update_many as engine_update_many
 
         B = 64
-        lfs = [make_lf(problem, device=local_rank)[0] for _ in range(B)]
+        base, rates = lf.lengths.copy(), lf.rates()
+        step_dist = [np.ascontiguousarray(np.nan_to_num(step_lengths(base, k))[:, None] * rates[None, :])
+                     for k in range(7)]  # fmt: skip
+        lfs = [make_lf(problem, device=ctx.local_rank)[0] for _ in range(B)]
         engines = [f.engine for f in lfs]
         for f in lfs:
             f.get_log_likelihood()
@@ -650,50 +1028,61 @@ def run_ours(args):
         del one_by_one
         for f in lfs:
             f.engine.close()
+    lf.engine.close()
+    del lf
+
+    # ---- what else `north_star` names, in the same line (default config only) ------------------------
+    extras = args.config == "c2" and not args.columns and args.kind == "evolved" and not args.no_extra
+    c4 = c5 = None
+    if extras and world == 1:
+        try:
+            rec = measure_workload(ctx, args, "c4", None, "evolved", steps=min(args.steps, 300), warmup=3, shard=0,
+                                   with_dropin=not args.no_dropin, with_partial=False)  # fmt: skip
+            rec.pop("problem")
+            rec.pop("lf").engine.close()
+            if not args.no_cpu:
+                rec["cpu_baseline"] = cpu_baseline_subprocess(args, "c4")
+            c4 = slim(rec)
+            c4["workload"] = f"c4: {CONFIGS['c4'][4]}"
+        except Exception as err:  # noqa: BLE001
+            c4 = {"error": repr(err)}
+        torch.cuda.empty_cache()
+    if extras:
+        try:
+            c5 = c5_strong_block(ctx, steps=min(args.steps, 50 if world == 1 else 200), warmup=3)
+        except Exception as err:  # noqa: BLE001
+            c5 = {"error": repr(err)}
+        ok = ctx.sum_over_ranks(1.0 if (c5 and "value" in c5) else 0.0)
+        if ok != world and c5 and "value" in c5:
+            c5 = {"error": "another rank failed"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     cpu_rec = None
     if world == 1 and not args.no_cpu:
-        # in a fresh process: torch's OpenMP runtime settings must not throttle the CPU arm
-        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
-               "--kind", args.kind, "--steps", "20", "--warmup", "1"]  # fmt: skip  (bounded: ~10-30 s)
-        if args.columns:
-            cmd += ["--columns", str(args.columns)]
-        if args.cpu_sample:
-            cmd += ["--cpu-sample", str(args.cpu_sample)]
-        env = {k: v for k, v in os.environ.items() if not k.startswith("OMP_")}
-        try:
-            res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-            cpu_rec = json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]
-        except Exception as err:  # noqa: BLE001 - the GPU line must still be printed
-            cpu_rec = {"error": f"cpu baseline failed: {err!r}"}
+        cpu_rec = cpu_baseline_subprocess(args, args.config, args.columns, args.kind, args.cpu_sample)
 
-    value = total_units * args.steps / dev_s
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": dev_s / args.steps * 1e3,
+        "metric": METRIC, "value": main_rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": main_rec["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, problem),
-        "e2e": {"value": total_units * args.steps / e2e_s, "unit": UNIT,
-                "ms_per_step": e2e_s / args.steps * 1e3,
-                "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": 8,
-                "api": "LikelihoodFunction.set_param_rule + get_log_likelihood (host Q/eig, "
-                       "c3_set_eigen, c3_set_distances, c3_evaluate)"},
-        "gpu_launches": int(launches),
-        "clocks": clock_rec,
-        "roofline": roofline,
+        "e2e": main_rec["e2e"], "e2e_mirror": main_rec["e2e_mirror"],
+        "gpu_launches": main_rec["gpu_launches"], "graph_replays": main_rec["graph_replays"],
+        "clocks": main_rec["clocks"],
+        "roofline": main_rec["roofline"],
         "cpu_baseline": cpu_rec,
-        "units": {"U_gp_per_step": total_units, "U_mv_per_step": total_umv,
-                  "lf_evals_per_s": args.steps / dev_s,
-                  "root_patterns_per_gpu": int(lf.patterns.root.n_rows - 1),
-                  "node_rows_per_step": int(st["last_node_rows"])},
-        "partial_update": partial,
+        "units": main_rec["units"],
+        "partial_update": main_rec["partial_update"],
         "many_small": many,
-        "allreduce": ({"kind": "fused into the reduction kernel (peer-memory mailboxes over NVLink)",
-                       "check": allreduce_check} if fused else
-                      ({"kind": "NCCL all-reduce of one double per step"} if world > 1 else None)),
-        "setup": {**setup_t, "device_bytes": int(st["device_bytes"]),
-                  "partial_bytes": int(st["partial_bytes"]), "levels": int(st["n_levels"])},
-        "lnL": lnl,
+        "allreduce": main_rec["allreduce"],
+        "setup": main_rec["setup"],
+        "lnL": main_rec["lnL"],
+        "c4": c4,
+        "c5_strong": c5,
         "host": {"cpu_count": os.cpu_count()},
     }  # fmt: skip
     print(json.dumps(line))
@@ -713,6 +1102,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None, help="columns in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--port-only", action="store_true", help="reference arm: time only the oracle port")
+    ap.add_argument("--no-full-reference", dest="full_reference", action="store_false",
+                    help="reference arm: only the bounded sample, not the full-size run")
+    ap.add_argument("--no-extra", action="store_true", help="our arm: skip the c4 and c5_strong blocks")
+    ap.add_argument("--no-dropin", action="store_true", help="our arm: skip the end-to-end leg through real cogent3")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus != world and world == 1 and args.gpus > 1:

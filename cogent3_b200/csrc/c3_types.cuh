@@ -76,11 +76,27 @@ struct CommSlot {
   double value;
   unsigned long long epoch;  // evaluation number the value belongs to (written after the value)
 };
+// The evaluation number lives in DEVICE memory (epoch_ctr, bumped by the reduction's last CTA), not in a
+// kernel argument: the launch is then identical from one evaluation to the next and can be replayed from
+// a CUDA graph.  Every rank evaluates in lock-step, so the counters agree.
 struct CommArgs {
   int32_t nranks;  // 0: not sharded
   int32_t rank;
-  unsigned long long epoch;
+  unsigned long long* epoch_ctr;
   CommSlot* peer[C3_MAX_RANKS];  // mailbox of every rank: [2 parities][nranks] slots (own included)
+};
+// a peer that never shows up (30 s): the reduction writes this NaN, the host turns it into an error
+constexpr unsigned long long C3_TIMEOUT_NAN_BITS = 0x7ff8dead00000001ull;
+
+// where the scalar of an evaluation goes.  h_lnl / h_seq are MAPPED pinned host words: the value, then
+// (after a system fence) a sequence number the host spins on -- no stream synchronisation on the
+// blocking path.  seq_ctr is the device-side count of published results (graph replays bump it too).
+struct ResultSink {
+  double* d_lnl;
+  double* d_lnl2;  // optional second device destination (c3_evaluate_device)
+  volatile double* h_lnl;
+  volatile unsigned long long* h_seq;
+  unsigned long long* seq_ctr;
 };
 
 // one tree level inside a fused "small levels" launch

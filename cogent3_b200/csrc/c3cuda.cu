@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -135,8 +137,17 @@ struct c3_engine {
   unsigned int* d_done = nullptr;  // per work item completion counters of the dataflow launches
   int64_t off_dep = 0;
   cudaEvent_t block_copied = nullptr;
-  double* h_lnl = nullptr;  // mapped pinned result
+  // mapped pinned result: the value and, after it, the sequence number of the evaluation that wrote it
+  // (the blocking path spins on that word instead of synchronising the stream)
+  double* h_lnl = nullptr;
   double* h_lnl_dev = nullptr;
+  volatile unsigned long long* h_seq = nullptr;
+  unsigned long long* h_seq_dev = nullptr;
+  unsigned long long* d_seq = nullptr;    // device-side count of published results
+  unsigned long long* d_epoch = nullptr;  // device-side evaluation number of the fused all-reduce
+  unsigned long long seq_issued = 0;      // results the issued evaluations will have published
+  bool spin_wait = true;                  // C3_SPIN=0: cudaStreamSynchronize
+  bool auto_futile = false;  // rescaling was tried for a -inf and did not help (a pattern with likelihood 0)
 
   // model state (host)
   std::vector<int32_t> qslot;       // [n_nodes*K]
@@ -151,6 +162,7 @@ struct c3_engine {
   double cached_lnl = NAN;
   bool have_cached = false;
   bool deferred_pending = false;  // c3_evaluate_many: launched, result not collected yet
+  bool async_pending = false;     // c3_evaluate_device work may still be running on the stream
 
   // sharded runs: fused all-reduce through peer mailboxes (c3_comm_*)
   CommArgs comm{};            // nranks == 0: not attached
@@ -202,6 +214,18 @@ struct c3_engine {
 
 namespace {
 
+// cudaFuncSetAttribute is per device (context): one engine per GPU in one process (c3_create(device, ...),
+// c3_comm_attach(device_ptrs=...)) must opt in on EVERY device it runs on, not only the first
+struct DeviceOnce {
+  uint64_t done[4] = {0, 0, 0, 0};
+  bool need(int device) {
+    const int d = device & 255;
+    if (done[d >> 6] & (1ull << (d & 63))) return false;
+    done[d >> 6] |= 1ull << (d & 63);
+    return true;
+  }
+};
+
 template <typename Kern>
 int set_max_smem(Kern kern, size_t bytes) {
   if (bytes > 48 * 1024) {
@@ -214,13 +238,12 @@ int set_max_smem(Kern kern, size_t bytes) {
 template <int MP>
 int launch_dmma(c3_engine* e, const PruneArgs& a, bool is_root, int grid) {
   const size_t smem = DmmaCfg<MP>::SMEM_BYTES;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need(e->device)) {
     int rc = set_max_smem(prune_dmma_kernel<MP, false>, smem);
     if (rc) return rc;
     rc = set_max_smem(prune_dmma_kernel<MP, true>, smem);
     if (rc) return rc;
-    configured = true;
   }
   if (is_root)
     prune_dmma_kernel<MP, true><<<grid, DMMA_THREADS, smem, e->stream>>>(a);
@@ -232,13 +255,12 @@ int launch_dmma(c3_engine* e, const PruneArgs& a, bool is_root, int grid) {
 template <int MP>
 int launch_dmma_reg(c3_engine* e, const PruneArgs& a, bool is_root) {
   const size_t smem = DRegCfg<MP>::SMEM_BYTES;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need(e->device)) {
     int rc = set_max_smem(prune_dmma_reg_kernel<MP, false>, smem);
     if (rc) return rc;
     rc = set_max_smem(prune_dmma_reg_kernel<MP, true>, smem);
     if (rc) return rc;
-    configured = true;
   }
   const int grid = std::max(1, std::min(a.total_tiles, e->n_sm));
   cudaLaunchConfig_t cfg = {};
@@ -265,13 +287,12 @@ int launch_dmma_edge(c3_engine* e, const PruneArgs& a, bool root_only3) {
   using Cfg = DECfg<DE_RA, DE_STG>;
   const size_t smem_p = (size_t)MP * (MP + 8) * sizeof(double);
   const size_t smem = smem_p + (DE_STG ? (size_t)Cfg::WARPS * 2 * 8 * (MP + 8) * sizeof(double) : 0);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need(e->device)) {
     int rc = set_max_smem(prune_dmma_edge_kernel<MP, 2, true, DE_RA, DE_STG>, smem);
     if (rc) return rc;
     rc = set_max_smem(prune_dmma_edge_kernel<MP, 3, false, 1>, smem_p);
     if (rc) return rc;
-    configured = true;
   }
   const int grid = std::max(1, std::min(a.total_tiles, e->n_sm));
   cudaLaunchConfig_t cfg = {};
@@ -300,13 +321,12 @@ int dmma_blocks_per_sm(int MP) {
 template <int K, int NC>
 int launch_strip(c3_engine* e, const PruneArgs& a, bool is_root) {
   using Cfg = P4SCfg<K, NC>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need(e->device)) {
     int rc = set_max_smem(prune4_strip_kernel<K, NC, false>, Cfg::SMEM_BYTES);
     if (rc) return rc;
     rc = set_max_smem(prune4_strip_kernel<K, NC, true>, Cfg::SMEM_BYTES);
     if (rc) return rc;
-    configured = true;
   }
   // one CTA per SM (shared memory bound); never more warps than strips
   const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + Cfg::WARPS - 1) / Cfg::WARPS));
@@ -350,11 +370,10 @@ int launch_reg(c3_engine* e, const PruneArgs& a, bool is_root) {
 
 template <int K>
 int launch_flow(c3_engine* e, const PruneArgs& a, const int32_t* d_dep, unsigned int* d_done) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need(e->device)) {
     int rc = set_max_smem(prune4_flow_kernel<K>, sizeof(FlowSmem));
     if (rc) return rc;
-    configured = true;
   }
   // every CTA must be resident (the kernel waits on other CTAs' progress): one CTA per SM
   const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + 7) / 8));
@@ -587,6 +606,10 @@ int ensure_slots(c3_engine* e, int n) {
 
 int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out, bool deferred = false);
 int finish_deferred(c3_engine* e, double* host_out);
+int collect_result(c3_engine* e);
+void resync_results(c3_engine* e);
+bool wants_auto_rescale(const c3_engine* e);
+int after_auto_rescale(c3_engine* e);
 int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used);
 int activate_rescaling(c3_engine* e);
 void deactivate_rescaling(c3_engine* e);
@@ -726,8 +749,12 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   C3_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   e->own_stream = true;
   C3_CUDA(cudaEventCreateWithFlags(&e->block_copied, cudaEventDisableTiming));
-  C3_CUDA(cudaHostAlloc(&e->h_lnl, sizeof(double), cudaHostAllocMapped));
+  C3_CUDA(cudaHostAlloc(&e->h_lnl, 64, cudaHostAllocMapped));
+  std::memset(e->h_lnl, 0, 64);
   C3_CUDA(cudaHostGetDevicePointer(&e->h_lnl_dev, e->h_lnl, 0));
+  e->h_seq = reinterpret_cast<volatile unsigned long long*>(e->h_lnl + 1);
+  e->h_seq_dev = reinterpret_cast<unsigned long long*>(e->h_lnl_dev + 1);
+  if (const char* env = getenv("C3_SPIN")) e->spin_wait = atoi(env) != 0;
   e->stats.n_levels = e->n_levels;
   e->stats.padded_states = e->MP;
   *out = e;
@@ -1232,6 +1259,8 @@ int c3_finalize(c3_engine* e) {
   e->d_lh = reinterpret_cast<double*>(e->d_pool + o_lh);
   e->d_tile_sums = reinterpret_cast<double*>(e->d_pool + o_tiles);
   e->d_counter = reinterpret_cast<unsigned int*>(e->d_pool + o_counter);
+  e->d_seq = reinterpret_cast<unsigned long long*>(e->d_pool + o_counter + 8);
+  e->d_epoch = reinterpret_cast<unsigned long long*>(e->d_pool + o_counter + 16);
   e->d_lnl = reinterpret_cast<double*>(e->d_pool + o_lnl);
   e->d_done = reinterpret_cast<unsigned int*>(e->d_pool + o_done);
   C3_CUDA(cudaMemcpyAsync(e->d_counts, e->counts.data(), root_rows * sizeof(double),
@@ -1504,17 +1533,48 @@ int c3_evaluate_many(c3_engine** engines, int n, double* lnL) {
     if (brc != C3_OK) return brc;
     if (used_batch) return C3_OK;
   }
-  // launch every engine's evaluation on its own stream, then collect: small problems overlap
+  // launch every engine's evaluation on its own stream (and device), then collect: small problems
+  // overlap, and engines whose reductions exchange shard values (c3_comm_attach) are all in flight
+  // before anybody waits
   int rc = C3_OK;
   int launched = 0;
   for (; launched < n; ++launched) {
     rc = run_evaluation(engines[launched], nullptr, false, nullptr, true);
     if (rc != C3_OK) break;
   }
+  bool any_auto = false;
   for (int i = 0; i < launched; ++i) {
-    const int rc2 = finish_deferred(engines[i], lnL + i);
+    c3_engine* e = engines[i];
+    if (e->deferred_pending) {
+      e->deferred_pending = false;
+      const int rc2 = collect_result(e);
+      if (rc == C3_OK) rc = rc2;
+    }
+    lnL[i] = e->cached_lnl;
+    any_auto = any_auto || (rc == C3_OK && wants_auto_rescale(e));
+  }
+  if (rc != C3_OK || launched < n || !any_auto) return rc;
+  // a -inf somewhere: the engines concerned switch to rescaled rows TOGETHER (sharded engines all see
+  // the same total and must re-evaluate in lock-step) and are evaluated again, launched before waited for
+  std::vector<c3_engine*> again;
+  for (int i = 0; i < n; ++i)
+    if (wants_auto_rescale(engines[i])) again.push_back(engines[i]);
+  for (c3_engine* e : again) {
+    rc = activate_rescaling(e);
+    if (rc != C3_OK) return rc;
+  }
+  for (c3_engine* e : again) {
+    rc = run_evaluation(e, nullptr, false, nullptr, true);
+    if (rc != C3_OK) return rc;
+  }
+  for (c3_engine* e : again) {
+    e->deferred_pending = false;
+    const int rc2 = collect_result(e);
     if (rc == C3_OK) rc = rc2;
   }
+  if (rc == C3_OK)
+    for (c3_engine* e : again) after_auto_rescale(e);
+  for (int i = 0; i < n; ++i) lnL[i] = engines[i]->cached_lnl;
   return rc;
 }
 
@@ -1559,15 +1619,35 @@ int c3_comm_attach(c3_engine* e, int nranks, int rank, const unsigned char* ipc_
   C3_REQUIRE(ipc_handles != nullptr || device_ptrs != nullptr || nranks == 1, "no peer mailboxes given");
   C3_REQUIRE(e->comm.nranks == 0, "already attached");
   C3_CUDA(cudaSetDevice(e->device));
+  C3_REQUIRE(e->finalized, "call c3_finalize first");
   CommArgs c{};
   c.nranks = nranks;
   c.rank = rank;
-  c.epoch = 0;
+  c.epoch_ctr = e->d_epoch;
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  // evaluations are numbered from 1 (epoch 0 is what an empty mailbox slot holds).  The mailbox itself
+  // is zeroed when it is allocated and again by c3_comm_detach -- never here: a peer that attached
+  // earlier may already be writing into it
+  C3_CUDA(cudaMemset(e->d_epoch, 0, sizeof(unsigned long long)));
   for (int r = 0; r < nranks; ++r) {
     if (r == rank) {
       c.peer[r] = e->d_mailbox;
     } else if (device_ptrs != nullptr) {
       C3_REQUIRE(device_ptrs[r] != nullptr, "null peer mailbox");
+      // an engine on another GPU of this process: its mailbox must be mapped into this device
+      cudaPointerAttributes attr{};
+      if (cudaPointerGetAttributes(&attr, device_ptrs[r]) == cudaSuccess && attr.type == cudaMemoryTypeDevice &&
+          attr.device != e->device) {
+        int can = 0;
+        C3_CUDA(cudaDeviceCanAccessPeer(&can, e->device, attr.device));
+        if (!can) return fail(C3_ERR_CUDA, "no peer access between the devices of the sharded engines");
+        const cudaError_t perr = cudaDeviceEnablePeerAccess(attr.device, 0);
+        if (perr != cudaSuccess && perr != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(C3_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(perr));
+        cudaGetLastError();
+      } else {
+        cudaGetLastError();
+      }
       c.peer[r] = static_cast<CommSlot*>(device_ptrs[r]);
     } else {
       cudaIpcMemHandle_t h;
@@ -1585,6 +1665,7 @@ int c3_comm_attach(c3_engine* e, int nranks, int rank, const unsigned char* ipc_
     }
   }
   e->comm = c;
+  clear_graphs(e);  // the reduction's arguments changed
   // a cached value is a shard value: it must not be served as the total
   e->have_cached = false;
   e->reduce_dirty = true;
@@ -1597,7 +1678,10 @@ int c3_comm_detach(c3_engine* e) {
   C3_CUDA(cudaStreamSynchronize(e->stream));
   for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
   e->ipc_opened.clear();
+  // every rank has consumed the values of the last common evaluation: nobody writes here any more
+  if (e->d_mailbox) C3_CUDA(cudaMemset(e->d_mailbox, 0, (size_t)2 * e->mailbox_ranks * sizeof(CommSlot)));
   e->comm = CommArgs{};
+  clear_graphs(e);
   e->have_cached = false;
   e->reduce_dirty = true;
   return C3_OK;
@@ -2015,8 +2099,9 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   int64_t n_launch = 0;
   e->prof.clear();
   e->events_used = 0;
-  CommArgs comm = e->comm;
-  if (comm.nranks > 1) comm.epoch = ++e->comm.epoch;  // every rank evaluates in lock-step
+  const CommArgs comm = e->comm;  // (its evaluation number lives in device memory: every rank evaluates in lock-step)
+  const bool to_host = blocking || deferred;
+  const ResultSink sink{e->d_lnl, device_out, to_host ? e->h_lnl_dev : nullptr, e->h_seq_dev, e->d_seq};
 
   // small problems whose root sits in the (last) small-levels launch: that launch also reduces
   // (prune4_small_kernel's tail: the same tiles and summation trees, one launch fewer)
@@ -2036,8 +2121,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     const int threads = (M <= 4) ? 32 : (M <= 16 ? 64 : (M <= 32 ? 256 : 1024));
     // sP + exp(roots) + (large M) the staged W / evI planes, complex-capable
     const size_t smem = (size_t)(MP * MP + 2 * M + (M > 8 ? 4 * M * (M | 1) : 0)) * sizeof(double);
-    static bool cfg = false;
-    if (!cfg) { int rc = set_max_smem(expm_eigen_kernel, (size_t)(64 * 64 + 128 + 4 * 64 * 65) * 8); if (rc) return rc; cfg = true; }
+    static DeviceOnce cfg;
+    if (cfg.need(e->device)) { int rc = set_max_smem(expm_eigen_kernel, (size_t)(64 * 64 + 128 + 4 * 64 * 65) * 8); if (rc) return rc; }
     ProfScope ps(e, 0, 0, 0);
     expm_eigen_kernel<<<n_eigen, threads, smem, e->stream>>>(d_jobs, e->d_slots, e->slot_stride, e->d_edges,
                                                             M, MP, K);
@@ -2046,8 +2131,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   if (n_pade > 0) {
     const int threads = (M <= 4) ? 32 : (M <= 16 ? 128 : (M <= 32 ? 256 : 1024));
     const size_t smem = (size_t)5 * MP * MP * sizeof(double);
-    static bool cfg = false;
-    if (!cfg) { int rc = set_max_smem(expm_pade_kernel, (size_t)5 * 64 * 64 * 8); if (rc) return rc; cfg = true; }
+    static DeviceOnce cfg;
+    if (cfg.need(e->device)) { int rc = set_max_smem(expm_pade_kernel, (size_t)5 * 64 * 64 * 8); if (rc) return rc; }
     ProfScope ps(e, 1, 0, 0);
     expm_pade_kernel<<<n_pade, threads, smem, e->stream>>>(d_jobs + n_eigen, e->d_slots, e->slot_stride,
                                                           e->d_edges, M, MP, K);
@@ -2083,11 +2168,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       cfg.gridDim = dim3(ctas);
       cfg.blockDim = dim3(SMALL_THREADS);
       cfg.dynamicSmemBytes = sizeof(SmallSmem);
-      static bool small_cfg = false;
-      if (!small_cfg) {
+      static DeviceOnce small_cfg;
+      if (small_cfg.need(e->device)) {
         int rc = set_max_smem(prune4_small_kernel, sizeof(SmallSmem));
         if (rc) return rc;
-        small_cfg = true;
       }
       cfg.stream = e->stream;
       cudaLaunchAttribute attr[2];
@@ -2105,9 +2189,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
         tail.counts = e->d_counts;
         tail.n_rows = e->n_rows[e->root];
         tail.n_tiles = (int)((tail.n_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
-        tail.d_lnl = e->d_lnl;
-        tail.d_lnl2 = device_out;
-        tail.h_lnl = (blocking || deferred) ? e->h_lnl_dev : nullptr;
+        tail.sink = sink;
       }
       cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel, a, d_small, ll.n_small, ll.n_work,
                                            ll.n_work + ll.n_small, tail);
@@ -2156,9 +2238,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     const double* a_lh = e->d_lh;
     const double* a_bp = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
     const double* a_counts = e->d_counts;
-    volatile double* a_host = (blocking || deferred) ? e->h_lnl_dev : nullptr;
     cudaError_t err = cudaLaunchKernelEx(&cfg, lnl_reduce_kernel, a_lh, a_bp, a_counts, (int64_t)rows, K, n_tiles,
-                                         e->d_tile_sums, e->d_counter, e->d_lnl, device_out, a_host, comm,
+                                         e->d_tile_sums, e->d_counter, sink, comm,
                                          (const int32_t*)(e->rescale_active ? e->scale_rec[e->root].d_exps : nullptr));
     ++n_launch;
     if (err == cudaSuccess) err = cudaGetLastError();
@@ -2170,7 +2251,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   // ---- direct launches, or capture / replay of this structure's graph ---------------------------
   bool graphed = false;
   e->plan = c3_engine::PlanStats{n_eigen + n_pade, n_dirty_nodes, node_rows, alg_bytes, flops, h2d_bytes};
-  const bool graph_ok = e->use_graphs && !e->profiling && comm.nranks <= 1 && !any_flow;
+  const bool graph_ok = e->use_graphs && !e->profiling && !any_flow;
   if (e->batch_mode != 0 && !graph_ok) return fail(C3_ERR_INVALID, "engine cannot take part in a batch graph");
   if (graph_ok) {
     std::vector<int32_t> sig;
@@ -2258,6 +2339,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   } else if (e->batch_mode == 0) {
     C3_CUDA(cudaEventRecord(e->block_copied, e->stream));  // (a replay frees the staging buffer when it is through)
   }
+  if (to_host) ++e->seq_issued;  // the launches just issued (or replayed, or captured) publish one more result
   commit_evaluation(e, n_launch, graphed && e->batch_mode == 0);
 
   if (deferred) {
@@ -2265,25 +2347,22 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     return C3_OK;
   }
   if (blocking) {
-    cudaError_t err = cudaStreamSynchronize(e->stream);
-    if (err != cudaSuccess) {
-      e->have_cached = false;
-      c3_invalidate(e);
-      return fail(C3_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(err));
-    }
-    for (auto& r : e->prof) cudaEventElapsedTime(&r.ms, r.a, r.b);
-    e->cached_lnl = *e->h_lnl;
-    e->have_cached = true;
-    if (!std::isfinite(e->cached_lnl) && e->rescale_mode == C3_RESCALE_AUTO && !e->rescale_active) {
+    int rc = collect_result(e);
+    if (rc) return rc;
+    if (wants_auto_rescale(e)) {
       // some pattern's likelihood left the FP64 range (the reference returns -inf here,
-      // evolve/likelihood_tree.py:10): switch to rescaled rows for good and evaluate again.
+      // evolve/likelihood_tree.py:10): switch to rescaled rows and evaluate again.
       // Sharded runs: every rank sees the same total, so every rank takes this branch.
-      int rc = activate_rescaling(e);
+      rc = activate_rescaling(e);
       if (rc) return rc;
-      return run_evaluation(e, device_out, blocking, host_out, deferred);
+      rc = run_evaluation(e, device_out, blocking, nullptr, deferred);
+      if (rc) return rc;
+      rc = after_auto_rescale(e);
+      if (rc) return rc;
     }
     if (host_out) *host_out = e->cached_lnl;
   } else {
+    e->async_pending = true;
     e->have_cached = true;  // value lives in d_lnl; the host copy is refreshed lazily
     e->cached_lnl = NAN;
     e->reduce_dirty = true;  // a later blocking call must re-run the reduction for the host value
@@ -2291,22 +2370,94 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   return C3_OK;
 }
 
+// after a real stream synchronisation the mapped words hold the last result: take its number as issued
+void resync_results(c3_engine* e) {
+  cudaStreamSynchronize(e->stream);
+  e->seq_issued = *e->h_seq;
+}
+
+// Wait for the result of the last evaluation issued towards the host and cache it.  The reduction
+// writes the value and then (system fence in between) its sequence number into mapped pinned memory;
+// spinning on that word returns within a PCIe write of the kernel's last store, where
+// cudaStreamSynchronize adds the driver's completion path (several microseconds -- a tenth of a
+// brca1-sized evaluation).  Long evaluations fall back to the blocking synchronisation.
+int collect_result(c3_engine* e) {
+  cudaError_t err = cudaSuccess;
+  bool synced = false;
+  if (e->spin_wait && !e->profiling) {
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned n = 0;
+    while (*e->h_seq != e->seq_issued) {
+      if ((++n & 255u) == 0 &&
+          std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) {
+        err = cudaStreamSynchronize(e->stream);
+        synced = true;
+        break;
+      }
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  } else {
+    err = cudaStreamSynchronize(e->stream);
+    synced = true;
+  }
+  if (err != cudaSuccess) {
+    e->have_cached = false;
+    c3_invalidate(e);
+    cudaGetLastError();
+    e->seq_issued = *e->h_seq;
+    return fail(C3_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(err));
+  }
+  if (synced) e->seq_issued = *e->h_seq;  // stream order: the words hold the last result whatever its number
+  for (auto& r : e->prof) cudaEventElapsedTime(&r.ms, r.a, r.b);
+  e->async_pending = false;  // stream order: everything issued before the reduction is through as well
+  e->cached_lnl = *e->h_lnl;
+  e->have_cached = true;
+  unsigned long long bits;
+  std::memcpy(&bits, &e->cached_lnl, sizeof bits);
+  if (bits == C3_TIMEOUT_NAN_BITS) {
+    // the fused all-reduce gave up waiting for a peer: the ranks are out of step, no value to return
+    e->have_cached = false;
+    c3_invalidate(e);
+    return fail(C3_ERR_CUDA, "fused all-reduce: a peer rank did not deliver its shard value within 30 s");
+  }
+  if (std::isfinite(e->cached_lnl)) e->auto_futile = false;
+  return C3_OK;
+}
+
+// AUTO rescaling switches on for a log-likelihood of -inf only: NaN (bad parameters) and +inf are the
+// caller's business (the optimiser treats them as out of bounds), as they are with the reference
+bool wants_auto_rescale(const c3_engine* e) {
+  return e->rescale_mode == C3_RESCALE_AUTO && !e->rescale_active && !e->auto_futile &&
+         std::isinf(e->cached_lnl) && e->cached_lnl < 0;
+}
+
+// ... and stays on only if it helped: a pattern whose likelihood is truly 0 (an impossible fixed motif,
+// a zero in P) is -inf with and without rescaling, which would otherwise cost 5-38 % for good
+int after_auto_rescale(c3_engine* e) {
+  if (e->rescale_active && std::isinf(e->cached_lnl) && e->cached_lnl < 0) {
+    const double keep = e->cached_lnl;
+    deactivate_rescaling(e);  // (everything is recomputed, plainly, by the next evaluation)
+    e->auto_futile = true;
+    e->cached_lnl = keep;
+  }
+  return C3_OK;
+}
+
 int finish_deferred(c3_engine* e, double* host_out) {
   if (e->deferred_pending) {
-    cudaError_t err = cudaStreamSynchronize(e->stream);
     e->deferred_pending = false;
-    if (err != cudaSuccess) {
-      e->have_cached = false;
-      c3_invalidate(e);
-      return fail(C3_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(err));
-    }
-    for (auto& r : e->prof) cudaEventElapsedTime(&r.ms, r.a, r.b);
-    e->cached_lnl = *e->h_lnl;
-    e->have_cached = true;
-    if (!std::isfinite(e->cached_lnl) && e->rescale_mode == C3_RESCALE_AUTO && !e->rescale_active) {
-      int rc = activate_rescaling(e);
+    int rc = collect_result(e);
+    if (rc) return rc;
+    if (wants_auto_rescale(e)) {
+      rc = activate_rescaling(e);
       if (rc) return rc;
-      return run_evaluation(e, nullptr, true, host_out);
+      rc = run_evaluation(e, nullptr, true, nullptr);
+      if (rc) return rc;
+      rc = after_auto_rescale(e);
+      if (rc) return rc;
     }
   }
   if (host_out) *host_out = e->cached_lnl;
@@ -2331,7 +2482,9 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
       return C3_OK;
     for (const Slot& s : e->slots)
       if (s.dirty) return C3_OK;  // rate matrices changed: their upload is not part of the graph
-    if (e->rescale_mode == C3_RESCALE_ON && !e->rescale_active) return C3_OK;
+    // a pending change of the rescaling mode is applied by the per-engine path (it drops every
+    // batch graph: nothing below may hold a reference into g_batches across it)
+    if ((e->rescale_mode == C3_RESCALE_ON) != e->rescale_active && e->rescale_mode != C3_RESCALE_AUTO) return C3_OK;
     for (int j = 0; j < i; ++j)
       if (engines[j] == e) return C3_OK;
     key ^= (uint64_t)(uintptr_t)e;
@@ -2386,6 +2539,7 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
       for (int i = 0; i < n; ++i) {
         engines[i]->deferred_pending = false;
         c3_invalidate(engines[i]);
+        resync_results(engines[i]);  // (what was captured never ran)
       }
       return C3_OK;
     }
@@ -2398,6 +2552,7 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
       for (int i = 0; i < n; ++i) {
         engines[i]->deferred_pending = false;
         c3_invalidate(engines[i]);
+        resync_results(engines[i]);
       }
       return C3_OK;
     }
@@ -2417,10 +2572,18 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
     if (!same) return C3_OK;  // e.g. a single-branch update this time: the per-engine path plans again
     for (int i = 0; i < n; ++i) {
       commit_evaluation(engines[i], bg.n_launch[i], true);
+      ++engines[i]->seq_issued;
       engines[i]->deferred_pending = true;
     }
   }
   cudaStream_t s0 = engines[0]->stream;
+  // the graph runs from s0: asynchronous work still pending on another engine's own stream
+  // (c3_evaluate_device) must be through before the replay touches that engine's buffers
+  for (int i = 0; i < n; ++i)
+    if (engines[i]->async_pending) {
+      C3_CUDA(cudaStreamSynchronize(engines[i]->stream));
+      engines[i]->async_pending = false;
+    }
   C3_CUDA(cudaGraphLaunch(bg.exec, s0));
   // (no block_copied records: the call waits for the whole graph below, so every staging buffer is free again
   // by the time anybody plans the next evaluation)
@@ -2430,6 +2593,7 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
       engines[i]->deferred_pending = false;
       engines[i]->have_cached = false;
       c3_invalidate(engines[i]);
+      engines[i]->seq_issued = *engines[i]->h_seq;
     }
     return fail(C3_ERR_CUDA, std::string("batched evaluation failed: ") + cudaGetErrorString(err));
   }
@@ -2437,12 +2601,20 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
   for (int i = 0; i < n; ++i) {
     c3_engine* e = engines[i];
     e->deferred_pending = false;
+    e->async_pending = false;
+    e->seq_issued = *e->h_seq;  // (the whole graph is through: the mapped words hold this batch's results)
     e->cached_lnl = *e->h_lnl;
     e->have_cached = true;
+    if (std::isfinite(e->cached_lnl)) e->auto_futile = false;
     lnL[i] = e->cached_lnl;
-    if (!std::isfinite(e->cached_lnl) && e->rescale_mode == C3_RESCALE_AUTO && !e->rescale_active) {
+  }
+  for (int i = 0; i < n; ++i) {
+    c3_engine* e = engines[i];
+    if (wants_auto_rescale(e)) {
       int rc2 = activate_rescaling(e);  // (drops the batch graphs: the structures change)
-      if (rc2 == C3_OK) rc2 = run_evaluation(e, nullptr, true, lnL + i);
+      if (rc2 == C3_OK) rc2 = run_evaluation(e, nullptr, true, nullptr);
+      if (rc2 == C3_OK) rc2 = after_auto_rescale(e);
+      lnL[i] = e->cached_lnl;
       if (rc == C3_OK) rc = rc2;
       if (rc2 != C3_OK) break;
     }

@@ -18,6 +18,11 @@
 
 namespace c3 {
 
+// numpy.maximum(result, 0.0) (maths/matrix_exponentiation.py:40) PROPAGATES NaN; fmax(NaN, 0) would
+// return 0 and turn a NaN rate matrix / distance into a finite likelihood
+__device__ __forceinline__ double clamp0(double v) { return v < 0.0 ? 0.0 : v; }
+
+
 // tip_state[u] >= 0: row u is the indicator of that one state (an unambiguous symbol), so its inner
 // product with the rows of P is just a column of P -- the same bits as the sum (every other term is
 // fma(0, x, s) = s).  Only ambiguity codes and the gap row run the sum.  (ncu on the 61-state
@@ -124,7 +129,7 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
           a10 += w1r * v0r - w1i * v0i;
           a11 += w1r * v1r - w1i * v1i;
         }
-        const double r[2][2] = {{fmax(a00, 0.0), fmax(a01, 0.0)}, {fmax(a10, 0.0), fmax(a11, 0.0)}};
+        const double r[2][2] = {{clamp0(a00), clamp0(a01)}, {clamp0(a10), clamp0(a11)}};
         for (int di = 0; di < 2; ++di)
           for (int dj = 0; dj < 2; ++dj)
             if (i0 + di * T < M && j0 + dj * T < M) {
@@ -146,7 +151,7 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
           // Re(w * evI[j,k])             (numpy.inner(...).real)
           acc += wr * br - wi * bi;
         }
-        acc = fmax(acc, 0.0);
+        acc = clamp0(acc);
         sP[i * MP + j] = acc;
         Pout[i * MP + j] = acc;
       }
@@ -181,7 +186,7 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
           a10 += w1 * v0;
           a11 += w1 * v1;
         }
-        const double r[2][2] = {{fmax(a00, 0.0), fmax(a01, 0.0)}, {fmax(a10, 0.0), fmax(a11, 0.0)}};
+        const double r[2][2] = {{clamp0(a00), clamp0(a01)}, {clamp0(a10), clamp0(a11)}};
         for (int di = 0; di < 2; ++di)
           for (int dj = 0; dj < 2; ++dj)
             if (i0 + di * T < M && j0 + dj * T < M) {
@@ -194,7 +199,7 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
         const int i = o / M, j = o - i * M;
         double acc = 0.0;
         for (int k = 0; k < M; ++k) acc += (evT[i * M + k] * s_er[k]) * evI[j * M + k];
-        acc = fmax(acc, 0.0);
+        acc = clamp0(acc);
         sP[i * MP + j] = acc;
         Pout[i * MP + j] = acc;
       }

@@ -1181,14 +1181,25 @@ __device__ __forceinline__ double reduce_tile_partial(const double* __restrict__
 
 // the reduction of a small problem done by the small-levels kernel itself (no separate launch)
 constexpr int SMALL_REDUCE_MAX_TILES = 8;
+__device__ __forceinline__ void publish_result(const ResultSink& r, double total) {
+  *r.d_lnl = total;
+  if (r.d_lnl2) *r.d_lnl2 = total;
+  if (r.h_lnl) {
+    *r.h_lnl = total;
+    __threadfence_system();  // the value is visible to the host before the sequence number is
+    const unsigned long long s = *r.seq_ctr + 1;
+    *r.seq_ctr = s;
+    *r.h_seq = s;
+  }
+  __threadfence_system();
+}
+
 struct ReduceTail {
   const double* bprobs;
   const double* counts;
   int64_t n_rows;
   int n_tiles;  // 0: no fused reduction
-  double* d_lnl;
-  double* d_lnl2;
-  volatile double* h_lnl;
+  ResultSink sink;
 };
 
 // n_work_total / n_prefix_total: sizes of the launch's work and prefix arrays.  When they
@@ -1294,12 +1305,7 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
     if (t < REDUCE_THREADS)
       for (int i = t; i < tail.n_tiles; i += REDUCE_THREADS) acc += s_tiles[i];
     const double total = block_sum(acc, s_warp);
-    if (t == 0) {
-      *tail.d_lnl = total;
-      if (tail.d_lnl2) *tail.d_lnl2 = total;
-      if (tail.h_lnl) *tail.h_lnl = total;
-      __threadfence_system();
-    }
+    if (t == 0) publish_result(tail.sink, total);
   }
 }
 
@@ -2069,9 +2075,7 @@ __global__ void __launch_bounds__(REDUCE_THREADS)
 lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bprobs,
                   const double* __restrict__ counts, int64_t n_rows, int K, int n_tiles,
                   double* __restrict__ tile_sums, unsigned int* __restrict__ counter,
-                  double* __restrict__ d_lnl, double* __restrict__ d_lnl2,
-                  volatile double* __restrict__ h_lnl, const CommArgs comm,
-                  const int32_t* __restrict__ root_exp) {
+                  const ResultSink sink, const CommArgs comm, const int32_t* __restrict__ root_exp) {
   __shared__ double s_warp[REDUCE_THREADS / 32];
   __shared__ bool s_last;
   pdl_wait();  // launched early (programmatic dependent launch): lh is the root launch's output
@@ -2094,42 +2098,56 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
   double total = block_sum(acc, s_warp);
   if (comm.nranks > 1) {
     __shared__ double s_shard[C3_MAX_RANKS];
+    __shared__ int s_ok[C3_MAX_RANKS];
     __shared__ double s_local;
-    if (threadIdx.x == 0) s_local = total;
+    __shared__ unsigned long long s_epoch;
+    if (threadIdx.x == 0) {
+      s_local = total;
+      // this evaluation's number: one more than the last one's (only this CTA ever touches the counter)
+      s_epoch = *comm.epoch_ctr + 1;
+      *comm.epoch_ctr = s_epoch;
+    }
     __syncthreads();
     const int r = threadIdx.x;
     if (r < comm.nranks) {
-      const int parity = (int)(comm.epoch & 1ull);
+      const unsigned long long epoch = s_epoch;
+      const int parity = (int)(epoch & 1ull);
       // my value into rank r's mailbox
       CommSlot* dst = comm.peer[r] + parity * comm.nranks + comm.rank;
       *reinterpret_cast<volatile double*>(&dst->value) = s_local;
-      st_release_sys_u64(&dst->epoch, comm.epoch);
+      st_release_sys_u64(&dst->epoch, epoch);
       // rank r's value out of my mailbox
       const CommSlot* src = comm.peer[comm.rank] + parity * comm.nranks + r;
       const unsigned long long t0 = globaltimer_ns();
-      double v = __longlong_as_double(0x7ff8000000000000ll);  // NaN unless the peer shows up
+      double v = 0.0;
+      int ok = 0;
       while (true) {
-        if (ld_acquire_sys_u64(&src->epoch) == comm.epoch) {
+        if (ld_acquire_sys_u64(&src->epoch) == epoch) {
           v = *reinterpret_cast<const volatile double*>(&src->value);
+          ok = 1;
           break;
         }
         if (globaltimer_ns() - t0 > 30000000000ull) break;
         __nanosleep(200);
       }
       s_shard[r] = v;
+      s_ok[r] = ok;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       total = 0.0;
-      for (int i = 0; i < comm.nranks; ++i) total += s_shard[i];
+      bool all = true;
+      for (int i = 0; i < comm.nranks; ++i) {
+        total += s_shard[i];
+        all = all && s_ok[i] != 0;
+      }
+      // a peer that never showed up: a marked NaN (the host returns an error, not a value)
+      if (!all) total = __longlong_as_double((long long)C3_TIMEOUT_NAN_BITS);
     }
   }
   if (threadIdx.x == 0) {
-    *d_lnl = total;
-    if (d_lnl2) *d_lnl2 = total;
-    if (h_lnl) *h_lnl = total;
     *counter = 0u;
-    __threadfence_system();
+    publish_result(sink, total);
   }
 }
 

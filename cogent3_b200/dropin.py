@@ -245,12 +245,13 @@ def _build(cogent3_modules):
 
         name = "gpu_lnL"
 
-        def setup(self, edge_names, internal_names, n_bins, engine_factory, device, n_loci=1):
+        def setup(self, edge_names, internal_names, n_bins, engine_factory, device, n_loci=1, devices=None):
             self.edge_names = list(edge_names)
             self.internal_names = list(internal_names)
             self.n_bins = n_bins
             self.engine_factory = engine_factory
             self.device = device
+            self.devices = list(devices) if devices else None
             # id(lht) -> state, least recently used first.  The Defn instance (and so this cache) is
             # shared by every locus cell behind SumDefn(*tll.across_dimension("locus", ...)): it must
             # hold one engine per locus plus one for the Calculator's 1-deep undo
@@ -283,7 +284,14 @@ def _build(cogent3_modules):
             # a new alignment (or locus): flatten cogent3's own pattern tables -- they stay
             # the source of truth -- and make the tables resident on the device
             topo, patterns = from_reference_lht(lht)
-            engine = self.engine_factory(patterns, self.n_bins, device=self.device)
+            if self.devices and len(self.devices) > 1:
+                # site patterns sharded over several GPUs of this process (cogent3_b200/multidevice.py)
+                from .multidevice import MultiDeviceEngine
+
+                engine = MultiDeviceEngine(patterns, self.n_bins, devices=self.devices, engine_cls=self.engine_factory)
+            else:
+                device = self.devices[0] if self.devices else self.device
+                engine = self.engine_factory(patterns, self.n_bins, device=device)
             node_of = {name: i for i, name in enumerate(topo.names)}
             st = {
                 "lht": lht,
@@ -466,7 +474,7 @@ def _build(cogent3_modules):
             return eng.evaluate()
 
     def make_total_loglikelihood_defn(tree, leaves, psubs, mprobs, bprobs, bin_names, locus_names,
-                                      sites_independent, engine_factory, device, factors=None):  # fmt: skip
+                                      sites_independent, engine_factory, device, factors=None, devices=None):  # fmt: skip
         """same signature and role as the reference function of this name
         (evolve/likelihood_calculation.py:125-134), plus the engine selection"""
         if not sites_independent:
@@ -500,7 +508,7 @@ def _build(cogent3_modules):
             tll = GpuFactoredLogLikelihoodDefn(
                 *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
                 engine_factory=engine_factory, device=device, has_rate=rate is not None,
-                n_loci=len(locus_names),
+                n_loci=len(locus_names), devices=devices,
             )  # fmt: skip
         else:
             for name in edge_names:
@@ -511,7 +519,7 @@ def _build(cogent3_modules):
                     args.append(p_e.select_from_dimension("bin", bin_names[0]))
             tll = GpuLogLikelihoodDefn(
                 *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
-                engine_factory=engine_factory, device=device, n_loci=len(locus_names),
+                engine_factory=engine_factory, device=device, n_loci=len(locus_names), devices=devices,
             )  # fmt: skip
         if len(locus_names) > 1:
             tll = SumDefn(*tll.across_dimension("locus", locus_names))
@@ -521,11 +529,12 @@ def _build(cogent3_modules):
 
     class CudaAlignmentLikelihoodFunction(parameter_controller.AlignmentLikelihoodFunction):
         """``AlignmentLikelihoodFunction`` (evolve/parameter_controller.py:511-570) whose
-        likelihood sub-graph runs on the GPU.  Extra constructor keywords:
-        ``engine_factory`` (test seam) and ``device``."""
+        likelihood sub-graph runs on the GPU.  Extra constructor keywords: ``device`` (CUDA ordinal),
+        ``devices=[0, 1, ...]`` (site patterns sharded over several GPUs of this process),
+        ``engine_factory`` (test seam)."""
 
         def make_likelihood_defn(self, sites_independent=True, discrete_edges=None,
-                                 engine_factory=None, device=0, factored=True):  # fmt: skip
+                                 engine_factory=None, device=0, factored=True, devices=None):  # fmt: skip
             # constructor kwargs land in _serialisable (parameter_controller.py:62-66);
             # a callable cannot be serialised, so it is dropped from there
             self._serialisable.pop("engine_factory", None)
@@ -575,7 +584,7 @@ def _build(cogent3_modules):
             return make_total_loglikelihood_defn(
                 self.tree, leaves, psubs, defns["word_probs"], defns["bprobs"],
                 self.bin_names, self.locus_names, sites_independent,
-                engine_factory or _default_engine_factory, device, factors=factors,
+                engine_factory or _default_engine_factory, device, factors=factors, devices=devices,
             )  # fmt: skip
 
         def set_motif_probs_from_data(self, align, locus=None, is_constant=None, include_ambiguity=False,
@@ -631,7 +640,7 @@ def _build(cogent3_modules):
             util/deserialise.py:118-140); the engine seams are not construction arguments"""
             data = super().to_rich_dict()
             data["type"] = "cogent3.evolve.parameter_controller.AlignmentLikelihoodFunction"
-            for key in ("engine_factory", "device", "factored"):
+            for key in ("engine_factory", "device", "devices", "factored"):
                 data.get("likelihood_construction", {}).pop(key, None)
             return data
 

@@ -622,3 +622,44 @@ def test_solved_models_and_measure_evals_per_second():
     calc = lf.make_calculator()
     rate = calc.measure_evals_per_second(time_limit=0.2, wall=True)
     assert rate > 0
+
+
+def test_patterns_sharded_over_devices_in_one_process():
+    """``devices=[...]``: the root's pattern rows are dealt in contiguous blocks to one engine per device;
+    lnL, per-pattern and per-column values are those of the unsharded function.  On a box
+    with one GPU all shards live on device 0 (the host logic and the fused mailbox sum are the same)."""
+    from cogent3_b200 import _lib
+
+    n_dev = max(1, _lib.device_count()) if ON_GPU else 1
+    tree, aln = small_problem(n_tips=10, L=900, seed=23)
+    mk = lambda: get_model("GTR", ordered_param="rate", distribution="gamma")  # noqa: E731
+    for n_shards in (2, 3, 8):
+        devices = [i % n_dev for i in range(n_shards)]
+        with installed():
+            lf = mk().make_likelihood_function(tree, bins=4, devices=devices)
+            one = mk().make_likelihood_function(tree, bins=4)
+            ref = mk().make_likelihood_function(tree, bins=4, backend="cpu")
+        for f in (ref, one, lf):
+            f.set_alignment(aln)
+            f.set_param_rule("bprobs", is_constant=True)
+            f.set_param_rule("rate_shape", value=0.6)
+            f.set_param_rule("A/G", value=2.9)
+        assert_same(ref, lf, rel=1e-12)
+        assert abs(lf.get_log_likelihood() - one.get_log_likelihood()) <= 1e-12 * abs(one.get_log_likelihood())
+        eng = lf._engine()
+        assert type(eng).__name__ == "MultiDeviceEngine" and len(eng.engines) == n_shards
+        np.testing.assert_allclose(np.asarray(lf.get_param_value("lh", bin="bin1")),
+                                   np.asarray(one.get_param_value("lh", bin="bin1")), rtol=0, atol=1e-15)  # fmt: skip
+        np.testing.assert_allclose(lf.get_full_length_likelihoods(), ref.get_full_length_likelihoods(), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(lf.get_bin_probs().array, ref.get_bin_probs().array, atol=1e-13)
+        for f in (ref, lf):
+            f.set_param_rule("length", edge=tree.get_tip_names()[3], value=0.33)
+        assert_same(ref, lf, rel=1e-12)
+        calc, rcalc = lf.make_calculator(), ref.make_calculator()
+        where = {(p.name, repr(p.scope)): i for i, p in enumerate(rcalc.opt_pars)}
+        perm = np.array([where[(p.name, repr(p.scope))] for p in calc.opt_pars])
+        x = np.array(rcalc.get_value_array())
+        for k in range(3):
+            xk = x * (1.0 + 0.01 * (k + 1))
+            a, b = rcalc(xk), calc(xk[perm])
+            assert abs(a - b) <= 1e-12 * abs(a)

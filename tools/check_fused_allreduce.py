@@ -20,8 +20,14 @@ from cogent3_b200.sharded import ShardedLikelihoodFunction  # noqa: E402
 from cogent3_b200.synthetic import make_workload  # noqa: E402
 
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-torch.cuda.set_device(local_rank)
-dist.init_process_group("nccl")
+world_env = int(os.environ.get("WORLD_SIZE", "1"))
+n_dev = torch.cuda.device_count()
+# fewer GPUs than ranks (the 1-GPU test box): the ranks share devices -- CUDA IPC maps a mailbox of
+# another PROCESS on the same device just as well -- and the process group is gloo (NCCL refuses two
+# ranks on one GPU); the reference value is then the host sum of the all-gathered shard values
+SHARED = n_dev < world_env
+torch.cuda.set_device(local_rank % n_dev)
+dist.init_process_group("gloo" if SHARED else "nccl")
 rank, world = dist.get_rank(), dist.get_world_size()
 m = hostmodels.get_model("GTR")
 topo, lengths, codes = make_workload(20, 200_000, 4, kind="evolved", seed=31)
@@ -33,6 +39,18 @@ def build(force_nccl):
     else:
         os.environ.pop("C3_SHARD_NCCL", None)
     lf = ShardedLikelihoodFunction(m, topo, bins=4)
+    if SHARED and force_nccl:
+        # no NCCL here: the shard value comes back to the host and the ranks' values are gathered
+        def host_sum(self=lf):
+            self.lf._sync()
+            vals = [None] * world
+            dist.all_gather_object(vals, self.lf.engine.evaluate())
+            total = 0.0
+            for v in vals:
+                total += v
+            return total
+
+        lf.get_log_likelihood = host_sum
     lf.set_alignment(codes)
     lf.set_motif_probs(np.array([0.2, 0.3, 0.25, 0.25]))
     lf.lengths[:-1] = np.asarray(lengths)[:-1]
