@@ -14,15 +14,24 @@ metric   pattern.edge partial updates/s = U_gp / time, with U_gp = K * sum over 
          per-node compression tables -- the same numerator for GPU and CPU.
 value    steps timed on the device (CUDA events on the engine's stream), pattern tables
          and partials resident in HBM, parameters arriving from the host each step.
-e2e      the same steps through the public API (LikelihoodFunction.set_param_rule /
-         get_log_likelihood): host Q build + eigendecomposition, H2D of the parameter
-         block, all kernels, D2H of the scalar; wall-clock with a device sync each side.
+e2e      the same metric END TO END THROUGH THE PRODUCT: unmodified cogent3 (baseline/_ref)
+         with cogent3_b200.install(); `calc = lf.make_calculator(); calc(x_k)` with every
+         optimisable parameter changed -- the call the reference arm times: cogent3's own
+         Q build, eigendecomposition and Calculator sweep on the host, host buffers into
+         c3_set_eigen / c3_update, all kernels, the scalar back through mapped pinned
+         memory; wall clock with a device sync each side.  (`e2e_mirror`: the same steps
+         through the repo's cogent3-free mirror API.)
 roofline the pruning kernels of one step: algorithmic bytes / CUDA-event time per launch
          (c3_get_launch_profile), against MEASURED_PEAKS.json.
-cpu_baseline  the oracle port (oracle/engine.py) on the host cores, bounded sample.
+cpu_baseline  unmodified cogent3 (kind "reference") on a bounded sample of the columns, the
+         oracle port next to it; `--impl reference` times cogent3 on the FULL C2 workload.
+c4       (default config, N = 1) the CNFGTR 61-state config measured the same way, roofline
+         bound "tensor" against max(DMMA issue-loop peak, cuBLAS DGEMM 8192^3) of this run.
+c5_strong  (default config) the ONE 10M-column C5 alignment split over the N ranks.
 
 With N>1 (torchrun) every rank holds its own column shard of the same size (weak
-scaling); the only collective is the NCCL all-reduce of the scalar lnL.
+scaling); the sum over ranks of the scalar lnL is fused into the reduction
+kernel (peer-memory mailboxes), NCCL all-reduce as the fallback.
 """
 
 from __future__ import annotations
@@ -379,8 +388,10 @@ def cogent3_arm(problem, cfg, budget_s=120.0, sample_columns=None, steps=20, war
                 if k >= steps or (k >= 3 and time.perf_counter() - t_start > budget_s / 2):
                     break
             calc(x)
-            evals = {"measure_evals_per_second": float(calc.measure_evals_per_second(time_limit=0.5, wall=True)),
-                     "single_parameter_real_changes_per_s": single_parameter_rate(calc, x, budget_s=1.0)} if Ls <= 60_000 else None  # fmt: skip
+            # the reference's own probe needs ~2 rounds over all parameters before it returns: small samples only
+            evals = {"measure_evals_per_second": (float(calc.measure_evals_per_second(time_limit=0.5, wall=True))
+                                                  if Ls <= 60_000 else None),
+                     "single_parameter_real_changes_per_s": single_parameter_rate(calc, x, budget_s=2.0, max_evals=400)}  # fmt: skip
         t = float(np.mean(times))
         rec = {"value": u_gp / t, "unit": UNIT, "cores": 1 if limit == 1 else os.cpu_count(),
                "kind": "reference", "mode": f"cogent3 Calculator, {label}",

@@ -40,6 +40,9 @@ class C3Stats(ctypes.Structure):
         ("graph_replays", c_int64),
         ("n_levels", c_int32),
         ("padded_states", c_int32),
+        ("wave_launches", c_int64),
+        ("wave_entries", c_int64),
+        ("wave_noops", c_int64),
     ]
 
     def as_dict(self):

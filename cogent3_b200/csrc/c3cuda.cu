@@ -134,6 +134,26 @@ struct c3_engine {
   // time is lower than the per-level launches' sum (C2 0.267 vs 0.289 ms, C3 0.435 vs 0.585 ms) but
   // the per-level launches overlap through programmatic dependent launch, so the STEP is not faster
   bool use_flow = false;
+  // wavefront kernel (prune4_wave_kernel): every dirty binary node of the sweep in one persistent launch, all
+  // levels streaming at once; the static strip schedule of a structure is built on the host the second time the
+  // structure comes up and kept on the device.  C3_WAVE=0 disables.
+  bool use_wave = true;
+  int wave_lag = 4;          // chunks between a strip and the strips it depends on (C3_WAVE_LAG)
+  int wave_prio = 128;       // strips a parent runs behind its children in the schedule's priority order (C3_WAVE_PRIO)
+  int64_t wave_min_strips = 4096;  // smaller sweeps keep the per-level / small-levels launches (C3_WAVE_MIN)
+  std::vector<char> idx_mono;      // [n_nodes] idx_c[p] <= p for every child and row (first-seen numbering)
+  struct WaveSched {
+    std::vector<int32_t> work;  // the structure: dirty non-root nodes, ascending
+    int2* d_sched = nullptr;
+    unsigned* d_done = nullptr;
+    int n_chunks = 0, grid = 0;
+    int64_t bytes = 0, strips = 0, noops = 0;
+    uint64_t last_use = 0;
+    double build_ms = 0;
+  };
+  std::unordered_map<uint64_t, WaveSched> waves;
+  std::unordered_map<uint64_t, int> wave_seen;
+  int64_t wave_bytes = 0;
   unsigned int* d_done = nullptr;  // per work item completion counters of the dataflow launches
   int64_t off_dep = 0;
   cudaEvent_t block_copied = nullptr;
@@ -413,6 +433,165 @@ int launch_reg2(c3_engine* e, const PruneArgs& a, bool is_root) {
   return C3_OK;
 }
 
+// ---- wavefront kernel: the static strip schedule of one structure (set of dirty non-root nodes) -----------
+// Strips are visited in priority order  w = k + prio * height(node)  (a parent `prio` strips behind its
+// children) and placed greedily into chunks of GW entries: a strip goes into the first chunk with room that lies
+// at least `lag` chunks after the chunks of the child strips it depends on (strip k of a node needs strips <= k of
+// its children: idx_c[p] <= p).  Entries of a chunk are ordered by (node, strip), so a warp keeps meeting the same
+// node chunk after chunk; positions nobody could fill are no-op entries.
+void free_wave(c3_engine* e, c3_engine::WaveSched& ws) {
+  if (ws.d_sched) cudaFree(ws.d_sched);
+  if (ws.d_done) cudaFree(ws.d_done);
+  e->wave_bytes -= ws.bytes;
+  e->stats.device_bytes -= ws.bytes;
+  ws.d_sched = nullptr;
+  ws.d_done = nullptr;
+  ws.bytes = 0;
+}
+
+int build_wave_schedule(c3_engine* e, const std::vector<int>& nodes, c3_engine::WaveSched& ws) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const int K = e->K, ROWS = 128 / K, W = (int)nodes.size();
+  const int grid = e->n_sm, GW = grid * WAVE_WARPS, lag = e->wave_lag, prio = e->wave_prio;
+  std::vector<int> wi(e->n_nodes, -1);
+  for (int i = 0; i < W; ++i) wi[nodes[i]] = i;
+  std::vector<int64_t> strips(W), off(W + 1, 0), start(W);
+  std::vector<int> h(W, 0), kid0(W), kid1(W);
+  for (int i = 0; i < W; ++i) {  // ascending node ids: children before parents
+    const int n = nodes[i];
+    strips[i] = (e->n_rows[n] + ROWS - 1) / ROWS;
+    off[i + 1] = off[i] + strips[i];
+    kid0[i] = wi[e->children[n][0]];
+    kid1[i] = wi[e->children[n][1]];
+    if (kid0[i] >= 0) h[i] = std::max(h[i], h[kid0[i]] + 1);
+    if (kid1[i] >= 0) h[i] = std::max(h[i], h[kid1[i]] + 1);
+    start[i] = (int64_t)prio * h[i];
+  }
+  const int64_t total = off[W];
+  if (total >= INT32_MAX) return fail(C3_ERR_INVALID, "too many strips for a wave schedule");
+  std::vector<int32_t> chunk_of((size_t)total);
+  std::vector<int32_t> fill;
+  fill.reserve((size_t)(total / GW + 64));
+  int64_t first_open = 0;
+  // items by starting wave
+  std::vector<int> order(W);
+  for (int i = 0; i < W; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return start[a] < start[b]; });
+  std::vector<int> active;
+  int next = 0;
+  int64_t remaining = total;
+  for (int64_t w = 0; remaining > 0; ++w) {
+    bool grew = false;
+    while (next < W && start[order[next]] <= w) {
+      active.push_back(order[next++]);
+      grew = true;
+    }
+    if (active.empty()) {
+      w = start[order[next]] - 1;  // (nothing active: jump to the next start)
+      continue;
+    }
+    if (grew) std::sort(active.begin(), active.end());
+    size_t keep = 0;
+    for (size_t ai = 0; ai < active.size(); ++ai) {
+      const int i = active[ai];
+      const int64_t k = w - start[i];
+      if (k >= strips[i]) continue;  // finished: dropped from the active list
+      int64_t earliest = 0;
+      if (kid0[i] >= 0) earliest = std::max<int64_t>(earliest, chunk_of[off[kid0[i]] + std::min(k, strips[kid0[i]] - 1)] + lag);
+      if (kid1[i] >= 0) earliest = std::max<int64_t>(earliest, chunk_of[off[kid1[i]] + std::min(k, strips[kid1[i]] - 1)] + lag);
+      int64_t j = std::max(earliest, first_open);
+      while (j < (int64_t)fill.size() && fill[j] == GW) ++j;
+      if (j >= (int64_t)fill.size()) fill.resize((size_t)j + 1, 0);
+      fill[j] += 1;
+      chunk_of[off[i] + k] = (int32_t)j;
+      while (first_open < (int64_t)fill.size() && fill[first_open] == GW) ++first_open;
+      --remaining;
+      if (k + 1 < strips[i]) active[keep++] = i;
+    }
+    active.resize(keep);
+  }
+  const int64_t n_chunks = (int64_t)fill.size();
+  if (n_chunks * GW >= ((int64_t)1 << 31)) return fail(C3_ERR_INVALID, "wave schedule too long");
+  std::vector<int2> sched((size_t)(n_chunks * GW), make_int2(-1, 0));
+  std::vector<int32_t> cursor((size_t)n_chunks, 0);
+  for (int i = 0; i < W; ++i)
+    for (int64_t k = 0; k < strips[i]; ++k) {
+      const int32_t c = chunk_of[off[i] + k];
+      sched[(size_t)c * GW + cursor[c]++] = make_int2(i, (int)k);
+    }
+  if (getenv("C3_WAVE_VERIFY")) {
+    // every strip exactly once; every dependency at least `lag` chunks earlier; no strip that depends on
+    // anything inside the first `lag` chunks
+    std::vector<char> seen((size_t)total, 0);
+    for (int64_t c = 0; c < n_chunks; ++c)
+      for (int g = 0; g < GW; ++g) {
+        const int2 en = sched[(size_t)c * GW + g];
+        if (en.x < 0) continue;
+        if (en.x >= W || en.y < 0 || en.y >= strips[en.x] || seen[off[en.x] + en.y] || chunk_of[off[en.x] + en.y] != c)
+          return fail(C3_ERR_INVALID, "wave schedule: bad entry");
+        seen[off[en.x] + en.y] = 1;
+        for (int kid : {kid0[en.x], kid1[en.x]}) {
+          if (kid < 0) continue;
+          const int64_t ck = std::min<int64_t>(en.y, strips[kid] - 1);
+          if (chunk_of[off[kid] + ck] + lag > c) return fail(C3_ERR_INVALID, "wave schedule: dependency too close");
+        }
+      }
+    for (int64_t t = 0; t < total; ++t)
+      if (!seen[t]) return fail(C3_ERR_INVALID, "wave schedule: strip missing");
+  }
+  ws.work.assign(nodes.begin(), nodes.end());
+  ws.n_chunks = (int)n_chunks;
+  ws.grid = grid;
+  ws.strips = total;
+  ws.noops = n_chunks * GW - total;
+  const int64_t bytes = (int64_t)sched.size() * sizeof(int2) + n_chunks * (int64_t)sizeof(unsigned);
+  // keep the schedules of a few structures (a full sweep: 8 B per strip); least recently used go first
+  while (!e->waves.empty() && e->wave_bytes + bytes > ((int64_t)1 << 30)) {
+    auto victim = e->waves.begin();
+    for (auto it = e->waves.begin(); it != e->waves.end(); ++it)
+      if (it->second.last_use < victim->second.last_use) victim = it;
+    cudaStreamSynchronize(e->stream);
+    free_wave(e, victim->second);
+    e->waves.erase(victim);
+  }
+  C3_CUDA(cudaMalloc(&ws.d_sched, sched.size() * sizeof(int2)));
+  cudaError_t err = cudaMalloc(&ws.d_done, (size_t)std::max<int64_t>(1, n_chunks) * sizeof(unsigned));
+  if (err != cudaSuccess) {
+    cudaFree(ws.d_sched);
+    ws.d_sched = nullptr;
+    return fail(C3_ERR_MEMORY, "device memory exhausted (wave schedule)");
+  }
+  C3_CUDA(cudaMemcpy(ws.d_sched, sched.data(), sched.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  ws.bytes = bytes;
+  e->wave_bytes += bytes;
+  e->stats.device_bytes += bytes;
+  ws.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (getenv("C3_WAVE_VERBOSE"))
+    fprintf(stderr, "[c3cuda] wave schedule: %d nodes, %lld strips, %lld chunks of %d (%.1f%% no-ops), lag %d, built in %.1f ms\n",
+            W, (long long)total, (long long)n_chunks, GW, 100.0 * ws.noops / std::max<int64_t>(1, n_chunks * GW), lag,
+            ws.build_ms);
+  return C3_OK;
+}
+
+template <int K>
+int launch_wave(c3_engine* e, const PruneArgs& a, const c3_engine::WaveSched& ws) {
+  // every CTA must be resident (warps wait for other warps' progress): a cooperative launch, one CTA per SM
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ws.grid);
+  cfg.blockDim = dim3(WAVE_WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_wave_kernel<K>, a, (const int2*)ws.d_sched, ws.n_chunks, ws.d_done,
+                                       e->wave_lag);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("wave launch: ") + cudaGetErrorString(err));
+  return C3_OK;
+}
+
 // kind: 0 = generic kernels (prune4_kernel / prune_dmma_kernel); 2, 3 = strip kernel for
 // nodes with that many children (4-state, K in {1,2,4}); 6 = register-pipeline DMMA kernel
 int launch_prune(c3_engine* e, const PruneArgs& a, bool is_root, int kind) {
@@ -687,6 +866,10 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   if (const char* env = getenv("C3_REG1")) e->use_reg2 = atoi(env) == 0;
   if (const char* env = getenv("C3_FLOW")) e->use_flow = atoi(env) != 0;
+  if (const char* env = getenv("C3_WAVE")) e->use_wave = atoi(env) != 0;
+  if (const char* env = getenv("C3_WAVE_LAG")) e->wave_lag = std::max(3, std::min(12, atoi(env)));
+  if (const char* env = getenv("C3_WAVE_PRIO")) e->wave_prio = std::max(1, atoi(env));
+  if (const char* env = getenv("C3_WAVE_MIN")) e->wave_min_strips = std::max(1, atoi(env));
   e->store_root = !(e->use_dmma ? e->edge_major
                                 : (e->use_strip && e->use_reg2 && !e->use_ring && !e->use_flow));
   if (const char* env = getenv("C3_STORE_ROOT")) e->store_root = e->store_root || atoi(env) != 0;
@@ -732,6 +915,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   for (int n = 0; n < n_nodes; ++n)
     if (!e->children[n].empty()) e->level_nodes[e->level[n]].push_back(n);
   e->n_rows.assign(n_nodes, 0);
+  e->idx_mono.assign(n_nodes, 0);
   e->tip_table.resize(n_nodes);
   e->idx32.resize(n_nodes);
   e->qslot.assign((size_t)n_nodes * n_bins, 0);
@@ -774,6 +958,8 @@ int c3_destroy(c3_engine* e) {
   if (e->d_pool) cudaFree(e->d_pool);
   if (e->d_scale_pool) cudaFree(e->d_scale_pool);
   clear_graphs(e);
+  for (auto& w : e->waves) free_wave(e, w.second);
+  e->waves.clear();
   if (e->d_slots) cudaFree(e->d_slots);
   if (e->d_block) cudaFree(e->d_block);
   if (e->h_block) cudaFreeHost(e->h_block);
@@ -824,6 +1010,7 @@ int c3_set_node_patterns(c3_engine* e, int node, const int64_t* indexes, int64_t
   e->n_rows[node] = n_rows;
   std::vector<int32_t>& ix = e->idx32[node];
   ix.resize(C * (size_t)n_rows);
+  bool mono = true;
   for (size_t c = 0; c < C; ++c) {
     const int child = e->children[node][c];
     const int64_t child_rows = e->n_rows[child];
@@ -832,8 +1019,10 @@ int c3_set_node_patterns(c3_engine* e, int node, const int64_t* indexes, int64_t
       const int64_t v = indexes[c * n_rows + p];
       if (v < 0 || v >= child_rows) return fail(C3_ERR_INVALID, "child row index out of range");
       ix[c * n_rows + p] = (int32_t)v;
+      mono = mono && v <= p;
     }
   }
+  e->idx_mono[node] = mono ? 1 : 0;  // cogent3's first-seen numbering guarantees it (wave kernel precondition)
   return C3_OK;
 }
 
@@ -1008,8 +1197,14 @@ int c3_compress_alignment(c3_engine* e, const uint8_t* codes, int64_t n_columns,
                               cudaMemcpyHostToDevice, e->stream);
         if (err != cudaSuccess) { rc = fail(C3_ERR_CUDA, cudaGetErrorString(err)); break; }
       }
-      err = cudaStreamSynchronize(e->stream);
+      // idx_c[p] <= p (first-seen numbering): checked, not assumed (sc.total is free again here)
+      cudaMemsetAsync(sc.total, 0, sizeof(unsigned), e->stream);
+      cmp_check_monotone_kernel<<<grid, CMP_THREADS, 0, e->stream>>>(e->d_idx_tmp[n], C, rows, sc.total);
+      unsigned not_mono = 1;
+      err = cudaMemcpyAsync(&not_mono, sc.total, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream);
+      if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
       if (err != cudaSuccess) { rc = fail(C3_ERR_CUDA, cudaGetErrorString(err)); break; }
+      e->idx_mono[n] = not_mono ? 0 : 1;
       if (!keep_index)
         for (int k : kids) {
           cudaFree(e->d_index[k]);
@@ -1909,9 +2104,51 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     return C3_OK;
   }
 
+  // ---- wavefront launch?  every dirty non-root node binary, first-seen tables, enough strips, and the
+  // structure has come up before (its schedule is built once and kept on the device) --------------------
+  c3_engine::WaveSched* wave = nullptr;
+  std::vector<int> wave_nodes;
+  if (e->use_wave && !e->use_dmma && e->use_strip && e->use_reg2 && !e->use_ring && !e->use_flow &&
+      (K == 1 || K == 2 || K == 4) && !e->rescale_active && e->batch_mode == 0 && recompute[e->root]) {
+    bool ok = true;
+    int64_t strips = 0;
+    const int rows_per_strip = 128 / K;
+    for (int n = 0; n < N - 1 && ok; ++n) {
+      if (!recompute[n]) continue;
+      ok = e->children[n].size() == 2 && e->idx_mono[n];
+      wave_nodes.push_back(n);
+      strips += (e->n_rows[n] + rows_per_strip - 1) / rows_per_strip;
+    }
+    ok = ok && !wave_nodes.empty() && (int)wave_nodes.size() <= WAVE_MAXW && strips >= e->wave_min_strips;
+    if (ok) {
+      uint64_t h = 1469598103934665603ull;
+      for (int n : wave_nodes) { h ^= (uint32_t)n; h *= 1099511628211ull; }
+      auto it = e->waves.find(h);
+      if (it != e->waves.end() && it->second.work.size() == wave_nodes.size() &&
+          std::equal(wave_nodes.begin(), wave_nodes.end(), it->second.work.begin())) {
+        wave = &it->second;
+      } else if (it == e->waves.end() && ++e->wave_seen[h] >= 2) {
+        c3_engine::WaveSched ws;
+        const int rc = build_wave_schedule(e, wave_nodes, ws);
+        if (rc == C3_OK) {
+          wave = &e->waves.emplace(h, std::move(ws)).first->second;
+          e->wave_seen.erase(h);
+        } else if (rc != C3_ERR_MEMORY) {
+          return rc;
+        }
+      } else if (e->wave_seen.size() > 4096) {
+        e->wave_seen.clear();
+      }
+    }
+    if (wave) wave->last_use = ++e->graph_clock;
+  }
+  std::vector<char> in_wave(N, 0);
+  if (wave)
+    for (int n : wave_nodes) in_wave[n] = 1;
+
   int32_t* work = reinterpret_cast<int32_t*>(e->h_block + e->off_work);
   int32_t* prefix = reinterpret_cast<int32_t*>(e->h_block + e->off_prefix);
-  // kind: 0 generic, 1 fused small levels, 2/3 strip kernel (see launch_prune)
+  // kind: 0 generic, 1 fused small levels, 2/3 strip kernel (see launch_prune), 7 the wavefront launch
   struct LevelLaunch {
     int work_off, prefix_off, n_work, total_tiles;
     bool is_root;
@@ -1953,6 +2190,21 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   };
   const bool flow_ok = e->use_flow && !e->use_dmma && e->use_strip && !e->use_ring && (K == 1 || K == 2 || K == 4) &&
                        !e->rescale_active;  // rescaling runs between levels
+  if (wave) {
+    // one launch for every dirty node below the root; the per-level loop below then only sees the root
+    LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, 7, 0, 0};
+    const int64_t bytes0 = alg_bytes, flops0 = flops;
+    for (int n : wave_nodes) {
+      work[w_off + ll.n_work++] = n;
+      account(n);
+      recompute[n] = 0;  // (handled; n_dirty_nodes keeps counting it)
+    }
+    ll.total_tiles = (int)wave->strips;
+    ll.bytes = alg_bytes - bytes0;
+    ll.flops = flops - flops0;
+    w_off += ll.n_work;
+    launches.push_back(ll);
+  }
   for (int l = 1; l <= e->n_levels; ++l) {
     int64_t units = 0;
     int n_dirty = 0;
@@ -2194,6 +2446,18 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel, a, d_small, ll.n_small, ll.n_work,
                                            ll.n_work + ll.n_small, tail);
       if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("small-level launch: ") + cudaGetErrorString(err));
+    } else if (ll.kind == 7) {
+      C3_CUDA(cudaMemsetAsync(wave->d_done, 0, (size_t)std::max(1, wave->n_chunks) * sizeof(unsigned), e->stream));
+      int rc = C3_ERR_INVALID;
+      switch (K) {
+        case 1: rc = launch_wave<1>(e, a, *wave); break;
+        case 2: rc = launch_wave<2>(e, a, *wave); break;
+        case 4: rc = launch_wave<4>(e, a, *wave); break;
+      }
+      if (rc) return rc;
+      e->stats.wave_launches += 1;
+      e->stats.wave_entries = (int64_t)wave->n_chunks * wave->grid * WAVE_WARPS;
+      e->stats.wave_noops = wave->noops;
     } else if (ll.kind == 5) {
       const int32_t* d_dep = reinterpret_cast<const int32_t*>(e->d_block + e->off_dep) + 2 * ll.work_off;
       int rc = C3_ERR_INVALID;
@@ -2251,7 +2515,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   // ---- direct launches, or capture / replay of this structure's graph ---------------------------
   bool graphed = false;
   e->plan = c3_engine::PlanStats{n_eigen + n_pade, n_dirty_nodes, node_rows, alg_bytes, flops, h2d_bytes};
-  const bool graph_ok = e->use_graphs && !e->profiling && !any_flow;
+  const bool graph_ok = e->use_graphs && !e->profiling && !any_flow && wave == nullptr;  // (cooperative launch: not captured)
   if (e->batch_mode != 0 && !graph_ok) return fail(C3_ERR_INVALID, "engine cannot take part in a batch graph");
   if (graph_ok) {
     std::vector<int32_t> sig;

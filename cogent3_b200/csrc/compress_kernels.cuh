@@ -223,6 +223,17 @@ cmp_counts_to_double_kernel(long long n, const unsigned* __restrict__ counts, do
     out[i] = (double)counts[i];
 }
 
+// first-seen numbering implies idx_c[p] <= p for every child (the wave kernel's precondition): *bad is raised
+// when a table does not have the property
+__global__ void __launch_bounds__(CMP_THREADS)
+cmp_check_monotone_kernel(const int32_t* __restrict__ idx, int n_children, long long rows, unsigned* __restrict__ bad) {
+  const long long total = (long long)n_children * rows;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const long long p = o % rows;
+    if (idx[o] > p) atomicOr(bad, 1u);
+  }
+}
+
 // per-column likelihoods lh[index[col]] of one bin (LikelihoodTreeEdge.get_full_length_likelihoods,
 // evolve/likelihood_tree.py:93-94)
 __global__ void __launch_bounds__(CMP_THREADS)

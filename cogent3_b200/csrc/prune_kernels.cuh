@@ -801,6 +801,235 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
 }
 
 // ---------------------------------------------------------------------------------------
+// 4-state WAVEFRONT kernel ("wave"): every dirty binary node of the sweep in ONE persistent launch,
+// all tree levels streaming AT THE SAME TIME.
+//
+// A launch per level costs ~11 us of ramp, drain and imbalance whatever its size (fit over the C2
+// levels: time = 11-15 us + bytes / 6.2 TB/s -- a third of a C2 step for 10 launches), and a
+// parent's gather finds its children's rows in HBM although they were written microseconds ago.
+// cogent3 numbers patterns in first-seen order, so for every node idx_c[p] <= p (the distinct child
+// patterns seen in the first columns are no more than the distinct parent tuples; checked per node
+// when the tables arrive): strip k of a node (rows [k R, (k+1) R)) only needs strips <= k of its
+// children.  So the strips of ALL nodes are laid out by the host in one static schedule, sorted by
+// wave index  w = k + LAG * height(node): a parent runs LAG strips behind its children, every level
+// is active at once, and what a parent gathers is what its children stored a few microseconds
+// earlier -- still in the 126 MB L2.  DRAM then mostly sees the writes.
+//
+// Mechanics.  The schedule is cut into CHUNKS of GW entries (GW = resident warps); warp g takes entry
+// g of every chunk, chunk after chunk, with the register pipeline of prune4_reg2_kernel (two strips
+// in flight, gather indexes two steps ahead).  The host places a strip only into a chunk that lies
+// at least `lag` chunks after the chunks of the child strips it depends on (greedy list scheduling;
+// a position with nothing eligible is a no-op entry).  Completion is tracked per chunk:
+//   * after the stores of its entry of chunk i a warp fences and counts itself in a shared-memory slot
+//     of its CTA; the CTA's last warp does  red  chunk_done[i] += 1  (148 atomics per chunk, not 1184);
+//   * before it GATHERS rows for its entry of chunk j it makes sure that chunk_done[j - lag] == #CTAs,
+//     i.e. EVERY warp has stored its entry of chunk j - lag (and so of all earlier chunks: a warp
+//     counts its chunks in order).  The counter is read early (relaxed, at L2) and only looked at
+//     after the FMA block; in steady state it is already there.
+// A warp only ever waits for strictly earlier chunks, so the warp holding the smallest unfinished
+// chunk can always proceed: no deadlock as long as every CTA is resident (cooperative launch).
+// Rows of a node are read by no SM before that wait has passed, so no L1 can hold a stale line.
+// Arithmetic per row is that of every other 4-state kernel (same FMA order): bit-identical results.
+// ---------------------------------------------------------------------------------------
+constexpr int WAVE_MAXW = 256;   // work items (dirty nodes) per wave launch
+constexpr int WAVE_WARPS = 8;
+constexpr int WAVE_RING = 16;    // schedule entries staged per warp (two halves of 8)
+
+struct WaveSmem {
+  WorkDesc<2> work[WAVE_MAXW];
+};
+
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// schedule entry: .x = work item (-1: nothing to do at this position), .y = strip number inside the node
+template <int K>
+__global__ void __launch_bounds__(WAVE_WARPS * 32, 1)
+prune4_wave_kernel(const PruneArgs a, const int2* __restrict__ sched, int n_chunks, unsigned* __restrict__ chunk_done,
+                   int lag) {
+  constexpr int NC = 2, U = 4;
+  constexpr int ROWS = 32 * U / K;  // pattern rows per strip
+  __shared__ WaveSmem sd;
+  __shared__ __align__(16) double sPall[WAVE_WARPS][NC * K * P4S_PSTRIDE];
+  __shared__ int2 sRing[WAVE_WARPS][WAVE_RING];
+  __shared__ unsigned sCount[16];  // warps of this CTA through with chunk i (slot i & 15: the warps of the launch are
+                                   // never more than `lag` < 16 chunks apart)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sP = sPall[warp];
+  int2* ring = sRing[warp];
+
+  pdl_trigger();
+  for (int i = threadIdx.x; i < a.n_work; i += blockDim.x) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    WorkDesc<NC>& wd = sd.work[i];
+    wd.out = nd.out;
+    wd.n_rows = nd.n_rows;
+    wd.fixed_motif = nd.fixed_motif;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const ChildRef ch = a.childs[nd.child_begin + c];
+      wd.src[c] = ch.src;
+      wd.idx[c] = ch.idx;
+      wd.P[c] = ch.P;
+    }
+  }
+  // entry g of a chunk goes to warp (g / #CTAs) of CTA (g % #CTAs): a chunk that is only partly filled
+  // (the ramps of the schedule) still spreads over every SM
+  const int gw = warp * gridDim.x + blockIdx.x;
+  const int GW = gridDim.x * WAVE_WARPS;
+  const int b = lane % K;
+  const int slot = lane / K;
+  // this warp's entries of chunks [0, 16) into its ring
+  if (lane < WAVE_RING) ring[lane] = (lane < n_chunks) ? __ldg(sched + (int64_t)lane * GW + gw) : make_int2(-1, 0);
+  if (threadIdx.x < 16) sCount[threadIdx.x] = 0u;
+  const unsigned n_cta = gridDim.x;
+  __syncthreads();
+
+  auto entry = [&](int i) -> int2 { return (i < n_chunks) ? ring[i & (WAVE_RING - 1)] : make_int2(-1, 0); };
+  auto load_idx = [&](int32_t(&ix)[NC][U], const int2 e) {
+    if (e.x < 0) return;
+    const WorkDesc<NC>& wd = sd.work[e.x];
+    const int64_t row0 = (int64_t)e.y * ROWS;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t p = row0 + u * (32 / K) + slot;
+      if (p >= wd.n_rows) p = wd.n_rows - 1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) ix[c][u] = __ldg(wd.idx[c] + p);
+    }
+  };
+  int known_done = -1;  // every chunk <= known_done is complete
+  // rows this launch wrote earlier: plain (coherent) loads after the chunk they depend on is complete
+  auto gather = [&](d4(&x)[NC][U], const int32_t(&ix)[NC][U], const int2 e) {
+    if (e.x < 0) return;
+    const WorkDesc<NC>& wd = sd.work[e.x];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int u = 0; u < U; ++u) x[c][u] = ld256(wd.src[c] + ((int64_t)ix[c][u] * K + b) * 4);
+  };
+  auto wait_chunk = [&](int need, unsigned early) {
+    if (need <= known_done) return;
+    if (early != n_cta) {
+      while (ld_acquire_gpu_u32(chunk_done + need) != n_cta) __nanosleep(64);
+    }
+    known_done = need;
+  };
+
+  int p_w = -1;
+  // compute the entry of chunk i from x; refill x with the entry of chunk i + 2 (indexes ix, requested two
+  // steps ago); then request the indexes of the entry of chunk i + 4 into ix
+  auto step = [&](d4(&x)[NC][U], int32_t(&ix)[NC][U], int i) {
+    const int2 cur = entry(i);
+    const int2 nxt = entry(i + 2);
+    // the counter the refill depends on, requested now, looked at after the FMAs
+    const int need = i + 2 - lag;
+    unsigned early = n_cta;
+    if (need > known_done) early = ld_relaxed_gpu_u32(chunk_done + need);
+    // every 8 chunks: the entries of chunks [i + 8, i + 16) into the ring half that was just left
+    // (the half holding chunks [i, i + 8) is still being read)
+    int2 fresh = make_int2(-1, 0);
+    const bool reload = (i & 7) == 0 && i + 8 < n_chunks;
+    if (reload && lane < 8 && i + 8 + lane < n_chunks) fresh = __ldg(sched + (int64_t)(i + 8 + lane) * GW + gw);
+    d4 acc[U];
+    if (cur.x >= 0) {
+      const WorkDesc<NC>& wd = sd.work[cur.x];
+      if (cur.x != p_w) {
+        __syncwarp();
+        for (int o = lane; o < NC * K * 16; o += 32) {
+          const int c = o / (K * 16);
+          const int rem = o - c * (K * 16);
+          const double* P = wd.P[c];
+          sP[(c * K + (rem >> 4)) * P4S_PSTRIDE + (rem & 15)] = P ? P[rem] : (((rem & 15) % 5 == 0) ? 1.0 : 0.0);
+        }
+        p_w = cur.x;
+        __syncwarp();
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double* Pc = sP + (c * K + b) * P4S_PSTRIDE;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const double2 p01 = *reinterpret_cast<const double2*>(Pc + 4 * k4);
+          const double2 p23 = *reinterpret_cast<const double2*>(Pc + 4 * k4 + 2);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const double y =
+                fma(x[c][u].w, p23.y, fma(x[c][u].z, p23.x, fma(x[c][u].y, p01.y, x[c][u].x * p01.x)));
+            double& t = (k4 == 0) ? acc[u].x : (k4 == 1) ? acc[u].y : (k4 == 2) ? acc[u].z : acc[u].w;
+            t = (c == 0) ? y : t * y;
+          }
+        }
+      }
+    }
+    // every warp waits, also one with nothing to gather: it keeps the warps of the launch within `lag`
+    // chunks of each other (the shared-memory slots above and the host's placement rely on it)
+    wait_chunk(need, early);
+    gather(x, ix, nxt);
+    load_idx(ix, entry(i + 4));
+    if (cur.x >= 0) {
+      const WorkDesc<NC>& wd = sd.work[cur.x];
+      const int64_t node_row0 = (int64_t)cur.y * ROWS;
+      const int c_fixed = wd.fixed_motif;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t p = node_row0 + u * (32 / K) + slot;
+        if (c_fixed >= 0) {
+          if (c_fixed != 0) acc[u].x = 0.0;
+          if (c_fixed != 1) acc[u].y = 0.0;
+          if (c_fixed != 2) acc[u].z = 0.0;
+          if (c_fixed != 3) acc[u].w = 0.0;
+        }
+        if (p < wd.n_rows) st256(wd.out + (p * K + b) * 4, acc[u]);
+      }
+    }
+    // this warp's entry of chunk i is stored (or was empty): tell everybody
+    __syncwarp();
+    if (lane == 0) {
+      if (cur.x >= 0) __threadfence();  // (cumulative over the other lanes' stores through __syncwarp)
+      if (atomicAdd(&sCount[i & 15], 1u) == WAVE_WARPS - 1) {
+        sCount[i & 15] = 0u;  // the slot is next used for chunk i + 16
+        __threadfence();
+        atomicAdd(chunk_done + i, 1u);
+      }
+    }
+    if (reload) {
+      // (all lanes are past their reads of the other half: entry(i + 4) above was the last one of this step
+      //  and lies in [i, i + 8))
+      __syncwarp();
+      if (lane < 8) ring[(i + 8 + lane) & (WAVE_RING - 1)] = fresh;
+      __syncwarp();
+    }
+  };
+
+  d4 xa[NC][U], xb[NC][U];
+  int32_t ia[NC][U], ib[NC][U];
+  // prologue: entries of chunks 0, 1 into the buffers; indexes of chunks 2, 3 into the index sets
+  load_idx(ia, entry(0));  // static data: may overlap the previous launch
+  load_idx(ib, entry(1));
+  pdl_wait();
+  // (the host never places a strip that depends on anything into the first `lag` chunks)
+  if (n_chunks > 0) gather(xa, ia, entry(0));
+  if (n_chunks > 1) gather(xb, ib, entry(1));
+  load_idx(ia, entry(2));
+  load_idx(ib, entry(3));
+
+#pragma unroll 1
+  for (int i = 0; i < n_chunks; i += 2) {
+    step(xa, ia, i);
+    if (i + 1 < n_chunks) step(xb, ib, i + 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // 4-state DATAFLOW kernel: several consecutive tree levels in ONE persistent launch.
 //
 // Per-level launches cost ~15 us each of ramp-up / tail / launch latency (fit over the C2

@@ -59,6 +59,9 @@ typedef struct c3_stats {
   int64_t graph_replays;      /* evaluations issued as ONE cudaGraphLaunch      */
   int32_t n_levels;           /* tree levels (kernel launches of a full sweep)  */
   int32_t padded_states;      /* row stride of a partial row, in doubles        */
+  int64_t wave_launches;      /* sweeps issued as ONE wavefront launch (all levels at once) */
+  int64_t wave_entries;       /* schedule entries of the last wavefront launch  */
+  int64_t wave_noops;         /* ... of which no-op positions                   */
 } c3_stats;
 
 C3_API int c3_abi_version(void);

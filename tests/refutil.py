@@ -41,6 +41,7 @@ def import_reference():
     if not reference_available():
         return None
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+    os.environ.setdefault("COGENT3_REFERENCE_ROOT", REF_SRC)  # where the stevedore shim finds pyproject.toml
     for p in (SHIMS, REF_SRC):
         if p not in sys.path:
             sys.path.insert(0, p)
