@@ -139,6 +139,9 @@ struct c3_engine {
   // structure comes up and kept on the device.  C3_WAVE=0 disables.
   bool use_wave = true;
   int wave_lag = 4;          // chunks between a strip and the strips it depends on (C3_WAVE_LAG)
+  int wave_group = 1;        // chunks per completion signal (C3_WAVE_GROUP)
+  int64_t wave_prefix = 0;   // > 0: the wave launch takes only the tree's lower levels, up to the first level with
+                             // more strips than this; the big levels keep their own launches (C3_WAVE_PREFIX)
   int wave_prio = 128;       // strips a parent runs behind its children in the schedule's priority order (C3_WAVE_PRIO)
   int64_t wave_min_strips = 4096;  // smaller sweeps keep the per-level / small-levels launches (C3_WAVE_MIN)
   std::vector<char> idx_mono;      // [n_nodes] idx_c[p] <= p for every child and row (first-seen numbering)
@@ -452,7 +455,10 @@ void free_wave(c3_engine* e, c3_engine::WaveSched& ws) {
 int build_wave_schedule(c3_engine* e, const std::vector<int>& nodes, c3_engine::WaveSched& ws) {
   const auto t0 = std::chrono::steady_clock::now();
   const int K = e->K, ROWS = 128 / K, W = (int)nodes.size();
-  const int grid = e->n_sm, GW = grid * WAVE_WARPS, lag = e->wave_lag, prio = e->wave_prio;
+  const int grid = e->n_sm, GW = grid * WAVE_WARPS, lag = e->wave_lag, prio = e->wave_prio, R = e->wave_group;
+  // the kernel gathers for chunk j once every GROUP that ends at or before chunk j - lag is complete: a strip
+  // whose dependency sits in chunk d may go into chunk j >= ceil((d + 1) / R) R + lag - 1
+  auto after = [&](int64_t d) { return (d + 1 + R - 1) / R * R + lag - 1; };
   std::vector<int> wi(e->n_nodes, -1);
   for (int i = 0; i < W; ++i) wi[nodes[i]] = i;
   std::vector<int64_t> strips(W), off(W + 1, 0), start(W);
@@ -497,8 +503,8 @@ int build_wave_schedule(c3_engine* e, const std::vector<int>& nodes, c3_engine::
       const int64_t k = w - start[i];
       if (k >= strips[i]) continue;  // finished: dropped from the active list
       int64_t earliest = 0;
-      if (kid0[i] >= 0) earliest = std::max<int64_t>(earliest, chunk_of[off[kid0[i]] + std::min(k, strips[kid0[i]] - 1)] + lag);
-      if (kid1[i] >= 0) earliest = std::max<int64_t>(earliest, chunk_of[off[kid1[i]] + std::min(k, strips[kid1[i]] - 1)] + lag);
+      if (kid0[i] >= 0) earliest = std::max<int64_t>(earliest, after(chunk_of[off[kid0[i]] + std::min(k, strips[kid0[i]] - 1)]));
+      if (kid1[i] >= 0) earliest = std::max<int64_t>(earliest, after(chunk_of[off[kid1[i]] + std::min(k, strips[kid1[i]] - 1)]));
       int64_t j = std::max(earliest, first_open);
       while (j < (int64_t)fill.size() && fill[j] == GW) ++j;
       if (j >= (int64_t)fill.size()) fill.resize((size_t)j + 1, 0);
@@ -533,7 +539,7 @@ int build_wave_schedule(c3_engine* e, const std::vector<int>& nodes, c3_engine::
         for (int kid : {kid0[en.x], kid1[en.x]}) {
           if (kid < 0) continue;
           const int64_t ck = std::min<int64_t>(en.y, strips[kid] - 1);
-          if (chunk_of[off[kid] + ck] + lag > c) return fail(C3_ERR_INVALID, "wave schedule: dependency too close");
+          if (after(chunk_of[off[kid] + ck]) > c) return fail(C3_ERR_INVALID, "wave schedule: dependency too close");
         }
       }
     for (int64_t t = 0; t < total; ++t)
@@ -567,8 +573,8 @@ int build_wave_schedule(c3_engine* e, const std::vector<int>& nodes, c3_engine::
   e->stats.device_bytes += bytes;
   ws.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (getenv("C3_WAVE_VERBOSE"))
-    fprintf(stderr, "[c3cuda] wave schedule: %d nodes, %lld strips, %lld chunks of %d (%.1f%% no-ops), lag %d, built in %.1f ms\n",
-            W, (long long)total, (long long)n_chunks, GW, 100.0 * ws.noops / std::max<int64_t>(1, n_chunks * GW), lag,
+    fprintf(stderr, "[c3cuda] wave schedule: %d nodes, %lld strips, %lld chunks of %d (%.1f%% no-ops), lag %d, group %d, built in %.1f ms\n",
+            W, (long long)total, (long long)n_chunks, GW, 100.0 * ws.noops / std::max<int64_t>(1, n_chunks * GW), lag, R,
             ws.build_ms);
   return C3_OK;
 }
@@ -587,7 +593,7 @@ int launch_wave(c3_engine* e, const PruneArgs& a, const c3_engine::WaveSched& ws
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_wave_kernel<K>, a, (const int2*)ws.d_sched, ws.n_chunks, ws.d_done,
-                                       e->wave_lag);
+                                       e->wave_lag, e->wave_group);
   if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("wave launch: ") + cudaGetErrorString(err));
   return C3_OK;
 }
@@ -870,6 +876,8 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_WAVE_LAG")) e->wave_lag = std::max(3, std::min(12, atoi(env)));
   if (const char* env = getenv("C3_WAVE_PRIO")) e->wave_prio = std::max(1, atoi(env));
   if (const char* env = getenv("C3_WAVE_MIN")) e->wave_min_strips = std::max(1, atoi(env));
+  if (const char* env = getenv("C3_WAVE_GROUP")) e->wave_group = std::max(1, std::min(32, atoi(env)));
+  if (const char* env = getenv("C3_WAVE_PREFIX")) e->wave_prefix = std::max(0, atoi(env));
   e->store_root = !(e->use_dmma ? e->edge_major
                                 : (e->use_strip && e->use_reg2 && !e->use_ring && !e->use_flow));
   if (const char* env = getenv("C3_STORE_ROOT")) e->store_root = e->store_root || atoi(env) != 0;
@@ -2113,13 +2121,30 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     bool ok = true;
     int64_t strips = 0;
     const int rows_per_strip = 128 / K;
+    // prefix mode: only the lower levels, up to (not including) the first level with more strips than
+    // wave_prefix; the big levels above keep their own launches
+    int top_level = e->n_levels;
+    if (e->wave_prefix > 0) {
+      top_level = 0;
+      int n_levels_in = 0;
+      for (int l = 1; l <= e->n_levels; ++l) {
+        int64_t s_l = 0;
+        for (int n : e->level_nodes[l])
+          if (recompute[n] && n != e->root) s_l += (e->n_rows[n] + rows_per_strip - 1) / rows_per_strip;
+        if (s_l > e->wave_prefix) break;
+        top_level = l;
+        n_levels_in += s_l > 0;
+      }
+      ok = n_levels_in >= 2 && top_level < e->n_levels;
+    }
     for (int n = 0; n < N - 1 && ok; ++n) {
-      if (!recompute[n]) continue;
+      if (!recompute[n] || e->level[n] > top_level) continue;
       ok = e->children[n].size() == 2 && e->idx_mono[n];
       wave_nodes.push_back(n);
       strips += (e->n_rows[n] + rows_per_strip - 1) / rows_per_strip;
     }
-    ok = ok && !wave_nodes.empty() && (int)wave_nodes.size() <= WAVE_MAXW && strips >= e->wave_min_strips;
+    ok = ok && !wave_nodes.empty() && (int)wave_nodes.size() <= WAVE_MAXW &&
+         strips >= (e->wave_prefix > 0 ? 64 : e->wave_min_strips);
     if (ok) {
       uint64_t h = 1469598103934665603ull;
       for (int n : wave_nodes) { h ^= (uint32_t)n; h *= 1099511628211ull; }

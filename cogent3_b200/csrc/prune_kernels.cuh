@@ -854,7 +854,7 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
 template <int K>
 __global__ void __launch_bounds__(WAVE_WARPS * 32, 1)
 prune4_wave_kernel(const PruneArgs a, const int2* __restrict__ sched, int n_chunks, unsigned* __restrict__ chunk_done,
-                   int lag) {
+                   int lag, int group) {
   constexpr int NC = 2, U = 4;
   constexpr int ROWS = 32 * U / K;  // pattern rows per strip
   __shared__ WaveSmem sd;
@@ -906,7 +906,11 @@ prune4_wave_kernel(const PruneArgs a, const int2* __restrict__ sched, int n_chun
       for (int c = 0; c < NC; ++c) ix[c][u] = __ldg(wd.idx[c] + p);
     }
   };
-  int known_done = -1;  // every chunk <= known_done is complete
+  // Completion is signalled per GROUP of `group` consecutive chunks (one fence per warp and group: the fence
+  // waits for everything the warp has in flight, loads included -- per chunk it cost more than the chunk):
+  // chunk_done[g] counts the CTAs through with chunks [g group, (g + 1) group).
+  int known_done = -1;  // every GROUP <= known_done is complete
+  bool stored = false;  // this warp has stores that no fence has covered yet
   // rows this launch wrote earlier: plain (coherent) loads after the chunk they depend on is complete
   auto gather = [&](d4(&x)[NC][U], const int32_t(&ix)[NC][U], const int2 e) {
     if (e.x < 0) return;
@@ -930,8 +934,10 @@ prune4_wave_kernel(const PruneArgs a, const int2* __restrict__ sched, int n_chun
   auto step = [&](d4(&x)[NC][U], int32_t(&ix)[NC][U], int i) {
     const int2 cur = entry(i);
     const int2 nxt = entry(i + 2);
-    // the counter the refill depends on, requested now, looked at after the FMAs
-    const int need = i + 2 - lag;
+    // the counter the refill depends on (the last group that lies entirely at or before chunk i + 2 - lag; the
+    // host places a strip accordingly), requested now, looked at after the FMAs
+    const int last_ok = i + 2 - lag + 1;  // chunks < last_ok must be complete
+    const int need = (last_ok >= group) ? last_ok / group - 1 : -1;
     unsigned early = n_cta;
     if (need > known_done) early = ld_relaxed_gpu_u32(chunk_done + need);
     // every 8 chunks: the entries of chunks [i + 8, i + 16) into the ring half that was just left
@@ -990,16 +996,21 @@ prune4_wave_kernel(const PruneArgs a, const int2* __restrict__ sched, int n_chun
         }
         if (p < wd.n_rows) st256(wd.out + (p * K + b) * 4, acc[u]);
       }
+      stored = true;
     }
-    // this warp's entry of chunk i is stored (or was empty): tell everybody
-    __syncwarp();
-    if (lane == 0) {
-      if (cur.x >= 0) __threadfence();  // (cumulative over the other lanes' stores through __syncwarp)
-      if (atomicAdd(&sCount[i & 15], 1u) == WAVE_WARPS - 1) {
-        sCount[i & 15] = 0u;  // the slot is next used for chunk i + 16
-        __threadfence();
-        atomicAdd(chunk_done + i, 1u);
+    // this warp's entries of a whole group are stored (or were empty): tell everybody
+    if ((i + 1) % group == 0 || i + 1 == n_chunks) {
+      const int g = i / group;
+      __syncwarp();
+      if (lane == 0) {
+        if (stored) __threadfence();  // (cumulative over the other lanes' stores through __syncwarp)
+        if (atomicAdd(&sCount[g & 15], 1u) == WAVE_WARPS - 1) {
+          sCount[g & 15] = 0u;  // the slot is next used for group g + 16
+          __threadfence();
+          atomicAdd(chunk_done + g, 1u);
+        }
       }
+      stored = false;
     }
     if (reload) {
       // (all lanes are past their reads of the other half: entry(i + 4) above was the last one of this step

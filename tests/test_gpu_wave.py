@@ -14,10 +14,10 @@ from cogent3_b200.synthetic import make_workload
 
 pytestmark = pytest.mark.gpu
 
-WAVE_ENV = ("C3_WAVE", "C3_WAVE_MIN", "C3_WAVE_LAG", "C3_WAVE_PRIO", "C3_WAVE_VERIFY")
+WAVE_ENV = ("C3_WAVE", "C3_WAVE_MIN", "C3_WAVE_LAG", "C3_WAVE_PRIO", "C3_WAVE_VERIFY", "C3_WAVE_GROUP", "C3_WAVE_PREFIX")
 
 
-def build(monkeypatch, model, topo, lengths, codes, bins, wave, lag=None, prio=None):
+def build(monkeypatch, model, topo, lengths, codes, bins, wave, lag=None, prio=None, group=None, prefix=None):
     for k in WAVE_ENV:
         monkeypatch.delenv(k, raising=False)
     monkeypatch.setenv("C3_WAVE", "1" if wave else "0")
@@ -27,6 +27,10 @@ def build(monkeypatch, model, topo, lengths, codes, bins, wave, lag=None, prio=N
         monkeypatch.setenv("C3_WAVE_LAG", str(lag))
     if prio:
         monkeypatch.setenv("C3_WAVE_PRIO", str(prio))
+    if group:
+        monkeypatch.setenv("C3_WAVE_GROUP", str(group))
+    if prefix:
+        monkeypatch.setenv("C3_WAVE_PREFIX", str(prefix))
     m = hostmodels.get_model(model)
     lf = LikelihoodFunction(m, topo, bins=bins)
     lf.set_alignment(codes.astype(np.int64), np.eye(4))
@@ -50,20 +54,23 @@ def same_rows(a, b, topo, bins):
 
 
 @pytest.mark.parametrize(
-    "model,n_tips,L,bins,kind,lag,prio",
+    "model,n_tips,L,bins,kind,lag,prio,group,prefix",
     [
-        ("GTR", 24, 60_000, 4, "evolved", None, None),
-        ("HKY85", 16, 40_000, 1, "dense", 3, 16),
-        ("HKY85", 20, 50_000, 2, "evolved", 6, 400),
-        ("HKY85", 40, 300_000, 4, "evolved", None, None),
-        ("GTR", 12, 3_000, 4, "dense", 12, 1),
+        ("GTR", 24, 60_000, 4, "evolved", None, None, None, None),
+        ("HKY85", 16, 40_000, 1, "dense", 3, 16, None, None),
+        ("HKY85", 20, 50_000, 2, "evolved", 6, 400, 4, None),
+        ("HKY85", 40, 300_000, 4, "evolved", None, None, 8, None),
+        ("GTR", 12, 3_000, 4, "dense", 12, 1, 16, None),
+        ("GTR", 40, 300_000, 4, "evolved", None, None, None, 600),  # prefix mode: only the lower levels
+        ("HKY85", 30, 200_000, 1, "evolved", 3, None, 2, 300),
     ],
 )
-def test_wave_launch_is_bit_identical_to_the_level_launches(model, n_tips, L, bins, kind, lag, prio, monkeypatch):
+def test_wave_launch_is_bit_identical_to_the_level_launches(model, n_tips, L, bins, kind, lag, prio, group, prefix,
+                                                            monkeypatch):
     m = hostmodels.get_model(model)
     topo, lengths, codes = make_workload(n_tips, L, m.n_states, kind=kind, seed=13)
     plain = build(monkeypatch, model, topo, lengths, codes, bins, wave=False)
-    wave = build(monkeypatch, model, topo, lengths, codes, bins, wave=True, lag=lag, prio=prio)
+    wave = build(monkeypatch, model, topo, lengths, codes, bins, wave=True, lag=lag, prio=prio, group=group, prefix=prefix)
     base = plain.lengths.copy()
     # full sweeps: the schedule of a structure is built the second time it comes up
     for k in range(4):
@@ -84,7 +91,7 @@ def test_wave_launch_is_bit_identical_to_the_level_launches(model, n_tips, L, bi
                 lf.set_param_rule("length", edge=topo.names[n], value=v)
             assert plain.get_log_likelihood() == wave.get_log_likelihood()
     same_rows(plain, wave, topo, bins)
-    assert wave.engine.stats()["wave_launches"] > before
+    assert prefix or wave.engine.stats()["wave_launches"] > before
     # fixed motifs (ancestral reconstruction): a node's rows masked
     internal = [n for n in range(topo.n_nodes - 1) if not topo.is_tip[n]]
     for motif in (0, 3):

@@ -23,16 +23,29 @@ PY
 }
 CFG="--config c2"
 run c2_wave0 C3_WAVE=0
-run c2_wave1 C3_WAVE=1
-run c2_lag3 C3_WAVE=1 C3_WAVE_LAG=3
-run c2_lag6 C3_WAVE=1 C3_WAVE_LAG=6
-run c2_lag8 C3_WAVE=1 C3_WAVE_LAG=8
-run c2_prio32 C3_WAVE=1 C3_WAVE_PRIO=32
-run c2_prio512 C3_WAVE=1 C3_WAVE_PRIO=512
+run c2_g1 C3_WAVE=1
+run c2_g4 C3_WAVE=1 C3_WAVE_GROUP=4
+run c2_g8 C3_WAVE=1 C3_WAVE_GROUP=8
+run c2_g16 C3_WAVE=1 C3_WAVE_GROUP=16
+run c2_g8l8 C3_WAVE=1 C3_WAVE_GROUP=8 C3_WAVE_LAG=8
+run c2_p1k C3_WAVE=1 C3_WAVE_PREFIX=1200
+run c2_p3k C3_WAVE=1 C3_WAVE_PREFIX=3000
+run c2_p10k C3_WAVE=1 C3_WAVE_PREFIX=10000
+run c2_p10kg2 C3_WAVE=1 C3_WAVE_PREFIX=10000 C3_WAVE_GROUP=2
+run c2_p10kl3 C3_WAVE=1 C3_WAVE_PREFIX=10000 C3_WAVE_LAG=3
 CFG="--config c3"
 run c3_wave0 C3_WAVE=0
-run c3_wave1 C3_WAVE=1
+run c3_g8 C3_WAVE=1 C3_WAVE_GROUP=8
+run c3_p3k C3_WAVE=1 C3_WAVE_PREFIX=3000
+run c3_p10k C3_WAVE=1 C3_WAVE_PREFIX=10000
 CFG="--config c5 --columns 1250000"
 run c5s_wave0 C3_WAVE=0
-run c5s_wave1 C3_WAVE=1
-grep -h "wave schedule" $OUT/${TAG}_*.err | sort | uniq -c | head -20
+run c5s_g8 C3_WAVE=1 C3_WAVE_GROUP=8
+run c5s_p10k C3_WAVE=1 C3_WAVE_PREFIX=10000
+grep -h "wave schedule" $OUT/${TAG}_*.err | sort | uniq -c | sort -rn | head -12
+for f in c2_wave0 c2_p10k c2_g8; do python - <<PY
+import json
+d=json.loads(open('$OUT/${TAG}_$f.json').read().strip().splitlines()[-1])
+print('$f', [(x['kind'], x['ms']) for x in d['roofline']['per_launch']])
+PY
+done
