@@ -798,17 +798,31 @@ def measure_workload(ctx, args, cfg, columns, kind, steps, warmup, shard, clocks
         sel = edges if len(edges) <= 128 else list(np.random.default_rng(0).choice(edges, 128, replace=False))
         d = np.nan_to_num(base)[:, None] * rates[None, :]
         eng.update(d)
-        units = 0
+        # the inputs of the timed loop are prepared outside it: one distance table per update (ONE branch differs
+        # from the previous table), the unit count of every update
+        tables, units = [], 0
+        for rep in range(3 if len(sel) < 512 else 1):
+            for n in sel:
+                d2 = d.copy()
+                d2[n] *= 1.01 + 0.001 * rep
+                tables.append(d2)
+                units += lf.patterns.work_units(bins, nodes=set(lf.topo.ancestors(n)))[1]
+        for d2 in tables[: len(sel)]:  # warm-up: every structure has been planned (and graph-captured) once
+            eng.update(d2)
+        eng.update(d)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for n in sel:
-            d2 = d.copy()
-            d2[n] *= 1.01
+        for d2 in tables:
             eng.update(d2)
-            units += lf.patterns.work_units(bins, nodes=set(lf.topo.ancestors(n)))[1]
         t_part = time.perf_counter() - t0
-        partial = {"evals_per_s": len(sel) / t_part, "updates_per_s": units / t_part,
-                   "edges_sampled": len(sel), "mean_units_per_eval": units / len(sel)}  # fmt: skip
+        eng.set_profiling(True)
+        eng.update(tables[0])
+        eng.update(tables[1])
+        launches_of_one = [{"kind": r["kind"], "us": round(r["ms"] * 1e3, 2)} for r in eng.launch_profile()]
+        eng.set_profiling(False)
+        partial = {"evals_per_s": len(tables) / t_part, "updates_per_s": units / t_part, "us_per_eval": t_part / len(tables) * 1e6,
+                   "edges_sampled": len(sel), "evals_timed": len(tables), "mean_units_per_eval": units / len(tables),
+                   "launches_of_one_update": launches_of_one}  # fmt: skip
 
     # ---- N > 1: the fused all-reduce against an NCCL all-reduce of the shard values ----------
     allreduce_check = None
@@ -893,8 +907,10 @@ def c5_strong_block(ctx, steps, warmup):
     codes = np.concatenate(parts, axis=1) if len(parts) > 1 else parts[0]
     del parts
     t_gen = time.perf_counter() - t0
+    # (motif probabilities fixed, not counted from the rank's own columns: every rank, and every N, must
+    #  evaluate the SAME likelihood function -- the total lnL is then the same number at N = 1, 2, 4, 8)
     problem = (model_name, topo, lengths, codes, np.eye(m.n_states), bins,
-               {"params": {"kappa": 4.0}, "rate_shape": 0.5})  # fmt: skip
+               {"params": {"kappa": 4.0}, "rate_shape": 0.5, "mprobs": np.full(m.n_states, 1.0 / m.n_states)})  # fmt: skip
     try:
         lf, setup_t = make_lf(problem, device=ctx.local_rank, stream=ctx.stream)
     except MemoryError as err:

@@ -118,6 +118,16 @@ struct c3_engine {
   int64_t off_pi = 0, off_bprobs = 0, off_jobs = 0, off_work = 0, off_prefix = 0, off_small = 0;
   bool use_small = true;  // fused small-levels kernel (C3_NO_SMALL=1 disables)
   bool use_small_reduce = true;  // ... which also reduces when the root is in it (C3_NO_SMALL_REDUCE=1 disables)
+  // "medium" levels (more units than one cluster takes, up to grid_units_per_thread units per thread of the whole
+  // GPU) join the small-levels group, which then runs as ONE cooperative launch over every SM with grid barriers
+  // between levels instead of a launch per level (C3_NO_GRID_SMALL=1 disables, C3_GRID_UNITS=n)
+  bool use_grid_small = false;  // opt-in (C3_GRID_SMALL=1): measured no faster than the launches it replaces, DESIGN.md lesson 17
+  int grid_units_per_thread = 4;
+  unsigned int* d_grid_bar = nullptr;
+  int path_variant = 1;   // 0: 1024 threads x 3 units, 1: 512 x 6, 2: 256 x 11 (C3_PATH_VARIANT)
+  bool use_path = false;  // opt-in (C3_PATH=1): single-branch updates of small problems by ONE CTA that walks the dirty
+                          // path with the rows in shared memory -- measured slower than the small-levels launch
+                          // (one SM has to issue every instruction of a level), DESIGN.md lesson 18
   bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
   // M != 4: every node stores its rows already multiplied by the P of the branch above it, one
   // contraction per NODE row (prune_dmma_edge_kernel); C3_EDGE_MAJOR=0: the parent-major kernels
@@ -136,8 +146,8 @@ struct c3_engine {
   bool use_flow = false;
   // wavefront kernel (prune4_wave_kernel): every dirty binary node of the sweep in one persistent launch, all
   // levels streaming at once; the static strip schedule of a structure is built on the host the second time the
-  // structure comes up and kept on the device.  C3_WAVE=0 disables.
-  bool use_wave = true;
+  // structure comes up and kept on the device.
+  bool use_wave = false;  // opt-in (C3_WAVE=1): measured slower than the per-level launches, DESIGN.md lesson 16
   int wave_lag = 4;          // chunks between a strip and the strips it depends on (C3_WAVE_LAG)
   int wave_group = 1;        // chunks per completion signal (C3_WAVE_GROUP)
   int64_t wave_prefix = 0;   // > 0: the wave launch takes only the tree's lower levels, up to the first level with
@@ -866,6 +876,10 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_SMALL")) e->use_small = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_SMALL_REDUCE")) e->use_small_reduce = atoi(env) == 0;
+  if (const char* env = getenv("C3_PATH")) e->use_path = atoi(env) != 0;
+  if (const char* env = getenv("C3_PATH_VARIANT")) e->path_variant = std::max(0, std::min(2, atoi(env)));
+  if (const char* env = getenv("C3_GRID_SMALL")) e->use_grid_small = atoi(env) != 0;
+  if (const char* env = getenv("C3_GRID_UNITS")) e->grid_units_per_thread = std::max(1, std::min(64, atoi(env)));
   if (const char* env = getenv("C3_DMMA_REG")) e->use_dmma_reg = atoi(env) != 0;
   e->edge_major = e->use_dmma;
   if (const char* env = getenv("C3_EDGE_MAJOR")) e->edge_major = e->use_dmma && atoi(env) != 0;
@@ -1464,6 +1478,7 @@ int c3_finalize(c3_engine* e) {
   e->d_counter = reinterpret_cast<unsigned int*>(e->d_pool + o_counter);
   e->d_seq = reinterpret_cast<unsigned long long*>(e->d_pool + o_counter + 8);
   e->d_epoch = reinterpret_cast<unsigned long long*>(e->d_pool + o_counter + 16);
+  e->d_grid_bar = reinterpret_cast<unsigned int*>(e->d_pool + o_counter + 32);
   e->d_lnl = reinterpret_cast<double*>(e->d_pool + o_lnl);
   e->d_done = reinterpret_cast<unsigned int*>(e->d_pool + o_done);
   C3_CUDA(cudaMemcpyAsync(e->d_counts, e->counts.data(), root_rows * sizeof(double),
@@ -2180,6 +2195,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     int64_t bytes, flops;
     int kind;
     int small_off, n_small;  // kind 1: range of SmallLevel records
+    int grid;                // kind 1: > 0 = a cooperative launch of that many CTAs with grid barriers (medium levels)
   };
   std::vector<LevelLaunch> launches;
   SmallLevel* small = reinterpret_cast<SmallLevel*>(e->h_block + e->off_small);
@@ -2230,6 +2246,51 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     w_off += ll.n_work;
     launches.push_back(ll);
   }
+  // ---- path launch?  the dirty set is ONE path to the root (a single branch length moved: the optimiser's
+  // inner loop) on a problem small enough for one CTA's shared memory: prune4_path_kernel, which also reduces
+  bool path_launch = false;
+  int path_buf_units = 0;
+  if (e->use_path && !wave && !e->use_dmma && !e->rescale_active && e->comm.nranks <= 1 && recompute[e->root] &&
+      e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE) {
+    std::vector<int> chain;
+    bool ok = true;
+    int64_t max_units = 0;
+    for (int n = 0; n < N && ok; ++n) {
+      if (!recompute[n]) continue;
+      if (!chain.empty() && e->parent[chain.back()] != n) ok = false;  // (ascending ids: a path is visited bottom-up)
+      ok = ok && e->children[n].size() <= (size_t)PATH_MAX_CHILDREN;
+      chain.push_back(n);
+      if (n != e->root) max_units = std::max<int64_t>(max_units, e->n_rows[n] * K);
+    }
+    ok = ok && !chain.empty() && chain.back() == e->root && (int)chain.size() <= PATH_MAX_NODES;
+    const size_t head = (sizeof(PathSmemHead) + 255) / 256 * 256;
+    const size_t smem = head + (size_t)chain.size() * PATH_MAX_CHILDREN * K * 16 * sizeof(double) +
+                        2 * (size_t)std::max<int64_t>(max_units, 1) * 4 * sizeof(double);
+    ok = ok && smem <= 220 * 1024;
+    if (ok) {
+      LevelLaunch ll{w_off, p_off, 0, 0, true, 0, 0, 9, 0, 0};
+      const int64_t bytes0 = alg_bytes, flops0 = flops;
+      for (size_t i = 0; i < chain.size(); ++i) {
+        const int n = chain[i];
+        work[w_off + ll.n_work] = n;
+        int slot = -1;
+        if (i > 0)
+          for (size_t c = 0; c < e->children[n].size(); ++c)
+            if (e->children[n][c] == chain[i - 1]) slot = (int)c;
+        dep[w_off + ll.n_work] = slot;
+        ++ll.n_work;
+        account(n);
+        recompute[n] = 0;
+      }
+      ll.total_tiles = (int)smem;  // (dynamic shared memory of the launch)
+      ll.bytes = alg_bytes - bytes0;
+      ll.flops = flops - flops0;
+      w_off += ll.n_work;
+      launches.push_back(ll);
+      path_launch = true;
+      path_buf_units = (int)std::max<int64_t>(max_units, 1);
+    }
+  }
   for (int l = 1; l <= e->n_levels; ++l) {
     int64_t units = 0;
     int n_dirty = 0;
@@ -2241,7 +2302,11 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
         other_kinds = other_kinds || kind_of_node(e, n) != 2;
       }
     if (n_dirty == 0) continue;
-    if (e->use_small && !e->use_dmma && units <= SMALL_LEVEL_UNITS) {
+    const int64_t small_limit =
+        (e->use_grid_small && !e->rescale_active)
+            ? std::max<int64_t>(SMALL_LEVEL_UNITS, (int64_t)e->grid_units_per_thread * e->n_sm * SMALL_THREADS)
+            : SMALL_LEVEL_UNITS;
+    if (e->use_small && !e->use_dmma && units <= small_limit) {
       close_flow();
       // extend (or open) a fused launch covering consecutive small levels
       if (open_small < 0) {
@@ -2273,6 +2338,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       g.total_tiles += (int)u;
       g.bytes += alg_bytes - bytes0;
       g.flops += flops - flops0;
+      if (u > SMALL_LEVEL_UNITS)  // a medium level: the whole group runs grid-wide, one thread per unit where possible
+        g.grid = std::max(g.grid, (int)std::min<int64_t>(e->n_sm, (u + SMALL_THREADS - 1) / SMALL_THREADS));
       // a scaled node is rescaled right after its launch: it must be in the group's LAST level
       if (e->rescale_active)
         for (int n : e->level_nodes[l])
@@ -2382,9 +2449,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
 
   // small problems whose root sits in the (last) small-levels launch: that launch also reduces
   // (prune4_small_kernel's tail: the same tiles and summation trees, one launch fewer)
-  const bool fuse_reduce = e->use_small_reduce && !launches.empty() && launches.back().kind == 1 &&
-                           launches.back().is_root && !e->rescale_active && comm.nranks <= 1 &&
-                           e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE;
+  const bool fuse_reduce = path_launch ||
+                           (e->use_small_reduce && !launches.empty() && launches.back().kind == 1 &&
+                            launches.back().grid == 0 && launches.back().is_root && !e->rescale_active && comm.nranks <= 1 &&
+                            e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE);
 
   // every stream operation of the evaluation (issued directly, or into a graph capture)
   bool capturing = false;
@@ -2435,9 +2503,33 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     a.M = M;
     a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
     a.lh_out = e->d_lh;
-    ProfScope ps(e, ll.kind == 1 ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
+    ProfScope ps(e, (ll.kind == 1 || ll.kind == 9) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
     if (ll.kind == 1) {
       const SmallLevel* d_small = reinterpret_cast<const SmallLevel*>(e->d_block + e->off_small) + ll.small_off;
+      if (ll.grid > 0) {
+        // medium levels: every SM, a cooperative launch (the grid barrier needs every CTA resident)
+        static DeviceOnce grid_cfg;
+        if (grid_cfg.need(e->device)) {
+          int rc = set_max_smem(prune4_small_kernel<true>, sizeof(SmallSmem));
+          if (rc) return rc;
+        }
+        C3_CUDA(cudaMemsetAsync(e->d_grid_bar, 0, sizeof(unsigned int), e->stream));
+        cudaLaunchConfig_t gcfg = {};
+        gcfg.gridDim = dim3(ll.grid);
+        gcfg.blockDim = dim3(SMALL_THREADS);
+        gcfg.dynamicSmemBytes = sizeof(SmallSmem);
+        gcfg.stream = e->stream;
+        cudaLaunchAttribute gattr[1];
+        gattr[0].id = cudaLaunchAttributeCooperative;
+        gattr[0].val.cooperative = 1;
+        gcfg.attrs = gattr;
+        gcfg.numAttrs = 1;
+        cudaError_t gerr = cudaLaunchKernelEx(&gcfg, prune4_small_kernel<true>, a, d_small, ll.n_small, ll.n_work,
+                                              ll.n_work + ll.n_small, ReduceTail{}, e->d_grid_bar);
+        if (gerr != cudaSuccess) return fail(C3_ERR_CUDA, std::string("medium-level launch: ") + cudaGetErrorString(gerr));
+        ++n_launch;
+        continue;
+      }
       // one cluster; fewer CTAs when there is little work (cluster size must divide the grid)
       int ctas = SMALL_CLUSTER;
       while (ctas > 1 && (int64_t)(ctas / 2) * SMALL_THREADS >= ll.total_tiles / std::max(1, ll.n_small)) ctas /= 2;
@@ -2447,7 +2539,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       cfg.dynamicSmemBytes = sizeof(SmallSmem);
       static DeviceOnce small_cfg;
       if (small_cfg.need(e->device)) {
-        int rc = set_max_smem(prune4_small_kernel, sizeof(SmallSmem));
+        int rc = set_max_smem(prune4_small_kernel<false>, sizeof(SmallSmem));
         if (rc) return rc;
       }
       cfg.stream = e->stream;
@@ -2468,9 +2560,41 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
         tail.n_tiles = (int)((tail.n_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
         tail.sink = sink;
       }
-      cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel, a, d_small, ll.n_small, ll.n_work,
-                                           ll.n_work + ll.n_small, tail);
+      cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel<false>, a, d_small, ll.n_small, ll.n_work,
+                                           ll.n_work + ll.n_small, tail, (unsigned*)nullptr);
       if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("small-level launch: ") + cudaGetErrorString(err));
+    } else if (ll.kind == 9) {
+      const size_t smem = (size_t)ll.total_tiles;
+      static DeviceOnce path_cfg;
+      if (path_cfg.need(e->device)) {
+        int rc = set_max_smem(prune4_path_kernel<1024, 3>, 220 * 1024);
+        if (rc == C3_OK) rc = set_max_smem(prune4_path_kernel<512, 6>, 220 * 1024);
+        if (rc == C3_OK) rc = set_max_smem(prune4_path_kernel<256, 11>, 220 * 1024);
+        if (rc) return rc;
+      }
+      const int threads = e->path_variant == 0 ? 1024 : (e->path_variant == 1 ? 512 : 256);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(1);
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = e->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ReduceTail tail{};
+      tail.bprobs = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
+      tail.counts = e->d_counts;
+      tail.n_rows = e->n_rows[e->root];
+      tail.n_tiles = (int)((tail.n_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
+      tail.sink = sink;
+      const int32_t* d_dirty = reinterpret_cast<const int32_t*>(e->d_block + e->off_dep) + ll.work_off;
+      cudaError_t err;
+      if (e->path_variant == 0) err = cudaLaunchKernelEx(&cfg, prune4_path_kernel<1024, 3>, a, d_dirty, path_buf_units, tail);
+      else if (e->path_variant == 1) err = cudaLaunchKernelEx(&cfg, prune4_path_kernel<512, 6>, a, d_dirty, path_buf_units, tail);
+      else err = cudaLaunchKernelEx(&cfg, prune4_path_kernel<256, 11>, a, d_dirty, path_buf_units, tail);
+      if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("path launch: ") + cudaGetErrorString(err));
     } else if (ll.kind == 7) {
       C3_CUDA(cudaMemsetAsync(wave->d_done, 0, (size_t)std::max(1, wave->n_chunks) * sizeof(unsigned), e->stream));
       int rc = C3_ERR_INVALID;
@@ -2553,6 +2677,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     for (const LevelLaunch& ll : launches) {
       sig.push_back(ll.kind); sig.push_back(ll.work_off); sig.push_back(ll.prefix_off); sig.push_back(ll.n_work);
       sig.push_back(ll.total_tiles); sig.push_back(ll.is_root ? 1 : 0); sig.push_back(ll.small_off); sig.push_back(ll.n_small);
+      sig.push_back(ll.grid);
     }
     for (int i = 0; i < w_off; ++i) sig.push_back(work[i]);  // (rescale launches name their nodes)
     uint64_t h = 1469598103934665603ull;

@@ -1446,15 +1446,32 @@ struct ReduceTail {
 // fit, every descriptor the units need is staged in shared memory first, so the
 // dependent-load chain per level is just  gather index -> child row  (P and the
 // descriptors no longer sit on it).
+//
+// GRID = true ("medium levels"): the same walk by the WHOLE GPU -- one CTA per SM, cooperative launch, a
+// grid barrier (arrive on a counter in device memory, spin until everybody has) between levels.  The
+// levels between the small ones and the streaming ones (C2: 1 MB and 15 MB, after two tiny ones) each cost
+// a launch of their own ~11-15 us whatever they hold; here a level costs a barrier (~2 us) plus its two
+// dependent global latencies.  `bar` is zeroed by the host before the launch.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire_gpu_u32(bar) < target) __nanosleep(32);
+  }
+  __syncthreads();
+}
+
+template <bool GRID>
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
 prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, int n_levels,
-                    int n_work_total, int n_prefix_total, const ReduceTail tail) {
+                    int n_work_total, int n_prefix_total, const ReduceTail tail, unsigned* __restrict__ bar) {
   extern __shared__ __align__(16) unsigned char small_raw[];
   SmallSmem& sm = *reinterpret_cast<SmallSmem*>(small_raw);
   pdl_trigger();
   const int K = a.K;
-  const unsigned nthreads = cluster_nctarank() * SMALL_THREADS;
-  const unsigned tid = cluster_ctarank() * SMALL_THREADS + threadIdx.x;
+  const unsigned nthreads = (GRID ? gridDim.x : cluster_nctarank()) * SMALL_THREADS;
+  const unsigned tid = (GRID ? blockIdx.x : cluster_ctarank()) * SMALL_THREADS + threadIdx.x;
   bool staged = n_work_total <= SMALL_MAX_WORK && n_levels <= SMALL_MAX_LEVELS;
   if (staged) {
     for (int i = threadIdx.x; i < n_levels; i += SMALL_THREADS) sm.levels[i] = levels[i];
@@ -1522,9 +1539,12 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
         a.lh_out[p * K + b] = lh;
       }
     }
-    if (li + 1 < n_levels) cluster_barrier();
+    if (li + 1 < n_levels) {
+      if (GRID) grid_barrier(bar, (unsigned)(li + 1) * gridDim.x);
+      else cluster_barrier();
+    }
   }
-  if (tail.n_tiles > 0) {
+  if (!GRID && tail.n_tiles > 0) {
     // the root was in this launch and the problem is small: the site-weighted reduction right here
     // (same tiles, same per-thread rows, same summation trees as lnl_reduce_kernel: same bits), by
     // the cluster's first CTA once every CTA's lh values are there
@@ -1533,6 +1553,202 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
     __shared__ double s_warp[SMALL_THREADS / 32];
     __shared__ double s_tiles[SMALL_REDUCE_MAX_TILES];
     const int t = (int)threadIdx.x;
+    for (int tile = 0; tile < tail.n_tiles; ++tile) {
+      const double acc = (t < REDUCE_THREADS)
+                             ? reduce_tile_partial(a.lh_out, tail.bprobs, tail.counts, tail.n_rows, K, tile, t, nullptr)
+                             : 0.0;
+      const double total = block_sum(acc, s_warp);  // (the warps past REDUCE_THREADS add +0.0)
+      if (t == 0) s_tiles[tile] = total;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    if (t < REDUCE_THREADS)
+      for (int i = t; i < tail.n_tiles; i += REDUCE_THREADS) acc += s_tiles[i];
+    const double total = block_sum(acc, s_warp);
+    if (t == 0) publish_result(tail.sink, total);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 4-state PATH kernel: the optimiser's inner loop on real-data sizes.
+//
+// Powell / simulated annealing move ONE branch length at a time (maths/scipy_optimize.py:371-383,
+// 488-541); the dirty set of such an update is a single path from the node above the changed branch
+// to the root: one node per level, each the parent of the previous one.  Through the small-levels
+// launch that is one cluster barrier plus two dependent global latencies per level -- ~2.5 us x 11
+// levels on brca1, the bulk of a 65 us update.  Here ONE CTA walks the path and keeps the rows of the
+// node it has just computed in SHARED memory: the next node gathers its dirty child from there (no
+// global round trip, a block barrier instead of a cluster barrier); its clean children come from
+// global memory, where they have been all along.  Every node's rows are still written to global
+// memory (they are the resident state later updates start from), the root's lh likewise, and the
+// site-weighted reduction follows in the same launch -- the same tiles and summation trees as
+// lnl_reduce_kernel, the same per-unit arithmetic as every other 4-state kernel: bit-identical.
+// Applies when rows x K of every node on the path fit two shared-memory buffers (brca1: 2764 rows).
+// ---------------------------------------------------------------------------------------
+constexpr int PATH_THREADS_MAX = 1024;
+constexpr int PATH_MAX_NODES = 64;
+constexpr int PATH_MAX_CHILDREN = 3;
+
+struct PathSmemHead {
+  NodeDesc nodes[PATH_MAX_NODES];
+  ChildRef childs[PATH_MAX_NODES * PATH_MAX_CHILDREN];
+  int32_t dirty_child[PATH_MAX_NODES];
+};
+
+// dirty_child[i]: which child slot of work item i is work item i - 1 (-1 for the first)
+// <threads per CTA, units per thread worked as one batch>: brca1 has 2764 units per level
+template <int PATH_THREADS, int PATH_UPT>
+__global__ void __launch_bounds__(PATH_THREADS, 1)
+prune4_path_kernel(const PruneArgs a, const int32_t* __restrict__ dirty_child, int buf_units, const ReduceTail tail) {
+  extern __shared__ __align__(32) unsigned char path_raw[];
+  PathSmemHead& sh = *reinterpret_cast<PathSmemHead*>(path_raw);
+  constexpr size_t HEAD = (sizeof(PathSmemHead) + 255) / 256 * 256;
+  double* sP = reinterpret_cast<double*>(path_raw + HEAD);  // [n_work][3][K][16]
+  const int K = a.K;
+  const int n_work = a.n_work;
+  double* buf0 = sP + (size_t)n_work * PATH_MAX_CHILDREN * K * 16;
+  double* buf1 = buf0 + (size_t)buf_units * 4;
+  const int t = (int)threadIdx.x;
+
+  pdl_trigger();
+  for (int i = t; i < n_work; i += PATH_THREADS) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    sh.nodes[i] = nd;
+    sh.dirty_child[i] = dirty_child[i];
+    for (int c = 0; c < nd.n_children && c < PATH_MAX_CHILDREN; ++c)
+      sh.childs[i * PATH_MAX_CHILDREN + c] = a.childs[nd.child_begin + c];
+  }
+  __syncthreads();
+  pdl_wait();  // the P matrices / tip tables of the expm launch
+  {
+    const int per_item = PATH_MAX_CHILDREN * K * 16;
+    for (int o = t; o < n_work * per_item; o += PATH_THREADS) {
+      const int i = o / per_item, rem = o - i * per_item;
+      const int c = rem / (K * 16), e16 = rem - c * (K * 16);
+      const double* P = (c < sh.nodes[i].n_children) ? sh.childs[i * PATH_MAX_CHILDREN + c].P : nullptr;
+      if (P != nullptr) sP[o] = P[e16];
+    }
+  }
+  __syncthreads();
+
+  double* prev = buf0;  // rows of work item i - 1, [rows][K][4]
+  double* cur = buf1;
+  // Every thread owns up to PATH_UPT units of a level (u = t + j * PATH_THREADS) and works them as a BATCH:
+  // the gather indexes of a level are requested while the previous level is finishing, the rows of a clean
+  // child are requested for the whole batch before any of them is used -- a level costs about one global
+  // latency, not (units per thread) x (two dependent latencies).  Levels with more units fall back to the
+  // unit-at-a-time loop.
+  constexpr int UPT = PATH_UPT;
+  int32_t ix[UPT][PATH_MAX_CHILDREN];
+  auto request_idx = [&](int i) {
+    if (i >= n_work) return;
+    const NodeDesc& nd = sh.nodes[i];
+    const int units = (int)nd.n_rows * K;
+    if (units > UPT * PATH_THREADS) return;
+#pragma unroll
+    for (int j = 0; j < UPT; ++j) {
+      const int u = t + j * PATH_THREADS;
+      if (u < units) {
+        const int p = u / K;
+#pragma unroll
+        for (int c = 0; c < PATH_MAX_CHILDREN; ++c)
+          if (c < nd.n_children) ix[j][c] = __ldg(sh.childs[i * PATH_MAX_CHILDREN + c].idx + p);
+      }
+    }
+  };
+  request_idx(0);
+  for (int i = 0; i < n_work; ++i) {
+    const NodeDesc nd = sh.nodes[i];
+    const ChildRef* ch = sh.childs + i * PATH_MAX_CHILDREN;
+    const double* Pi = sP + (size_t)i * PATH_MAX_CHILDREN * K * 16;
+    const int dc = sh.dirty_child[i];
+    const int units = (int)nd.n_rows * K;
+    auto finish = [&](d4 acc, int u) {
+      const int p = u / K, b = u - p * K;
+      if (nd.fixed_motif >= 0) {
+        if (nd.fixed_motif != 0) acc.x = 0.0;
+        if (nd.fixed_motif != 1) acc.y = 0.0;
+        if (nd.fixed_motif != 2) acc.z = 0.0;
+        if (nd.fixed_motif != 3) acc.w = 0.0;
+      }
+      if (nd.out != nullptr) st256(nd.out + ((int64_t)p * K + b) * 4, acc);
+      if (nd.is_root) {
+        const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
+        a.lh_out[(int64_t)p * K + b] = lh;
+      } else {
+        double* dst = cur + (size_t)u * 4;
+        dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
+      }
+    };
+    if (units <= UPT * PATH_THREADS) {
+      d4 acc[UPT];
+#pragma unroll
+      for (int c = 0; c < PATH_MAX_CHILDREN; ++c) {
+        if (c >= nd.n_children) break;
+        d4 x[UPT];
+        if (c == dc) {
+#pragma unroll
+          for (int j = 0; j < UPT; ++j) {
+            const int u = t + j * PATH_THREADS;
+            if (u < units) {
+              const double* src = prev + ((size_t)ix[j][c] * K + (u % K)) * 4;
+              x[j].x = src[0]; x[j].y = src[1]; x[j].z = src[2]; x[j].w = src[3];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < UPT; ++j) {  // the whole batch in flight together
+            const int u = t + j * PATH_THREADS;
+            if (u < units) x[j] = ld256(ch[c].src + ((int64_t)ix[j][c] * K + (u % K)) * 4);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) {
+          const int u = t + j * PATH_THREADS;
+          if (u < units) {
+            const d4 y = (ch[c].P != nullptr) ? matvec4(Pi + (c * K + (u % K)) * 16, x[j]) : x[j];
+            if (c == 0) acc[j] = y;
+            else { acc[j].x *= y.x; acc[j].y *= y.y; acc[j].z *= y.z; acc[j].w *= y.w; }
+          }
+        }
+      }
+      request_idx(i + 1);  // (static tables: in flight across the stores and the barrier)
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) {
+        const int u = t + j * PATH_THREADS;
+        if (u < units) finish(acc[j], u);
+      }
+    } else {
+      for (int u = t; u < units; u += PATH_THREADS) {
+        const int p = u / K, b = u - p * K;
+        d4 acc;
+#pragma unroll
+        for (int c = 0; c < PATH_MAX_CHILDREN; ++c) {
+          if (c >= nd.n_children) break;
+          const int32_t r = ch[c].idx[p];
+          d4 x;
+          if (c == dc) {
+            const double* src = prev + ((size_t)r * K + b) * 4;
+            x.x = src[0]; x.y = src[1]; x.z = src[2]; x.w = src[3];
+          } else {
+            x = ld256(ch[c].src + ((int64_t)r * K + b) * 4);
+          }
+          const d4 y = (ch[c].P != nullptr) ? matvec4(Pi + (c * K + b) * 16, x) : x;
+          if (c == 0) acc = y;
+          else { acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w; }
+        }
+        finish(acc, u);
+      }
+      request_idx(i + 1);
+    }
+    __syncthreads();
+    double* tmp = prev; prev = cur; cur = tmp;
+  }
+  if (tail.n_tiles > 0) {
+    // (the lh values were written by this CTA: visible to it after the barrier above)
+    static_assert(PATH_THREADS >= REDUCE_THREADS, "the reduction tail works with REDUCE_THREADS threads");
+    __shared__ double s_warp[PATH_THREADS_MAX / 32];
+    __shared__ double s_tiles[SMALL_REDUCE_MAX_TILES];
     for (int tile = 0; tile < tail.n_tiles; ++tile) {
       const double acc = (t < REDUCE_THREADS)
                              ? reduce_tile_partial(a.lh_out, tail.bprobs, tail.counts, tail.n_rows, K, tile, t, nullptr)

@@ -245,13 +245,17 @@ def _build(cogent3_modules):
 
         name = "gpu_lnL"
 
-        def setup(self, edge_names, internal_names, n_bins, engine_factory, device, n_loci=1, devices=None):
+        def setup(self, edge_names, internal_names, n_bins, engine_factory, device, n_loci=1, devices=None,
+                  return_lh=False):
             self.edge_names = list(edge_names)
             self.internal_names = list(internal_names)
             self.n_bins = n_bins
             self.engine_factory = engine_factory
             self.device = device
             self.devices = list(devices) if devices else None
+            # phylo-HMM (sites_independent=False): the value of the Defn is the per-bin, per-pattern root
+            # likelihoods (pruning on the device); the reference's own SiteHmm reduces them over the sites
+            self.return_lh = bool(return_lh)
             # id(lht) -> state, least recently used first.  The Defn instance (and so this cache) is
             # shared by every locus cell behind SumDefn(*tll.across_dimension("locus", ...)): it must
             # hold one engine per locus plus one for the Calculator's 1-deep undo
@@ -382,11 +386,31 @@ def _build(cogent3_modules):
             for node, f in zip(st["internal_ids"], fixed, strict=True):
                 fm[node] = -1 if f in (None, -1) else int(f)
             eng.set_fixed_motifs(fm)
-            return eng.evaluate()
+            return self._finish(eng)
+
+        def _finish(self, eng):
+            from . import batch as _batch
+
+            lockstep = _batch.current()
+            # inside cogent3_b200.batch.run_lockstep the evaluations of several optimiser threads meet in one
+            # c3_evaluate_many call; otherwise the engine is evaluated right here
+            value = eng.evaluate() if lockstep is None else lockstep.evaluate(eng)
+            if self.return_lh:
+                return tuple(eng.get_lh(b) for b in range(self.n_bins))
+            return value
 
         def engine_for(self, lht):
             st = self._engines.get(id(lht))
             return None if st is None or st["lht"] is not lht else st["engine"]
+
+    class HmmTotalDefn(CalculationDefn):
+        """``tll = CallDefn(blh, *lh.across_dimension("bin", ...))`` (evolve/likelihood_calculation.py:157) with the
+        K per-bin arrays arriving as one value from the engine Defn"""
+
+        name = "tll"
+
+        def calc(self, blh, lhs):
+            return blh(*lhs)
 
     class GpuFactoredLogLikelihoodDefn(GpuLogLikelihoodDefn):
         """The same terminal Defn fed with the FACTORS of the psubs instead of the psubs:
@@ -471,16 +495,18 @@ def _build(cogent3_modules):
                     fm[node] = -1 if f in (None, -1) else int(f)
                 eng.set_fixed_motifs(fm)
                 st["last_fixed"] = fixed
-            return eng.evaluate()
+            return self._finish(eng)
 
     def make_total_loglikelihood_defn(tree, leaves, psubs, mprobs, bprobs, bin_names, locus_names,
                                       sites_independent, engine_factory, device, factors=None, devices=None):  # fmt: skip
         """same signature and role as the reference function of this name
         (evolve/likelihood_calculation.py:125-134), plus the engine selection"""
-        if not sites_independent:
-            raise NotImplementedError(
-                "the phylo-HMM (sites_independent=False) is out of scope (SURVEY §8a)"
-            )
+        # phylo-HMM (SURVEY §8 f-4): with several bins and sites_independent=False the per-bin root likelihoods
+        # are reduced over the SITES by a hidden Markov model (PatchSiteDistribution / SiteHmm,
+        # evolve/likelihood_calculation.py:197-235,260-296) instead of being mixed per pattern.  The pruning --
+        # all of the O(patterns x edges) work -- runs on the device as usual; the reduction is the reference's own
+        # code on the K x patterns array the engine hands back.
+        hmm = (not sites_independent) and len(bin_names) > 1
         fixed_motifs = NonParamDefn("fixed_motif", ["edge"])
         lht = FastLikelihoodTreeDefn(leaves, tree=tree)
         leaves.__dict__["_memo_cap"] = lht.__dict__["_memo_cap"] = len(locus_names) + 1
@@ -508,7 +534,7 @@ def _build(cogent3_modules):
             tll = GpuFactoredLogLikelihoodDefn(
                 *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
                 engine_factory=engine_factory, device=device, has_rate=rate is not None,
-                n_loci=len(locus_names), devices=devices,
+                n_loci=len(locus_names), devices=devices, return_lh=hmm,
             )  # fmt: skip
         else:
             for name in edge_names:
@@ -520,7 +546,15 @@ def _build(cogent3_modules):
             tll = GpuLogLikelihoodDefn(
                 *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
                 engine_factory=engine_factory, device=device, n_loci=len(locus_names), devices=devices,
+                return_lh=hmm,
             )  # fmt: skip
+        if hmm:
+            from cogent3.recalculation.definition import CalcDefn, CallDefn, ProbabilityParamDefn
+
+            switch = ProbabilityParamDefn("bin_switch", dimensions=["locus"])
+            site_pattern = CalcDefn(likelihood_calculation.PatchSiteDistribution, name="bdist")(switch, bprobs)
+            blh = CallDefn(site_pattern, lht, name="bindex")
+            tll = HmmTotalDefn(blh, tll)
         if len(locus_names) > 1:
             tll = SumDefn(*tll.across_dimension("locus", locus_names))
         else:
@@ -571,6 +605,7 @@ def _build(cogent3_modules):
                     # keep (exponentiator, distance) symbolic, one LazyPsub cell per (edge, bin)
                     psubs = LazyPsubDefn(*original.args)
             self._factors = factors
+            self._hmm = (not sites_independent) and len(self.bin_names) > 1
             self._gpu_defn_factory = None
             leaves = defns["align"]
             if type(leaves) is substitution_calculation.AlignmentAdaptDefn:
@@ -698,7 +733,7 @@ def _build(cogent3_modules):
                 bin_ = kw.get("bin")
                 b = 0 if bin_ is None else list(self.bin_names).index(bin_)
                 return self._engine(kw.get("locus")).get_lh(b)
-            if par_name in ("bindex", "bdist"):
+            if par_name in ("bindex", "bdist") and not getattr(self, "_hmm", False):
                 locus = kw.get("locus")
                 lkw = {} if locus is None else {"locus": locus}
                 dist = likelihood_calculation.BinnedSiteDistribution(
@@ -722,7 +757,7 @@ def _build(cogent3_modules):
     # picklable by reference (process-parallel apps, app/evo.py bootstrap with parallel=True, pickle
     # likelihood functions): the classes are reachable as attributes of this module
     exported = (CudaAlignmentLikelihoodFunction, GpuLogLikelihoodDefn, LazyPsubDefn,
-                GpuFactoredLogLikelihoodDefn, FastAlignmentAdaptDefn, FastLikelihoodTreeDefn)  # fmt: skip
+                GpuFactoredLogLikelihoodDefn, FastAlignmentAdaptDefn, FastLikelihoodTreeDefn, HmmTotalDefn)  # fmt: skip
     for cls in exported:
         cls.__module__ = __name__
         cls.__qualname__ = cls.__name__
@@ -746,7 +781,8 @@ def _classes():
 
 
 _CLASS_NAMES = ("CudaAlignmentLikelihoodFunction", "GpuLogLikelihoodDefn", "LazyPsubDefn",
-                "GpuFactoredLogLikelihoodDefn", "FastAlignmentAdaptDefn", "FastLikelihoodTreeDefn")  # fmt: skip
+                "GpuFactoredLogLikelihoodDefn", "FastAlignmentAdaptDefn", "FastLikelihoodTreeDefn",
+                "HmmTotalDefn")  # fmt: skip
 
 
 def __getattr__(name):
@@ -793,8 +829,9 @@ def make_likelihood_function(model, tree, motif_probs_from_align=None, optimise_
 #     lf = get_model("GTR").make_likelihood_function(tree, backend="cpu")   # the reference class
 #
 # every stock caller (apps, bootstrap, hypothesis tests, tree search) builds the CUDA class.  What the
-# engine does not cover stays with the reference class: unaligned sequences (pair-HMM alignment) and
-# the phylo-HMM (``sites_independent=False``).
+# engine does not cover stays with the reference class: unaligned sequences (pair-HMM alignment).  The
+# phylo-HMM (``sites_independent=False``) prunes on the device and reduces over the sites with the
+# reference's own SiteHmm.
 # ---------------------------------------------------------------------------------------
 _STOCK_MAKE_LF = None
 INSTALL_STATS = {"cuda": 0, "reference": 0}
@@ -828,7 +865,7 @@ def install(default_backend="cuda", device=0, devices=None, engine_factory=None)
         backend = backend or default_backend
         if backend not in ("cuda", "cpu"):
             raise ValueError(f"unknown backend {backend!r}")
-        if backend == "cpu" or not aligned or kw.get("sites_independent", True) is False:
+        if backend == "cpu" or not aligned:
             INSTALL_STATS["reference"] += 1
             for key in ("device", "devices", "engine_factory", "factored"):
                 kw.pop(key, None)

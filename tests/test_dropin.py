@@ -663,3 +663,67 @@ def test_patterns_sharded_over_devices_in_one_process():
             xk = x * (1.0 + 0.01 * (k + 1))
             a, b = rcalc(xk), calc(xk[perm])
             assert abs(a - b) <= 1e-12 * abs(a)
+
+
+def test_phylo_hmm_prunes_on_the_engine():
+    """``sites_independent=False`` (PatchSiteDistribution / SiteHmm,
+    evolve/likelihood_calculation.py:197-296): the per-bin root likelihoods come from the engine, the reduction
+    over the sites is the reference's own hidden Markov model; lnL, posterior bin probabilities and the
+    optimiser's path are the stock class's"""
+    tree, aln = small_problem(n_tips=8, L=600, seed=31)
+    mk = lambda: get_model("HKY85", ordered_param="rate", distribution="gamma")  # noqa: E731
+    with installed():
+        lf = mk().make_likelihood_function(tree, bins=4, sites_independent=False)
+        ref = mk().make_likelihood_function(tree, bins=4, sites_independent=False, backend="cpu")
+    assert type(lf).__name__ == "CudaAlignmentLikelihoodFunction"
+    for f in (ref, lf):
+        f.set_alignment(aln)
+        f.set_param_rule("bprobs", is_constant=True)
+        f.set_param_rule("rate_shape", value=0.7)
+        f.set_param_rule("kappa", value=3.1)
+        f.set_param_rule("bin_switch", value=0.3)
+    assert_same(ref, lf, rel=1e-12)
+    assert lf._engine().stats()["evaluations"] > 0
+    np.testing.assert_allclose(lf.get_bin_probs().array, ref.get_bin_probs().array, rtol=1e-10, atol=1e-13)
+    for f in (ref, lf):
+        f.set_param_rule("bin_switch", value=0.05)
+        f.set_param_rule("length", edge=tree.get_tip_names()[1], value=0.4)
+    assert_same(ref, lf, rel=1e-12)
+    assert lf.get_num_free_params() == ref.get_num_free_params()
+    # the optimiser's view: the same points through both Calculators (their parameter orders differ)
+    rc, lc = ref.make_calculator(), lf.make_calculator()
+    where = {(p.name, repr(p.scope)): i for i, p in enumerate(rc.opt_pars)}
+    perm = np.array([where[(p.name, repr(p.scope))] for p in lc.opt_pars])
+    x = np.array(rc.get_value_array())
+    rng = np.random.default_rng(1)
+    for _ in range(6):
+        xk = x * (1.0 + 0.05 * rng.standard_normal(len(x)))
+        a, b = rc(xk), lc(xk[perm])
+        assert abs(a - b) <= 1e-11 * abs(a)
+
+
+def test_many_likelihood_functions_optimised_in_lockstep():
+    """N independent cogent3 optimisations (model fits over many alignments, bootstrap replicates)
+    run concurrently, their evaluations batched into one device call per round (cogent3_b200/batch.py); every
+    function ends where its own sequential ``lf.optimise()`` ends"""
+    from cogent3_b200.batch import log_likelihoods, optimise_many
+
+    problems = [small_problem(n_tips=6, L=150 + 10 * k, seed=40 + k) for k in range(6)]
+
+    def build():
+        out = []
+        for tree, aln in problems:
+            lf = make_likelihood_function(get_model("HKY85"), tree, engine_factory=FACTORY)
+            lf.set_alignment(aln)
+            out.append(lf)
+        return out
+
+    seq, par = build(), build()
+    for lf in seq:
+        lf.optimise(local=True, show_progress=False, max_evaluations=400, limit_action="ignore")
+    _, stats = optimise_many(par, return_stats=True, local=True, max_evaluations=400, limit_action="ignore")
+    assert stats["mean_batch"] > 2.0, stats  # the evaluations really met in batches
+    for a, b in zip(seq, par, strict=True):
+        assert abs(a.get_log_likelihood() - b.get_log_likelihood()) <= 1e-9 * abs(a.get_log_likelihood())
+        assert b.get_param_value("kappa") == pytest.approx(a.get_param_value("kappa"), rel=1e-6)
+    np.testing.assert_allclose(log_likelihoods(par), [lf.get_log_likelihood() for lf in par], rtol=1e-13)

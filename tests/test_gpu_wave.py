@@ -141,3 +141,49 @@ def test_wave_steps_aside_for_polytomies_and_rescaling(monkeypatch):
             lf.set_param_rule("length", edge="i", value=0.2 + 0.01 * k)
         assert plain.get_log_likelihood() == wave.get_log_likelihood()
     assert wave.engine.stats()["wave_launches"] == n_wave  # rescaled rows: level launches
+
+
+@pytest.mark.parametrize("model,n_tips,L,bins", [("HKY85", 30, 2500, 1), ("GTR", 18, 700, 4), ("HKY85", 55, 3000, 2)])
+def test_path_launch_is_bit_identical(model, n_tips, L, bins, monkeypatch):
+    """single-branch updates of small problems go through prune4_path_kernel (one CTA walks the dirty path with
+    the rows in shared memory and reduces): bit-identical to the small-levels launch it replaces, update after
+    update, and the rows it leaves in global memory are what later updates start from"""
+    m = hostmodels.get_model(model)
+    topo, lengths, codes = make_workload(n_tips, L, m.n_states, kind="dense", seed=17)
+
+    def make(no_path):
+        for k in WAVE_ENV + ("C3_PATH",):
+            monkeypatch.delenv(k, raising=False)
+        if not no_path:
+            monkeypatch.setenv("C3_PATH", "1")
+        lf = LikelihoodFunction(m, topo, bins=bins)
+        lf.set_alignment(codes.astype(np.int64), np.eye(4))
+        lf.set_motif_probs_from_data()
+        lf.lengths[:-1] = np.asarray(lengths)[:-1]
+        for k, p in enumerate(m.parameter_order):
+            lf.set_param_rule(p, value=0.5 + 0.37 * k)
+        if bins > 1:
+            lf.set_param_rule("rate_shape", value=0.6)
+        return lf
+
+    plain, path = make(True), make(False)
+    assert plain.get_log_likelihood() == path.get_log_likelihood()
+    rng = np.random.default_rng(2)
+    launches = []
+    for step in range(60):  # (past the CUDA-graph capture threshold of a structure)
+        n = int(rng.choice(topo.edges)) if step % 3 else int(topo.edges[step % 5])
+        v = float(rng.uniform(0.01, 0.6))
+        for lf in (plain, path):
+            lf.set_param_rule("length", edge=topo.names[n], value=v)
+        assert plain.get_log_likelihood() == path.get_log_likelihood(), step
+        launches.append((plain.engine.stats()["last_launches"], path.engine.stats()["last_launches"]))
+    same_rows(plain, path, topo, bins)
+    assert all(b <= a for a, b in launches)
+    # a rate-matrix parameter: every edge dirty -> not a path, the usual launches; then paths again
+    for lf in (plain, path):
+        lf.set_param_rule(m.parameter_order[0], value=2.2)
+    assert plain.get_log_likelihood() == path.get_log_likelihood()
+    for lf in (plain, path):
+        lf.set_motif_probs(np.array([0.1, 0.2, 0.3, 0.4]))  # only the root is dirty: a path of one node
+    assert plain.get_log_likelihood() == path.get_log_likelihood()
+    same_rows(plain, path, topo, bins)
