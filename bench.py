@@ -686,6 +686,24 @@ def dropin_leg(ctx, problem, cfg, steps, warmup, expect_units):
         h2d += eng.stats()["last_h2d_bytes"]
     ctx.barrier()
     wall = time.perf_counter() - t0
+    # the same steps with only the branch lengths moving (no new rate matrix, so no eigendecomposition on the
+    # host: the other kind of step an optimiser makes; at 61 states numpy's eig is most of a full step's host time)
+    is_length = np.array([p.name == "length" for p in calc.opt_pars])
+    lengths_only = None
+    if is_length.any() and not is_length.all():
+        def length_point(k):
+            xk = x.copy()
+            xk[is_length] = calculator_points(x, k)[is_length]
+            return xk
+
+        for w in range(2):
+            step(length_point(200 + w))
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            step(length_point(k))
+        ctx.barrier()
+        lengths_only = ctx.max_over_ranks(time.perf_counter() - t0) / steps * 1e3
     evals = None
     if ctx.world == 1:
         calc(x)
@@ -698,6 +716,7 @@ def dropin_leg(ctx, problem, cfg, steps, warmup, expect_units):
         eng.comm_detach()
     st = eng.stats()
     return {"wall_s": wall, "h2d": h2d, "lnL0": lnl0, "lnL_last": float(lnl), "fused": fused, "lf_evals": evals,
+            "lengths_only_ms": lengths_only,
             "graph_replays": int(st["graph_replays"]), "n_parameters": int(len(x)),
             "setup": {**t_setup, "first_evaluation_s": t_first, "make_calculator_s": t_calc}}  # fmt: skip
 
@@ -878,6 +897,10 @@ def measure_workload(ctx, args, cfg, columns, kind, steps, warmup, shard, clocks
                              "reference arm times); unmodified cogent3 from baseline/_ref on the host, libc3cuda on "
                              "the device",
                       "n_parameters": dropin["n_parameters"], "lf_evals": dropin["lf_evals"],
+                      "lengths_only": ({"ms_per_step": dropin["lengths_only_ms"],
+                                        "value": total_units / (dropin["lengths_only_ms"] * 1e-3),
+                                        "step": "every branch length changed, rate-matrix parameters unchanged"}
+                                       if dropin.get("lengths_only_ms") else None),
                       "fused_allreduce": dropin["fused"], "graph_replays": dropin["graph_replays"],
                       "setup": dropin["setup"], "lnL_first": dropin["lnL0"]}  # fmt: skip
     else:

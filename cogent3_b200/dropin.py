@@ -454,21 +454,27 @@ def _build(cogent3_modules):
             except Exception:  # noqa: BLE001 - an exotic exponentiator with an array-valued __eq__
                 same_qds = last is not None and all(a is b for a, b in zip(qds, last, strict=True))
             if not same_qds:
-                # (re)assign exponentiators to q slots; rare: only when a rate-matrix parameter moved
+                # (re)assign exponentiators to q slots: whenever a rate-matrix parameter moved.  The E*K
+                # entries name only a few DISTINCT objects (one for a time-homogeneous model, one per edge
+                # with per-edge Q), so the per-entry work is numpy's: ids -> unique -> slot of each
+                ids = np.fromiter(map(id, qds), dtype=np.int64, count=len(qds))
+                _uniq, first, inverse = np.unique(ids, return_index=True, return_inverse=True)
+                slot_of_uniq = np.empty(len(first), np.int32)
                 live, host = set(), {}
-                k = 0
-                for node in edge_ids:
-                    for b in range(K):
-                        ex = qds[k]
-                        k += 1
-                        slot = self._slot_for(st, ex)
-                        if slot is None:
-                            host[(node, b)] = ex  # not an eigen / Pade exponentiator: P on the host
-                            qslots[node, b] = -1
-                        else:
-                            live.add(slot)
-                            st["psub_obj"].pop((node, b), None)
-                            qslots[node, b] = slot
+                for u, f in enumerate(first):
+                    slot = self._slot_for(st, qds[int(f)])
+                    slot_of_uniq[u] = -1 if slot is None else slot
+                    if slot is not None:
+                        live.add(slot)
+                per_entry = slot_of_uniq[inverse.reshape(-1)].reshape(E, K)
+                qslots[edge_ids, :] = per_entry
+                if (per_entry < 0).any():
+                    # not an eigen / Pade exponentiator: P on the host for those (edge, bin)s
+                    for e_i, b in zip(*np.nonzero(per_entry < 0), strict=True):
+                        host[(edge_ids[int(e_i)], int(b))] = qds[int(e_i) * K + int(b)]
+                if st["psub_obj"]:
+                    for key in [k for k in st["psub_obj"] if k not in host]:
+                        st["psub_obj"].pop(key, None)
                 eng.set_edge_qslots(qslots)  # negative entries are left alone by the engine
                 for slot in [s for s in st["slot_obj"] if s not in live]:
                     ex = st["slot_obj"].pop(slot)
