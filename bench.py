@@ -1030,6 +1030,85 @@ def cpu_baseline_subprocess(args, cfg, columns=None, kind="evolved", cpu_sample=
         return {"error": f"cpu baseline failed: {err!r}"}
 
 
+def many_small_block(ctx, problem, lf, B=64):
+    """many small alignments at once: B independent engines of the same size, all branch lengths
+    changed, through c3_update_many (every engine on its own stream; a batch that keeps coming up is ONE graph)"""
+    from cogent3_b200.engine import update_many as engine_update_many
+
+    torch = ctx.torch
+    base, rates = lf.lengths.copy(), lf.rates()
+    step_dist = [np.ascontiguousarray(np.nan_to_num(step_lengths(base, k))[:, None] * rates[None, :])
+                 for k in range(7)]  # fmt: skip
+    lfs = [make_lf(problem, device=ctx.local_rank)[0] for _ in range(B)]
+    engines = [f.engine for f in lfs]
+    for f in lfs:
+        f.get_log_likelihood()
+
+    def many_step(k):
+        return engine_update_many(engines, step_dist[k % 7])
+
+    for k in range(20):  # (past the engines' graph-capture threshold: steady state)
+        many_step(k)
+    n_rep = 100
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(n_rep):
+        vals = many_step(k)
+    t_many = (time.perf_counter() - t0) / n_rep
+    t_seq = 0.0
+    for k in range(5):  # the same work, one blocking evaluation after the other
+        d = np.nan_to_num(step_lengths(base, 1000 + k))[:, None] * rates[None, :]
+        for e_ in engines:
+            e_.set_distances(d)
+        t0 = time.perf_counter()
+        one_by_one = [e_.evaluate() for e_ in engines]
+        t_seq += (time.perf_counter() - t0) / 5
+    del one_by_one
+    for f in lfs:
+        f.engine.close()
+    return {"engines": B, "evals_per_s": B / t_many, "ms_per_batch": t_many * 1e3,
+            "one_at_a_time_evals_per_s": B / t_seq, "all_equal": bool(len(set(vals)) == 1),
+            "api": "c3_update_many: every engine on its own stream; a batch that keeps coming up is ONE CUDA graph"}
+
+
+def lockstep_block(ctx, problem, B=16, n_evals=300):
+    """the same idea THROUGH cogent3: B likelihood functions built by sm.make_likelihood_function (hook installed),
+    each driven by its own thread making real one-parameter changes through Calculator.change (an optimiser's
+    inner loop); cogent3_b200.batch lets their evaluations meet in one c3_evaluate_many call per round"""
+    if import_cogent3() is None:
+        return None
+    from cogent3_b200.batch import run_lockstep
+
+    calcs = []
+    for _ in range(B):
+        lf, _t = build_cogent3_lf(problem, "c1", backend="cuda", device=ctx.local_rank)
+        lf.get_log_likelihood()
+        calcs.append(lf.make_calculator())
+    xs = [np.array(c.get_value_array(), float) for c in calcs]
+
+    def drive(calc, x, n):
+        k = 0
+        for _ in range(n):
+            i = k % len(x)
+            k += 1
+            calc.change([(i, x[i] * (1.0 + 1e-6 * (1 + k % 89)))])
+
+    for c, x in zip(calcs, xs, strict=True):
+        drive(c, x, 40)  # warm-up (graph capture thresholds)
+    t0 = time.perf_counter()
+    for c, x in zip(calcs, xs, strict=True):
+        drive(c, x, n_evals)
+    t_seq = time.perf_counter() - t0
+    run_lockstep([(lambda c=c, x=x: drive(c, x, 40)) for c, x in zip(calcs, xs, strict=True)])
+    t0 = time.perf_counter()
+    _res, batch = run_lockstep([(lambda c=c, x=x: drive(c, x, n_evals)) for c, x in zip(calcs, xs, strict=True)])
+    t_par = time.perf_counter() - t0
+    return {"likelihood_functions": B, "evals_each": n_evals,
+            "one_after_the_other_evals_per_s": B * n_evals / t_seq, "lockstep_evals_per_s": B * n_evals / t_par,
+            "mean_batch": batch.evaluations / max(1, batch.batches),
+            "api": "cogent3 Calculator.change in B threads, evaluations batched by cogent3_b200.batch (c3_evaluate_many)"}
+
+
 def run_ours(args):
     ctx = Ctx()
     torch, dist, world, rank = ctx.torch, ctx.dist, ctx.world, ctx.rank
@@ -1039,51 +1118,34 @@ def run_ours(args):
                                 with_dropin=not args.no_dropin and (args.columns or CONFIGS[args.config][2]) <= 2_500_000)  # fmt: skip
     problem, lf = main_rec.pop("problem"), main_rec.pop("lf")
 
-    # ---- many small alignments at once: B independent likelihood functions --
-    many = None
+    many = lockstep = None
     if world == 1 and args.config == "c1":
-        from cogent3_b200.engine import update_many as engine_update_many
-
-        B = 64
-        base, rates = lf.lengths.copy(), lf.rates()
-        step_dist = [np.ascontiguousarray(np.nan_to_num(step_lengths(base, k))[:, None] * rates[None, :])
-                     for k in range(7)]  # fmt: skip
-        lfs = [make_lf(problem, device=ctx.local_rank)[0] for _ in range(B)]
-        engines = [f.engine for f in lfs]
-        for f in lfs:
-            f.get_log_likelihood()
-
-        def many_step(k):
-            return engine_update_many(engines, step_dist[k % 7])
-
-        for k in range(20):  # (past the engines' graph-capture threshold: steady state)
-            many_step(k)
-        n_rep = 100
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for k in range(n_rep):
-            vals = many_step(k)
-        t_many = (time.perf_counter() - t0) / n_rep
-        t_seq = 0.0
-        for k in range(5):  # the same work, one blocking evaluation after the other
-            d = np.nan_to_num(step_lengths(base, 1000 + k))[:, None] * rates[None, :]
-            for e_ in engines:
-                e_.set_distances(d)
-            t0 = time.perf_counter()
-            one_by_one = [e_.evaluate() for e_ in engines]
-            t_seq += (time.perf_counter() - t0) / 5
-        many = {"engines": B, "evals_per_s": B / t_many, "ms_per_batch": t_many * 1e3,
-                "one_at_a_time_evals_per_s": B / t_seq, "all_equal": bool(len(set(vals)) == 1),
-                "api": "c3_update_many: every engine on its own stream; a batch that keeps coming up is ONE CUDA graph"}
-        del one_by_one
-        for f in lfs:
-            f.engine.close()
+        many = many_small_block(ctx, problem, lf)
+        if not args.no_dropin:
+            try:
+                lockstep = lockstep_block(ctx, problem)
+            except Exception as err:  # noqa: BLE001
+                lockstep = {"error": repr(err)}
     lf.engine.close()
     del lf
 
     # ---- what else `north_star` names, in the same line (default config only) ------------------------
     extras = args.config == "c2" and not args.columns and args.kind == "evolved" and not args.no_extra
-    c4 = c5 = None
+    c4 = c5 = c1 = None
+    if extras and world == 1:
+        # C1: the one BASELINE config on real data (brca1, 55 taxa x 3009 columns): latency, not bandwidth
+        try:
+            rec = measure_workload(ctx, args, "c1", None, "evolved", steps=min(10 * args.steps, 2000), warmup=20, shard=0,
+                                   with_dropin=not args.no_dropin)  # fmt: skip
+            p1, lf1 = rec.pop("problem"), rec.pop("lf")
+            c1 = {"workload": f"c1: {CONFIGS['c1'][4]}", "us_per_full_evaluation": rec["ms_per_step"] * 1e3,
+                  "full_evals_per_s": rec["units"]["lf_evals_per_s"], "partial_update": rec["partial_update"],
+                  "e2e": rec["e2e"], "many_small": many_small_block(ctx, p1, lf1)}
+            if not args.no_dropin:
+                c1["lockstep"] = lockstep_block(ctx, p1)
+            lf1.engine.close()
+        except Exception as err:  # noqa: BLE001
+            c1 = {"error": repr(err)}
     if extras and world == 1:
         try:
             rec = measure_workload(ctx, args, "c4", None, "evolved", steps=min(args.steps, 300), warmup=3, shard=0,
@@ -1127,7 +1189,8 @@ def run_ours(args):
         "cpu_baseline": cpu_rec,
         "units": main_rec["units"],
         "partial_update": main_rec["partial_update"],
-        "many_small": many,
+        "many_small": many, "lockstep": lockstep,
+        "c1": c1,
         "allreduce": main_rec["allreduce"],
         "setup": main_rec["setup"],
         "lnL": main_rec["lnL"],

@@ -94,6 +94,7 @@ SIGNATURES = {
     "c3_comm_mailbox": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_uint8)]),
     "c3_comm_attach": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint8), POINTER(c_void_p)]),
     "c3_comm_detach": (c_int, [c_void_p]),
+    "c3_hmm_reduce": (c_int, [c_void_p, c_int, _pi32, _pd, _pd, _pd, _pd]),
     "c3_get_lh": (c_int, [c_void_p, c_int, _pd, c_int64]),
     "c3_get_psub": (c_int, [c_void_p, c_int, c_int, _pd]),
     "c3_get_partials": (c_int, [c_void_p, c_int, c_int, _pd, c_int64]),

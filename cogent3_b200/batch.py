@@ -166,3 +166,32 @@ def log_likelihoods(lfs) -> np.ndarray:
         if isinstance(r, BaseException):
             raise r
     return np.array(results, float)
+
+
+def run_estimate_distances(dist_calc, dist_opt_args=None, aln_opt_args=None, max_concurrent=64):
+    """``EstimateDistances.run`` (evolve/distance.py:182-234) with the n (n - 1) / 2 two-taxon (or three-taxon)
+    fits optimised CONCURRENTLY, their evaluations in lock-step batches (the pairwise path).
+    ``dist_calc`` is a stock ``cogent3.evolve.distance.EstimateDistances``; ``cogent3_b200.install()`` must be
+    active so that the fits build CUDA likelihood functions.  Results land where ``run`` puts them
+    (``dist_calc.get_pairwise_distances()`` etc. work afterwards)."""
+    from cogent3.evolve.distance import get_name_combinations
+
+    dist_opt_args = dict(dist_opt_args or {})
+    aln_opt_args = dict(aln_opt_args or {})
+    dist_opt_args["local"] = dist_opt_args.get("local", True)
+    aln_opt_args["local"] = aln_opt_args.get("local", True)
+    dist_opt_args.setdefault("show_progress", False)
+    combos = get_name_combinations(dist_calc._seq_collection.names, 3 if dist_calc._threeway else 2)
+    stats = {"batches": 0, "evaluations": 0}
+    for start in range(0, len(combos), max_concurrent):
+        chunk = combos[start : start + max_concurrent]
+        jobs = [(lambda comp=comp: dist_calc._doset(comp, dict(dist_opt_args), dict(aln_opt_args))) for comp in chunk]
+        results, batch = run_lockstep(jobs)
+        for comp, value in zip(chunk, results, strict=True):
+            if isinstance(value, BaseException):
+                raise value
+            dist_calc._param_ests[comp] = value
+        stats["batches"] += batch.batches
+        stats["evaluations"] += batch.evaluations
+    stats["mean_batch"] = stats["evaluations"] / max(1, stats["batches"])
+    return stats

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -26,6 +27,7 @@
 #include "compress_kernels.cuh"
 #include "expm_kernels.cuh"
 #include "prune_kernels.cuh"
+#include "hmm_kernels.cuh"
 
 using namespace c3;
 
@@ -249,9 +251,16 @@ namespace {
 
 // cudaFuncSetAttribute is per device (context): one engine per GPU in one process (c3_create(device, ...),
 // c3_comm_attach(device_ptrs=...)) must opt in on EVERY device it runs on, not only the first
+// Engines are single-threaded objects (like cogent3's Calculator), but SEVERAL engines may be driven from
+// several host threads at once (cogent3_b200.batch: ctypes releases the GIL during a call): what engines share
+// -- the per-device opt-in flags, the batch-graph registry -- is guarded.
+std::mutex g_once_mutex;
+std::recursive_mutex g_batch_mutex;
+
 struct DeviceOnce {
   uint64_t done[4] = {0, 0, 0, 0};
   bool need(int device) {
+    std::lock_guard<std::mutex> lock(g_once_mutex);
     const int d = device & 255;
     if (done[d >> 6] & (1ull << (d & 63))) return false;
     done[d >> 6] |= 1ull << (d & 63);
@@ -766,6 +775,7 @@ cudaEvent_t g_fork = nullptr;
 std::vector<cudaEvent_t> g_joins;
 
 void clear_batches() {
+  std::lock_guard<std::recursive_mutex> lock(g_batch_mutex);
   for (auto& b : g_batches)
     if (b.second.exec) cudaGraphExecDestroy(b.second.exec);
   g_batches.clear();
@@ -1371,6 +1381,45 @@ int c3_get_site_lh(c3_engine* e, int bin, double* out, int64_t n_columns) {
   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
   cudaFree(d_out);
   if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("c3_get_site_lh: ") + cudaGetErrorString(err));
+  return C3_OK;
+}
+
+int c3_hmm_reduce(c3_engine* e, int n_patches, const int32_t* patch_of_bin, const double* weight_of_bin,
+                  const double* switch_matrix, const double* patch_probs, double* lnL) {
+  C3_REQUIRE(e && patch_of_bin && weight_of_bin && switch_matrix && patch_probs && lnL, "null pointer");
+  C3_REQUIRE(e->finalized && e->have_cached, "no evaluation yet");
+  C3_REQUIRE(n_patches == 2, "the device reduction handles two patches (cogent3's PatchSiteDistribution)");
+  C3_REQUIRE(e->d_root_index != nullptr && e->n_columns >= 0,
+             "the column numbering is not on the device (c3_compress_alignment / c3_set_column_index)");
+  C3_REQUIRE(e->K <= 64, "too many bins");
+  C3_CUDA(cudaSetDevice(e->device));
+  HmmArgs a{};
+  a.lh = e->d_lh;
+  a.index = e->d_root_index;
+  a.root_exp = e->rescale_active ? e->scale_rec[e->root].d_exps : nullptr;
+  a.n_sites = e->n_columns;
+  a.K = e->K;
+  for (int b = 0; b < e->K; ++b) {
+    C3_REQUIRE(patch_of_bin[b] == 0 || patch_of_bin[b] == 1, "bad patch number");
+    a.patch_of_bin[b] = patch_of_bin[b];
+    a.weight_of_bin[b] = weight_of_bin[b];
+  }
+  for (int i = 0; i < 4; ++i) a.sw[i] = switch_matrix[i];
+  a.patch_probs[0] = patch_probs[0];
+  a.patch_probs[1] = patch_probs[1];
+  const int n_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((e->n_columns + HMM_THREADS * 16 - 1) / (HMM_THREADS * 16),
+                                                                 (int64_t)e->n_sm * 8));
+  Hmm2* d_blocks = nullptr;
+  double* d_out = nullptr;
+  C3_CUDA(cudaMalloc(&d_blocks, (size_t)n_blocks * sizeof(Hmm2) + sizeof(double)));
+  d_out = reinterpret_cast<double*>(d_blocks + n_blocks);
+  hmm_chunk_kernel<<<n_blocks, HMM_THREADS, 0, e->stream>>>(a, d_blocks);
+  hmm_final_kernel<<<1, 32, 0, e->stream>>>(a, d_blocks, n_blocks, d_out);
+  e->stats.kernel_launches += 2;
+  cudaError_t err = cudaMemcpyAsync(lnL, d_out, sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(d_blocks);
+  if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("c3_hmm_reduce: ") + cudaGetErrorString(err));
   return C3_OK;
 }
 
@@ -2888,6 +2937,7 @@ int finish_deferred(c3_engine* e, double* host_out) {
 int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
   *used = 0;
   if (n < 2) return C3_OK;
+  std::lock_guard<std::recursive_mutex> lock(g_batch_mutex);
   uint64_t key = 1469598103934665603ull;
   for (int i = 0; i < n; ++i) {
     c3_engine* e = engines[i];

@@ -253,8 +253,11 @@ def _build(cogent3_modules):
             self.engine_factory = engine_factory
             self.device = device
             self.devices = list(devices) if devices else None
-            # phylo-HMM (sites_independent=False): the value of the Defn is the per-bin, per-pattern root
-            # likelihoods (pruning on the device); the reference's own SiteHmm reduces them over the sites
+            # phylo-HMM (sites_independent=False): the LAST argument is the reference's ``SiteHmm`` (the value
+            # of its "bindex" Defn); the per-bin root likelihoods the engine has just computed are reduced
+            # over the SITES by that model instead of being mixed per pattern.  Everything the result
+            # depends on is an argument of this ONE cell, so whatever the Calculator presents (undo
+            # included) the engine re-derives its state from the inputs in front of it
             self.return_lh = bool(return_lh)
             # id(lht) -> state, least recently used first.  The Defn instance (and so this cache) is
             # shared by every locus cell behind SumDefn(*tll.across_dimension("locus", ...)): it must
@@ -338,6 +341,9 @@ def _build(cogent3_modules):
 
         def calc(self, lht, root, mprobs, *rest):
             K = self.n_bins
+            blh = None
+            if self.return_lh:
+                blh, rest = rest[-1], rest[:-1]
             if K > 1:
                 bprobs, rest = rest[0], rest[1:]
             else:
@@ -386,9 +392,9 @@ def _build(cogent3_modules):
             for node, f in zip(st["internal_ids"], fixed, strict=True):
                 fm[node] = -1 if f in (None, -1) else int(f)
             eng.set_fixed_motifs(fm)
-            return self._finish(eng)
+            return self._finish(eng, blh)
 
-        def _finish(self, eng):
+        def _finish(self, eng, blh=None):
             from . import batch as _batch
 
             lockstep = _batch.current()
@@ -396,21 +402,22 @@ def _build(cogent3_modules):
             # c3_evaluate_many call; otherwise the engine is evaluated right here
             value = eng.evaluate() if lockstep is None else lockstep.evaluate(eng)
             if self.return_lh:
-                return tuple(eng.get_lh(b) for b in range(self.n_bins))
+                # SiteHmm.__call__ (evolve/likelihood_calculation.py:265-269): its reduction over the sites --
+                # log_dot_reduce, a Python loop over every column (evolve/likelihood_tree.py:168-176) -- runs on
+                # the device when the engine offers it (c3_hmm_reduce: a parallel product of the per-site 2 x 2
+                # matrices over the likelihoods that are already there); else the reference's own loop
+                distrib = getattr(blh, "distrib", None)
+                if hasattr(eng, "hmm_reduce") and distrib is not None:
+                    tm = distrib.transition_matrix
+                    matrix, start = np.asarray(tm.Matrix, float), np.asarray(tm.StationaryProbs, float)
+                    if matrix.shape == (2, 2) and start.shape == (2,):
+                        return eng.hmm_reduce(distrib.alloc, distrib.bprobs, matrix, start)
+                return blh(*[eng.get_lh(b) for b in range(self.n_bins)])
             return value
 
         def engine_for(self, lht):
             st = self._engines.get(id(lht))
             return None if st is None or st["lht"] is not lht else st["engine"]
-
-    class HmmTotalDefn(CalculationDefn):
-        """``tll = CallDefn(blh, *lh.across_dimension("bin", ...))`` (evolve/likelihood_calculation.py:157) with the
-        K per-bin arrays arriving as one value from the engine Defn"""
-
-        name = "tll"
-
-        def calc(self, blh, lhs):
-            return blh(*lhs)
 
     class GpuFactoredLogLikelihoodDefn(GpuLogLikelihoodDefn):
         """The same terminal Defn fed with the FACTORS of the psubs instead of the psubs:
@@ -436,6 +443,9 @@ def _build(cogent3_modules):
 
         def calc(self, lht, root, mprobs, *rest):
             K, E = self.n_bins, len(self.edge_names)
+            blh = None
+            if self.return_lh:
+                blh, rest = rest[-1], rest[:-1]
             if K > 1:
                 bprobs, rest = rest[0], rest[1:]
             else:
@@ -501,7 +511,7 @@ def _build(cogent3_modules):
                     fm[node] = -1 if f in (None, -1) else int(f)
                 eng.set_fixed_motifs(fm)
                 st["last_fixed"] = fixed
-            return self._finish(eng)
+            return self._finish(eng, blh)
 
     def make_total_loglikelihood_defn(tree, leaves, psubs, mprobs, bprobs, bin_names, locus_names,
                                       sites_independent, engine_factory, device, factors=None, devices=None):  # fmt: skip
@@ -522,6 +532,13 @@ def _build(cogent3_modules):
         edge_names = [e.name for e in edges]
         args = [lht, root, mprobs.select_from_dimension("edge", "root")]
         multi_bin = len(bin_names) > 1
+        tail_args = []
+        if hmm:
+            from cogent3.recalculation.definition import CalcDefn, CallDefn, ProbabilityParamDefn
+
+            switch = ProbabilityParamDefn("bin_switch", dimensions=["locus"])
+            site_pattern = CalcDefn(likelihood_calculation.PatchSiteDistribution, name="bdist")(switch, bprobs)
+            tail_args.append(CallDefn(site_pattern, lht, name="bindex"))
         if multi_bin:
             args.append(bprobs)
         args.extend(fixed_motifs.select_from_dimension("edge", name) for name in internal)
@@ -537,6 +554,7 @@ def _build(cogent3_modules):
             args.extend(select(length, "edge", name) for name in edge_names)
             if rate is not None:
                 args.extend(select(rate, "bin", b) for b in bin_names)
+            args.extend(tail_args)
             tll = GpuFactoredLogLikelihoodDefn(
                 *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
                 engine_factory=engine_factory, device=device, has_rate=rate is not None,
@@ -549,18 +567,12 @@ def _build(cogent3_modules):
                     args.extend(p_e.across_dimension("bin", bin_names))
                 else:
                     args.append(p_e.select_from_dimension("bin", bin_names[0]))
+            args.extend(tail_args)
             tll = GpuLogLikelihoodDefn(
                 *args, edge_names=edge_names, internal_names=internal, n_bins=len(bin_names),
                 engine_factory=engine_factory, device=device, n_loci=len(locus_names), devices=devices,
                 return_lh=hmm,
             )  # fmt: skip
-        if hmm:
-            from cogent3.recalculation.definition import CalcDefn, CallDefn, ProbabilityParamDefn
-
-            switch = ProbabilityParamDefn("bin_switch", dimensions=["locus"])
-            site_pattern = CalcDefn(likelihood_calculation.PatchSiteDistribution, name="bdist")(switch, bprobs)
-            blh = CallDefn(site_pattern, lht, name="bindex")
-            tll = HmmTotalDefn(blh, tll)
         if len(locus_names) > 1:
             tll = SumDefn(*tll.across_dimension("locus", locus_names))
         else:
@@ -763,7 +775,7 @@ def _build(cogent3_modules):
     # picklable by reference (process-parallel apps, app/evo.py bootstrap with parallel=True, pickle
     # likelihood functions): the classes are reachable as attributes of this module
     exported = (CudaAlignmentLikelihoodFunction, GpuLogLikelihoodDefn, LazyPsubDefn,
-                GpuFactoredLogLikelihoodDefn, FastAlignmentAdaptDefn, FastLikelihoodTreeDefn, HmmTotalDefn)  # fmt: skip
+                GpuFactoredLogLikelihoodDefn, FastAlignmentAdaptDefn, FastLikelihoodTreeDefn)  # fmt: skip
     for cls in exported:
         cls.__module__ = __name__
         cls.__qualname__ = cls.__name__
@@ -787,8 +799,7 @@ def _classes():
 
 
 _CLASS_NAMES = ("CudaAlignmentLikelihoodFunction", "GpuLogLikelihoodDefn", "LazyPsubDefn",
-                "GpuFactoredLogLikelihoodDefn", "FastAlignmentAdaptDefn", "FastLikelihoodTreeDefn",
-                "HmmTotalDefn")  # fmt: skip
+                "GpuFactoredLogLikelihoodDefn", "FastAlignmentAdaptDefn", "FastLikelihoodTreeDefn")  # fmt: skip
 
 
 def __getattr__(name):

@@ -300,6 +300,18 @@ class LikelihoodEngine:
         """asynchronous; writes lnL to ``device_ptr`` (a double in device memory)"""
         _lib.check(self._lib.c3_evaluate_device(self._h, c_void_p(device_ptr)))
 
+    def hmm_reduce(self, patch_of_bin, weight_of_bin, switch_matrix, patch_probs) -> float:
+        """phylo-HMM reduction over the sites of the last evaluation's per-bin root likelihoods
+        (c3_hmm_reduce; SiteHmm.__call__ / log_dot_reduce of the reference)"""
+        pb = np.ascontiguousarray(patch_of_bin, np.int32)
+        wb = np.ascontiguousarray(weight_of_bin, np.float64)
+        sw = np.ascontiguousarray(switch_matrix, np.float64)
+        pp = np.ascontiguousarray(patch_probs, np.float64)
+        assert pb.shape == (self.n_bins,) and wb.shape == (self.n_bins,) and sw.shape == (2, 2) and pp.shape == (2,)
+        out = c_double(0.0)
+        _lib.check(self._lib.c3_hmm_reduce(self._h, 2, _i32ptr(pb), _dptr(wb), _dptr(sw), _dptr(pp), byref(out)))
+        return out.value
+
     # -- accessors -------------------------------------------------------------
     def get_lh(self, bin_=0):
         out = np.empty(self.root_rows, np.float64)

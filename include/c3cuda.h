@@ -246,6 +246,20 @@ C3_API int c3_get_stats(c3_engine* e, c3_stats* out);
  *             evolve/likelihood_tree.py:93-94; likelihood_function.py:427-431).   */
 C3_API int c3_get_site_lh(c3_engine* e, int bin, double* out, int64_t n_columns);
 
+/* ---- phylo-HMM: the reduction over the SITES ------------------------
+ * c3_hmm_reduce: with sites_independent=False the per-bin root likelihoods of the last evaluation are
+ *             reduced by a hidden Markov model over two "patches" of bins instead of being mixed per
+ *             pattern: plhs[site][patch] = sum_{b in patch} weight_b lh_b[index[site]]
+ *             (PatchSiteDistribution.get_weighted_sum_lhs, evolve/likelihood_calculation.py:209-216),
+ *             state <- (switch . state) * plhs[site] over all sites with BASE = 2**100 rescaling, lnL =
+ *             log(sum(state)) + exponent log(BASE) (SiteHmm.__call__ :265-269; log_dot_reduce,
+ *             evolve/likelihood_tree.py:168-176 -- a Python loop over the columns).  On the device: a
+ *             parallel product of the 2 x 2 matrices diag(plhs[site]) . switch in site order.
+ *             patch_of_bin[K] in {0, 1}, weight_of_bin[K], switch_matrix[2 x 2] row-major
+ *             (SiteClassTransitionMatrix.Matrix), patch_probs[2] (its StationaryProbs).           */
+C3_API int c3_hmm_reduce(c3_engine* e, int n_patches, const int32_t* patch_of_bin, const double* weight_of_bin,
+                         const double* switch_matrix, const double* patch_probs, double* lnL);
+
 /* ---- per-launch timing (CUDA events on the engine's stream) ----------------------
  * With profiling on, every kernel launch of a blocking c3_evaluate is bracketed by
  * events.  c3_get_launch_profile returns, for the last evaluation and per launch:

@@ -727,3 +727,31 @@ def test_many_likelihood_functions_optimised_in_lockstep():
         assert abs(a.get_log_likelihood() - b.get_log_likelihood()) <= 1e-9 * abs(a.get_log_likelihood())
         assert b.get_param_value("kappa") == pytest.approx(a.get_param_value("kappa"), rel=1e-6)
     np.testing.assert_allclose(log_likelihoods(par), [lf.get_log_likelihood() for lf in par], rtol=1e-13)
+
+
+def test_pairwise_distances_in_lockstep():
+    """SURVEY §8 f-4, the pairwise path: ``EstimateDistances`` (evolve/distance.py:125-234) fits one two-taxon
+    likelihood function per pair; with the hook installed each is a CUDA function, and
+    ``batch.run_estimate_distances`` optimises the pairs concurrently -- same distances as the stock run"""
+    from cogent3.evolve.distance import EstimateDistances
+
+    from cogent3_b200.batch import run_estimate_distances
+
+    _tree, aln = small_problem(n_tips=6, L=300, seed=51)
+    stock = EstimateDistances(aln, get_model("HKY85"))
+    stock.run(show_progress=False)
+    want = stock.get_pairwise_distances()
+    with installed():
+        d = EstimateDistances(aln, get_model("HKY85"))
+        stats = run_estimate_distances(d)
+        got = d.get_pairwise_distances()
+        one = EstimateDistances(aln, get_model("HKY85"))
+        one.run(show_progress=False)  # the stock loop, every fit through the drop-in
+        seq = one.get_pairwise_distances()
+    assert stats["mean_batch"] > 3.0, stats
+    names = aln.names
+    for a in names:
+        for b in names:
+            if a != b:
+                assert got[(a, b)] == pytest.approx(want[(a, b)], rel=1e-5, abs=1e-7)
+                assert seq[(a, b)] == pytest.approx(want[(a, b)], rel=1e-5, abs=1e-7)
