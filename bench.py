@@ -971,6 +971,7 @@ def c5_strong_block(ctx, steps, warmup):
     ev1.record(ctx.stream)
     ctx.barrier()
     wall = time.perf_counter() - t0
+    lnl = device_step(0)  # (the reported value: always the same parameter point, whatever the step count)
     dev_s = ctx.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     wall = ctx.max_over_ranks(wall)
     total_units = ctx.sum_over_ranks(float(u_gp))
@@ -993,7 +994,8 @@ def c5_strong_block(ctx, steps, warmup):
         "scaling": "strong", "n_gpus": world, "columns_total": int(L), "columns_per_gpu": int(codes.shape[1]),
         "value": total_units * steps / dev_s, "unit": UNIT, "ms_per_step": dev_s / steps * 1e3, "steps": steps,
         "wall_ms_per_step": wall / steps * 1e3,
-        "lnL": lnl, "U_gp_per_step_all_ranks": total_units, "root_pattern_rows_all_ranks": rows,
+        "lnL": lnl, "lnL_note": "total over all ranks at the parameter point of step 0: the same number at every N",
+        "U_gp_per_step_all_ranks": total_units, "root_pattern_rows_all_ranks": rows,
         "pattern_note": "per-shard compression: every rank compresses its own columns, so the N-rank total of "
                         "pattern rows / updates is >= the 1-rank (global compression) figure",
         "hbm_gbs_algorithmic_all_ranks": alg_bytes / (dev_s / steps) / 1e9,

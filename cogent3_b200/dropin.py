@@ -113,6 +113,33 @@ def fast_likelihood_tree_leaf(likelihood_tree, sequence, alphabet, seq_name):
         return likelihood_tree.make_likelihood_tree_leaf(sequence, alphabet, seq_name)
 
 
+# ``lf.set_alignment`` needs every tip's table twice: for the motif counts (set_motif_probs_from_data) and for
+# the ``leaf_likelihoods`` Defn.  Same alignment, same sequence, same alphabet -> the same (immutable) leaf.
+_LEAF_CACHE: dict = {}
+
+
+def cached_likelihood_tree_leaf(likelihood_tree, align, seq_name, recode_gaps, alphabet):
+    import weakref
+
+    key = (id(align), seq_name, bool(recode_gaps))
+    hit = _LEAF_CACHE.get(key)
+    if hit is not None:
+        ref, alpha, leaf = hit
+        if ref() is align and (alpha is alphabet or alpha == alphabet):
+            return leaf
+    leaf = fast_likelihood_tree_leaf(likelihood_tree, align.get_gapped_seq(seq_name, recode_gaps), alphabet, seq_name)
+    if len(_LEAF_CACHE) > 2048:
+        for k in [k for k, (ref, _a, _l) in _LEAF_CACHE.items() if ref() is None]:
+            del _LEAF_CACHE[k]
+        if len(_LEAF_CACHE) > 2048:
+            _LEAF_CACHE.clear()
+    try:
+        _LEAF_CACHE[key] = (weakref.ref(align), alphabet, leaf)
+    except TypeError:  # an alignment type without weak references: no caching
+        pass
+    return leaf
+
+
 def fast_likelihood_tree_edge(likelihood_tree, children, edge_name):
     """``LikelihoodTreeEdge(children, edge_name)`` (evolve/likelihood_tree.py:13-70, pre-aligned
     children) without the per-column zip + dict loop"""
@@ -188,9 +215,7 @@ def _build(cogent3_modules):
                 return model.convert_alignment(alignment)  # a model with its own conversion
             alphabet = model.get_alphabet()
             leaves = {
-                name: fast_likelihood_tree_leaf(
-                    likelihood_tree, alignment.get_gapped_seq(name, model.recode_gaps), alphabet, name
-                )
+                name: cached_likelihood_tree_leaf(likelihood_tree, alignment, name, model.recode_gaps, alphabet)
                 for name in alignment.names
             }
             return _memo_put(self, (model, alignment), leaves)
@@ -659,8 +684,7 @@ def _build(cogent3_modules):
             alpha = mm.get_counted_alphabet()
             counts = None
             for seq_name in align.names:
-                sequence = align.get_gapped_seq(seq_name, self.model.recode_gaps)
-                leaf = fast_likelihood_tree_leaf(likelihood_tree, sequence, alpha, seq_name)
+                leaf = cached_likelihood_tree_leaf(likelihood_tree, align, seq_name, self.model.recode_gaps, alpha)
                 count = leaf.get_motif_counts(include_ambiguity=include_ambiguity)
                 counts = count.copy() if counts is None else counts + count
             if is_constant is None:

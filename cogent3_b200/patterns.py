@@ -22,6 +22,11 @@ from .tree import Topology
 
 _I64_MAX = np.iinfo(np.int64).max
 
+try:  # optional: only its hash-based ranking is used
+    from pandas import factorize as _factorize
+except Exception:  # noqa: BLE001
+    _factorize = None
+
 
 def first_seen_unique(keys: np.ndarray):
     """``_indexed`` for a 1-D integer key array.
@@ -38,8 +43,10 @@ def first_seen_unique(keys: np.ndarray):
     if span <= max(4 * L, 1 << 16) and span <= (1 << 27):
         # small key range: O(L) scatter instead of an O(L log L) sort
         k = (keys - kmin).astype(np.int64, copy=False)
+        # first column of every key: assign the column numbers in REVERSE order -- for a repeated index numpy
+        # keeps the last value assigned, i.e. the smallest column (ufunc.at does the same 10x slower)
         first_of_key = np.full(span, L, np.int64)
-        np.minimum.at(first_of_key, k, np.arange(L, dtype=np.int64))
+        first_of_key[k[::-1]] = np.arange(L - 1, -1, -1, dtype=np.int64)
         present = np.flatnonzero(first_of_key < L)
         first = first_of_key[present]
         order = np.argsort(first, kind="stable")
@@ -47,6 +54,14 @@ def first_seen_unique(keys: np.ndarray):
         rank_of_key = np.empty(span, np.int64)
         rank_of_key[present[order]] = np.arange(len(present), dtype=np.int64)
         index = rank_of_key[k]
+    elif _factorize is not None:
+        # wide key range: a hash table (pandas.factorize numbers the keys in first-seen order, O(L));
+        # the sort-based numpy path below is the fallback where pandas is not installed
+        index, _uniques = _factorize(np.ascontiguousarray(keys, np.int64))
+        index = index.astype(np.int64, copy=False)
+        n_unique = len(_uniques)
+        first = np.full(n_unique, L, np.int64)
+        first[index[::-1]] = np.arange(L - 1, -1, -1, dtype=np.int64)  # (first column of every key, as above)
     else:
         _, first_s, inverse = np.unique(keys, return_index=True, return_inverse=True)
         order = np.argsort(first_s, kind="stable")

@@ -383,3 +383,30 @@ def work_units(children_of, lht, n_bins=1, nodes=None):
             u_mv += lht[k].shape[0]
             u_gp += lht[n].shape[0]
     return n_bins * u_mv, n_bins * u_gp
+
+
+# ---- phylo-HMM reduction over the sites -----------------------------------------
+def patch_weighted_sum_lhs(alloc, weights, lhs):
+    """restates ``PatchSiteDistribution.get_weighted_sum_lhs``
+    (evolve/likelihood_calculation.py:209-216): result[patch] += lh_b * weight_b, bins in order"""
+    result = np.zeros((max(alloc) + 1, *lhs[0].shape), float)
+    temp = np.empty(lhs[0].shape, float)
+    for patch, weight, lh in zip(alloc, weights, lhs, strict=True):
+        temp[:] = lh
+        temp *= weight
+        result[patch] += temp
+    return result
+
+
+def log_dot_reduce(index, patch_probs, switch_probs, plhs):
+    """restates ``LikelihoodTreeEdge.log_dot_reduce`` (evolve/likelihood_tree.py:168-176): the forward
+    recursion of the site HMM with BASE = 2**100 rescaling.  ``plhs``: [patterns, patches]"""
+    BASE = 2.0**100
+    exponent = 0
+    state_probs = np.array(patch_probs, float)
+    for site in index:
+        state_probs = np.dot(switch_probs, state_probs) * plhs[site]
+        while max(state_probs) < 1.0:
+            state_probs *= BASE
+            exponent -= 1
+    return float(np.log(sum(state_probs)) + exponent * np.log(BASE))

@@ -755,3 +755,25 @@ def test_pairwise_distances_in_lockstep():
             if a != b:
                 assert got[(a, b)] == pytest.approx(want[(a, b)], rel=1e-5, abs=1e-7)
                 assert seq[(a, b)] == pytest.approx(want[(a, b)], rel=1e-5, abs=1e-7)
+
+
+def test_oracle_hmm_restatement_is_pinned_to_the_live_reference():
+    """oracle.log_dot_reduce / patch_weighted_sum_lhs (the checker of c3_hmm_reduce in tests/test_gpu_parity.py)
+    against the reference's SiteHmm on the stock class: the same bits"""
+    if ON_GPU:
+        pytest.skip("pins the CPU oracle: build container")
+    from oracle import oracle
+
+    tree, aln = small_problem(n_tips=6, L=300, seed=3)
+    sm = get_model("HKY85", ordered_param="rate", distribution="gamma")
+    lf = sm.make_likelihood_function(tree, bins=4, sites_independent=False)
+    lf.set_alignment(aln)
+    lf.set_param_rule("bin_switch", value=0.2)
+    lf.set_param_rule("rate_shape", value=0.8)
+    want = lf.get_log_likelihood()
+    blh = lf.get_param_value("bindex")
+    d = blh.distrib
+    lhs = [np.asarray(lf.get_param_value("lh", bin=b)) for b in lf.bin_names]
+    plhs = np.ascontiguousarray(oracle.patch_weighted_sum_lhs(d.alloc, d.bprobs, lhs).T)
+    tm = d.transition_matrix
+    assert oracle.log_dot_reduce(blh.root.index, tm.StationaryProbs, tm.Matrix, plhs) == want

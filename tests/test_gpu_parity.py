@@ -510,3 +510,38 @@ def test_batched_graph_of_many_engines_matches_individual_evaluations(monkeypatc
         last = tables[0] if step % 2 else d
     replays = [e.stats()["graph_replays"] for e in engines]
     assert min(replays) >= 5, replays  # captured at the third batch, replayed for the full sweeps after it
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_tips,L,rescale", [(10, 30_000, False), (24, 120_000, False), (16, 5_000, True)])
+def test_phylo_hmm_reduction_over_the_sites(n_tips, L, rescale):
+    """c3_hmm_reduce (a parallel product of per-site 2 x 2 matrices) against the oracle's restatement of the
+    reference's sequential loop (log_dot_reduce, evolve/likelihood_tree.py:168-176) on the same per-bin root
+    likelihoods; with per-pattern rescaling active the exponents are folded in"""
+    from oracle import oracle
+
+    m = hostmodels.get_model("HKY85")
+    topo, lengths, codes = make_workload(n_tips, L, 4, kind="evolved", seed=23)
+    lf = LikelihoodFunction(m, topo, bins=4)
+    lf.set_alignment(codes.astype(np.int64), np.eye(4))
+    lf.set_motif_probs_from_data()
+    lf.lengths[:-1] = np.asarray(lengths)[:-1]
+    lf.set_param_rule("kappa", value=2.7)
+    lf.set_param_rule("rate_shape", value=0.6)
+    if rescale:
+        lf.engine.set_rescaling("on", 4)
+    lf.get_log_likelihood()
+    assert lf.engine.rescaling()[0] == rescale
+    K = 4
+    alloc = [0, 0, 1, 1]  # PatchSiteDistribution.__init__ (evolve/likelihood_calculation.py:198-207)
+    bprobs = np.array([0.1, 0.3, 0.35, 0.25])
+    pprobs = np.array([bprobs[:2].sum(), bprobs[2:].sum()])
+    weights = [bprobs[i] / pprobs[alloc[i]] for i in range(K)]
+    s = 0.2  # bin_switch: SiteClassTransitionMatrix (evolve/likelihood_calculation.py:188-194 analogue)
+    switch = np.array([[1 - s * pprobs[1], s * pprobs[1]], [s * pprobs[0], 1 - s * pprobs[0]]]).T
+    got = lf.engine.hmm_reduce(alloc, weights, switch, pprobs)
+    lhs = [lf.engine.get_lh(b) for b in range(K)]
+    plhs = np.ascontiguousarray(oracle.patch_weighted_sum_lhs(alloc, weights, lhs).T)
+    index = lf.patterns.root.index
+    want = oracle.log_dot_reduce(np.asarray(index), pprobs, switch, plhs)
+    assert abs(got - want) <= 1e-10 * abs(want), (got, want)
