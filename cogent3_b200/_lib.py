@@ -75,6 +75,7 @@ SIGNATURES = {
     "c3_get_site_lh": (c_int, [c_void_p, c_int, _pd, c_int64]),
     "c3_set_eigen": (c_int, [c_void_p, c_int, _pd, _pd, _pd, c_int]),
     "c3_set_Q": (c_int, [c_void_p, c_int, _pd]),
+    "c3_set_tn93": (c_int, [c_void_p, c_int, _pd, c_double, c_double]),
     "c3_set_edge_qslots": (c_int, [c_void_p, _pi32]),
     "c3_set_psub": (c_int, [c_void_p, c_int, c_int, _pd]),
     "c3_set_distances": (c_int, [c_void_p, _pd]),

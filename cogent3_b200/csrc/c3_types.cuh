@@ -46,6 +46,7 @@ enum ExpmMode : int32_t {
   EXPM_EIGEN_COMPLEX = 1,
   EXPM_PADE = 2,
   EXPM_FIXED = 3,  // P supplied by the host; only the tip table is refreshed
+  EXPM_TN93 = 4,   // closed form for F81 / HKY85 / TN93 (calc_TN93_P): slot = pi[4], alpha1, alpha2
 };
 
 struct ExpmJob {

@@ -1631,6 +1631,23 @@ int c3_set_Q(c3_engine* e, int q_slot, const double* Q) {
   return C3_OK;
 }
 
+int c3_set_tn93(c3_engine* e, int q_slot, const double* pi, double alpha1, double alpha2) {
+  C3_REQUIRE(e && pi, "null pointer");
+  C3_REQUIRE(e->M == 4 && !e->use_dmma, "the closed form is for four nucleotide states (T, C, A, G)");
+  C3_REQUIRE(q_slot >= 0 && q_slot < (1 << 20), "bad q slot");
+  C3_CUDA(cudaSetDevice(e->device));
+  int rc = ensure_slots(e, q_slot + 1);
+  if (rc) return rc;
+  Slot& s = e->slots[q_slot];
+  s.mode = EXPM_TN93;
+  s.data.assign((size_t)e->slot_stride, 0.0);
+  for (int i = 0; i < 4; ++i) s.data[i] = pi[i];
+  s.data[4] = alpha1;
+  s.data[5] = alpha2;
+  s.dirty = true;
+  return C3_OK;
+}
+
 int c3_set_edge_qslots(c3_engine* e, const int32_t* q) {
   C3_REQUIRE(e && q, "null pointer");
   for (int n = 0; n < e->n_nodes - 1; ++n)

@@ -77,6 +77,37 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
   }
   const double* slot = slots + (int64_t)job.slot * slot_stride;
   const double t = job.t;
+  if (job.mode == EXPM_TN93) {
+    // closed form for the F81 / HKY85 / TN93 family, alphabet order T, C, A, G: restates calc_TN93_P
+    // (evolve/solved_models_numba.py:9-51) expression by expression (PredefinedNucleotide.calc_psub_matrix,
+    // evolve/solved_models.py:43-49, is F81, HKY85 or TN93 when passed 0, 1 or 2 parameters)
+    if (threadIdx.x < 16) {
+      const double* pi = slot;
+      const double alpha[2] = {slot[4], slot[5]};
+      const double pi_star[2] = {pi[0] + pi[1], pi[2] + pi[3]};
+      const double mu[2] = {alpha[0] * pi_star[0] + 1.0 * pi_star[1], 1.0 * pi_star[0] + alpha[1] * pi_star[1]};
+      double scale_factor = 0.0;
+      for (int motif = 0; motif < 4; ++motif) {
+        const int i = motif / 2, other = 1 - i;
+        scale_factor += (alpha[i] * pi[2 * i + 1 - motif % 2] + pi_star[other]) * pi[motif];
+      }
+      const double time = t / scale_factor;
+      const double e_beta_t = exp(-time);
+      const double transversion = 1 - e_beta_t;
+      const int row = threadIdx.x / 4, column = threadIdx.x % 4;
+      const int i = row / 2, j = column / 2, other = 1 - i;
+      const double e_mu_t = exp(-mu[i] * time);
+      const double transition = 1 + (pi_star[other] * e_beta_t - e_mu_t) / pi_star[i];
+      double p = (i == j) ? transition : transversion;
+      p *= pi[column];
+      if (row == column) p += e_mu_t;
+      sP[row * MP + column] = p;
+      Pout[row * MP + column] = p;
+    }
+    __syncthreads();
+    tip_inner_update(ed, sP, job.bin, M, MP, K);
+    return;
+  }
   // Large alphabets (codons): stage W = evT * exp(t roots) and evI in shared memory so the
   // M^3 contraction reads shared memory (odd row stride: conflict free) instead of
   // uncoalesced global memory.  sW / sI live behind sP in the dynamic allocation.

@@ -43,6 +43,27 @@ def _default_engine_factory(patterns, n_bins, device=0, stream=None):
     return LikelihoodEngine(patterns, n_bins=n_bins, device=device, stream=stream)
 
 
+class SolvedExponentiator:
+    """the "exponentiator" of a model built with ``rate_matrix_required=False`` (F81 / HKY85 / TN93,
+    ``PredefinedNucleotide``, evolve/solved_models.py:17-58): there is no Q and no eigendecomposition, P(t) has a
+    closed form in (pi, kappa_y, kappa_r).  Held by ``LazyPsub`` like the eigen / Pade objects, so that the engine
+    computes every P on the device (c3_set_tn93) -- and materialises to exactly the reference's matrix
+    (``model.calc_psub_matrix``) when cogent3 reads a psub."""
+
+    __slots__ = ("model", "pi", "kappas")
+
+    def __init__(self, model, pi, kappas):
+        self.model, self.pi, self.kappas = model, pi, tuple(kappas)
+
+    def __call__(self, t):
+        return self.model.calc_psub_matrix(self.pi, t, *self.kappas)
+
+    def alphas(self):
+        kappa_y = self.kappas[0] if len(self.kappas) > 0 else 1.0
+        kappa_r = self.kappas[1] if len(self.kappas) > 1 else kappa_y
+        return float(kappa_y), float(kappa_r)
+
+
 class LazyPsub:
     """value of the ``psubs`` Defn in the CUDA graph: the exponentiator and the distance
     instead of the exponentiated matrix, so that P(t) is computed on the device
@@ -222,6 +243,14 @@ def _build(cogent3_modules):
 
         __getstate__ = _memo_free_state
 
+    def _is_solved_psubs(psubs):
+        try:
+            from cogent3.evolve.solved_models import PredefinedNucleotide
+        except Exception:  # noqa: BLE001
+            return False
+        calc = getattr(psubs, "calc", None)
+        return getattr(calc, "__func__", None) is PredefinedNucleotide.calc_psub_matrix
+
     def _reference_convert_sequence(model):
         from cogent3.evolve.substitution_model import _SubstitutionModel
 
@@ -260,6 +289,31 @@ def _build(cogent3_modules):
 
         def calc(self, exponentiator, distance):
             return LazyPsub(exponentiator, distance)
+
+    class SolvedLazyPsubDefn(CalculationDefn):
+        """``psubs = CalcDefn(model.calc_psub_matrix)(word_probs, distance, *rate_params)``
+        (evolve/solved_models.py:22-41) without the call: one shared ``SolvedExponentiator`` per distinct
+        (pi, kappas), so all (edge, bin)s of a scope exponentiate from ONE device slot"""
+
+        name = "psubs"
+
+        def setup(self, model):
+            self.model = model
+            self._made = []  # [(pi object, kappas, exponentiator)], identity / value keyed, a handful of entries
+
+        def calc(self, pi, time, *kappas):
+            for p, k, ex in self._made:
+                if p is pi and k == kappas:
+                    return LazyPsub(ex, time)
+            ex = SolvedExponentiator(self.model, pi, kappas)
+            self._made.append((pi, kappas, ex))
+            del self._made[:-8]
+            return LazyPsub(ex, time)
+
+        def __getstate__(self):
+            d = dict(self.__dict__)
+            d["_made"] = []
+            return d
 
     class GpuLogLikelihoodDefn(CalculationDefn):
         """total log-likelihood of one locus, computed by libc3cuda.
@@ -358,6 +412,8 @@ def _build(cogent3_modules):
                 eng.set_eigen(slot, ex.roots, ex.evT, ex.evI)
             elif isinstance(ex, PadeExponentiator):
                 eng.set_Q(slot, np.asarray(ex.Q, float))
+            elif isinstance(ex, SolvedExponentiator) and hasattr(eng, "set_tn93"):
+                eng.set_tn93(slot, np.asarray(ex.pi, float), *ex.alphas())
             else:
                 return None
             st["slot_of"][id(ex)] = slot
@@ -647,6 +703,13 @@ def _build(cogent3_modules):
                 else:
                     # keep (exponentiator, distance) symbolic, one LazyPsub cell per (edge, bin)
                     psubs = LazyPsubDefn(*original.args)
+            elif _is_solved_psubs(psubs):
+                # rate_matrix_required=False: P has a closed form, computed on the device (c3_set_tn93)
+                original = psubs
+                for arg in original.args:
+                    if original in arg.clients:
+                        arg.clients.remove(original)
+                psubs = SolvedLazyPsubDefn(*original.args, model=self.model)
             self._factors = factors
             self._hmm = (not sites_independent) and len(self.bin_names) > 1
             self._gpu_defn_factory = None
@@ -799,7 +862,8 @@ def _build(cogent3_modules):
     # picklable by reference (process-parallel apps, app/evo.py bootstrap with parallel=True, pickle
     # likelihood functions): the classes are reachable as attributes of this module
     exported = (CudaAlignmentLikelihoodFunction, GpuLogLikelihoodDefn, LazyPsubDefn,
-                GpuFactoredLogLikelihoodDefn, FastAlignmentAdaptDefn, FastLikelihoodTreeDefn)  # fmt: skip
+                GpuFactoredLogLikelihoodDefn, FastAlignmentAdaptDefn, FastLikelihoodTreeDefn,
+                SolvedLazyPsubDefn)  # fmt: skip
     for cls in exported:
         cls.__module__ = __name__
         cls.__qualname__ = cls.__name__
@@ -823,7 +887,8 @@ def _classes():
 
 
 _CLASS_NAMES = ("CudaAlignmentLikelihoodFunction", "GpuLogLikelihoodDefn", "LazyPsubDefn",
-                "GpuFactoredLogLikelihoodDefn", "FastAlignmentAdaptDefn", "FastLikelihoodTreeDefn")  # fmt: skip
+                "GpuFactoredLogLikelihoodDefn", "FastAlignmentAdaptDefn", "FastLikelihoodTreeDefn",
+                "SolvedLazyPsubDefn")  # fmt: skip
 
 
 def __getattr__(name):

@@ -222,6 +222,12 @@ class LikelihoodEngine:
         assert Q.shape == (self.n_states, self.n_states)
         _lib.check(self._lib.c3_set_Q(self._h, slot, _dptr(Q)))
 
+    def set_tn93(self, slot, pi, alpha1, alpha2):
+        """closed-form slot of the F81 / HKY85 / TN93 family (calc_TN93_P); pi in T, C, A, G order"""
+        pi = np.ascontiguousarray(pi, dtype=np.float64)
+        assert pi.shape == (4,) and self.n_states == 4
+        _lib.check(self._lib.c3_set_tn93(self._h, slot, _dptr(pi), float(alpha1), float(alpha2)))
+
     def set_edge_qslots(self, qslots):
         q = np.ascontiguousarray(np.broadcast_to(qslots, (self.n_nodes, self.n_bins)), np.int32)
         _lib.check(self._lib.c3_set_edge_qslots(self._h, _i32ptr(q)))

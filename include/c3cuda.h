@@ -146,6 +146,12 @@ C3_API int c3_set_column_index(c3_engine* e, const int64_t* index, int64_t n_col
 C3_API int c3_set_eigen(c3_engine* e, int q_slot, const double* roots, const double* evT,
                  const double* evI, int is_complex);
 C3_API int c3_set_Q(c3_engine* e, int q_slot, const double* Q);
+/* c3_set_tn93: the closed-form P of the F81 / HKY85 / TN93 family for models built with
+ *             rate_matrix_required=False (PredefinedNucleotide.calc_psub_matrix, evolve/solved_models.py:43-49
+ *             -> calc_TN93_P, evolve/solved_models_numba.py:9-51): pi[4] in T, C, A, G order, alpha1 = kappa_y,
+ *             alpha2 = kappa_r (1, 1 for F81; kappa, kappa for HKY85).  P(t) is then computed on the device
+ *             for every (edge, bin) that uses the slot, like the eigen and Pade slots.                       */
+C3_API int c3_set_tn93(c3_engine* e, int q_slot, const double* pi, double alpha1, double alpha2);
 C3_API int c3_set_edge_qslots(c3_engine* e, const int32_t* q_slot_of_edge_bin);
 C3_API int c3_set_psub(c3_engine* e, int node, int bin, const double* P);
 C3_API int c3_set_distances(c3_engine* e, const double* distance_of_edge_bin);

@@ -95,6 +95,9 @@ class OracleEngine:
     def set_Q(self, slot, Q):
         self.slots[slot] = oracle.PadeExponentiator(np.array(Q))
 
+    def set_tn93(self, slot, pi, alpha1, alpha2):
+        self.slots[slot] = oracle.TN93Exponentiator(pi, alpha1, alpha2)
+
     def set_edge_qslots(self, q):
         q = np.broadcast_to(q, (self.n_nodes, self.n_bins))
         for n, b in zip(*np.nonzero(q >= 0), strict=True):  # negative: leave as is

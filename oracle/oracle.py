@@ -410,3 +410,47 @@ def log_dot_reduce(index, patch_probs, switch_probs, plhs):
             state_probs *= BASE
             exponent -= 1
     return float(np.log(sum(state_probs)) + exponent * np.log(BASE))
+
+
+# ---- closed-form P of the F81 / HKY85 / TN93 family ------------------------------
+def calc_TN93_P(mprobs, time, alpha1, alpha2):
+    """restates numba ``calc_TN93_P`` (evolve/solved_models_numba.py:9-51), alphabet order T, C, A, G
+    (``PredefinedNucleotide.calc_psub_matrix``, evolve/solved_models.py:43-49: F81 / HKY85 / TN93 when
+    passed 0 / 1 / 2 rate parameters)"""
+    import math
+
+    mprobs = np.asarray(mprobs, float)
+    alpha = (alpha1, alpha2)
+    pi_star = (mprobs[0] + mprobs[1], mprobs[2] + mprobs[3])
+    mu = (alpha1 * pi_star[0] + 1.0 * pi_star[1], 1.0 * pi_star[0] + alpha2 * pi_star[1])
+    scale_factor = 0.0
+    for motif in range(4):
+        i = motif // 2
+        other = 1 - i
+        scale_factor += (alpha[i] * mprobs[2 * i + 1 - motif % 2] + pi_star[other]) * mprobs[motif]
+    time = time / scale_factor
+    e_beta_t = math.exp(-time)
+    transversion = 1 - e_beta_t
+    e_mu_t = [math.exp(-mu[i] * time) for i in range(2)]
+    transition = [1 + (pi_star[1 - i] * e_beta_t - e_mu_t[i]) / pi_star[i] for i in range(2)]
+    result = np.empty((4, 4), float)
+    for row in range(4):
+        i = row // 2
+        for column in range(4):
+            j = column // 2
+            p = transition[i] if i == j else transversion
+            p *= mprobs[column]
+            if row == column:
+                p += e_mu_t[i]
+            result[row, column] = p
+    return result
+
+
+class TN93Exponentiator:
+    """slot object of the closed-form family: ``__call__(t)`` like the other exponentiators"""
+
+    def __init__(self, pi, alpha1, alpha2):
+        self.pi, self.alpha1, self.alpha2 = np.array(pi, float), float(alpha1), float(alpha2)
+
+    def __call__(self, t):
+        return calc_TN93_P(self.pi, t, self.alpha1, self.alpha2)

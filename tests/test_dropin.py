@@ -619,6 +619,17 @@ def test_solved_models_and_measure_evals_per_second():
             f.set_param_rule("length", edge=tree.get_tip_names()[2], value=0.21)
         assert_same(ref, lf, rel=1e-12)
         np.testing.assert_allclose(lf.get_full_length_likelihoods(), ref.get_full_length_likelihoods(), rtol=1e-12, atol=1e-300)
+        # P(t) comes from ONE closed-form slot of the engine (c3_set_tn93), not from a host matrix per (edge, bin)
+        st = next(iter(lf._gpu_defn()._engines.values()))
+        assert [type(ex).__name__ for ex in st["slot_obj"].values()] == ["SolvedExponentiator"]
+        assert not st["psub_obj"]
+        np.testing.assert_allclose(lf.get_psub_for_edge(tree.get_tip_names()[2]).to_array(),
+                                   ref.get_psub_for_edge(tree.get_tip_names()[2]).to_array(), rtol=0, atol=1e-15)  # fmt: skip
+        eng = lf._engine()
+        if hasattr(eng, "get_psub"):
+            node = st["topo"].names.index(tree.get_tip_names()[2])
+            np.testing.assert_allclose(eng.get_psub(node, 0), ref.get_psub_for_edge(tree.get_tip_names()[2]).to_array(),
+                                       rtol=0, atol=1e-14)  # fmt: skip
     calc = lf.make_calculator()
     rate = calc.measure_evals_per_second(time_limit=0.2, wall=True)
     assert rate > 0

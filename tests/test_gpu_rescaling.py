@@ -165,3 +165,41 @@ def test_rescaled_per_pattern_values(model, n_tips, L, bins):
     want_post = np.stack([(b * lh) for b, lh in zip(ref.engine.bprobs, lhs, strict=True)])
     want_post = (want_post / want_post.sum(axis=0)).astype(float)
     assert np.max(np.abs(post - want_post)) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_non_finite_values_behave_like_the_reference():
+    """NaN propagates (numpy.maximum(P, 0) keeps NaN, maths/matrix_exponentiation.py:40; the optimiser treats a
+    NaN / -inf lnL as out of bounds, maths/optimisers.py:116-118) and does NOT switch per-pattern rescaling on;
+    a log-likelihood of -inf that rescaling cannot help (a pattern whose likelihood is truly 0: an impossible
+    fixed motif) does not leave rescaling switched on either -- the engine goes back to the plain products"""
+    from cogent3_b200 import models as hostmodels
+    from cogent3_b200.likelihood import LikelihoodFunction
+    from cogent3_b200.synthetic import make_workload
+
+    m = hostmodels.get_model("HKY85")
+    topo, lengths, codes = make_workload(10, 2000, 4, kind="evolved", seed=9)
+    lf = LikelihoodFunction(m, topo, bins=1)
+    lf.set_alignment(codes.astype(np.int64), np.eye(4))
+    lf.set_motif_probs_from_data()
+    lf.lengths[:-1] = np.asarray(lengths)[:-1]
+    good = lf.get_log_likelihood()
+    assert np.isfinite(good) and lf.engine.rescaling() == (False, 0)
+    # a NaN distance: NaN out, rescaling stays off, the next good point is evaluated normally
+    d = np.nan_to_num(lf.lengths.copy())[:, None].copy()
+    bad = d.copy()
+    bad[3] = np.nan
+    assert np.isnan(lf.engine.update(bad))
+    assert lf.engine.rescaling() == (False, 0)
+    assert lf.engine.update(d) == good
+    # a zero in P (supplied matrix) under the observed data: likelihood exactly 0 for some patterns -> -inf,
+    # which rescaling cannot change; afterwards the engine is back on the plain path and still right
+    P = np.eye(4)  # no substitutions at all on a tip branch with differing states below/above
+    tip = int(topo.tips[0])
+    lf.engine.set_psub(tip, 0, P)
+    v = lf.engine.evaluate()
+    if np.isinf(v) and v < 0:
+        assert lf.engine.rescaling()[0] is False
+        v2 = lf.engine.evaluate()
+        assert np.isinf(v2) and v2 < 0
+        assert lf.engine.rescaling()[0] is False
