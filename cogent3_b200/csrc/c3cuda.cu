@@ -126,6 +126,12 @@ struct c3_engine {
   bool use_grid_small = false;  // opt-in (C3_GRID_SMALL=1): measured no faster than the launches it replaces, DESIGN.md lesson 17
   int grid_units_per_thread = 4;
   unsigned int* d_grid_bar = nullptr;
+  // recomputing kernel (prune4_rec_kernel): a run of consecutive small / medium levels (at most rec_units units
+  // each, at least one of them too big for the small-levels cluster) becomes launches of up to REC_DEPTH + 1 levels
+  // without any barrier.  C3_REC=1 enables, C3_REC_UNITS=n.
+  bool use_rec = false;  // opt-in (C3_REC=1): bit-identical, no faster (DESIGN.md lesson 16d)
+  int64_t rec_units = 400000;
+  int64_t off_rec = 0;
   int path_variant = 1;   // 0: 1024 threads x 3 units, 1: 512 x 6, 2: 256 x 11 (C3_PATH_VARIANT)
   bool use_path = false;  // opt-in (C3_PATH=1): single-branch updates of small problems by ONE CTA that walks the dirty
                           // path with the rows in shared memory -- measured slower than the small-levels launch
@@ -888,6 +894,8 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_SMALL_REDUCE")) e->use_small_reduce = atoi(env) == 0;
   if (const char* env = getenv("C3_PATH")) e->use_path = atoi(env) != 0;
   if (const char* env = getenv("C3_PATH_VARIANT")) e->path_variant = std::max(0, std::min(2, atoi(env)));
+  if (const char* env = getenv("C3_REC")) e->use_rec = atoi(env) != 0;
+  if (const char* env = getenv("C3_REC_UNITS")) e->rec_units = std::max(1, atoi(env));
   if (const char* env = getenv("C3_GRID_SMALL")) e->use_grid_small = atoi(env) != 0;
   if (const char* env = getenv("C3_GRID_UNITS")) e->grid_units_per_thread = std::max(1, std::min(64, atoi(env)));
   if (const char* env = getenv("C3_DMMA_REG")) e->use_dmma_reg = atoi(env) != 0;
@@ -1578,6 +1586,7 @@ int c3_finalize(c3_engine* e) {
   e->off_prefix = b;  b += align_up((int64_t)(2 * n_internal + 4 * e->n_levels + 8) * sizeof(int32_t), 16);
   e->off_small = b;   b += align_up((int64_t)(e->n_levels + 1) * sizeof(SmallLevel), 16);
   e->off_dep = b;     b += align_up((int64_t)2 * n_internal * sizeof(int32_t), 16);
+  e->off_rec = b;     b += align_up((int64_t)REC_MAX_CHILDREN * n_internal * sizeof(int32_t), 16);
   e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
   e->block_bytes = b;
   C3_CUDA(cudaHostAlloc(&e->h_block, (size_t)b, cudaHostAllocDefault));
@@ -2147,8 +2156,9 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
           const int s = e->qslot[i];
           if (s >= (int)e->slots.size() || e->slots[s].mode < 0)
             return fail(C3_ERR_INVALID, "an (edge, bin) uses a q slot that was never set");
-          if (!e->have_dist || std::isnan(e->dist[i]))
-            return fail(C3_ERR_INVALID, "distances not set");
+          // (a NaN distance that WAS set flows through like in the reference: NaN P, NaN lnL, which the
+          //  optimiser treats as out of bounds, maths/optimisers.py:116-118)
+          if (!e->have_dist) return fail(C3_ERR_INVALID, "distances not set");
           mode = e->slots[s].mode;
         }
         const bool is_pade = (mode == EXPM_PADE);
@@ -2357,7 +2367,94 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       path_buf_units = (int)std::max<int64_t>(max_units, 1);
     }
   }
+  // ---- recomputing launches: runs of consecutive small / medium levels, REC_DEPTH + 1 levels per launch -------
+  std::vector<int> rec_phase(e->n_levels + 2, -1);  // level -> phase (launch) number, -1: the usual launches
+  std::vector<int> rec_first;                        // first level of every phase
+  if (e->use_rec && !e->use_dmma && e->use_small && !e->rescale_active && !path_launch) {
+    std::vector<int64_t> level_units(e->n_levels + 2, 0);
+    std::vector<char> level_ok(e->n_levels + 2, 0);
+    for (int l = 1; l <= e->n_levels; ++l) {
+      bool ok = true;
+      int n_dirty_l = 0;
+      for (int n : e->level_nodes[l])
+        if (recompute[n]) {
+          level_units[l] += e->n_rows[n] * K;
+          ++n_dirty_l;
+          ok = ok && e->children[n].size() <= (size_t)REC_MAX_CHILDREN;
+        }
+      level_ok[l] = ok && n_dirty_l > 0 && level_units[l] <= e->rec_units;
+    }
+    int l = 1;
+    while (l <= e->n_levels) {
+      if (!level_ok[l]) { ++l; continue; }
+      int l2 = l;
+      bool any_medium = false;
+      int n_items = 0;
+      while (l2 <= e->n_levels && level_ok[l2]) {
+        any_medium = any_medium || level_units[l2] > SMALL_LEVEL_UNITS;
+        ++l2;
+      }
+      // (a run of tiny levels only -- a brca1-sized problem -- stays with the cluster kernel, which also reduces)
+      if (any_medium && l2 - l >= 2) {
+        for (int a0 = l; a0 < l2;) {
+          int a1 = a0;
+          n_items = 0;
+          int64_t units_sum = 0;
+          while (a1 < l2 && a1 - a0 <= REC_DEPTH) {
+            int items_l = 0;
+            for (int n : e->level_nodes[a1]) items_l += recompute[n] ? 1 : 0;
+            if (n_items + items_l > REC_MAX_WORK || units_sum + level_units[a1] > INT32_MAX / 2) break;
+            n_items += items_l;
+            units_sum += level_units[a1];
+            ++a1;
+          }
+          if (a1 == a0) break;  // (a single level with more work items than a launch stages: the usual launches)
+          if (a1 - a0 >= 2) {
+            for (int x = a0; x < a1; ++x) rec_phase[x] = (int)rec_first.size();
+            rec_first.push_back(a0);
+          }
+          a0 = a1;
+        }
+      }
+      l = l2;
+    }
+  }
+  int32_t* rec_child = reinterpret_cast<int32_t*>(e->h_block + e->off_rec);
   for (int l = 1; l <= e->n_levels; ++l) {
+    if (rec_phase[l] >= 0) {
+      if (rec_first[rec_phase[l]] != l) continue;  // emitted with the phase's first level
+      open_small = -1;
+      close_flow();
+      const int phase = rec_phase[l];
+      LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, 10, 0, 0};
+      const int64_t bytes0 = alg_bytes, flops0 = flops;
+      std::vector<int> item_of(N, -1);
+      int64_t u = 0;
+      for (int x = l; x <= e->n_levels && rec_phase[x] == phase; ++x)
+        for (int n : e->level_nodes[x]) {
+          if (!recompute[n]) continue;
+          item_of[n] = ll.n_work;
+          work[w_off + ll.n_work] = n;
+          prefix[p_off + ll.n_work] = (int32_t)u;
+          u += e->n_rows[n] * K;
+          for (int c = 0; c < REC_MAX_CHILDREN; ++c) {
+            const bool has = c < (int)e->children[n].size();
+            // children live on lower levels: numbered before their parents, so item_of is final for them
+            rec_child[(w_off + ll.n_work) * REC_MAX_CHILDREN + c] = has ? item_of[e->children[n][c]] : -1;
+          }
+          ++ll.n_work;
+          ll.is_root = ll.is_root || (n == e->root);
+          account(n);
+        }
+      prefix[p_off + ll.n_work] = (int32_t)u;
+      ll.total_tiles = (int)u;
+      ll.bytes = alg_bytes - bytes0;
+      ll.flops = flops - flops0;
+      w_off += ll.n_work;
+      p_off += ll.n_work + 1;
+      launches.push_back(ll);
+      continue;
+    }
     int64_t units = 0;
     int n_dirty = 0;
     bool other_kinds = false;
@@ -2569,7 +2666,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     a.M = M;
     a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
     a.lh_out = e->d_lh;
-    ProfScope ps(e, (ll.kind == 1 || ll.kind == 9) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
+    ProfScope ps(e, (ll.kind == 1 || ll.kind == 9 || ll.kind == 10) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
     if (ll.kind == 1) {
       const SmallLevel* d_small = reinterpret_cast<const SmallLevel*>(e->d_block + e->off_small) + ll.small_off;
       if (ll.grid > 0) {
@@ -2629,6 +2726,26 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel<false>, a, d_small, ll.n_small, ll.n_work,
                                            ll.n_work + ll.n_small, tail, (unsigned*)nullptr);
       if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("small-level launch: ") + cudaGetErrorString(err));
+    } else if (ll.kind == 10) {
+      static DeviceOnce rec_cfg;
+      if (rec_cfg.need(e->device)) {
+        int rc = set_max_smem(prune4_rec_kernel, sizeof(RecSmem));
+        if (rc) return rc;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((ll.total_tiles + REC_THREADS - 1) / REC_THREADS,
+                                                                         (int64_t)e->n_sm * 4)));
+      cfg.blockDim = dim3(REC_THREADS);
+      cfg.dynamicSmemBytes = sizeof(RecSmem);
+      cfg.stream = e->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const int32_t* d_child = reinterpret_cast<const int32_t*>(e->d_block + e->off_rec) + (int64_t)ll.work_off * REC_MAX_CHILDREN;
+      cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_rec_kernel, a, d_child);
+      if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("rec launch: ") + cudaGetErrorString(err));
     } else if (ll.kind == 9) {
       const size_t smem = (size_t)ll.total_tiles;
       static DeviceOnce path_cfg;

@@ -1570,6 +1570,109 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
 }
 
 // ---------------------------------------------------------------------------------------
+// 4-state RECOMPUTING kernel ("rec"): several consecutive tree levels in one launch WITHOUT any barrier.
+//
+// The lower levels of a tree hold little data (C2: 0.3, 1.1 and 15 MB for levels 1-2, 3, 4) but each costs a
+// launch or a barrier plus two dependent global latencies -- 47 us of a 360 us C2 step, most of a brca1-sized
+// one.  What makes a level wait for the one below is only that it LOADS the rows the level below has stored.
+// Here a unit (row, bin) of a node does not load the rows of a child that is computed in the same launch: it
+// RECOMPUTES them, recursively, down to children whose rows are already there (tips, clean nodes, nodes of an
+// earlier launch).  A node REC_DEPTH levels above the bottom of the launch evaluates a subtree of at most
+// 2^REC_DEPTH - 1 nodes per unit -- a few dozen FP64 FMAs that nobody waits for -- and in exchange every node of
+// all the launch's levels is computed at once: no barrier, one chain of ~REC_DEPTH + 1 dependent loads.  Every
+// node still stores its own rows (the resident state later updates start from).  Each row is the same expression
+// over the same inputs whoever evaluates it: bit-identical to the level-by-level kernels.
+// ---------------------------------------------------------------------------------------
+constexpr int REC_THREADS = 256;
+constexpr int REC_MAX_WORK = 192;    // work items (dirty nodes) per launch
+constexpr int REC_MAX_CHILDREN = 3;
+constexpr int REC_DEPTH = 3;         // recursion depth: a launch spans at most REC_DEPTH + 1 levels
+constexpr int REC_MAX_P = 192;       // P matrices kept in shared memory
+
+struct RecSmem {
+  NodeDesc nodes[REC_MAX_WORK];
+  ChildRef childs[REC_MAX_WORK * REC_MAX_CHILDREN];
+  int32_t child_work[REC_MAX_WORK * REC_MAX_CHILDREN];  // work item that computes the child in THIS launch, or -1
+  int32_t prefix[REC_MAX_WORK + 1];
+  double P[REC_MAX_P * 16];
+};
+
+template <int D>
+__device__ d4 rec_eval(const RecSmem& sm, bool p_staged, int wi, int64_t p, int b, int K) {
+  const NodeDesc& nd = sm.nodes[wi];
+  d4 acc;
+  for (int c = 0; c < nd.n_children; ++c) {
+    const ChildRef& ch = sm.childs[wi * REC_MAX_CHILDREN + c];
+    const int32_t r = ch.idx[p];
+    const int cw = sm.child_work[wi * REC_MAX_CHILDREN + c];
+    d4 x;
+    if (D > 0 && cw >= 0) {
+      x = rec_eval<(D > 0 ? D - 1 : 0)>(sm, p_staged, cw, r, b, K);  // computed in this launch: recompute, do not wait
+    } else {
+      x = ld256(ch.src + ((int64_t)r * K + b) * 4);  // rows that are already there
+    }
+    d4 y = x;
+    if (ch.P != nullptr) {
+      y = p_staged ? matvec4(sm.P + ((wi * REC_MAX_CHILDREN + c) * K + b) * 16, x) : matvec4(ch.P + b * 16, x);
+    }
+    if (c == 0) acc = y;
+    else { acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w; }
+  }
+  if (nd.fixed_motif >= 0) {
+    if (nd.fixed_motif != 0) acc.x = 0.0;
+    if (nd.fixed_motif != 1) acc.y = 0.0;
+    if (nd.fixed_motif != 2) acc.z = 0.0;
+    if (nd.fixed_motif != 3) acc.w = 0.0;
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(REC_THREADS)
+prune4_rec_kernel(const PruneArgs a, const int32_t* __restrict__ child_work) {
+  extern __shared__ __align__(16) unsigned char rec_raw[];
+  RecSmem& sm = *reinterpret_cast<RecSmem*>(rec_raw);
+  pdl_trigger();
+  const int K = a.K;
+  const int n_work = a.n_work;
+  for (int i = threadIdx.x; i <= n_work; i += REC_THREADS) sm.prefix[i] = a.tile_prefix[i];
+  for (int i = threadIdx.x; i < n_work; i += REC_THREADS) {
+    const NodeDesc nd = a.nodes[a.work_node[i]];
+    sm.nodes[i] = nd;
+    for (int c = 0; c < nd.n_children && c < REC_MAX_CHILDREN; ++c) {
+      sm.childs[i * REC_MAX_CHILDREN + c] = a.childs[nd.child_begin + c];
+      sm.child_work[i * REC_MAX_CHILDREN + c] = child_work[i * REC_MAX_CHILDREN + c];
+    }
+  }
+  __syncthreads();
+  pdl_wait();  // the P matrices / tip tables of the expm launch, rows of earlier launches
+  const bool p_staged = (int64_t)n_work * REC_MAX_CHILDREN * K <= REC_MAX_P;
+  if (p_staged) {
+    const int per_item = REC_MAX_CHILDREN * K * 16;
+    for (int o = threadIdx.x; o < n_work * per_item; o += REC_THREADS) {
+      const int i = o / per_item, rem = o - i * per_item;
+      const int c = rem / (K * 16), e16 = rem - c * (K * 16);
+      const double* P = (c < sm.nodes[i].n_children) ? sm.childs[i * REC_MAX_CHILDREN + c].P : nullptr;
+      if (P != nullptr) sm.P[o] = P[e16];
+    }
+    __syncthreads();
+  }
+  const int total = a.total_tiles;  // (row, bin) units of all work items
+  for (int u = blockIdx.x * REC_THREADS + threadIdx.x; u < total; u += gridDim.x * REC_THREADS) {
+    const int wi = find_work(sm.prefix, n_work, u);
+    const int local = u - sm.prefix[wi];
+    const int64_t p = local / K;
+    const int b = local - (int)p * K;
+    const d4 acc = rec_eval<REC_DEPTH>(sm, p_staged, wi, p, b, K);
+    const NodeDesc& nd = sm.nodes[wi];
+    if (nd.out != nullptr) st256(nd.out + (p * K + b) * 4, acc);
+    if (nd.is_root) {
+      const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
+      a.lh_out[p * K + b] = lh;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // 4-state PATH kernel: the optimiser's inner loop on real-data sizes.
 //
 // Powell / simulated annealing move ONE branch length at a time (maths/scipy_optimize.py:371-383,

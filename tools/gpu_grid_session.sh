@@ -3,7 +3,7 @@ cd "$(dirname "$0")/.." || exit 1
 OUT=gpurun_out; mkdir -p $OUT
 TAG=${1:-g}
 python __graft_entry__.py > $OUT/${TAG}_build.log 2>&1
-timeout -k 10 900 python -m pytest tests/test_gpu_wave.py tests/test_gpu_parity.py tests/test_gpu_rescaling.py -q --no-header -rf > $OUT/${TAG}_pytest.log 2>&1
+timeout -k 10 900 python -m pytest tests/test_gpu_rec.py tests/test_gpu_parity.py tests/test_gpu_rescaling.py -q --no-header -rf > $OUT/${TAG}_pytest.log 2>&1
 tail -4 $OUT/${TAG}_pytest.log
 B="python bench.py --steps 200 --warmup 5 --no-extra --no-dropin --no-cpu"
 run() { local name=$1; shift
@@ -21,18 +21,18 @@ PY
 )"
 }
 CFG="--config c2"
-run c2_nogrid C3_NO_GRID_SMALL=1
-run c2_grid4 C3_GRID_UNITS=4
-run c2_grid2 C3_GRID_UNITS=2
-run c2_grid16 C3_GRID_UNITS=16
+run c2_norec C3_NO_REC=1
+run c2_rec C3_X=1
+run c2_rec1m C3_REC_UNITS=1000000
+run c2_rec150k C3_REC_UNITS=150000
 CFG="--config c3"
-run c3_nogrid C3_NO_GRID_SMALL=1
-run c3_grid4 C3_GRID_UNITS=4
-run c3_grid16 C3_GRID_UNITS=16
+run c3_norec C3_NO_REC=1
+run c3_rec C3_X=1
+run c3_rec1m C3_REC_UNITS=1000000
 CFG="--config c5 --columns 1250000"
-run c5s_nogrid C3_NO_GRID_SMALL=1
-run c5s_grid4 C3_GRID_UNITS=4
+run c5s_norec C3_NO_REC=1
+run c5s_rec C3_X=1
 CFG="--config c2 --columns 100000"
-run c2s_nogrid C3_NO_GRID_SMALL=1
-run c2s_grid4 C3_GRID_UNITS=4
-run c2s_grid16 C3_GRID_UNITS=16
+run c2s_norec C3_NO_REC=1
+run c2s_rec C3_X=1
+run c2s_rec1m C3_REC_UNITS=1000000
