@@ -549,6 +549,15 @@ def dgemm_peak_tflops(ctx, n=8192, reps=3):
         return None
 
 
+def roofline_rows_of_step(eng, base, rates):
+    """per-launch records (kind, algorithmic bytes, ...) of one profiled full evaluation"""
+    eng.set_profiling(True)
+    eng.update(np.nan_to_num(base * (1.0 + 1e-3 * 5))[:, None] * rates[None, :])
+    rows = eng.launch_profile()
+    eng.set_profiling(False)
+    return rows
+
+
 def roofline_of(ctx, lf, eng, base, rates, cfg, kind, columns):
     """per-launch CUDA events of full evaluations (c3_get_launch_profile) -> the roofline object"""
     eng.set_profiling(True)
@@ -857,6 +866,15 @@ def measure_workload(ctx, args, cfg, columns, kind, steps, warmup, shard, clocks
 
     st = eng.stats()
     root_patterns = int(lf.patterns.root.n_rows - 1)
+    # the WHOLE device-timed step against the roofline: every launch's algorithmic bytes (pruning launches and
+    # the reduction) over the step's own time -- launches on several streams overlap, so the sum of per-launch
+    # durations above no longer adds up to the step
+    if lf.model.n_states == 4:
+        step_bytes = sum(r["bytes"] for r in roofline_rows_of_step(eng, base, rates))
+        t_step = dev_s / steps
+        roofline["whole_step"] = {"alg_bytes_per_step": step_bytes, "ms_per_step": t_step * 1e3,
+                                  "achieved": step_bytes / t_step / 1e9, "frac": step_bytes / t_step / 1e9 / roofline["peak"],
+                                  "note": "all launches of a device-timed step (per-rank), algorithmic bytes / step time"}  # fmt: skip
     out = {
         "problem": problem, "lf": lf,
         "value": total_units * steps / dev_s, "ms_per_step": dev_s / steps * 1e3, "steps": steps,

@@ -129,6 +129,16 @@ struct c3_engine {
   // recomputing kernel (prune4_rec_kernel): a run of consecutive small / medium levels (at most rec_units units
   // each, at least one of them too big for the small-levels cluster) becomes launches of up to REC_DEPTH + 1 levels
   // without any barrier.  C3_REC=1 enables, C3_REC_UNITS=n.
+  // independent root subtrees on their own streams: the sweep is launched per (subtree of a root child, level)
+  // instead of per level, every subtree on a stream of its own, so that one subtree's launch ramps up on the SMs
+  // another one's launch is draining from (the ~14 us of ramp + drain per streaming launch, lesson 16).
+  // Opt-in (C3_STREAMS=1): bit-identical, measured slower (C2 0.394 vs 0.364 ms: 22 smaller launches instead of 10,
+  // each with its own ramp and drain; DESIGN.md lesson 16e).
+  bool use_streams = false;
+  std::vector<cudaStream_t> aux_streams;
+  std::vector<cudaEvent_t> aux_done;
+  cudaEvent_t aux_fork = nullptr;
+  std::vector<int> subtree_of;  // [n_nodes] index of the root child above the node (the root: -1)
   bool use_rec = false;  // opt-in (C3_REC=1): bit-identical, no faster (DESIGN.md lesson 16d)
   int64_t rec_units = 400000;
   int64_t off_rec = 0;
@@ -895,6 +905,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_PATH")) e->use_path = atoi(env) != 0;
   if (const char* env = getenv("C3_PATH_VARIANT")) e->path_variant = std::max(0, std::min(2, atoi(env)));
   if (const char* env = getenv("C3_REC")) e->use_rec = atoi(env) != 0;
+  if (const char* env = getenv("C3_STREAMS")) e->use_streams = atoi(env) != 0;
   if (const char* env = getenv("C3_REC_UNITS")) e->rec_units = std::max(1, atoi(env));
   if (const char* env = getenv("C3_GRID_SMALL")) e->use_grid_small = atoi(env) != 0;
   if (const char* env = getenv("C3_GRID_UNITS")) e->grid_units_per_thread = std::max(1, std::min(64, atoi(env)));
@@ -949,6 +960,13 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (e->children[e->root].empty()) {
     delete e;
     return fail(C3_ERR_INVALID, "root has no children");
+  }
+  e->subtree_of.assign(n_nodes, -1);
+  {
+    int t = 0;
+    for (int c : e->children[e->root]) e->subtree_of[c] = t++;
+    for (int n = n_nodes - 2; n >= 0; --n)  // parents before children (post-order numbering)
+      if (e->subtree_of[n] < 0 && e->parent[n] >= 0) e->subtree_of[n] = e->subtree_of[e->parent[n]];
   }
   e->n_levels = e->level[e->root];
   e->level_nodes.resize(e->n_levels + 1);
@@ -1005,6 +1023,9 @@ int c3_destroy(c3_engine* e) {
   if (e->h_block) cudaFreeHost(e->h_block);
   if (e->h_lnl) cudaFreeHost(e->h_lnl);
   if (e->block_copied) cudaEventDestroy(e->block_copied);
+  for (cudaStream_t st : e->aux_streams) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : e->aux_done) cudaEventDestroy(ev);
+  if (e->aux_fork) cudaEventDestroy(e->aux_fork);
   for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -2272,6 +2293,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     int kind;
     int small_off, n_small;  // kind 1: range of SmallLevel records
     int grid;                // kind 1: > 0 = a cooperative launch of that many CTAs with grid barriers (medium levels)
+    int stream;              // 0: the engine's stream; t > 0: the stream of root subtree t
   };
   std::vector<LevelLaunch> launches;
   SmallLevel* small = reinterpret_cast<SmallLevel*>(e->h_block + e->off_small);
@@ -2367,10 +2389,55 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       path_buf_units = (int)std::max<int64_t>(max_units, 1);
     }
   }
+  // ---- launch groups: the dirty nodes of one tree level -- or, with several root subtrees streaming, of one
+  // (root subtree, level): a subtree only depends on itself, so its launches go to a stream of their own and
+  // ramp up while another subtree's launch drains (group 0 unused; the root is the last group, on stream 0)
+  std::vector<std::vector<int>> lv_nodes;
+  std::vector<int> lv_stream;
+  int n_streams_used = 1;
+  {
+    bool streams = e->use_streams && !e->rescale_active && wave == nullptr && !path_launch && !e->use_flow &&
+                   !e->profiling && e->batch_mode == 0 && e->children[e->root].size() >= 2;
+    if (streams) {
+      // worth it only when at least two subtrees have a level that streams (more units than the cluster takes)
+      std::vector<char> big(e->children[e->root].size(), 0);
+      for (int n = 0; n < N - 1; ++n)
+        if (recompute[n] && e->n_rows[n] * K > SMALL_LEVEL_UNITS) big[e->subtree_of[n]] = 1;
+      int n_big = 0;
+      for (char b : big) n_big += b;
+      streams = n_big >= 2;
+    }
+    lv_nodes.emplace_back();
+    lv_stream.push_back(0);
+    if (!streams) {
+      for (int l = 1; l <= e->n_levels; ++l) {
+        lv_nodes.push_back(e->level_nodes[l]);
+        lv_stream.push_back(0);
+      }
+    } else {
+      const int T = (int)e->children[e->root].size();
+      n_streams_used = T;
+      // subtree-major: a subtree's consecutive small levels can still fuse into one small-levels launch; the
+      // streams decouple execution order from issue order
+      for (int t = 0; t < T; ++t)
+        for (int l = 1; l <= e->n_levels; ++l) {
+          std::vector<int> g;
+          for (int n : e->level_nodes[l])
+            if (n != e->root && e->subtree_of[n] == t) g.push_back(n);
+          if (g.empty()) continue;
+          lv_nodes.push_back(std::move(g));
+          lv_stream.push_back(t);  // subtree 0 stays on the engine's stream
+        }
+      lv_nodes.push_back(std::vector<int>{e->root});
+      lv_stream.push_back(0);
+    }
+  }
+  const int n_groups = (int)lv_nodes.size() - 1;
+  const bool by_level = n_streams_used == 1;  // group l == tree level l
   // ---- recomputing launches: runs of consecutive small / medium levels, REC_DEPTH + 1 levels per launch -------
-  std::vector<int> rec_phase(e->n_levels + 2, -1);  // level -> phase (launch) number, -1: the usual launches
+  std::vector<int> rec_phase(std::max(e->n_levels, n_groups) + 2, -1);  // level -> phase (launch) number, -1: the usual launches
   std::vector<int> rec_first;                        // first level of every phase
-  if (e->use_rec && !e->use_dmma && e->use_small && !e->rescale_active && !path_launch) {
+  if (e->use_rec && by_level && !e->use_dmma && e->use_small && !e->rescale_active && !path_launch) {
     std::vector<int64_t> level_units(e->n_levels + 2, 0);
     std::vector<char> level_ok(e->n_levels + 2, 0);
     for (int l = 1; l <= e->n_levels; ++l) {
@@ -2420,7 +2487,13 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     }
   }
   int32_t* rec_child = reinterpret_cast<int32_t*>(e->h_block + e->off_rec);
-  for (int l = 1; l <= e->n_levels; ++l) {
+  int open_small_stream = 0;
+  for (int l = 1; l <= n_groups; ++l) {
+    const int g_stream = lv_stream[l];
+    if (g_stream != open_small_stream) {
+      open_small = -1;  // (a fused small-levels launch never spans two streams)
+      open_small_stream = g_stream;
+    }
     if (rec_phase[l] >= 0) {
       if (rec_first[rec_phase[l]] != l) continue;  // emitted with the phase's first level
       open_small = -1;
@@ -2458,7 +2531,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     int64_t units = 0;
     int n_dirty = 0;
     bool other_kinds = false;
-    for (int n : e->level_nodes[l])
+    for (int n : lv_nodes[l])
       if (recompute[n]) {
         units += e->n_rows[n] * K;
         ++n_dirty;
@@ -2473,7 +2546,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       close_flow();
       // extend (or open) a fused launch covering consecutive small levels
       if (open_small < 0) {
-        launches.push_back(LevelLaunch{w_off, p_off, 0, 0, false, 0, 0, 1, n_small_total, 0});
+        launches.push_back(LevelLaunch{w_off, p_off, 0, 0, false, 0, 0, 1, n_small_total, 0, 0, g_stream});
         open_small = (int)launches.size() - 1;
       }
       LevelLaunch& g = launches[open_small];
@@ -2483,7 +2556,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       sl.n_work = 0;
       int64_t u = 0;
       const int64_t bytes0 = alg_bytes, flops0 = flops;
-      for (int n : e->level_nodes[l]) {
+      for (int n : lv_nodes[l]) {
         if (!recompute[n]) continue;
         work[w_off + sl.n_work] = n;
         prefix[p_off + sl.n_work] = (int32_t)u;
@@ -2505,12 +2578,12 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
         g.grid = std::max(g.grid, (int)std::min<int64_t>(e->n_sm, (u + SMALL_THREADS - 1) / SMALL_THREADS));
       // a scaled node is rescaled right after its launch: it must be in the group's LAST level
       if (e->rescale_active)
-        for (int n : e->level_nodes[l])
+        for (int n : lv_nodes[l])
           if (recompute[n] && e->is_scaled[n]) open_small = -1;
       continue;
     }
     open_small = -1;
-    const std::vector<int>& order = e->level_nodes[l];
+    const std::vector<int>& order = lv_nodes[l];
     // nodes the dataflow kernel cannot take are launched on their own, BEFORE the group that
     // this level's binary nodes open (later levels of the group may depend on them)
     if (other_kinds || !flow_ok) close_flow();
@@ -2542,10 +2615,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
         }
         continue;
       }
-      LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, kind, 0, 0};
+      LevelLaunch ll{w_off, p_off, 0, 0, false, 0, 0, kind, 0, 0, 0, g_stream};
       int64_t tiles = 0;
       int64_t bytes0 = alg_bytes, flops0 = flops;
-      for (int n : e->level_nodes[l]) {
+      for (int n : lv_nodes[l]) {
         if (!recompute[n] || kind_of_node(e, n) != kind) continue;
         if (kind >= 2 && ll.n_work == (kind == 8 ? DE_MAXW : (kind == 6 ? DR_MAXW : P4S_MAXW))) {
           // the strip kernel stages at most P4S_MAXW descriptors: close this launch, open another
@@ -2556,7 +2629,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
           w_off += ll.n_work;
           p_off += ll.n_work + 1;
           launches.push_back(ll);
-          ll = LevelLaunch{w_off, p_off, 0, 0, false, 0, 0, kind, 0, 0};
+          ll = LevelLaunch{w_off, p_off, 0, 0, false, 0, 0, kind, 0, 0, 0, g_stream};
           tiles = 0;
           bytes0 = alg_bytes;
           flops0 = flops;
@@ -2653,8 +2726,51 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
 
   const int32_t* d_work = reinterpret_cast<const int32_t*>(e->d_block + e->off_work);
   const int32_t* d_prefix = reinterpret_cast<const int32_t*>(e->d_block + e->off_prefix);
+  // several root subtrees streaming: fork the subtrees' streams off the engine's stream here (the parameter block
+  // and the P matrices are in place), join them before the first launch that runs on the engine's stream again
+  // after them (the root)
+  const cudaStream_t main_stream = e->stream;
+  std::vector<char> forked(n_streams_used, 0);
+  struct StreamRestore {
+    c3_engine* e;
+    cudaStream_t s;
+    ~StreamRestore() { e->stream = s; }
+  } stream_restore{e, main_stream};
+  if (n_streams_used > 1) {
+    while ((int)e->aux_streams.size() < n_streams_used - 1) {
+      cudaStream_t st;
+      C3_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      e->aux_streams.push_back(st);
+      cudaEvent_t ev;
+      C3_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->aux_done.push_back(ev);
+    }
+    if (!e->aux_fork) C3_CUDA(cudaEventCreateWithFlags(&e->aux_fork, cudaEventDisableTiming));
+    C3_CUDA(cudaEventRecord(e->aux_fork, main_stream));
+  }
+  bool joined = n_streams_used == 1;
   for (size_t li = 0; li < launches.size(); ++li) {
     const LevelLaunch& ll = launches[li];
+    if (n_streams_used > 1) {
+      if (ll.stream > 0) {
+        const cudaStream_t st = e->aux_streams[ll.stream - 1];
+        if (!forked[ll.stream]) {
+          C3_CUDA(cudaStreamWaitEvent(st, e->aux_fork, 0));
+          forked[ll.stream] = 1;
+        }
+        e->stream = st;
+      } else {
+        e->stream = main_stream;
+        if (!joined && ll.is_root) {
+          for (int t = 1; t < n_streams_used; ++t)
+            if (forked[t]) {
+              C3_CUDA(cudaEventRecord(e->aux_done[t - 1], e->aux_streams[t - 1]));
+              C3_CUDA(cudaStreamWaitEvent(main_stream, e->aux_done[t - 1], 0));
+            }
+          joined = true;
+        }
+      }
+    }
     PruneArgs a;
     a.nodes = e->d_nodes;
     a.childs = e->d_childs;
@@ -2816,6 +2932,15 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       }
     }
   }
+  e->stream = main_stream;
+  if (!joined) {
+    for (int t = 1; t < n_streams_used; ++t)
+      if (forked[t]) {
+        C3_CUDA(cudaEventRecord(e->aux_done[t - 1], e->aux_streams[t - 1]));
+        C3_CUDA(cudaStreamWaitEvent(main_stream, e->aux_done[t - 1], 0));
+      }
+    joined = true;
+  }
   if (!fuse_reduce) {
     const int64_t rows = e->n_rows[e->root];
     const int n_tiles = (int)((rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
@@ -2860,7 +2985,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     for (const LevelLaunch& ll : launches) {
       sig.push_back(ll.kind); sig.push_back(ll.work_off); sig.push_back(ll.prefix_off); sig.push_back(ll.n_work);
       sig.push_back(ll.total_tiles); sig.push_back(ll.is_root ? 1 : 0); sig.push_back(ll.small_off); sig.push_back(ll.n_small);
-      sig.push_back(ll.grid);
+      sig.push_back(ll.grid); sig.push_back(ll.stream);
     }
     for (int i = 0; i < w_off; ++i) sig.push_back(work[i]);  // (rescale launches name their nodes)
     uint64_t h = 1469598103934665603ull;

@@ -3,7 +3,7 @@ cd "$(dirname "$0")/.." || exit 1
 OUT=gpurun_out; mkdir -p $OUT
 TAG=${1:-g}
 python __graft_entry__.py > $OUT/${TAG}_build.log 2>&1
-timeout -k 10 900 python -m pytest tests/test_gpu_rec.py tests/test_gpu_parity.py tests/test_gpu_rescaling.py -q --no-header -rf > $OUT/${TAG}_pytest.log 2>&1
+timeout -k 10 900 python -m pytest tests/test_gpu_streams.py tests/test_gpu_parity.py tests/test_gpu_rescaling.py tests/test_gpu_fullsize.py -q --no-header -rf > $OUT/${TAG}_pytest.log 2>&1
 tail -4 $OUT/${TAG}_pytest.log
 B="python bench.py --steps 200 --warmup 5 --no-extra --no-dropin --no-cpu"
 run() { local name=$1; shift
@@ -21,18 +21,20 @@ PY
 )"
 }
 CFG="--config c2"
-run c2_norec C3_NO_REC=1
-run c2_rec C3_X=1
-run c2_rec1m C3_REC_UNITS=1000000
-run c2_rec150k C3_REC_UNITS=150000
+run c2_st0 C3_STREAMS=0
+run c2_st1 C3_STREAMS=1
+run c2_st1b C3_STREAMS=1
 CFG="--config c3"
-run c3_norec C3_NO_REC=1
-run c3_rec C3_X=1
-run c3_rec1m C3_REC_UNITS=1000000
+run c3_st0 C3_STREAMS=0
+run c3_st1 C3_STREAMS=1
+CFG="--config c4"
+run c4_st0 C3_STREAMS=0
+run c4_st1 C3_STREAMS=1
 CFG="--config c5 --columns 1250000"
-run c5s_norec C3_NO_REC=1
-run c5s_rec C3_X=1
+run c5s_st0 C3_STREAMS=0
+run c5s_st1 C3_STREAMS=1
 CFG="--config c2 --columns 100000"
-run c2s_norec C3_NO_REC=1
-run c2s_rec C3_X=1
-run c2s_rec1m C3_REC_UNITS=1000000
+run c2s_st0 C3_STREAMS=0
+run c2s_st1 C3_STREAMS=1
+CFG="--config c1"
+run c1_st1 C3_STREAMS=1
