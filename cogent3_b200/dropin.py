@@ -32,6 +32,7 @@ from collections import OrderedDict
 
 import numpy as np
 
+from . import batch as _batch
 from .patterns import from_reference_lht
 
 __all__ = ["CudaAlignmentLikelihoodFunction", "make_likelihood_function", "install", "uninstall", "installed"]
@@ -384,6 +385,7 @@ def _build(cogent3_modules):
                 "engine": engine,
                 "topo": topo,
                 "edge_ids": [node_of[n] for n in self.edge_names],
+                "edge_ids_arr": np.array([node_of[n] for n in self.edge_names], np.intp),
                 "internal_ids": [node_of[n] for n in self.internal_names],
                 "slot_of": {},  # id(exponentiator) -> slot
                 "slot_obj": {},  # slot -> exponentiator (strong ref: ids are not recycled)
@@ -476,8 +478,6 @@ def _build(cogent3_modules):
             return self._finish(eng, blh)
 
         def _finish(self, eng, blh=None):
-            from . import batch as _batch
-
             lockstep = _batch.current()
             # inside cogent3_b200.batch.run_lockstep the evaluations of several optimiser threads meet in one
             # c3_evaluate_many call; otherwise the engine is evaluated right here
@@ -575,7 +575,7 @@ def _build(cogent3_modules):
             d = np.array(lengths, np.float64)[:, None]
             if self.has_rate:
                 d = d * np.array(rates, np.float64)[None, :]
-            dist[edge_ids, :] = d
+            dist[st["edge_ids_arr"], :] = d
             for (node, b), ex in st["host_ex"].items():
                 key = (ex, float(dist[node, b]))
                 prev = st["psub_obj"].get((node, b))
@@ -583,9 +583,13 @@ def _build(cogent3_modules):
                     eng.set_psub(node, b, np.asarray(ex(key[1]), float))
                     st["psub_obj"][(node, b)] = key
             eng.set_distances(dist)
-            eng.set_root_mprobs(np.asarray(mprobs, float))
-            if bprobs is not None:
+            # unchanged inputs keep object identity between calls (calculation.py:431-438)
+            if st.get("last_mprobs") is not mprobs:
+                eng.set_root_mprobs(np.asarray(mprobs, float))
+                st["last_mprobs"] = mprobs
+            if bprobs is not None and st.get("last_bprobs") is not bprobs:
                 eng.set_bin_probs(np.asarray(bprobs, float))
+                st["last_bprobs"] = bprobs
             if st.get("last_fixed") != fixed:
                 fm = np.full(st["topo"].n_nodes, -1, np.int32)
                 for node, f in zip(st["internal_ids"], fixed, strict=True):

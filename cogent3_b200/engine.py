@@ -238,7 +238,10 @@ class LikelihoodEngine:
 
     def set_distances(self, dist):
         """``dist[n_nodes, n_bins]`` = length[edge] * rate[bin] (root row ignored)."""
-        d = np.ascontiguousarray(np.broadcast_to(dist, (self.n_nodes, self.n_bins)), np.float64)
+        d = dist
+        if not (isinstance(d, np.ndarray) and d.dtype == np.float64 and d.shape == (self.n_nodes, self.n_bins)
+                and d.flags.c_contiguous):
+            d = np.ascontiguousarray(np.broadcast_to(dist, (self.n_nodes, self.n_bins)), np.float64)
         self._dist = d
         _lib.check(self._lib.c3_set_distances(self._h, _dptr(d)))
 
