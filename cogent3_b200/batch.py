@@ -34,61 +34,77 @@ def current():
     return getattr(_LOCAL, "batch", None)
 
 
+class _Seat:
+    """one waiting thread: its own lock to sleep on (no shared condition to fight over on wake-up)"""
+
+    __slots__ = ("lock", "result")
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.lock.acquire()
+        self.result = None
+
+
 class Lockstep:
-    """rendezvous of the engine evaluations of several threads (see the module docstring)"""
+    """rendezvous of the engine evaluations of several threads (see the module docstring).
+
+    A thread that arrives takes a seat and sleeps on the seat's own lock; the thread that completes the round
+    (every live thread is seated) runs the batched call outside the mutex and releases every seat with its
+    value.  No condition variable: a notify_all would send all sleepers after one mutex at once."""
 
     def __init__(self, n_threads: int):
-        self.cv = threading.Condition()
+        self.mutex = threading.Lock()
         self.live = int(n_threads)
-        self.waiting: dict[int, object] = {}
-        self.results: dict[int, object] = {}
-        self.round = 0
+        self.waiting: list = []  # [(seat, engine)]
         self.batches = 0
         self.evaluations = 0
+        self._seats = threading.local()
 
     # -- called by the drop-in's terminal Defn (dropin.GpuLogLikelihoodDefn._finish) ---------------------
     def evaluate(self, engine) -> float:
-        me = threading.get_ident()
-        with self.cv:
-            self.waiting[me] = engine
+        seat = getattr(self._seats, "seat", None)
+        if seat is None:
+            seat = self._seats.seat = _Seat()
+        with self.mutex:
+            self.waiting.append((seat, engine))
+            batch = None
             if len(self.waiting) >= self.live:
-                self._fire()
-            else:
-                my_round = self.round
-                while self.round == my_round:
-                    self.cv.wait()
-            out = self.results.pop(me)
+                batch, self.waiting = self.waiting, []
+        if batch is not None:
+            self._run(batch)
+        seat.lock.acquire()  # released by whoever ran the round (possibly this very thread)
+        out = seat.result
         if isinstance(out, BaseException):
             raise out
         return out
 
-    def _fire(self):
-        """(cv held) every live thread is waiting: one batched call for all of them"""
-        keys = list(self.waiting)
-        engines = [self.waiting[k] for k in keys]
-        self.waiting.clear()
+    def _run(self, batch):
+        """one batched call for every seated thread; every seat gets its own outcome"""
+        engines = [e for _s, e in batch]
         try:
             values = _evaluate_engines(engines)
-        except Exception:  # noqa: BLE001 - find out whose evaluation failed: every thread gets its own outcome
+        except Exception:  # noqa: BLE001 - find out whose evaluation failed
             values = []
             for e in engines:
                 try:
                     values.append(e.evaluate())
                 except Exception as err:  # noqa: BLE001
                     values.append(err)
-        for k, v in zip(keys, values, strict=True):
-            self.results[k] = v
         self.batches += 1
-        self.evaluations += len(keys)
-        self.round += 1
-        self.cv.notify_all()
+        self.evaluations += len(batch)
+        for (seat, _e), v in zip(batch, values, strict=True):
+            seat.result = v
+            seat.lock.release()
 
     def leave(self):
         """a thread is through: the others must not wait for it any more"""
-        with self.cv:
+        with self.mutex:
             self.live -= 1
+            batch = None
             if self.waiting and len(self.waiting) >= self.live:
-                self._fire()
+                batch, self.waiting = self.waiting, []
+        if batch is not None:
+            self._run(batch)
 
 
 def _evaluate_engines(engines):

@@ -20,7 +20,7 @@ LIB = os.path.join(PKG, "libc3cuda.so")
 SOURCES = [os.path.join(CSRC, "c3cuda.cu")]
 HEADERS = [
     os.path.join(CSRC, f)
-    for f in ("c3_types.cuh", "expm_kernels.cuh", "prune_kernels.cuh", "compress_kernels.cuh", "hmm_kernels.cuh")
+    for f in ("c3_types.cuh", "expm_kernels.cuh", "prune_kernels.cuh", "lab_kernels.cuh", "compress_kernels.cuh", "hmm_kernels.cuh")
 ] + [os.path.join(ROOT, "include", "c3cuda.h")]
 
 NVCC_FLAGS = [

@@ -126,6 +126,7 @@ struct c3_engine {
   bool use_grid_small = false;  // opt-in (C3_GRID_SMALL=1): measured no faster than the launches it replaces, DESIGN.md lesson 17
   int grid_units_per_thread = 4;
   unsigned int* d_grid_bar = nullptr;
+  char* d_hmm_scratch = nullptr;  // c3_hmm_reduce: per-block products + the result
   // recomputing kernel (prune4_rec_kernel): a run of consecutive small / medium levels (at most rec_units units
   // each, at least one of them too big for the small-levels cluster) becomes launches of up to REC_DEPTH + 1 levels
   // without any barrier.  C3_REC=1 enables, C3_REC_UNITS=n.
@@ -1015,6 +1016,7 @@ int c3_destroy(c3_engine* e) {
   if (e->d_mailbox) cudaFree(e->d_mailbox);
   if (e->d_pool) cudaFree(e->d_pool);
   if (e->d_scale_pool) cudaFree(e->d_scale_pool);
+  if (e->d_hmm_scratch) cudaFree(e->d_hmm_scratch);
   clear_graphs(e);
   for (auto& w : e->waves) free_wave(e, w.second);
   e->waves.clear();
@@ -1438,16 +1440,19 @@ int c3_hmm_reduce(c3_engine* e, int n_patches, const int32_t* patch_of_bin, cons
   a.patch_probs[1] = patch_probs[1];
   const int n_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((e->n_columns + HMM_THREADS * 16 - 1) / (HMM_THREADS * 16),
                                                                  (int64_t)e->n_sm * 8));
-  Hmm2* d_blocks = nullptr;
-  double* d_out = nullptr;
-  C3_CUDA(cudaMalloc(&d_blocks, (size_t)n_blocks * sizeof(Hmm2) + sizeof(double)));
-  d_out = reinterpret_cast<double*>(d_blocks + n_blocks);
+  // scratch of the reduction: allocated on first use, kept (an optimiser calls this once per evaluation)
+  const size_t scratch_bytes = (size_t)e->n_sm * 8 * sizeof(Hmm2) + sizeof(double);
+  if (e->d_hmm_scratch == nullptr) {
+    C3_CUDA(cudaMalloc(&e->d_hmm_scratch, scratch_bytes));
+    e->stats.device_bytes += (int64_t)scratch_bytes;
+  }
+  Hmm2* d_blocks = reinterpret_cast<Hmm2*>(e->d_hmm_scratch);
+  double* d_out = reinterpret_cast<double*>(d_blocks + (size_t)e->n_sm * 8);
   hmm_chunk_kernel<<<n_blocks, HMM_THREADS, 0, e->stream>>>(a, d_blocks);
   hmm_final_kernel<<<1, 32, 0, e->stream>>>(a, d_blocks, n_blocks, d_out);
   e->stats.kernel_launches += 2;
   cudaError_t err = cudaMemcpyAsync(lnL, d_out, sizeof(double), cudaMemcpyDeviceToHost, e->stream);
   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-  cudaFree(d_blocks);
   if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("c3_hmm_reduce: ") + cudaGetErrorString(err));
   return C3_OK;
 }
