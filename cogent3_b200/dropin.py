@@ -97,6 +97,46 @@ class LazyPsub:
 
 
 # ---------------------------------------------------------------------------------------
+# a5: the gamma rate classes.  ``GammaDefn.calc`` (recalculation/definition.py:236-244) asks
+# ``scipy.stats.gamma.ppf`` for one median per bin; each call walks scipy's generic distribution
+# wrapper (argument broadcasting, support checks, ``place``) around ONE ``gammaincinv``: ~80 us per
+# bin, 0.32 ms of a 0.86 ms full-change step at C2 (profiles/r2_dropin_host_profile_c2.txt) -- as long
+# as the whole device sweep.  ``rv_continuous.ppf`` computes ``_ppf(q, a) * scale + loc`` with
+# ``gamma._ppf = scipy.special.gammaincinv(a, q)``, ``scale = 1 / a``, ``loc = 0``: the same three
+# floating-point operations are done here on the whole vector of percentiles.  Bit-identical
+# (tests/test_dropin.py::test_fast_gamma_rates_bit_identical); anything outside the plain case
+# (a percentile not strictly inside (0, 1), a non-positive or non-finite shape) goes to the reference.
+# ---------------------------------------------------------------------------------------
+def fast_gamma_rates(weights, a):
+    from scipy.special import gammaincinv
+
+    weights = weights / np.sum(weights)
+    percentiles = np.add.accumulate(weights) - weights * 0.5
+    shape = np.asarray(a)
+    if (shape.ndim != 0 or not np.isfinite(shape) or not shape > 0
+            or not ((percentiles > 0) & (percentiles < 1)).all()):  # fmt: skip
+        from cogent3.recalculation.definition import GammaDefn
+
+        return GammaDefn.calc(None, weights, a)
+    medians = gammaincinv(shape, percentiles) * np.asarray(1 / a) + 0
+    scale = np.sum(medians * weights)
+    return medians / scale
+
+
+def _use_fast_gamma(defns, definition):
+    """every ``GammaDefn`` reachable from the model's Defns computes its rates with ``fast_gamma_rates``
+    (an instance attribute: ``make_calc_function`` returns ``self.calc``, recalculation/definition.py:130-131)"""
+    seen, stack = set(), [d for d in defns.values() if d is not None]
+    while stack:
+        d = stack.pop()
+        if id(d) in seen:
+            continue
+        seen.add(id(d))
+        if type(d) is definition.GammaDefn and "calc" not in d.__dict__:
+            d.calc = fast_gamma_rates
+        stack.extend(getattr(d, "args", ()))
+
+# ---------------------------------------------------------------------------------------
 # cogent3's per-node pattern compression, vectorised (SURVEY §8f-2)
 #
 # ``lf.set_alignment`` spends its time in ``_indexed`` (evolve/likelihood_tree.py:186-203): a Python
@@ -678,6 +718,7 @@ def _build(cogent3_modules):
             self._serialisable.pop("factored", None)
             factors = None
             defns = self.model.make_param_controller_defns(bin_names=self.bin_names)
+            _use_fast_gamma(defns, definition)
             psubs = defns["psubs"]
             if discrete_edges is not None:
                 from cogent3.evolve.discrete_markov import PartialyDiscretePsubsDefn

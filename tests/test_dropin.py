@@ -121,6 +121,39 @@ def test_gtr_gamma_bins_and_posteriors():
     assert lf.get_G_statistic() == pytest.approx(ref.get_G_statistic(), rel=1e-10)
 
 
+def test_fast_gamma_rates_bit_identical():
+    """a5: the drop-in's GammaDefn computes the rate classes without scipy's distribution wrapper --
+    the same bits as the reference's calc (recalculation/definition.py:236-244), inside the likelihood
+    function too (the Defn's value is what both classes hand to ``distance``)"""
+    from cogent3.recalculation.definition import GammaDefn
+
+    from cogent3_b200.dropin import fast_gamma_rates
+
+    rng = np.random.default_rng(11)
+    for i in range(600):
+        k = int(rng.integers(2, 9))
+        w = rng.random(k) + 0.01 if i % 3 else np.ones(k) / k
+        a = float(np.exp(rng.uniform(np.log(1e-2), np.log(300.0))))
+        a = np.float64(a) if i % 2 else a
+        want, got = GammaDefn.calc(None, w, a), fast_gamma_rates(w, a)
+        assert want.dtype == got.dtype and want.tobytes() == got.tobytes(), (w, a)
+    # outside the plain case the reference's own code answers (an empty last bin puts a percentile at 1)
+    w = np.array([0.5, 0.5, 0.0])
+    np.testing.assert_array_equal(fast_gamma_rates(w, 0.7), GammaDefn.calc(None, w, 0.7))
+    tree, aln = small_problem()
+    mk = lambda: get_model("GTR", ordered_param="rate", distribution="gamma")  # noqa: E731
+    ref, lf = pair(mk, tree, aln, bins=4)
+    gamma = [d for d in lf.defns if type(d) is GammaDefn]
+    assert gamma and all(d.calc is fast_gamma_rates for d in gamma)
+    for shape in (0.05, 0.5, 1.7, 40.0):
+        for f in (ref, lf):
+            f.set_param_rule("rate_shape", value=shape)
+        for b in lf.bin_names:
+            assert lf.get_param_value("rate", bin=b) == ref.get_param_value("rate", bin=b)
+        assert_same(ref, lf)
+    pickle.loads(pickle.dumps(lf))
+
+
 def test_gn_time_heterogeneous_pade():
     tree, aln = small_problem(n_tips=6, L=150, seed=8)
     ref, lf = pair(lambda: get_model("GN"), tree, aln, expm="pade")
