@@ -68,6 +68,14 @@ struct PruneArgs {
   int32_t M;
   const double* pi;  // root only: [MP] (zero padded)
   double* lh_out;    // root only: [rows][K]
+  // "lean root" (regpipe2 root launch, K > 1): the launch mixes the rate classes itself and writes
+  // mix[p] = sum_b bprob_b lh_b[p] (8 B per row) instead of lh[p][K]; the reduction then reads mix and counts only.
+  // lh is recomputed when an accessor asks for it.
+  double* mix_out = nullptr;
+  const double* bprobs = nullptr;
+  // developer timeline (C3_TIMELINE=1): [entry_min, start_min (after the dependency wait), end_min, end_max] in
+  // globaltimer ns, per launch
+  unsigned long long* tl = nullptr;
 };
 
 // Site-pattern shards on several GPUs of one node: the reduction's last CTA exchanges the shard
@@ -98,6 +106,7 @@ struct ResultSink {
   volatile double* h_lnl;
   volatile unsigned long long* h_seq;
   unsigned long long* seq_ctr;
+  unsigned long long* tl = nullptr;  // developer timeline slot of the launch that publishes (see PruneArgs::tl)
 };
 
 // one tree level inside a fused "small levels" launch

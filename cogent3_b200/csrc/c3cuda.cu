@@ -153,6 +153,26 @@ struct c3_engine {
   bool edge_major = false;
   bool use_dmma_reg = true;  // warp-private register pipeline for M != 4 (C3_DMMA_REG=0: first version)
   bool use_reg2 = true;   // binary nodes: two strips in flight per warp (C3_REG1=1: the one-strip regpipe kernel)
+  // C3_REG2_U2=1: binary nodes by 16 warps x 2 rows per lane (strips of 64 units) instead of 8 x 4 (128): the same
+  // bytes in flight per SM in steps half as long -- the drain and the last-strip imbalance of a launch scale with
+  // the step
+  bool reg2_u2 = false;
+  int root_u = 2;  // rows per lane of the three-children instance: 2 (12 warps) or 3 (8 warps, C3_ROOT_U=3)
+  // lean root (C3_LEAN_ROOT=0 disables): the regpipe2 root launch writes mix[p] (8 B per row) instead of lh[p][K]
+  // and the reduction reads mix + counts only; lh is recomputed by the root launch alone when an accessor asks for
+  // it (ensure_lh), and stays materialised for the next LH_KEEP evaluations after such a request
+  bool lean_root = true;
+  bool lh_valid = true;   // d_lh holds the last evaluation's per-pattern likelihoods
+  int lh_keep = 0;        // evaluations that still write lh because an accessor read it recently
+  double* d_mix = nullptr;
+  struct RootLaunch { int work_off = 0, prefix_off = 0, n_work = 0, total_tiles = 0, kind = 0; } root_launch;
+  // developer timeline (C3_TIMELINE=1): globaltimer stamps of every pruning / reduction launch of the LAST
+  // evaluation, printed by c3_destroy
+  bool timeline = false;
+  unsigned long long* d_tl = nullptr;
+  unsigned long long* h_tl_init = nullptr;
+  int tl_launches = 0;
+  std::vector<int> tl_kinds;
   bool use_ring = false;  // C3_RING=1: the cp.async shared-memory ring version of the strip kernel
   // Nothing on the path reads the ROOT's partial rows (only lh = inner(plh_root, pi) goes on, and the
   // root is recomputed whenever anything changed), so by default they are neither allocated nor written
@@ -451,10 +471,17 @@ int launch_flow(c3_engine* e, const PruneArgs& a, const int32_t* d_dep, unsigned
   return C3_OK;
 }
 
+template <int K, int NC, int U, int WARPS>
+int launch_reg2_cfg(c3_engine* e, const PruneArgs& a, bool is_root);
+
 template <int K, int NC>
 int launch_reg2(c3_engine* e, const PruneArgs& a, bool is_root) {
-  constexpr int U = (NC == 2) ? 4 : 2;
-  constexpr int WARPS = (NC == 2) ? 8 : 12;
+  if (NC == 2) return e->reg2_u2 ? launch_reg2_cfg<K, 2, 2, 16>(e, a, is_root) : launch_reg2_cfg<K, 2, 4, 8>(e, a, is_root);
+  return e->root_u == 3 ? launch_reg2_cfg<K, 3, 3, 8>(e, a, is_root) : launch_reg2_cfg<K, 3, 2, 12>(e, a, is_root);
+}
+
+template <int K, int NC, int U, int WARPS>
+int launch_reg2_cfg(c3_engine* e, const PruneArgs& a, bool is_root) {
   const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + WARPS - 1) / WARPS));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -751,7 +778,8 @@ int64_t tiles_of_node(const c3_engine* e, int n, int kind) {
   if (kind == 6) return (int64_t)e->K * ((e->n_rows[n] + DR_TILE_ROWS - 1) / DR_TILE_ROWS);
   if (kind >= 2) {
     // strips of 128 (row, bin) units; regpipe2 walks three-children nodes in strips of 64
-    const int rows = ((kind == 3 && e->use_reg2 && !e->use_ring) ? 64 : 128) / e->K;
+    const int units = (!e->use_reg2 || e->use_ring) ? 128 : (kind == 3 ? 32 * e->root_u : (e->reg2_u2 ? 64 : 128));
+    const int rows = units / e->K;
     return (e->n_rows[n] + rows - 1) / rows;
   }
   if (!e->use_dmma) {
@@ -766,6 +794,7 @@ void commit_evaluation(c3_engine* e, int64_t n_launch, bool replayed) {
   std::fill(e->pdirty.begin(), e->pdirty.end(), 0);
   std::fill(e->node_dirty.begin(), e->node_dirty.end(), 0);
   e->reduce_dirty = false;
+  if (e->lh_keep > 0) --e->lh_keep;
   e->stats.evaluations += 1;
   e->stats.kernel_launches += n_launch;
   e->stats.last_launches = n_launch;
@@ -836,6 +865,7 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used);
 int activate_rescaling(c3_engine* e);
 void deactivate_rescaling(c3_engine* e);
 int launch_rescale(c3_engine* e, int node);
+int ensure_lh(c3_engine* e);
 
 cudaEvent_t next_event(c3_engine* e) {
   if (e->events_used == e->event_pool.size()) {
@@ -915,6 +945,10 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_EDGE_MAJOR")) e->edge_major = e->use_dmma && atoi(env) != 0;
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   if (const char* env = getenv("C3_REG1")) e->use_reg2 = atoi(env) == 0;
+  if (const char* env = getenv("C3_REG2_U2")) e->reg2_u2 = atoi(env) != 0;
+  if (const char* env = getenv("C3_ROOT_U")) e->root_u = atoi(env) == 3 ? 3 : 2;
+  if (const char* env = getenv("C3_LEAN_ROOT")) e->lean_root = atoi(env) != 0;
+  if (const char* env = getenv("C3_TIMELINE")) e->timeline = atoi(env) != 0;
   if (const char* env = getenv("C3_FLOW")) e->use_flow = atoi(env) != 0;
   if (const char* env = getenv("C3_WAVE")) e->use_wave = atoi(env) != 0;
   if (const char* env = getenv("C3_WAVE_LAG")) e->wave_lag = std::max(3, std::min(12, atoi(env)));
@@ -922,6 +956,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_WAVE_MIN")) e->wave_min_strips = std::max(1, atoi(env));
   if (const char* env = getenv("C3_WAVE_GROUP")) e->wave_group = std::max(1, std::min(32, atoi(env)));
   if (const char* env = getenv("C3_WAVE_PREFIX")) e->wave_prefix = std::max(0, atoi(env));
+  e->reg2_u2 = e->reg2_u2 && e->use_strip && e->use_reg2 && !e->use_ring && !e->use_flow && !e->use_wave;
   e->store_root = !(e->use_dmma ? e->edge_major
                                 : (e->use_strip && e->use_reg2 && !e->use_ring && !e->use_flow));
   if (const char* env = getenv("C3_STORE_ROOT")) e->store_root = e->store_root || atoi(env) != 0;
@@ -1004,10 +1039,31 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   return C3_OK;
 }
 
+// developer timeline of the LAST evaluation (C3_TIMELINE=1): microseconds after the first launch's entry
+void dump_timeline(c3_engine* e) {
+  if (!e->timeline || !e->d_tl || e->tl_launches <= 0) return;
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  std::vector<unsigned long long> t((size_t)e->tl_launches * 4);
+  if (cudaMemcpy(t.data(), e->d_tl, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  unsigned long long t0 = ~0ull;
+  for (int i = 0; i < e->tl_launches; ++i) t0 = std::min(t0, t[4 * i]);
+  fprintf(stderr, "c3 timeline (us) after %lld evaluations: launch kind | entry | start (after the dependency wait) | first warp out | last warp out\n",
+          (long long)e->stats.evaluations);
+  for (int i = 0; i < e->tl_launches; ++i) {
+    auto us = [&](unsigned long long v) { return (v == ~0ull || v == 0ull) ? -1.0 : (double)(v - t0) * 1e-3; };
+    fprintf(stderr, "c3 timeline %2d kind %3d | %8.2f | %8.2f | %8.2f | %8.2f\n", i,
+            i < (int)e->tl_kinds.size() ? e->tl_kinds[i] : -1, us(t[4 * i]), us(t[4 * i + 1]), us(t[4 * i + 2]),
+            us(t[4 * i + 3]));
+  }
+}
+
 int c3_destroy(c3_engine* e) {
   if (!e) return C3_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  dump_timeline(e);
+  if (e->d_tl) cudaFree(e->d_tl);
+  if (e->h_tl_init) cudaFreeHost(e->h_tl_init);
   for (int32_t* p : e->d_index)
     if (p) cudaFree(p);
   for (int32_t* p : e->d_idx_tmp)
@@ -1403,6 +1459,7 @@ int c3_get_site_lh(c3_engine* e, int bin, double* out, int64_t n_columns) {
   C3_REQUIRE(n_columns == e->n_columns, "bad column count");
   if (n_columns == 0) return C3_OK;
   C3_CUDA(cudaSetDevice(e->device));
+  { const int rc_lh = ensure_lh(e); if (rc_lh) return rc_lh; }
   double* d_out = nullptr;
   C3_CUDA(cudaMalloc(&d_out, (size_t)n_columns * sizeof(double)));
   const int grid = (int)std::min<int64_t>((n_columns + CMP_THREADS - 1) / CMP_THREADS, (int64_t)e->n_sm * 16);
@@ -1424,6 +1481,7 @@ int c3_hmm_reduce(c3_engine* e, int n_patches, const int32_t* patch_of_bin, cons
              "the column numbering is not on the device (c3_compress_alignment / c3_set_column_index)");
   C3_REQUIRE(e->K <= 64, "too many bins");
   C3_CUDA(cudaSetDevice(e->device));
+  { const int rc_lh = ensure_lh(e); if (rc_lh) return rc_lh; }
   HmmArgs a{};
   a.lh = e->d_lh;
   a.index = e->d_root_index;
@@ -1493,6 +1551,7 @@ int c3_finalize(c3_engine* e) {
   const int64_t root_rows = e->n_rows[e->root];
   const int64_t o_counts = carve(root_rows * sizeof(double));
   const int64_t o_lh = carve(root_rows * K * sizeof(double));
+  const int64_t o_mix = carve(root_rows * sizeof(double));
   const int64_t n_red_tiles = (root_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE;
   const int64_t o_tiles = carve(n_red_tiles * sizeof(double));
   const int64_t o_counter = carve(256);
@@ -1557,6 +1616,8 @@ int c3_finalize(c3_engine* e) {
   e->d_edges = reinterpret_cast<EdgeDesc*>(e->d_pool + o_edges);
   e->d_counts = reinterpret_cast<double*>(e->d_pool + o_counts);
   e->d_lh = reinterpret_cast<double*>(e->d_pool + o_lh);
+  e->d_mix = reinterpret_cast<double*>(e->d_pool + o_mix);
+  e->lh_valid = true;
   e->d_tile_sums = reinterpret_cast<double*>(e->d_pool + o_tiles);
   e->d_counter = reinterpret_cast<unsigned int*>(e->d_pool + o_counter);
   e->d_seq = reinterpret_cast<unsigned long long*>(e->d_pool + o_counter + 8);
@@ -1827,6 +1888,7 @@ int c3_get_scaled_lh(c3_engine* e, int bin, double* out, int64_t n_rows) {
   C3_REQUIRE(bin >= 0 && bin < e->K, "bad bin");
   C3_REQUIRE(n_rows == e->n_rows[e->root], "bad row count");
   C3_CUDA(cudaSetDevice(e->device));
+  { const int rc_lh = ensure_lh(e); if (rc_lh) return rc_lh; }
   C3_CUDA(cudaStreamSynchronize(e->stream));
   C3_CUDA(cudaMemcpy2D(out, sizeof(double), e->d_lh + bin, e->K * sizeof(double), sizeof(double),
                        (size_t)n_rows, cudaMemcpyDeviceToHost));
@@ -2018,6 +2080,7 @@ int c3_get_lh(c3_engine* e, int bin, double* out, int64_t n_rows) {
   C3_REQUIRE(bin >= 0 && bin < e->K, "bad bin");
   C3_REQUIRE(n_rows == e->n_rows[e->root], "bad row count");
   C3_CUDA(cudaSetDevice(e->device));
+  { const int rc_lh = ensure_lh(e); if (rc_lh) return rc_lh; }
   C3_CUDA(cudaStreamSynchronize(e->stream));
   C3_CUDA(cudaMemcpy2D(out, sizeof(double), e->d_lh + bin, e->K * sizeof(double), sizeof(double),
                        (size_t)n_rows, cudaMemcpyDeviceToHost));
@@ -2081,6 +2144,7 @@ int c3_get_stats(c3_engine* e, c3_stats* out) {
 
 int c3_set_profiling(c3_engine* e, int on) {
   C3_REQUIRE(e != nullptr, "null engine");
+  if (on != 0 && !e->profiling) dump_timeline(e);  // (C3_TIMELINE=1: the last UN-profiled evaluation)
   e->profiling = on != 0;
   return C3_OK;
 }
@@ -2139,6 +2203,39 @@ namespace {
 
 // deferred: launch everything like a blocking call (the scalar also goes to the mapped host word)
 // but do not wait; finish_deferred() collects it.  Lets many engines run concurrently.
+// Lean root: the last evaluation's root launch wrote mix[p], not lh[p][K].  An accessor that needs lh runs that
+// ONE launch again (same work list and parameter block, still on the device; the children's rows, the P
+// matrices and pi are those of the last evaluation) with the lh output -- no reduction, no result, nothing
+// committed: input changes still pending stay pending.  The next LH_KEEP evaluations write lh themselves.
+constexpr int LH_KEEP = 8;
+int ensure_lh(c3_engine* e) {
+  e->lh_keep = LH_KEEP;
+  if (e->lh_valid) return C3_OK;
+  if (e->deferred_pending) {
+    const int rc = collect_result(e);
+    e->deferred_pending = false;
+    if (rc) return rc;
+  }
+  const c3_engine::RootLaunch& rl = e->root_launch;
+  PruneArgs a;
+  a.nodes = e->d_nodes;
+  a.childs = e->d_childs;
+  a.work_node = reinterpret_cast<const int32_t*>(e->d_block + e->off_work) + rl.work_off;
+  a.tile_prefix = reinterpret_cast<const int32_t*>(e->d_block + e->off_prefix) + rl.prefix_off;
+  a.n_work = rl.n_work;
+  a.total_tiles = rl.total_tiles;
+  a.K = e->K;
+  a.M = e->M;
+  a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
+  a.lh_out = e->d_lh;
+  const int rc = launch_prune(e, a, true, rl.kind);
+  if (rc) return rc;
+  C3_CUDA(cudaStreamSynchronize(e->stream));
+  e->stats.kernel_launches += 1;
+  e->lh_valid = true;
+  return C3_OK;
+}
+
 int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out, bool deferred) {
   C3_REQUIRE(e->finalized, "call c3_finalize first");
   e->deferred_pending = false;
@@ -2213,11 +2310,15 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     } else {
       for (int c : e->children[n]) d = d || edge_touched[c] || recompute[c];
     }
+    // (lean root: the mixed values of the last evaluation are stale once the bin probabilities change, and there
+    //  is no lh to mix again: the root launch runs again)
+    if (n == e->root && e->reduce_dirty && !e->lh_valid) d = true;
     if (d) {
       recompute[n] = 1;
       ++n_dirty_nodes;
     }
   }
+  const bool root_dirty = recompute[e->root] != 0;
   e->last_skipped = false;
   if (n_dirty_nodes == 0 && n_eigen + n_pade == 0 && !e->reduce_dirty && e->have_cached) {
     e->last_skipped = true;
@@ -2695,9 +2796,53 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
                             launches.back().grid == 0 && launches.back().is_root && !e->rescale_active && comm.nranks <= 1 &&
                             e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE);
 
+  // lean root: the launch that holds the root is a regpipe2 launch of its own, several rate classes, no
+  // rescaling pass over lh, nobody has read lh lately
+  bool lean = false;
+  int root_li = -1;
+  for (size_t li = 0; li < launches.size(); ++li)
+    if (launches[li].is_root) root_li = (int)li;
+  if (e->lean_root && root_dirty && root_li >= 0 && !fuse_reduce && (K == 2 || K == 4) && !e->rescale_active &&
+      e->lh_keep == 0 && e->use_strip && e->use_reg2 && !e->use_ring && !e->use_dmma &&
+      (launches[root_li].kind == 2 || launches[root_li].kind == 3) && launches[root_li].n_work == 1) {
+    lean = true;
+    const int64_t saved = e->n_rows[e->root] * (K - 1) * 8;  // the root writes 8 B per row, not 8 K
+    alg_bytes -= saved;
+    launches[root_li].bytes -= saved;
+  }
+  if (root_dirty && root_li >= 0) {
+    const LevelLaunch& rl = launches[root_li];
+    e->root_launch.work_off = rl.work_off;
+    e->root_launch.prefix_off = rl.prefix_off;
+    e->root_launch.n_work = rl.n_work;
+    e->root_launch.total_tiles = rl.total_tiles;
+    e->root_launch.kind = rl.kind;
+    e->lh_valid = !lean;
+  }
+  const int64_t reduce_row_bytes = lean ? 16 : (int64_t)(K + 1) * 8;
+  if (e->timeline && e->d_tl == nullptr) {
+    C3_CUDA(cudaMalloc(&e->d_tl, 64 * 4 * sizeof(unsigned long long)));
+    C3_CUDA(cudaHostAlloc(&e->h_tl_init, 64 * 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    for (int i = 0; i < 64; ++i) {
+      e->h_tl_init[4 * i + 0] = e->h_tl_init[4 * i + 1] = e->h_tl_init[4 * i + 2] = ~0ull;
+      e->h_tl_init[4 * i + 3] = 0ull;
+    }
+  }
+
   // every stream operation of the evaluation (issued directly, or into a graph capture)
   bool capturing = false;
   auto issue = [&]() -> int {
+  int tl_n = 0;
+  if (e->timeline) {
+    C3_CUDA(cudaMemcpyAsync(e->d_tl, e->h_tl_init, 64 * 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
+    e->tl_kinds.clear();
+  }
+  auto tl_slot = [&](int kind) -> unsigned long long* {
+    if (!e->timeline || tl_n >= 64) return nullptr;
+    e->tl_kinds.push_back(kind);
+    e->tl_launches = tl_n + 1;
+    return e->d_tl + 4 * tl_n++;
+  };
   C3_CUDA(cudaMemcpyAsync(e->d_block, e->h_block, (size_t)std::min(used, e->block_bytes),
                           cudaMemcpyHostToDevice, e->stream));
   if (!capturing) C3_CUDA(cudaEventRecord(e->block_copied, e->stream));  // the staging buffer is free again
@@ -2787,6 +2932,11 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     a.M = M;
     a.pi = reinterpret_cast<const double*>(e->d_block + e->off_pi);
     a.lh_out = e->d_lh;
+    if (lean && (int)li == root_li) {
+      a.mix_out = e->d_mix;
+      a.bprobs = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
+    }
+    a.tl = tl_slot(ll.is_root ? 100 + ll.kind : ll.kind);
     ProfScope ps(e, (ll.kind == 1 || ll.kind == 9 || ll.kind == 10) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
     if (ll.kind == 1) {
       const SmallLevel* d_small = reinterpret_cast<const SmallLevel*>(e->d_block + e->off_small) + ll.small_off;
@@ -2950,7 +3100,9 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     const int64_t rows = e->n_rows[e->root];
     const int n_tiles = (int)((rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
     const int grid = std::min(n_tiles, e->n_sm * 8);
-    ProfScope ps(e, 4, rows * (K + 1) * 8, 0);
+    ProfScope ps(e, 4, rows * reduce_row_bytes, 0);
+    ResultSink rsink = sink;
+    rsink.tl = tl_slot(4);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(REDUCE_THREADS);
@@ -2964,9 +3116,11 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     const double* a_lh = e->d_lh;
     const double* a_bp = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
     const double* a_counts = e->d_counts;
+    const double* a_mixed = lean ? e->d_mix : nullptr;
     cudaError_t err = cudaLaunchKernelEx(&cfg, lnl_reduce_kernel, a_lh, a_bp, a_counts, (int64_t)rows, K, n_tiles,
-                                         e->d_tile_sums, e->d_counter, sink, comm,
-                                         (const int32_t*)(e->rescale_active ? e->scale_rec[e->root].d_exps : nullptr));
+                                         e->d_tile_sums, e->d_counter, rsink, comm,
+                                         (const int32_t*)(e->rescale_active ? e->scale_rec[e->root].d_exps : nullptr),
+                                         a_mixed);
     ++n_launch;
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("reduce launch: ") + cudaGetErrorString(err));
@@ -2983,7 +3137,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     std::vector<int32_t> sig;
     sig.reserve(16 + 8 * launches.size() + w_off);
     sig.push_back(n_eigen); sig.push_back(n_pade); sig.push_back((int32_t)std::min(used, e->block_bytes));
-    sig.push_back((e->rescale_active ? 1 : 0) | (fuse_reduce ? 2 : 0));
+    sig.push_back((e->rescale_active ? 1 : 0) | (fuse_reduce ? 2 : 0) | (lean ? 4 : 0));
     sig.push_back((int32_t)((uintptr_t)device_out & 0xffffffffu)); sig.push_back((int32_t)((uintptr_t)device_out >> 32));
     sig.push_back((blocking || deferred) ? 1 : 0);
     sig.push_back((int32_t)((uintptr_t)e->stream & 0xffffffffu)); sig.push_back((int32_t)((uintptr_t)e->stream >> 32));

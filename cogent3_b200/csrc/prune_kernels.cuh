@@ -257,6 +257,24 @@ struct StripSmem {
   int32_t prefix[P4S_MAXW + 1];
 };
 
+// developer timeline (PruneArgs::tl, C3_TIMELINE=1): when does a launch enter, start gathering, lose its first
+// warp, lose its last one -- in one time base across the launches of an UN-profiled (graph-replayed) step
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_first(unsigned long long* tl, int slot) {
+  if (tl != nullptr) atomicMin(tl + slot, tl_now());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl) {
+  if (tl != nullptr) {
+    const unsigned long long t = tl_now();
+    atomicMin(tl + 2, t);
+    atomicMax(tl + 3, t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // 4-state kernel, register pipeline with TWO strips in flight ("regpipe2", binary nodes) -- the
 // production kernel for the bulk of a tree.
@@ -282,6 +300,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
   double* sP = sPall[warp];
 
   pdl_trigger();
+  if (threadIdx.x == 0) tl_first(a.tl, 0);
   for (int i = threadIdx.x; i <= a.n_work; i += blockDim.x) sd.prefix[i] = a.tile_prefix[i];
   for (int i = threadIdx.x; i < a.n_work; i += blockDim.x) {
     const NodeDesc nd = a.nodes[a.work_node[i]];
@@ -304,6 +323,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
   const int total = a.total_tiles;
   const int b = lane % K;
   const int slot = lane / K;
+  // lean root: the rate classes of a row sit in K neighbouring lanes -- mix them here (the reduction's
+  // arithmetic: products added in class order starting from 0.0) and write 8 bytes per row instead of 8 K
+  const bool lean = ROOT && K > 1 && a.mix_out != nullptr;
+  double bp[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) bp[j] = lean ? a.bprobs[j] : 0.0;
 
   int i_w = 0, g_w = 0, c_w = 0, p_w = -1;
   auto load_idx = [&](int32_t(&ix)[NC][U], int s) {
@@ -377,12 +402,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
         if (c_fixed != 2) acc[u].z = 0.0;
         if (c_fixed != 3) acc[u].w = 0.0;
       }
-      if (p < wd.n_rows) {
-        if (!ROOT || wd.out != nullptr) st256(wd.out + (p * K + b) * 4, acc[u]);
-        if (ROOT) {
-          const double lh =
-              fma(acc[u].w, a.pi[3], fma(acc[u].z, a.pi[2], fma(acc[u].y, a.pi[1], acc[u].x * a.pi[0])));
-          a.lh_out[p * K + b] = lh;
+      if (p < wd.n_rows && (!ROOT || wd.out != nullptr)) st256(wd.out + (p * K + b) * 4, acc[u]);
+      if (ROOT) {
+        const double lh =
+            fma(acc[u].w, a.pi[3], fma(acc[u].z, a.pi[2], fma(acc[u].y, a.pi[1], acc[u].x * a.pi[0])));
+        if (!lean) {
+          if (p < wd.n_rows) a.lh_out[p * K + b] = lh;
+        } else {
+          double m = 0.0;
+#pragma unroll
+          for (int j = 0; j < K; ++j)
+            m = __dadd_rn(m, __dmul_rn(__shfl_sync(0xffffffffu, lh, slot * K + j), bp[j]));
+          if (b == 0 && p < wd.n_rows) a.mix_out[p] = m;
         }
       }
     }
@@ -394,6 +425,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
   if (gw < total) load_idx(ia, gw);  // static data: may overlap the previous launch
   if (gw + GW < total) load_idx(ib, gw + GW);
   pdl_wait();
+  if (threadIdx.x == 0) tl_first(a.tl, 1);
   if (gw < total) {
     gather_seek(gw);
 #pragma unroll
@@ -416,6 +448,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
     step(xa, ia, s);
     if (s + GW < total) step(xb, ib, s + GW);
   }
+  if (lane == 0) tl_end(a.tl);
 }
 
 __device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
@@ -525,7 +558,8 @@ __device__ __forceinline__ double block_sum(double v, double* s_warp) {
 // one thread's share of a reduction tile: rows base + u * REDUCE_THREADS + t  (t < REDUCE_THREADS)
 __device__ __forceinline__ double reduce_tile_partial(const double* __restrict__ lh, const double* __restrict__ bprobs,
                                                       const double* __restrict__ counts, int64_t n_rows, int K,
-                                                      int tile, int t, const int32_t* __restrict__ root_exp) {
+                                                      int tile, int t, const int32_t* __restrict__ root_exp,
+                                                      const double* __restrict__ mixed = nullptr) {
   constexpr int U = REDUCE_ROWS_PER_TILE / REDUCE_THREADS;
   const int64_t base = (int64_t)tile * REDUCE_ROWS_PER_TILE;
   // all loads of the thread's rows first (one 256-bit / 128-bit load per row for K = 4 / 2), then the logs
@@ -538,7 +572,9 @@ __device__ __forceinline__ double reduce_tile_partial(const double* __restrict__
     cnt[u] = 0.0;
     ex[u] = 0;
     if (p < n_rows) {
-      if (K == 1) {
+      if (mixed != nullptr) {
+        mix[u] = mixed[p];  // (lean root: the root launch mixed the classes, same arithmetic)
+      } else if (K == 1) {
         mix[u] = lh[p];
       } else if (K == 4) {
         const d4 v = ld256(lh + p * 4);
@@ -616,6 +652,7 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
   extern __shared__ __align__(16) unsigned char small_raw[];
   SmallSmem& sm = *reinterpret_cast<SmallSmem*>(small_raw);
   pdl_trigger();
+  if (threadIdx.x == 0) tl_first(a.tl, 0);
   const int K = a.K;
   const unsigned nthreads = (GRID ? gridDim.x : cluster_nctarank()) * SMALL_THREADS;
   const unsigned tid = (GRID ? blockIdx.x : cluster_ctarank()) * SMALL_THREADS + threadIdx.x;
@@ -632,6 +669,7 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
     __syncthreads();
   }
   pdl_wait();  // P matrices / tip tables of the expm launch, rows of earlier levels
+  if (threadIdx.x == 0) tl_first(a.tl, 1);
   // the P matrices of every staged child, per bin, into shared memory
   const bool p_staged = staged && (int64_t)n_work_total * SMALL_STAGED_CHILDREN * K <= SMALL_MAX_P;
   if (p_staged) {
@@ -691,6 +729,7 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
       else cluster_barrier();
     }
   }
+  if (threadIdx.x == 0) tl_end(a.tl);
   if (!GRID && tail.n_tiles > 0) {
     // the root was in this launch and the problem is small: the site-weighted reduction right here
     // (same tiles, same per-thread rows, same summation trees as lnl_reduce_kernel: same bits), by
@@ -816,6 +855,7 @@ __global__ void __launch_bounds__(DECfg<RA, STG>::THREADS, 1) prune_dmma_edge_ke
   const int g = lane >> 2, q = lane & 3;
 
   pdl_trigger();
+  if (tid == 0) tl_first(a.tl, 0);
   for (int i = tid; i <= a.n_work; i += THREADS) sd.prefix[i] = a.tile_prefix[i];
   for (int i = tid; i < a.n_work; i += THREADS) {
     const NodeDesc nd = a.nodes[a.work_node[i]];
@@ -897,6 +937,7 @@ __global__ void __launch_bounds__(DECfg<RA, STG>::THREADS, 1) prune_dmma_edge_ke
   };
   load_idx();  // static data: may overlap the previous launch
   pdl_wait();
+  if (tid == 0) tl_first(a.tl, 1);
   if (fc.st < st1) {
     fetch();
     next(ic);
@@ -1039,6 +1080,7 @@ __global__ void __launch_bounds__(DECfg<RA, STG>::THREADS, 1) prune_dmma_edge_ke
     }
     next(cc);
   }
+  if (lane == 0) tl_end(a.tl);
 }
 
 // plh of a node recomputed for the accessors: prod_c (P_c .) rows_c[idx_c[p]] (masked like the kernels).
@@ -1104,12 +1146,15 @@ __global__ void __launch_bounds__(REDUCE_THREADS)
 lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bprobs,
                   const double* __restrict__ counts, int64_t n_rows, int K, int n_tiles,
                   double* __restrict__ tile_sums, unsigned int* __restrict__ counter,
-                  const ResultSink sink, const CommArgs comm, const int32_t* __restrict__ root_exp) {
+                  const ResultSink sink, const CommArgs comm, const int32_t* __restrict__ root_exp,
+                  const double* __restrict__ mixed) {
   __shared__ double s_warp[REDUCE_THREADS / 32];
   __shared__ bool s_last;
+  if (threadIdx.x == 0) tl_first(sink.tl, 0);
   pdl_wait();  // launched early (programmatic dependent launch): lh is the root launch's output
+  if (threadIdx.x == 0) tl_first(sink.tl, 1);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const double acc = reduce_tile_partial(lh, bprobs, counts, n_rows, K, tile, (int)threadIdx.x, root_exp);
+    const double acc = reduce_tile_partial(lh, bprobs, counts, n_rows, K, tile, (int)threadIdx.x, root_exp, mixed);
     const double total = block_sum(acc, s_warp);
     if (threadIdx.x == 0) tile_sums[tile] = total;
   }
@@ -1177,6 +1222,7 @@ lnl_reduce_kernel(const double* __restrict__ lh, const double* __restrict__ bpro
   if (threadIdx.x == 0) {
     *counter = 0u;
     publish_result(sink, total);
+    tl_end(sink.tl);
   }
 }
 

@@ -203,10 +203,11 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
         codes = codes[: int(np.sum(topo.is_tip))]
 
     def build(env):
-        for k in ("C3_FLOW", "C3_RING", "C3_NO_STRIP", "C3_NO_SMALL", "C3_REG1"):
+        for k in ("C3_FLOW", "C3_RING", "C3_NO_STRIP", "C3_NO_SMALL", "C3_REG1", "C3_REG2_U2", "C3_ROOT_U"):
             monkeypatch.delenv(k, raising=False)
         for k in env:
-            monkeypatch.setenv(k, "1")
+            name, _, value = k.partition("=")
+            monkeypatch.setenv(name, value or "1")
         lf = LikelihoodFunction(m, topo, bins=bins)
         lf.set_alignment(codes.astype(np.int64), np.eye(4))
         lf.set_motif_probs_from_data()
@@ -217,7 +218,8 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
             lf.set_param_rule("rate_shape", value=0.6)
         return lf
 
-    variants = [(), ("C3_REG1",), ("C3_FLOW",), ("C3_RING",), ("C3_NO_STRIP",), ("C3_NO_SMALL",), ("C3_FLOW", "C3_NO_SMALL")]
+    variants = [(), ("C3_REG1",), ("C3_FLOW",), ("C3_RING",), ("C3_NO_STRIP",), ("C3_NO_SMALL",), ("C3_FLOW", "C3_NO_SMALL"),
+                ("C3_REG2_U2",), ("C3_ROOT_U=3",)]
     lfs = [build(v) for v in variants]
     vals = [lf.get_log_likelihood() for lf in lfs]
     assert len(set(vals)) == 1, vals
@@ -239,6 +241,59 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
         assert len(set(got)) == 1, got
         lfs[0].engine.invalidate()
         assert lfs[0].get_log_likelihood() == got[0]
+
+
+@pytest.mark.parametrize("bins,n_tips,L", [(4, 24, 60_000), (2, 14, 40_000), (4, 9, 300)])
+def test_lean_root_is_bit_identical_and_lh_comes_back_on_demand(bins, n_tips, L, monkeypatch):
+    """lean root (default): the regpipe2 root launch writes the class mixture mix[p] instead of lh[p][K] and the
+    reduction reads mix + counts.  lnL is bit-identical to C3_LEAN_ROOT=0; an accessor gets exactly the lh of the
+    full launch (the root launch runs again with the lh output); the next evaluations keep lh materialised, later
+    ones go lean again; a change of the bin probabilities alone re-mixes; graph replays included."""
+    m = hostmodels.get_model("GTR")
+    topo, lengths, codes = make_workload(n_tips, L, 4, kind="evolved", seed=21)
+
+    def build(lean):
+        monkeypatch.setenv("C3_LEAN_ROOT", "1" if lean else "0")
+        monkeypatch.setenv("C3_GRAPH_AFTER", "3")
+        lf = LikelihoodFunction(m, topo, bins=bins)
+        lf.set_alignment(codes.astype(np.int64), np.eye(4))
+        lf.set_motif_probs_from_data()
+        lf.lengths[:-1] = np.asarray(lengths)[:-1]
+        for k, p in enumerate(m.parameter_order):
+            lf.set_param_rule(p, value=0.5 + 0.37 * k)
+        lf.set_param_rule("rate_shape", value=0.6)
+        return lf
+
+    lean, full = build(True), build(False)
+    rng = np.random.default_rng(5)
+    edges = list(topo.edges)
+    for step in range(40):
+        if step % 3 == 0:  # every branch length
+            v = rng.uniform(0.01, 0.4, size=len(edges))
+            for lf in (lean, full):
+                for n, x in zip(edges, v, strict=True):
+                    lf.set_param_rule("length", edge=topo.names[n], value=float(x))
+        else:  # one branch
+            n = edges[int(rng.integers(len(edges)))]
+            v = float(rng.uniform(0.01, 0.5))
+            for lf in (lean, full):
+                lf.set_param_rule("length", edge=topo.names[n], value=v)
+        a, b = lean.get_log_likelihood(), full.get_log_likelihood()
+        assert a == b, (step, a, b)
+        if step % 7 == 6:
+            # the bin probabilities ALONE (engine level: no branch, no rate class moves): only the mixture changes
+            bp = rng.dirichlet(np.ones(bins) * 5.0)
+            got = []
+            for lf in (lean, full):
+                lf.engine.set_bin_probs(bp)
+                got.append(lf.engine.evaluate())
+            assert got[0] == got[1], (step, got)
+        if step in (4, 5, 20, 39):
+            for bin_ in range(bins):
+                np.testing.assert_array_equal(lean.engine.get_lh(bin_), full.engine.get_lh(bin_))
+            assert lean.engine.evaluate() == full.engine.evaluate()  # nothing pending was committed or lost
+    if L >= 10_000:  # (small problems reduce inside the small-levels launch and always write lh)
+        assert lean.engine.stats()["last_alg_bytes"] < full.engine.stats()["last_alg_bytes"]
 
 
 @pytest.mark.parametrize("env", [{"C3_EDGE_MAJOR": "0"}, {"C3_EDGE_MAJOR": "0", "C3_DMMA_REG": "0"}])
