@@ -43,6 +43,8 @@ class C3Stats(ctypes.Structure):
         ("wave_launches", c_int64),
         ("wave_entries", c_int64),
         ("wave_noops", c_int64),
+        ("lean_evaluations", c_int64),
+        ("chain_launches", c_int64),
     ]
 
     def as_dict(self):

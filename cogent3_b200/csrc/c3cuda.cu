@@ -147,6 +147,14 @@ struct c3_engine {
   bool use_path = false;  // opt-in (C3_PATH=1): single-branch updates of small problems by ONE CTA that walks the dirty
                           // path with the rows in shared memory -- measured slower than the small-levels launch
                           // (one SM has to issue every instruction of a level), DESIGN.md lesson 18
+  // chain kernel (prune4_chain_kernel): single-branch updates of small 4-state problems walked per ROOT row through
+  // composed gather tables, no barrier between the levels (C3_CHAIN=0 disables)
+  bool use_chain = true;
+  bool chain_ok = false;              // the composed tables exist (small problem, <= 3 children everywhere)
+  int32_t* d_chain_maps = nullptr;    // [n_nodes][root_rows]: root row -> row of the node
+  const int32_t** d_node_maps = nullptr;   // [n_nodes]
+  const int32_t** d_child_maps = nullptr;  // [child refs]
+  unsigned int* d_chain_ctr = nullptr;     // [1 + reduction tiles] completion counters of the chain launch
   bool use_pdl = true;    // programmatic dependent launch between levels (C3_NO_PDL=1 disables)
   // M != 4: every node stores its rows already multiplied by the P of the branch above it, one
   // contraction per NODE row (prune_dmma_edge_kernel); C3_EDGE_MAJOR=0: the parent-major kernels
@@ -157,18 +165,22 @@ struct c3_engine {
   // bytes in flight per SM in steps half as long -- the drain and the last-strip imbalance of a launch scale with
   // the step
   bool reg2_u2 = false;
-  int root_u = 2;  // rows per lane of the three-children instance: 2 (12 warps) or 3 (8 warps, C3_ROOT_U=3)
+  int root_u = 3;  // rows per lane of the three-children instance: 3 (8 warps, 255 registers) or 2 (12 warps, C3_ROOT_U=2)
   // lean root (C3_LEAN_ROOT=0 disables): the regpipe2 root launch writes mix[p] (8 B per row) instead of lh[p][K]
   // and the reduction reads mix + counts only; lh is recomputed by the root launch alone when an accessor asks for
   // it (ensure_lh), and stays materialised for the next LH_KEEP evaluations after such a request
   bool lean_root = true;
   bool lh_valid = true;   // d_lh holds the last evaluation's per-pattern likelihoods
+  bool last_lean = false; // the evaluation being planned / last issued has a lean root launch
+  bool last_chain = false; // ... is one chain launch
   int lh_keep = 0;        // evaluations that still write lh because an accessor read it recently
   double* d_mix = nullptr;
   struct RootLaunch { int work_off = 0, prefix_off = 0, n_work = 0, total_tiles = 0, kind = 0; } root_launch;
   // developer timeline (C3_TIMELINE=1): globaltimer stamps of every pruning / reduction launch of the LAST
   // evaluation, printed by c3_destroy
   bool timeline = false;
+  bool hostprof = false;   // C3_HOSTPROF=1: host nanoseconds of the blocking path (plan | issue or replay | wait), printed by c3_destroy
+  long long hp_plan_ns = 0, hp_issue_ns = 0, hp_wait_ns = 0, hp_n = 0;
   unsigned long long* d_tl = nullptr;
   unsigned long long* h_tl_init = nullptr;
   int tl_launches = 0;
@@ -795,6 +807,8 @@ void commit_evaluation(c3_engine* e, int64_t n_launch, bool replayed) {
   std::fill(e->node_dirty.begin(), e->node_dirty.end(), 0);
   e->reduce_dirty = false;
   if (e->lh_keep > 0) --e->lh_keep;
+  if (e->last_lean) e->stats.lean_evaluations += 1;
+  if (e->last_chain) e->stats.chain_launches += 1;
   e->stats.evaluations += 1;
   e->stats.kernel_launches += n_launch;
   e->stats.last_launches = n_launch;
@@ -934,6 +948,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_PDL")) e->use_pdl = atoi(env) == 0;
   if (const char* env = getenv("C3_NO_SMALL_REDUCE")) e->use_small_reduce = atoi(env) == 0;
   if (const char* env = getenv("C3_PATH")) e->use_path = atoi(env) != 0;
+  if (const char* env = getenv("C3_CHAIN")) e->use_chain = atoi(env) != 0;
   if (const char* env = getenv("C3_PATH_VARIANT")) e->path_variant = std::max(0, std::min(2, atoi(env)));
   if (const char* env = getenv("C3_REC")) e->use_rec = atoi(env) != 0;
   if (const char* env = getenv("C3_STREAMS")) e->use_streams = atoi(env) != 0;
@@ -946,9 +961,10 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   if (const char* env = getenv("C3_REG1")) e->use_reg2 = atoi(env) == 0;
   if (const char* env = getenv("C3_REG2_U2")) e->reg2_u2 = atoi(env) != 0;
-  if (const char* env = getenv("C3_ROOT_U")) e->root_u = atoi(env) == 3 ? 3 : 2;
+  if (const char* env = getenv("C3_ROOT_U")) e->root_u = atoi(env) == 2 ? 2 : 3;
   if (const char* env = getenv("C3_LEAN_ROOT")) e->lean_root = atoi(env) != 0;
   if (const char* env = getenv("C3_TIMELINE")) e->timeline = atoi(env) != 0;
+  if (const char* env = getenv("C3_HOSTPROF")) e->hostprof = atoi(env) != 0;
   if (const char* env = getenv("C3_FLOW")) e->use_flow = atoi(env) != 0;
   if (const char* env = getenv("C3_WAVE")) e->use_wave = atoi(env) != 0;
   if (const char* env = getenv("C3_WAVE_LAG")) e->wave_lag = std::max(3, std::min(12, atoi(env)));
@@ -1057,11 +1073,23 @@ void dump_timeline(c3_engine* e) {
   }
 }
 
+void dump_hostprof(c3_engine* e) {
+  if (e->hostprof && e->hp_n > 0)
+    fprintf(stderr, "c3 hostprof: %lld blocking evaluations since the last report, us per evaluation: plan %.2f | issue / replay %.2f | wait %.2f\n",
+            e->hp_n, e->hp_plan_ns * 1e-3 / e->hp_n, e->hp_issue_ns * 1e-3 / e->hp_n, e->hp_wait_ns * 1e-3 / e->hp_n);
+  e->hp_plan_ns = e->hp_issue_ns = e->hp_wait_ns = e->hp_n = 0;
+}
+
 int c3_destroy(c3_engine* e) {
   if (!e) return C3_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   dump_timeline(e);
+  dump_hostprof(e);
+  if (e->d_chain_maps) cudaFree(e->d_chain_maps);
+  if (e->d_node_maps) cudaFree(e->d_node_maps);
+  if (e->d_child_maps) cudaFree(e->d_child_maps);
+  if (e->d_chain_ctr) cudaFree(e->d_chain_ctr);
   if (e->d_tl) cudaFree(e->d_tl);
   if (e->h_tl_init) cudaFreeHost(e->h_tl_init);
   for (int32_t* p : e->d_index)
@@ -1662,6 +1690,41 @@ int c3_finalize(c3_engine* e) {
                           cudaMemcpyHostToDevice, e->stream));
   C3_CUDA(cudaMemcpyAsync(e->d_edges, h_edges.data(), N * sizeof(EdgeDesc), cudaMemcpyHostToDevice, e->stream));
 
+  // ---- chain kernel: root row -> row of every node (composition of the gather tables from the root down) ----
+  e->chain_ok = false;
+  if (e->use_chain && !e->use_dmma && (K == 1 || K == 2 || K == 4) &&
+      root_rows <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE) {
+    bool ok = true;
+    for (int n = 0; n < N; ++n) ok = ok && e->children[n].size() <= (size_t)CHAIN_MAX_CHILDREN;
+    if (ok) {
+      C3_CUDA(cudaMalloc(&e->d_chain_maps, (size_t)N * root_rows * sizeof(int32_t)));
+      C3_CUDA(cudaMalloc(&e->d_node_maps, (size_t)N * sizeof(int32_t*)));
+      C3_CUDA(cudaMalloc(&e->d_child_maps, (size_t)std::max<int64_t>(1, (int64_t)n_child_total) * sizeof(int32_t*)));
+      C3_CUDA(cudaMalloc(&e->d_chain_ctr, (1 + SMALL_REDUCE_MAX_TILES) * sizeof(unsigned int)));
+      C3_CUDA(cudaMemsetAsync(e->d_chain_ctr, 0, (1 + SMALL_REDUCE_MAX_TILES) * sizeof(unsigned int), e->stream));
+      std::vector<int32_t> iota((size_t)root_rows);
+      for (int64_t p = 0; p < root_rows; ++p) iota[p] = (int32_t)p;
+      auto map_of = [&](int n) { return e->d_chain_maps + (int64_t)n * root_rows; };
+      C3_CUDA(cudaMemcpyAsync(map_of(e->root), iota.data(), root_rows * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+      std::vector<const int32_t*> node_maps(N), child_maps((size_t)std::max<int64_t>(1, (int64_t)n_child_total), nullptr);
+      const int grid = (int)std::min<int64_t>((root_rows + 255) / 256, 1024);
+      for (int n = N - 1; n >= 0; --n) {  // parents before children (post-order numbering)
+        node_maps[n] = map_of(n);
+        for (size_t c = 0; c < e->children[n].size(); ++c) {
+          const int ch = e->children[n][c];
+          compose_map_kernel<<<grid, 256, 0, e->stream>>>(map_of(ch), map_of(n), e->d_idx[n] + c * e->n_rows[n], root_rows);
+          child_maps[e->child_begin[n] + c] = map_of(ch);
+        }
+      }
+      C3_CUDA(cudaGetLastError());
+      C3_CUDA(cudaMemcpyAsync(e->d_node_maps, node_maps.data(), node_maps.size() * sizeof(int32_t*), cudaMemcpyHostToDevice, e->stream));
+      C3_CUDA(cudaMemcpyAsync(e->d_child_maps, child_maps.data(), child_maps.size() * sizeof(int32_t*), cudaMemcpyHostToDevice, e->stream));
+      C3_CUDA(cudaStreamSynchronize(e->stream));  // (the host vectors go out of scope)
+      e->stats.device_bytes += (int64_t)N * root_rows * sizeof(int32_t);
+      e->chain_ok = true;
+    }
+  }
+
   // ---- per-evaluation parameter block -------------------------------------
   int n_internal = 0;
   for (int n = 0; n < N; ++n) n_internal += !e->children[n].empty();
@@ -2144,7 +2207,10 @@ int c3_get_stats(c3_engine* e, c3_stats* out) {
 
 int c3_set_profiling(c3_engine* e, int on) {
   C3_REQUIRE(e != nullptr, "null engine");
-  if (on != 0 && !e->profiling) dump_timeline(e);  // (C3_TIMELINE=1: the last UN-profiled evaluation)
+  if (on != 0 && !e->profiling) {
+    dump_timeline(e);  // (C3_TIMELINE=1: the last UN-profiled evaluation)
+    dump_hostprof(e);
+  }
   e->profiling = on != 0;
   return C3_OK;
 }
@@ -2238,6 +2304,7 @@ int ensure_lh(c3_engine* e) {
 
 int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host_out, bool deferred) {
   C3_REQUIRE(e->finalized, "call c3_finalize first");
+  const auto hp_t0 = std::chrono::steady_clock::now();
   e->deferred_pending = false;
   C3_REQUIRE(e->have_pi, "root motif probabilities not set");
   C3_CUDA(cudaSetDevice(e->device));
@@ -2452,9 +2519,45 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   }
   // ---- path launch?  the dirty set is ONE path to the root (a single branch length moved: the optimiser's
   // inner loop) on a problem small enough for one CTA's shared memory: prune4_path_kernel, which also reduces
+  // ---- chain launch?  the dirty set is ONE path to the root on a small problem: prune4_chain_kernel walks it
+  // per root row without a barrier, and reduces
+  bool chain_launch = false;
+  if (e->chain_ok && e->use_chain && !wave && !e->rescale_active && e->comm.nranks <= 1 && recompute[e->root] &&
+      e->use_small_reduce) {
+    std::vector<int> chain;
+    bool ok = true;
+    for (int n = 0; n < N && ok; ++n) {
+      if (!recompute[n]) continue;
+      if (!chain.empty() && e->parent[chain.back()] != n) ok = false;  // (ascending ids: a path is visited bottom-up)
+      chain.push_back(n);
+    }
+    ok = ok && !chain.empty() && chain.back() == e->root && (int)chain.size() <= CHAIN_MAX_NODES;
+    if (ok) {
+      LevelLaunch ll{w_off, p_off, 0, 0, true, 0, 0, 11, 0, 0};
+      const int64_t bytes0 = alg_bytes, flops0 = flops;
+      for (size_t i = 0; i < chain.size(); ++i) {
+        const int n = chain[i];
+        work[w_off + ll.n_work] = n;
+        int slot = -1;
+        if (i > 0)
+          for (size_t c = 0; c < e->children[n].size(); ++c)
+            if (e->children[n][c] == chain[i - 1]) slot = (int)c;
+        dep[w_off + ll.n_work] = slot;
+        ++ll.n_work;
+        account(n);
+        recompute[n] = 0;
+      }
+      ll.total_tiles = (int)(e->n_rows[e->root] * K);
+      ll.bytes = alg_bytes - bytes0;
+      ll.flops = flops - flops0;
+      w_off += ll.n_work;
+      launches.push_back(ll);
+      chain_launch = true;
+    }
+  }
   bool path_launch = false;
   int path_buf_units = 0;
-  if (e->use_path && !wave && !e->use_dmma && !e->rescale_active && e->comm.nranks <= 1 && recompute[e->root] &&
+  if (e->use_path && !chain_launch && !wave && !e->use_dmma && !e->rescale_active && e->comm.nranks <= 1 && recompute[e->root] &&
       e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE) {
     std::vector<int> chain;
     bool ok = true;
@@ -2502,7 +2605,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   std::vector<int> lv_stream;
   int n_streams_used = 1;
   {
-    bool streams = e->use_streams && !e->rescale_active && wave == nullptr && !path_launch && !e->use_flow &&
+    bool streams = e->use_streams && !e->rescale_active && wave == nullptr && !path_launch && !chain_launch && !e->use_flow &&
                    !e->profiling && e->batch_mode == 0 && e->children[e->root].size() >= 2;
     if (streams) {
       // worth it only when at least two subtrees have a level that streams (more units than the cluster takes)
@@ -2543,7 +2646,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   // ---- recomputing launches: runs of consecutive small / medium levels, REC_DEPTH + 1 levels per launch -------
   std::vector<int> rec_phase(std::max(e->n_levels, n_groups) + 2, -1);  // level -> phase (launch) number, -1: the usual launches
   std::vector<int> rec_first;                        // first level of every phase
-  if (e->use_rec && by_level && !e->use_dmma && e->use_small && !e->rescale_active && !path_launch) {
+  if (e->use_rec && by_level && !e->use_dmma && e->use_small && !e->rescale_active && !path_launch && !chain_launch) {
     std::vector<int64_t> level_units(e->n_levels + 2, 0);
     std::vector<char> level_ok(e->n_levels + 2, 0);
     for (int l = 1; l <= e->n_levels; ++l) {
@@ -2791,7 +2894,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
 
   // small problems whose root sits in the (last) small-levels launch: that launch also reduces
   // (prune4_small_kernel's tail: the same tiles and summation trees, one launch fewer)
-  const bool fuse_reduce = path_launch ||
+  e->last_chain = chain_launch;
+  const bool fuse_reduce = path_launch || chain_launch ||
                            (e->use_small_reduce && !launches.empty() && launches.back().kind == 1 &&
                             launches.back().grid == 0 && launches.back().is_root && !e->rescale_active && comm.nranks <= 1 &&
                             e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE);
@@ -2805,11 +2909,11 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   if (e->lean_root && root_dirty && root_li >= 0 && !fuse_reduce && (K == 2 || K == 4) && !e->rescale_active &&
       e->lh_keep == 0 && e->use_strip && e->use_reg2 && !e->use_ring && !e->use_dmma &&
       (launches[root_li].kind == 2 || launches[root_li].kind == 3) && launches[root_li].n_work == 1) {
+    // (the ALGORITHMIC bytes of the step keep counting lh[p][K] written once and read once: SURVEY §8d's figure
+    //  describes the algorithm, not what this launch happens to move -- 8 (K - 1) B per root row less, twice)
     lean = true;
-    const int64_t saved = e->n_rows[e->root] * (K - 1) * 8;  // the root writes 8 B per row, not 8 K
-    alg_bytes -= saved;
-    launches[root_li].bytes -= saved;
   }
+  e->last_lean = lean;
   if (root_dirty && root_li >= 0) {
     const LevelLaunch& rl = launches[root_li];
     e->root_launch.work_off = rl.work_off;
@@ -2819,7 +2923,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     e->root_launch.kind = rl.kind;
     e->lh_valid = !lean;
   }
-  const int64_t reduce_row_bytes = lean ? 16 : (int64_t)(K + 1) * 8;
+  const int64_t reduce_row_bytes = (int64_t)(K + 1) * 8;
   if (e->timeline && e->d_tl == nullptr) {
     C3_CUDA(cudaMalloc(&e->d_tl, 64 * 4 * sizeof(unsigned long long)));
     C3_CUDA(cudaHostAlloc(&e->h_tl_init, 64 * 4 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -2937,7 +3041,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       a.bprobs = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
     }
     a.tl = tl_slot(ll.is_root ? 100 + ll.kind : ll.kind);
-    ProfScope ps(e, (ll.kind == 1 || ll.kind == 9 || ll.kind == 10) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
+    ProfScope ps(e, (ll.kind == 1 || ll.kind == 9 || ll.kind == 10 || ll.kind == 11) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
     if (ll.kind == 1) {
       const SmallLevel* d_small = reinterpret_cast<const SmallLevel*>(e->d_block + e->off_small) + ll.small_off;
       if (ll.grid > 0) {
@@ -3017,6 +3121,32 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       const int32_t* d_child = reinterpret_cast<const int32_t*>(e->d_block + e->off_rec) + (int64_t)ll.work_off * REC_MAX_CHILDREN;
       cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_rec_kernel, a, d_child);
       if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("rec launch: ") + cudaGetErrorString(err));
+    } else if (ll.kind == 11) {
+      static DeviceOnce chain_cfg;
+      if (chain_cfg.need(e->device)) {
+        int rc = set_max_smem(prune4_chain_kernel, sizeof(ChainSmem));
+        if (rc) return rc;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)((ll.total_tiles + CHAIN_THREADS - 1) / CHAIN_THREADS));
+      cfg.blockDim = dim3(CHAIN_THREADS);
+      cfg.dynamicSmemBytes = sizeof(ChainSmem);
+      cfg.stream = e->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ReduceTail tail{};
+      tail.bprobs = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
+      tail.counts = e->d_counts;
+      tail.n_rows = e->n_rows[e->root];
+      tail.n_tiles = (int)((tail.n_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
+      tail.sink = sink;
+      const int32_t* d_dirty = reinterpret_cast<const int32_t*>(e->d_block + e->off_dep) + ll.work_off;
+      cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_chain_kernel, a, d_dirty, (const int32_t* const*)e->d_node_maps,
+                                           (const int32_t* const*)e->d_child_maps, tail, e->d_chain_ctr, e->d_tile_sums);
+      if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("chain launch: ") + cudaGetErrorString(err));
     } else if (ll.kind == 9) {
       const size_t smem = (size_t)ll.total_tiles;
       static DeviceOnce path_cfg;
@@ -3129,6 +3259,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   };  // issue
 
   // ---- direct launches, or capture / replay of this structure's graph ---------------------------
+  const auto hp_t1 = std::chrono::steady_clock::now();
   bool graphed = false;
   e->plan = c3_engine::PlanStats{n_eigen + n_pade, n_dirty_nodes, node_rows, alg_bytes, flops, h2d_bytes};
   const bool graph_ok = e->use_graphs && !e->profiling && !any_flow && wave == nullptr;  // (cooperative launch: not captured)
@@ -3228,8 +3359,17 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     return C3_OK;
   }
   if (blocking) {
+    const auto hp_t2 = std::chrono::steady_clock::now();
     int rc = collect_result(e);
     if (rc) return rc;
+    if (e->hostprof) {
+      const auto hp_t3 = std::chrono::steady_clock::now();
+      auto ns = [](auto a, auto b) { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+      e->hp_plan_ns += ns(hp_t0, hp_t1);
+      e->hp_issue_ns += ns(hp_t1, hp_t2);
+      e->hp_wait_ns += ns(hp_t2, hp_t3);
+      e->hp_n += 1;
+    }
     if (wants_auto_rescale(e)) {
       // some pattern's likelihood left the FP64 range (the reference returns -inf here,
       // evolve/likelihood_tree.py:10): switch to rescaled rows and evaluate again.
@@ -3268,7 +3408,16 @@ int collect_result(c3_engine* e) {
   if (e->spin_wait && !e->profiling) {
     const auto t0 = std::chrono::steady_clock::now();
     unsigned n = 0;
-    while (*e->h_seq != e->seq_issued) {
+    // (the device writes value, sequence number and check word without a fence between them: the triple counts
+    //  only when it is consistent -- publish_result)
+    auto arrived = [&]() {
+      if (e->h_seq[0] != e->seq_issued) return false;
+      unsigned long long bits;
+      const double v = *reinterpret_cast<volatile double*>(e->h_lnl);
+      std::memcpy(&bits, &v, sizeof bits);
+      return e->h_seq[1] == (bits ^ e->seq_issued) && e->h_seq[0] == e->seq_issued;
+    };
+    while (!arrived()) {
       if ((++n & 255u) == 0 &&
           std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) {
         err = cudaStreamSynchronize(e->stream);

@@ -608,13 +608,15 @@ __device__ __forceinline__ void publish_result(const ResultSink& r, double total
   *r.d_lnl = total;
   if (r.d_lnl2) *r.d_lnl2 = total;
   if (r.h_lnl) {
-    *r.h_lnl = total;
-    __threadfence_system();  // the value is visible to the host before the sequence number is
+    // three words into mapped host memory: the value, the sequence number the host spins on, and a check word
+    // (value bits ^ sequence).  The host accepts the triple only when it is consistent, so nothing has to order
+    // the three stores: no system-scope fence (two PCIe round trips, ~4 us of every evaluation) on this path
     const unsigned long long s = *r.seq_ctr + 1;
     *r.seq_ctr = s;
-    *r.h_seq = s;
+    r.h_lnl[0] = total;
+    r.h_seq[0] = s;
+    r.h_seq[1] = (unsigned long long)__double_as_longlong(total) ^ s;
   }
-  __threadfence_system();
 }
 
 struct ReduceTail {
@@ -752,6 +754,176 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
       for (int i = t; i < tail.n_tiles; i += REDUCE_THREADS) acc += s_tiles[i];
     const double total = block_sum(acc, s_warp);
     if (t == 0) publish_result(tail.sink, total);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 4-state "chain" kernel: a SINGLE-BRANCH update of a small problem (the optimiser's inner loop: one
+// branch length moves, the dirty nodes are the path from that branch to the root) in one launch with NO
+// barrier between the levels.
+//
+// The small-levels launch walks the path level by level: per level a cluster barrier plus two dependent
+// global latencies (gather index -> child row) -- 41 us for brca1's 11 levels.  But a pattern row of the root
+// only needs ONE row of every node on the path, and which one is static: the composition of the gather
+// tables from the root down (map_n[p] = row of node n that root row p looks at, built once per engine by
+// compose_map_kernel, n_nodes x root_rows int32).  So the thread of (root row p, bin b) walks the whole
+// path by itself: at every path node it gathers the rows of the CLEAN children at map_child[p] (all
+// addresses are known up front: every index of the walk is requested before the first row), multiplies
+// the row it carries in registers by the P of the branch it came up, stores the node's row at map_n[p]
+// (root rows that share a lower row compute -- and store -- the same bits) and moves on; at the root it
+// writes lh.  The last CTA to finish reduces (same tiles and summation trees as lnl_reduce_kernel).
+// Arithmetic per row is that of every other 4-state kernel (matvec4, children multiplied in order):
+// bit-identical to the level launches.
+// ---------------------------------------------------------------------------------------
+constexpr int CHAIN_MAX_NODES = 16;  // path length (tree depth) one launch walks
+constexpr int CHAIN_THREADS = REDUCE_THREADS;
+constexpr int CHAIN_MAX_CHILDREN = 3;
+
+struct ChainSmem {
+  NodeDesc nodes[CHAIN_MAX_NODES];
+  ChildRef childs[CHAIN_MAX_NODES * CHAIN_MAX_CHILDREN];
+  const int32_t* map_own[CHAIN_MAX_NODES];
+  const int32_t* map_child[CHAIN_MAX_NODES * CHAIN_MAX_CHILDREN];
+  int32_t dirty_child[CHAIN_MAX_NODES];
+  double P[CHAIN_MAX_NODES * CHAIN_MAX_CHILDREN * 4 * 16];  // [node][child][bin][16], K <= 4
+};
+
+// a.work_node[0 .. n_work): the path bottom-up (the last one is the root); dirty_child[i]: the child slot of
+// path node i that is path node i - 1 (-1 for i = 0).  node_maps[n] / child_maps[child ref]: root row -> row.
+__global__ void __launch_bounds__(CHAIN_THREADS)
+prune4_chain_kernel(const PruneArgs a, const int32_t* __restrict__ dirty_child,
+                    const int32_t* const* __restrict__ node_maps, const int32_t* const* __restrict__ child_maps,
+                    const ReduceTail tail, unsigned int* __restrict__ counters, double* __restrict__ tile_sums) {
+  extern __shared__ __align__(16) unsigned char chain_raw[];
+  ChainSmem& sm = *reinterpret_cast<ChainSmem*>(chain_raw);
+  __shared__ double s_warp[CHAIN_THREADS / 32];
+  __shared__ bool s_last;
+  const int K = a.K, n_work = a.n_work, t = (int)threadIdx.x;
+  pdl_trigger();
+  if (t == 0) tl_first(a.tl, 0);
+  for (int i = t; i < n_work; i += CHAIN_THREADS) {
+    const int node = a.work_node[i];
+    const NodeDesc nd = a.nodes[node];
+    sm.nodes[i] = nd;
+    sm.map_own[i] = node_maps[node];
+    sm.dirty_child[i] = dirty_child[i];
+    for (int c = 0; c < nd.n_children && c < CHAIN_MAX_CHILDREN; ++c) {
+      sm.childs[i * CHAIN_MAX_CHILDREN + c] = a.childs[nd.child_begin + c];
+      sm.map_child[i * CHAIN_MAX_CHILDREN + c] = child_maps[nd.child_begin + c];
+    }
+  }
+  __syncthreads();
+  const int64_t total = tail.n_rows * K;
+  const int64_t u = (int64_t)blockIdx.x * CHAIN_THREADS + t;
+  const bool active = u < total;
+  const int64_t p = active ? u / K : 0;
+  const int b = active ? (int)(u - p * K) : 0;
+  // every index of the walk (static tables: this may overlap the expm launch)
+  int32_t own[CHAIN_MAX_NODES], sib[CHAIN_MAX_NODES][CHAIN_MAX_CHILDREN];
+#pragma unroll
+  for (int i = 0; i < CHAIN_MAX_NODES; ++i) {
+    own[i] = 0;
+#pragma unroll
+    for (int c = 0; c < CHAIN_MAX_CHILDREN; ++c) sib[i][c] = 0;
+    if (i < n_work) {
+      const NodeDesc& nd = sm.nodes[i];
+      if (nd.out != nullptr) own[i] = __ldg(sm.map_own[i] + p);
+#pragma unroll
+      for (int c = 0; c < CHAIN_MAX_CHILDREN; ++c)
+        if (c < nd.n_children && c != sm.dirty_child[i]) sib[i][c] = __ldg(sm.map_child[i * CHAIN_MAX_CHILDREN + c] + p);
+    }
+  }
+  pdl_wait();  // the P matrices / tip tables of the expm launch
+  if (t == 0) tl_first(a.tl, 1);
+  {
+    const int per_item = CHAIN_MAX_CHILDREN * K * 16;
+    for (int o = t; o < n_work * per_item; o += CHAIN_THREADS) {
+      const int i = o / per_item, rem = o - i * per_item;
+      const int c = rem / (K * 16), e16 = rem - c * (K * 16);
+      const double* P = (c < sm.nodes[i].n_children) ? sm.childs[i * CHAIN_MAX_CHILDREN + c].P : nullptr;
+      if (P != nullptr) sm.P[(i * CHAIN_MAX_CHILDREN + c) * 64 + e16] = P[e16];
+    }
+  }
+  __syncthreads();
+  auto gather = [&](int i, d4(&x)[CHAIN_MAX_CHILDREN]) {
+    const NodeDesc& nd = sm.nodes[i];
+#pragma unroll
+    for (int c = 0; c < CHAIN_MAX_CHILDREN; ++c)
+      if (c < nd.n_children && c != sm.dirty_child[i])
+        x[c] = ld256(sm.childs[i * CHAIN_MAX_CHILDREN + c].src + ((int64_t)sib[i][c] * K + b) * 4);
+  };
+  d4 carry{0.0, 0.0, 0.0, 0.0};
+  d4 xn[CHAIN_MAX_CHILDREN];
+  gather(0, xn);
+#pragma unroll
+  for (int i = 0; i < CHAIN_MAX_NODES; ++i) {
+    if (i < n_work) {
+      d4 x[CHAIN_MAX_CHILDREN];
+#pragma unroll
+      for (int c = 0; c < CHAIN_MAX_CHILDREN; ++c) x[c] = xn[c];
+      if (i + 1 < n_work) gather(i + 1, xn);  // the next node's clean rows are in flight during this node's arithmetic
+      const NodeDesc& nd = sm.nodes[i];
+      const int dc = sm.dirty_child[i];
+      d4 acc{1.0, 1.0, 1.0, 1.0};
+#pragma unroll
+      for (int c = 0; c < CHAIN_MAX_CHILDREN; ++c) {
+        if (c < nd.n_children) {
+          const double* Pc = sm.P + ((i * CHAIN_MAX_CHILDREN + c) * 4 + b) * 16;
+          const d4 v = (c == dc) ? carry : x[c];
+          const d4 y = (sm.childs[i * CHAIN_MAX_CHILDREN + c].P != nullptr) ? matvec4(Pc, v) : v;
+          if (c == 0) acc = y;
+          else { acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w; }
+        }
+      }
+      if (nd.fixed_motif >= 0) {
+        if (nd.fixed_motif != 0) acc.x = 0.0;
+        if (nd.fixed_motif != 1) acc.y = 0.0;
+        if (nd.fixed_motif != 2) acc.z = 0.0;
+        if (nd.fixed_motif != 3) acc.w = 0.0;
+      }
+      if (active) {
+        if (nd.out != nullptr) st256(nd.out + ((int64_t)own[i] * K + b) * 4, acc);
+        if (nd.is_root) {
+          const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
+          a.lh_out[p * K + b] = lh;
+        }
+      }
+      carry = acc;
+    }
+  }
+  if (t == 0) tl_end(a.tl);
+  // ---- the site-weighted reduction: a reduction tile (1024 root rows) is the work of 4 K consecutive CTAs; the
+  // last of them to get here reduces the tile, the last of those adds the tiles in index order and publishes
+  // (same tiles, per-thread rows and summation trees as lnl_reduce_kernel: same bits)
+  __threadfence();
+  __syncthreads();
+  const int ctas_per_tile = REDUCE_ROWS_PER_TILE * K / CHAIN_THREADS;
+  const int tile = (int)blockIdx.x / ctas_per_tile;
+  const int ctas_here = min(ctas_per_tile, (int)gridDim.x - tile * ctas_per_tile);
+  if (t == 0) s_last = atomicAdd(counters + 1 + tile, 1u) == (unsigned)(ctas_here - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    const double acc = reduce_tile_partial(a.lh_out, tail.bprobs, tail.counts, tail.n_rows, K, tile, t, nullptr);
+    const double total_t = block_sum(acc, s_warp);
+    if (t == 0) {
+      tile_sums[tile] = total_t;
+      counters[1 + tile] = 0u;
+      __threadfence();
+      s_last = atomicAdd(counters, 1u) == (unsigned)(tail.n_tiles - 1);
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int i = t; i < tail.n_tiles; i += REDUCE_THREADS) acc += __ldcg(tile_sums + i);
+  const double result = block_sum(acc, s_warp);
+  if (t == 0) {
+    counters[0] = 0u;
+    publish_result(tail.sink, result);
+    tl_end(a.tl);  // (slot 3, the latest stamp: the result is out)
   }
 }
 

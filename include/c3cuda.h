@@ -62,6 +62,8 @@ typedef struct c3_stats {
   int64_t wave_launches;      /* sweeps issued as ONE wavefront launch (all levels at once) */
   int64_t wave_entries;       /* schedule entries of the last wavefront launch  */
   int64_t wave_noops;         /* ... of which no-op positions                   */
+  int64_t lean_evaluations;   /* evaluations whose root launch wrote the class mixture (8 B per row) instead of lh */
+  int64_t chain_launches;     /* single-path updates walked per root row by the chain kernel (no level barriers) */
 } c3_stats;
 
 C3_API int c3_abi_version(void);
