@@ -724,8 +724,21 @@ def dropin_leg(ctx, problem, cfg, steps, warmup, expect_units):
     if fused:
         eng.comm_detach()
     st = eng.stats()
+    optimise = None
+    if cfg == "c1" and ctx.world == 1:
+        # BASELINE configs[0]: lf.optimise() on brca1, the reference's own Powell (local=True) driving each arm --
+        # two fresh likelihood functions from the same starting point, wall-clock of the whole call
+        optimise = {}
+        for backend in ("cuda", "cpu"):
+            lf_o, _ = build_cogent3_lf(problem, cfg, backend=backend, device=ctx.local_rank)
+            lf_o.get_log_likelihood()
+            t0 = time.perf_counter()
+            lf_o.optimise(local=True, show_progress=False)
+            optimise[backend] = {"seconds": time.perf_counter() - t0, "lnL": float(lf_o.get_log_likelihood())}
+        optimise["speedup"] = optimise["cpu"]["seconds"] / optimise["cuda"]["seconds"]
+        optimise["api"] = "lf.optimise(local=True) of sm.make_likelihood_function(tree): cuda = cogent3_b200.install(), cpu = stock cogent3, same process"
     return {"wall_s": wall, "h2d": h2d, "lnL0": lnl0, "lnL_last": float(lnl), "fused": fused, "lf_evals": evals,
-            "lengths_only_ms": lengths_only,
+            "lengths_only_ms": lengths_only, "optimise": optimise,
             "graph_replays": int(st["graph_replays"]), "n_parameters": int(len(x)),
             "setup": {**t_setup, "first_evaluation_s": t_first, "make_calculator_s": t_calc}}  # fmt: skip
 
@@ -921,6 +934,8 @@ def measure_workload(ctx, args, cfg, columns, kind, steps, warmup, shard, clocks
                                        if dropin.get("lengths_only_ms") else None),
                       "fused_allreduce": dropin["fused"], "graph_replays": dropin["graph_replays"],
                       "setup": dropin["setup"], "lnL_first": dropin["lnL0"]}  # fmt: skip
+        if dropin.get("optimise"):
+            out["e2e"]["optimise"] = dropin["optimise"]
     else:
         why = (dropin or {}).get("error", "cogent3 (baseline/_ref) is not on this machine")
         out["e2e"] = dict(out["e2e_mirror"], note=f"drop-in leg unavailable ({why}): the mirror API instead")

@@ -150,6 +150,11 @@ struct c3_engine {
   // chain kernel (prune4_chain_kernel): single-branch updates of small 4-state problems walked per ROOT row through
   // composed gather tables, no barrier between the levels (C3_CHAIN=0 disables)
   bool use_chain = true;
+  // C3_CHAIN_FUSED=1: a single-branch update in the real eigen form as ONE launch -- parameters by value, the
+  // branch's P computed inside the chain launch, no parameter-block copy, no expm launch, no graph.  Bit-identical;
+  // opt-in because it measured no faster: what is left of an update is the launch / completion round trip between
+  // host and GPU (~20 us on the bench box whichever way the work is submitted), not device time (DESIGN lesson 17g)
+  bool use_chain_fused = false;
   bool chain_ok = false;              // the composed tables exist (small problem, <= 3 children everywhere)
   int32_t* d_chain_maps = nullptr;    // [n_nodes][root_rows]: root row -> row of the node
   const int32_t** d_node_maps = nullptr;   // [n_nodes]
@@ -949,6 +954,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_SMALL_REDUCE")) e->use_small_reduce = atoi(env) == 0;
   if (const char* env = getenv("C3_PATH")) e->use_path = atoi(env) != 0;
   if (const char* env = getenv("C3_CHAIN")) e->use_chain = atoi(env) != 0;
+  if (const char* env = getenv("C3_CHAIN_FUSED")) e->use_chain_fused = atoi(env) != 0;
   if (const char* env = getenv("C3_PATH_VARIANT")) e->path_variant = std::max(0, std::min(2, atoi(env)));
   if (const char* env = getenv("C3_REC")) e->use_rec = atoi(env) != 0;
   if (const char* env = getenv("C3_STREAMS")) e->use_streams = atoi(env) != 0;
@@ -2521,7 +2527,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   // inner loop) on a problem small enough for one CTA's shared memory: prune4_path_kernel, which also reduces
   // ---- chain launch?  the dirty set is ONE path to the root on a small problem: prune4_chain_kernel walks it
   // per root row without a barrier, and reduces
-  bool chain_launch = false;
+  bool chain_launch = false, chain_fused = false;
+  int chain_edge_node = -1, chain_edge_slot = 0;
   if (e->chain_ok && e->use_chain && !wave && !e->rescale_active && e->comm.nranks <= 1 && recompute[e->root] &&
       e->use_small_reduce) {
     std::vector<int> chain;
@@ -2553,6 +2560,21 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       w_off += ll.n_work;
       launches.push_back(ll);
       chain_launch = true;
+      // ONE launch for the whole update?  the jobs are the K rate classes of one branch under the lowest path node,
+      // all in the real eigen form; a plain blocking evaluation (batches and profiled runs keep the launch sequence)
+      if (n_pade == 0 && n_eigen == K && K <= 4 && M == 4 && e->batch_mode == 0 && !e->profiling && e->use_chain_fused) {
+        bool one = true;
+        for (int j = 0; j < K; ++j)
+          one = one && jobs[j].node == jobs[0].node && jobs[j].bin == j && jobs[j].mode == EXPM_EIGEN_REAL;
+        one = one && e->parent[jobs[0].node] == chain[0];
+        if (one) {
+          chain_fused = true;
+          chain_edge_node = jobs[0].node;
+          chain_edge_slot = 0;
+          for (size_t c = 0; c < e->children[chain[0]].size(); ++c)
+            if (e->children[chain[0]][c] == chain_edge_node) chain_edge_slot = (int)c;
+        }
+      }
     }
   }
   bool path_launch = false;
@@ -2884,7 +2906,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   std::memcpy(e->h_block + e->off_bprobs, e->bprobs.data(), K * sizeof(double));
   // one contiguous copy of the used part of the block
   const int64_t used = e->off_jobs + (int64_t)(n_eigen + n_pade) * sizeof(ExpmJob);
-  h2d_bytes += std::min(used, e->block_bytes);
+  if (!chain_fused) h2d_bytes += std::min(used, e->block_bytes);
   int64_t n_launch = 0;
   e->prof.clear();
   e->events_used = 0;
@@ -2947,12 +2969,14 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     e->tl_launches = tl_n + 1;
     return e->d_tl + 4 * tl_n++;
   };
+  if (!chain_fused) {  // (the fused chain launch carries its parameters by value)
   C3_CUDA(cudaMemcpyAsync(e->d_block, e->h_block, (size_t)std::min(used, e->block_bytes),
                           cudaMemcpyHostToDevice, e->stream));
   if (!capturing) C3_CUDA(cudaEventRecord(e->block_copied, e->stream));  // the staging buffer is free again
+  }
   if (any_flow) C3_CUDA(cudaMemsetAsync(e->d_done, 0, (size_t)w_off * sizeof(unsigned int), e->stream));
   const ExpmJob* d_jobs = reinterpret_cast<const ExpmJob*>(e->d_block + e->off_jobs);
-  if (n_eigen > 0) {
+  if (n_eigen > 0 && !chain_fused) {
     const int threads = (M <= 4) ? 32 : (M <= 16 ? 64 : (M <= 32 ? 256 : 1024));
     // sP + exp(roots) + (large M) the staged W / evI planes, complex-capable
     const size_t smem = (size_t)(MP * MP + 2 * M + (M > 8 ? 4 * M * (M | 1) : 0)) * sizeof(double);
@@ -3143,9 +3167,26 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       tail.n_rows = e->n_rows[e->root];
       tail.n_tiles = (int)((tail.n_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
       tail.sink = sink;
-      const int32_t* d_dirty = reinterpret_cast<const int32_t*>(e->d_block + e->off_dep) + ll.work_off;
-      cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_chain_kernel, a, d_dirty, (const int32_t* const*)e->d_node_maps,
-                                           (const int32_t* const*)e->d_child_maps, tail, e->d_chain_ctr, e->d_tile_sums);
+      ChainParams cp{};
+      for (int i = 0; i < ll.n_work; ++i) {
+        cp.work_node[i] = work[ll.work_off + i];
+        cp.dirty_child[i] = dep[ll.work_off + i];
+      }
+      for (int i = 0; i < 4; ++i) {
+        cp.pi[i] = e->pi[i];
+        cp.bprobs[i] = i < K ? e->bprobs[i] : 0.0;
+      }
+      cp.fused = chain_fused ? 1 : 0;
+      cp.edge_node = chain_edge_node;
+      cp.edge_slot = chain_edge_slot;
+      if (chain_fused)
+        for (int j = 0; j < K; ++j) {
+          cp.q_slot[j] = jobs[j].slot;
+          cp.t[j] = jobs[j].t;
+        }
+      cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_chain_kernel, a, cp, (const int32_t* const*)e->d_node_maps,
+                                           (const int32_t* const*)e->d_child_maps, tail, e->d_chain_ctr, e->d_tile_sums,
+                                           (const double*)e->d_slots, (int64_t)e->slot_stride, (const EdgeDesc*)e->d_edges);
       if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("chain launch: ") + cudaGetErrorString(err));
     } else if (ll.kind == 9) {
       const size_t smem = (size_t)ll.total_tiles;
@@ -3262,7 +3303,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   const auto hp_t1 = std::chrono::steady_clock::now();
   bool graphed = false;
   e->plan = c3_engine::PlanStats{n_eigen + n_pade, n_dirty_nodes, node_rows, alg_bytes, flops, h2d_bytes};
-  const bool graph_ok = e->use_graphs && !e->profiling && !any_flow && wave == nullptr;  // (cooperative launch: not captured)
+  const bool graph_ok = e->use_graphs && !e->profiling && !any_flow && wave == nullptr &&  // (cooperative launch: not captured)
+                        !chain_fused;  // (one launch with by-value parameters: nothing to replay)
   if (e->batch_mode != 0 && !graph_ok) return fail(C3_ERR_INVALID, "engine cannot take part in a batch graph");
   if (graph_ok) {
     std::vector<int32_t> sig;

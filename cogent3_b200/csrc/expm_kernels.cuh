@@ -27,6 +27,30 @@ __device__ __forceinline__ double clamp0(double v) { return v < 0.0 ? 0.0 : v; }
 // product with the rows of P is just a column of P -- the same bits as the sum (every other term is
 // fma(0, x, s) = s).  Only ambiguity codes and the gap row run the sum.  (ncu on the 61-state
 // launch: the sums over all rows were more than half of the kernel's instructions.)
+// one entry of tip_inner for a row that is not one-hot (ambiguity codes, the gap row); shared with the chain
+// kernel's fused expm so that both produce the same bits
+__device__ __forceinline__ double tip_inner_entry(const double* __restrict__ row, const double* sP, int i, int M, int MP) {
+  // the j loop starts at i: consecutive lanes (consecutive i) then read different shared
+  // memory banks of sP (row stride MP is a multiple of the bank count); the rows are 0/1
+  // indicators, so the rotated summation order only matters for ambiguity codes (~1 ulp)
+  double s = 0.0;
+  int j = (MP > 8) ? i : 0;
+  for (int n = 0; n < M; ++n) {
+    s = fma(row[j], sP[i * MP + j], s);
+    j = (j + 1 == M) ? 0 : j + 1;
+  }
+  return s;
+}
+
+// one entry of P = max(evT . diag(exp(t roots)) . evI^T, 0) in the real eigen form for small alphabets (k summed in
+// order, explicit roundings: the same bits wherever it is inlined -- expm_eigen_kernel and the chain kernel)
+__device__ __forceinline__ double expm_real_entry(const double* __restrict__ evT_row, const double* __restrict__ evI_row,
+                                                  const double* er, int M) {
+  double acc = 0.0;
+  for (int k = 0; k < M; ++k) acc = __fma_rn(__dmul_rn(evT_row[k], er[k]), evI_row[k], acc);
+  return clamp0(acc);
+}
+
 __device__ __forceinline__ void tip_inner_update(const EdgeDesc& ed, const double* sP, int bin,
                                                  int M, int MP, int K) {
   if (ed.tip_table == nullptr) return;
@@ -39,16 +63,7 @@ __device__ __forceinline__ void tip_inner_update(const EdgeDesc& ed, const doubl
     if (state >= 0) {
       s = sP[i * MP + state];
     } else {
-      const double* row = ed.tip_table + u * MP;
-      // the j loop starts at i: consecutive lanes (consecutive i) then read different shared
-      // memory banks of sP (row stride MP is a multiple of the bank count); the rows are 0/1
-      // indicators, so the rotated summation order only matters for ambiguity codes (~1 ulp)
-      s = 0.0;
-      int j = (MP > 8) ? i : 0;
-      for (int n = 0; n < M; ++n) {
-        s = fma(row[j], sP[i * MP + j], s);
-        j = (j + 1 == M) ? 0 : j + 1;
-      }
+      s = tip_inner_entry(ed.tip_table + u * MP, sP, i, M, MP);
     }
     ed.tip_inner[(u * K + bin) * MP + i] = s;
   }
@@ -228,9 +243,7 @@ __global__ void expm_eigen_kernel(const ExpmJob* __restrict__ jobs, const double
     } else {
       for (int o = threadIdx.x; o < MM; o += blockDim.x) {
         const int i = o / M, j = o - i * M;
-        double acc = 0.0;
-        for (int k = 0; k < M; ++k) acc += (evT[i * M + k] * s_er[k]) * evI[j * M + k];
-        acc = clamp0(acc);
+        const double acc = expm_real_entry(evT + i * M, evI + j * M, s_er, M);
         sP[i * MP + j] = acc;
         Pout[i * MP + j] = acc;
       }

@@ -788,29 +788,65 @@ struct ChainSmem {
   double P[CHAIN_MAX_NODES * CHAIN_MAX_CHILDREN * 4 * 16];  // [node][child][bin][16], K <= 4
 };
 
-// a.work_node[0 .. n_work): the path bottom-up (the last one is the root); dirty_child[i]: the child slot of
-// path node i that is path node i - 1 (-1 for i = 0).  node_maps[n] / child_maps[child ref]: root row -> row.
+// Everything an update needs beyond the resident tables travels BY VALUE in the launch (no parameter-block copy):
+// the path bottom-up (work_node, the last one is the root), dirty_child[i] = the child slot of path node i that
+// is path node i - 1 (-1 for i = 0), pi, the bin probabilities -- and, when the update is ONE branch whose P has
+// the real eigen form (`fused`), the K distances of that branch: every CTA then computes the K matrices itself
+// (64 K FMAs, the expm launch's own arithmetic: expm_real_entry), CTA 0 also writes them -- and, below a tip,
+// the tip's pre-multiplied table -- back to memory for later evaluations.  A single-branch update is then ONE
+// kernel launch: no copy, no expm launch, no graph.
+struct ChainParams {
+  int32_t work_node[CHAIN_MAX_NODES];
+  int32_t dirty_child[CHAIN_MAX_NODES];
+  double pi[4];
+  double bprobs[4];
+  int32_t fused;      // 1: the P of the branch below path node 0's child `edge_slot` is computed here
+  int32_t edge_node;  // the node below that branch
+  int32_t edge_slot;
+  int32_t pad;
+  int32_t q_slot[4];  // per bin: the slot holding roots | evT | evI
+  double t[4];        // per bin: distance
+};
+
+// node_maps[n] / child_maps[child ref]: root row -> row of the node / of the child
 __global__ void __launch_bounds__(CHAIN_THREADS)
-prune4_chain_kernel(const PruneArgs a, const int32_t* __restrict__ dirty_child,
+prune4_chain_kernel(const PruneArgs a, const ChainParams cp,
                     const int32_t* const* __restrict__ node_maps, const int32_t* const* __restrict__ child_maps,
-                    const ReduceTail tail, unsigned int* __restrict__ counters, double* __restrict__ tile_sums) {
+                    const ReduceTail tail, unsigned int* __restrict__ counters, double* __restrict__ tile_sums,
+                    const double* __restrict__ slots, int64_t slot_stride, const EdgeDesc* __restrict__ edges) {
   extern __shared__ __align__(16) unsigned char chain_raw[];
   ChainSmem& sm = *reinterpret_cast<ChainSmem*>(chain_raw);
   __shared__ double s_warp[CHAIN_THREADS / 32];
+  __shared__ double s_bp[4];
+  __shared__ __align__(16) double s_Pnew[4 * 16];  // fused: P of the changed branch, [bin][16]
   __shared__ bool s_last;
   const int K = a.K, n_work = a.n_work, t = (int)threadIdx.x;
   pdl_trigger();
   if (t == 0) tl_first(a.tl, 0);
+  if (t < 4) s_bp[t] = cp.bprobs[t];
   for (int i = t; i < n_work; i += CHAIN_THREADS) {
-    const int node = a.work_node[i];
+    const int node = cp.work_node[i];
     const NodeDesc nd = a.nodes[node];
     sm.nodes[i] = nd;
     sm.map_own[i] = node_maps[node];
-    sm.dirty_child[i] = dirty_child[i];
+    sm.dirty_child[i] = cp.dirty_child[i];
     for (int c = 0; c < nd.n_children && c < CHAIN_MAX_CHILDREN; ++c) {
       sm.childs[i * CHAIN_MAX_CHILDREN + c] = a.childs[nd.child_begin + c];
       sm.map_child[i * CHAIN_MAX_CHILDREN + c] = child_maps[nd.child_begin + c];
     }
+  }
+  const bool fused = cp.fused != 0;
+  if (fused && t < 16 * K) {
+    // P_b = max(evT . diag(exp(t_b roots)) . evI^T, 0): thread (b, i, j)
+    const int bin = t >> 4, o = t & 15, i = o >> 2, j = o & 3;
+    const double* slot = slots + (int64_t)cp.q_slot[bin] * slot_stride;
+    const double* roots = slot;
+    const double* evT = slot + 8;    // roots[2 M] | evT[2 M M] | evI[2 M M], M = 4, real parts first
+    const double* evI = evT + 32;
+    double er[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) er[k] = exp(cp.t[bin] * roots[k]);
+    s_Pnew[bin * 16 + o] = expm_real_entry(evT + i * 4, evI + j * 4, er, 4);
   }
   __syncthreads();
   const int64_t total = tail.n_rows * K;
@@ -818,7 +854,7 @@ prune4_chain_kernel(const PruneArgs a, const int32_t* __restrict__ dirty_child,
   const bool active = u < total;
   const int64_t p = active ? u / K : 0;
   const int b = active ? (int)(u - p * K) : 0;
-  // every index of the walk (static tables: this may overlap the expm launch)
+  // every index of the walk (static tables: this may overlap the previous launch)
   int32_t own[CHAIN_MAX_NODES], sib[CHAIN_MAX_NODES][CHAIN_MAX_CHILDREN];
 #pragma unroll
   for (int i = 0; i < CHAIN_MAX_NODES; ++i) {
@@ -833,16 +869,27 @@ prune4_chain_kernel(const PruneArgs a, const int32_t* __restrict__ dirty_child,
         if (c < nd.n_children && c != sm.dirty_child[i]) sib[i][c] = __ldg(sm.map_child[i * CHAIN_MAX_CHILDREN + c] + p);
     }
   }
-  pdl_wait();  // the P matrices / tip tables of the expm launch
+  pdl_wait();  // the expm launch's P matrices / tip tables; the rows and counters of the previous evaluation
   if (t == 0) tl_first(a.tl, 1);
+  const bool fused_tip = fused && sm.childs[cp.edge_slot].P == nullptr;  // the changed branch ends in a tip
   {
     const int per_item = CHAIN_MAX_CHILDREN * K * 16;
     for (int o = t; o < n_work * per_item; o += CHAIN_THREADS) {
       const int i = o / per_item, rem = o - i * per_item;
       const int c = rem / (K * 16), e16 = rem - c * (K * 16);
       const double* P = (c < sm.nodes[i].n_children) ? sm.childs[i * CHAIN_MAX_CHILDREN + c].P : nullptr;
-      if (P != nullptr) sm.P[(i * CHAIN_MAX_CHILDREN + c) * 64 + e16] = P[e16];
+      if (fused && i == 0 && c == cp.edge_slot) {
+        if (P != nullptr) sm.P[(i * CHAIN_MAX_CHILDREN + c) * 64 + e16] = s_Pnew[e16];  // (memory still holds the old P)
+      } else if (P != nullptr) {
+        sm.P[(i * CHAIN_MAX_CHILDREN + c) * 64 + e16] = P[e16];
+      }
     }
+  }
+  if (fused && blockIdx.x == 0) {
+    // for the evaluations to come: the new P and, below a tip, the tip's pre-multiplied table
+    const EdgeDesc ed = edges[cp.edge_node];
+    if (t < 16 * K) ed.P[t] = s_Pnew[t];
+    for (int bin = 0; bin < K; ++bin) tip_inner_update(ed, s_Pnew + bin * 16, bin, 4, 4, K);
   }
   __syncthreads();
   auto gather = [&](int i, d4(&x)[CHAIN_MAX_CHILDREN]) {
@@ -855,6 +902,25 @@ prune4_chain_kernel(const PruneArgs a, const int32_t* __restrict__ dirty_child,
   d4 carry{0.0, 0.0, 0.0, 0.0};
   d4 xn[CHAIN_MAX_CHILDREN];
   gather(0, xn);
+  if (fused_tip) {
+    // the changed branch ends in a tip: its row under the NEW P (memory still holds the old table) -- a column
+    // of P for a one-hot row, the full sum for an ambiguity code: tip_inner_update's arithmetic
+    const EdgeDesc& ed = edges[cp.edge_node];
+    int64_t urow = 0;
+#pragma unroll
+    for (int c = 0; c < CHAIN_MAX_CHILDREN; ++c)
+      if (c == cp.edge_slot) urow = sib[0][c];
+    const int state = ed.tip_state[urow];
+    const double* Pb = s_Pnew + b * 16;
+    d4 v;
+    v.x = (state >= 0) ? Pb[0 + state] : tip_inner_entry(ed.tip_table + urow * 4, Pb, 0, 4, 4);
+    v.y = (state >= 0) ? Pb[4 + state] : tip_inner_entry(ed.tip_table + urow * 4, Pb, 1, 4, 4);
+    v.z = (state >= 0) ? Pb[8 + state] : tip_inner_entry(ed.tip_table + urow * 4, Pb, 2, 4, 4);
+    v.w = (state >= 0) ? Pb[12 + state] : tip_inner_entry(ed.tip_table + urow * 4, Pb, 3, 4, 4);
+#pragma unroll
+    for (int c = 0; c < CHAIN_MAX_CHILDREN; ++c)
+      if (c == cp.edge_slot) xn[c] = v;
+  }
 #pragma unroll
   for (int i = 0; i < CHAIN_MAX_NODES; ++i) {
     if (i < n_work) {
@@ -884,7 +950,7 @@ prune4_chain_kernel(const PruneArgs a, const int32_t* __restrict__ dirty_child,
       if (active) {
         if (nd.out != nullptr) st256(nd.out + ((int64_t)own[i] * K + b) * 4, acc);
         if (nd.is_root) {
-          const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
+          const double lh = fma(acc.w, cp.pi[3], fma(acc.z, cp.pi[2], fma(acc.y, cp.pi[1], acc.x * cp.pi[0])));
           a.lh_out[p * K + b] = lh;
         }
       }
@@ -905,7 +971,7 @@ prune4_chain_kernel(const PruneArgs a, const int32_t* __restrict__ dirty_child,
   if (!s_last) return;
   __threadfence();
   {
-    const double acc = reduce_tile_partial(a.lh_out, tail.bprobs, tail.counts, tail.n_rows, K, tile, t, nullptr);
+    const double acc = reduce_tile_partial(a.lh_out, s_bp, tail.counts, tail.n_rows, K, tile, t, nullptr);
     const double total_t = block_sum(acc, s_warp);
     if (t == 0) {
       tile_sums[tile] = total_t;

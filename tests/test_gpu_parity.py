@@ -624,11 +624,20 @@ def test_chain_kernel_single_branch_updates_bit_identical(model, n_tips, L, bins
         topo, lengths = Topology.from_newick("(((a:0.1,b:0.2):0.1,(c:0.3,d:0.2):0.05):0.1,((e:0.1,f:0.1):0.2,(g:0.2,(h:0.1,i:0.3):0.1):0.1):0.2);")
         codes = codes[: int(np.sum(topo.is_tip))]
 
-    def build(chain):
+    # ambiguity codes (R, N) in 3 % of the cells: tip rows that are not one-hot take the summed form of the
+    # pre-multiplied tip table, also inside the fused launch
+    rows = np.vstack([np.eye(4), [[1.0, 0.0, 1.0, 0.0], [1.0, 1.0, 1.0, 1.0]]])
+    codes = codes.copy()
+    amb = np.random.default_rng(17).random(codes.shape)
+    codes[amb < 0.015] = 4
+    codes[amb > 0.985] = 5
+
+    def build(chain, fused=True):
         monkeypatch.setenv("C3_CHAIN", "1" if chain else "0")
+        monkeypatch.setenv("C3_CHAIN_FUSED", "1" if fused else "0")
         monkeypatch.setenv("C3_GRAPH_AFTER", "2")
         lf = LikelihoodFunction(m, topo, bins=bins)
-        lf.set_alignment(codes.astype(np.int64), np.eye(4))
+        lf.set_alignment(codes.astype(np.int64), rows)
         lf.set_motif_probs_from_data()
         lf.lengths[:-1] = np.asarray(lengths)[:-1]
         for k, p in enumerate(m.parameter_order):
@@ -637,33 +646,47 @@ def test_chain_kernel_single_branch_updates_bit_identical(model, n_tips, L, bins
             lf.set_param_rule("rate_shape", value=0.6)
         return lf
 
-    a, b = build(True), build(False)
-    assert a.get_log_likelihood() == b.get_log_likelihood()
+    # a: ONE launch per update (parameters by value, the branch's P computed in the launch); c: expm launch + chain
+    # launch behind a parameter-block copy (graph-replayed); b: expm + small-levels launch
+    a, b, c = build(True), build(False), build(True, fused=False)
+    assert a.get_log_likelihood() == b.get_log_likelihood() == c.get_log_likelihood()
     rng = np.random.default_rng(3)
     internal = [n for n in range(topo.n_nodes) if not topo.is_tip[n]]
     edges = list(topo.edges)
     for rep in range(3):
         for n in edges:
             v = float(rng.uniform(0.01, 0.6))
-            for lf in (a, b):
+            for lf in (a, b, c):
                 lf.set_param_rule("length", edge=topo.names[n], value=v)
-            va, vb = a.get_log_likelihood(), b.get_log_likelihood()
-            assert va == vb, (rep, topo.names[n], va, vb)
+            va, vb, vc = a.get_log_likelihood(), b.get_log_likelihood(), c.get_log_likelihood()
+            assert va == vb == vc, (rep, topo.names[n], va, vb, vc)
+            if rep == 1:
+                # the P (and, below a tip, the tip table) the fused launch left in memory is the expm launch's
+                for bin_ in range(bins):
+                    np.testing.assert_array_equal(a.engine.get_psub(n, bin_), b.engine.get_psub(n, bin_))
         for n in internal:
             for bin_ in range(bins):
                 np.testing.assert_array_equal(a.engine.get_partials(n, bin_), b.engine.get_partials(n, bin_))
+                np.testing.assert_array_equal(c.engine.get_partials(n, bin_), b.engine.get_partials(n, bin_))
         for bin_ in range(bins):
             np.testing.assert_array_equal(a.engine.get_lh(bin_), b.engine.get_lh(bin_))
+            np.testing.assert_array_equal(c.engine.get_lh(bin_), b.engine.get_lh(bin_))
         if rep == 0:
             # a fixed motif on an internal node of some paths (ancestral-state style masks)
             fm = np.full(topo.n_nodes, -1, np.int32)
             fm[internal[len(internal) // 2]] = 2
-            for lf in (a, b):
+            for lf in (a, b, c):
                 lf.engine.set_fixed_motifs(fm)
-            assert a.engine.evaluate() == b.engine.evaluate()
-    sa, sb = a.engine.stats(), b.engine.stats()
+            assert a.engine.evaluate() == b.engine.evaluate() == c.engine.evaluate()
+    # every branch moved: the next full sweep reads the tables the fused launches wrote back
+    for lf in (a, b, c):
+        lf.set_param_rule("rate_shape" if bins > 1 else m.parameter_order[0], value=0.77)
+    assert a.get_log_likelihood() == b.get_log_likelihood() == c.get_log_likelihood()
+    sa, sb, sc = a.engine.stats(), b.engine.stats(), c.engine.stats()
     assert sb["chain_launches"] == 0
-    assert sa["chain_launches"] >= len(edges) and sa["graph_replays"] > 0  # (paths longer than 16 nodes keep the level launches)
+    assert sa["chain_launches"] >= len(edges)  # (paths longer than 16 nodes keep the level launches)
+    assert sc["chain_launches"] == sa["chain_launches"] and sc["graph_replays"] > 0
+    assert sa["kernel_launches"] < sc["kernel_launches"]  # (no expm launch in front of a fused update)
     # the full sweep after invalidation agrees with the last chain update
     last = a.get_log_likelihood()
     a.engine.invalidate()

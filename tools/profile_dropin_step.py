@@ -38,4 +38,4 @@ pr.enable()
 for k in range(N):
     calc(bench.calculator_points(x, k))
 pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+pstats.Stats(pr).sort_stats("tottime").print_stats(45)
