@@ -45,6 +45,7 @@ class C3Stats(ctypes.Structure):
         ("wave_noops", c_int64),
         ("lean_evaluations", c_int64),
         ("chain_launches", c_int64),
+        ("walk_launches", c_int64),
     ]
 
     def as_dict(self):

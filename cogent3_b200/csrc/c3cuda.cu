@@ -150,6 +150,13 @@ struct c3_engine {
   // chain kernel (prune4_chain_kernel): single-branch updates of small 4-state problems walked per ROOT row through
   // composed gather tables, no barrier between the levels (C3_CHAIN=0 disables)
   bool use_chain = true;
+  // tree-walk kernel (prune4_walk_kernel): every other evaluation of such a problem -- full sweeps included -- the
+  // same way, with a per-thread value stack for the dirty children
+  // OPT-IN (C3_WALK=1): bit-identical, but brca1's full sweep walks in 45 us against the small-levels launch's 40 --
+  // ~220 instructions per node with 88 warps on the whole GPU (K = 1: 2764 units): latency of one warp's
+  // instruction stream, ncu profiles/r2_prune4_walk_ncu.txt; DESIGN lesson 17h
+  bool use_walk = false;
+  int64_t off_ops = 0;
   // C3_CHAIN_FUSED=1: a single-branch update in the real eigen form as ONE launch -- parameters by value, the
   // branch's P computed inside the chain launch, no parameter-block copy, no expm launch, no graph.  Bit-identical;
   // opt-in because it measured no faster: what is left of an update is the launch / completion round trip between
@@ -178,6 +185,7 @@ struct c3_engine {
   bool lh_valid = true;   // d_lh holds the last evaluation's per-pattern likelihoods
   bool last_lean = false; // the evaluation being planned / last issued has a lean root launch
   bool last_chain = false; // ... is one chain launch
+  bool last_walk = false;  // ... is one tree-walk launch
   int lh_keep = 0;        // evaluations that still write lh because an accessor read it recently
   double* d_mix = nullptr;
   struct RootLaunch { int work_off = 0, prefix_off = 0, n_work = 0, total_tiles = 0, kind = 0; } root_launch;
@@ -814,6 +822,7 @@ void commit_evaluation(c3_engine* e, int64_t n_launch, bool replayed) {
   if (e->lh_keep > 0) --e->lh_keep;
   if (e->last_lean) e->stats.lean_evaluations += 1;
   if (e->last_chain) e->stats.chain_launches += 1;
+  if (e->last_walk) e->stats.walk_launches += 1;
   e->stats.evaluations += 1;
   e->stats.kernel_launches += n_launch;
   e->stats.last_launches = n_launch;
@@ -954,6 +963,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_NO_SMALL_REDUCE")) e->use_small_reduce = atoi(env) == 0;
   if (const char* env = getenv("C3_PATH")) e->use_path = atoi(env) != 0;
   if (const char* env = getenv("C3_CHAIN")) e->use_chain = atoi(env) != 0;
+  if (const char* env = getenv("C3_WALK")) e->use_walk = atoi(env) != 0;
   if (const char* env = getenv("C3_CHAIN_FUSED")) e->use_chain_fused = atoi(env) != 0;
   if (const char* env = getenv("C3_PATH_VARIANT")) e->path_variant = std::max(0, std::min(2, atoi(env)));
   if (const char* env = getenv("C3_REC")) e->use_rec = atoi(env) != 0;
@@ -1722,6 +1732,23 @@ int c3_finalize(c3_engine* e) {
           child_maps[e->child_begin[n] + c] = map_of(ch);
         }
       }
+      // one storing root row per node row: the others get the top bit (map_first_kernel / map_mark_kernel); done
+      // after every composition has read the clean parent maps (compose masks the bit anyway)
+      {
+        int64_t max_rows = 1;
+        for (int n = 0; n < N; ++n) max_rows = std::max<int64_t>(max_rows, e->n_rows[n]);
+        int32_t* d_first = nullptr;
+        C3_CUDA(cudaMalloc(&d_first, (size_t)max_rows * sizeof(int32_t)));
+        for (int n = 0; n < N; ++n) {
+          if (e->children[n].empty() || n == e->root) continue;  // (tips are only gathered; the root map is the identity)
+          C3_CUDA(cudaMemsetAsync(d_first, 0x7f, (size_t)e->n_rows[n] * sizeof(int32_t), e->stream));
+          map_first_kernel<<<grid, 256, 0, e->stream>>>(map_of(n), d_first, root_rows);
+          map_mark_kernel<<<grid, 256, 0, e->stream>>>(map_of(n), d_first, root_rows);
+        }
+        cudaError_t ferr = cudaStreamSynchronize(e->stream);
+        cudaFree(d_first);
+        if (ferr != cudaSuccess) return fail(C3_ERR_CUDA, std::string("chain maps: ") + cudaGetErrorString(ferr));
+      }
       C3_CUDA(cudaGetLastError());
       C3_CUDA(cudaMemcpyAsync(e->d_node_maps, node_maps.data(), node_maps.size() * sizeof(int32_t*), cudaMemcpyHostToDevice, e->stream));
       C3_CUDA(cudaMemcpyAsync(e->d_child_maps, child_maps.data(), child_maps.size() * sizeof(int32_t*), cudaMemcpyHostToDevice, e->stream));
@@ -1743,6 +1770,7 @@ int c3_finalize(c3_engine* e) {
   e->off_small = b;   b += align_up((int64_t)(e->n_levels + 1) * sizeof(SmallLevel), 16);
   e->off_dep = b;     b += align_up((int64_t)2 * n_internal * sizeof(int32_t), 16);
   e->off_rec = b;     b += align_up((int64_t)REC_MAX_CHILDREN * n_internal * sizeof(int32_t), 16);
+  e->off_ops = b;     b += e->chain_ok ? align_up((int64_t)n_internal * sizeof(WalkOp), 16) : 0;
   e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
   e->block_bytes = b;
   C3_CUDA(cudaHostAlloc(&e->h_block, (size_t)b, cudaHostAllocDefault));
@@ -2577,9 +2605,79 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       }
     }
   }
+  // ---- walk launch?  any other dirty set of such a problem: prune4_walk_kernel evaluates every dirty node per root
+  // row, dirty children from a per-thread value stack (slots assigned here), clean ones from memory; it reduces
+  bool walk_launch = false;
+  int walk_slots = 0, walk_nP = 0, walk_ops = 0;
+  if (e->chain_ok && e->use_walk && !chain_launch && !wave && !e->rescale_active && e->comm.nranks <= 1 &&
+      recompute[e->root] && e->use_small_reduce && n_dirty_nodes <= WALK_MAX_OPS) {
+    WalkOp* ops = reinterpret_cast<WalkOp*>(e->h_block + e->off_ops);
+    std::vector<int> slot_of(N, -1);
+    std::vector<char> busy(WALK_MAX_SLOTS + 1, 0);
+    bool ok = true;
+    int n_ops = 0;
+    const int64_t root_rows = e->n_rows[e->root];
+    for (int n = 0; n < N && ok; ++n) {
+      if (!recompute[n]) continue;
+      WalkOp& op = ops[n_ops++];
+      std::memset(&op, 0, sizeof op);
+      op.out = e->h_nodes[n].out;
+      op.map_own = e->d_chain_maps + (int64_t)n * root_rows;
+      op.n_children = (int8_t)e->children[n].size();
+      op.fixed_motif = (int8_t)e->h_nodes[n].fixed_motif;
+      op.is_root = n == e->root;
+      for (int c = 0; c < 3; ++c) {
+        op.slot[c] = -1;
+        op.p_idx[c] = -1;
+      }
+      for (size_t c = 0; c < e->children[n].size(); ++c) {
+        const int ch = e->children[n][c];
+        op.src[c] = e->d_rows[ch];
+        op.P[c] = e->children[ch].empty() ? nullptr : e->d_P + (int64_t)ch * K * 16;
+        if (op.P[c] != nullptr) op.p_idx[c] = (int16_t)walk_nP++;
+        op.map_child[c] = e->d_chain_maps + (int64_t)ch * root_rows;
+        if (recompute[ch]) {
+          op.slot[c] = (int8_t)slot_of[ch];
+          busy[slot_of[ch]] = 0;  // (read before this node's own value is pushed: the slot may be taken again)
+        }
+      }
+      op.out_slot = -1;
+      if (n != e->root) {
+        int sl = 0;
+        while (sl < WALK_MAX_SLOTS && busy[sl]) ++sl;
+        if (sl == WALK_MAX_SLOTS) { ok = false; break; }
+        busy[sl] = 1;
+        slot_of[n] = sl;
+        op.out_slot = (int8_t)sl;
+        walk_slots = std::max(walk_slots, sl + 1);
+      }
+    }
+    walk_ops = n_ops;
+    auto walk_smem = [&]() {
+      return (size_t)walk_ops * sizeof(WalkOp) + (size_t)walk_slots * 2 * WALK_THREADS * sizeof(double2) +
+             (size_t)walk_nP * K * 16 * sizeof(double) + (size_t)walk_nP * sizeof(double*);
+    };
+    ok = ok && walk_smem() <= (size_t)200 * 1024;
+    if (ok && n_ops > 0) {
+      LevelLaunch ll{w_off, p_off, 0, 0, true, 0, 0, 12, 0, 0};
+      const int64_t bytes0 = alg_bytes, flops0 = flops;
+      for (int n = 0; n < N; ++n) {
+        if (!recompute[n]) continue;
+        work[w_off + ll.n_work++] = n;
+        account(n);
+        recompute[n] = 0;
+      }
+      ll.total_tiles = (int)(root_rows * K);
+      ll.bytes = alg_bytes - bytes0;
+      ll.flops = flops - flops0;
+      w_off += ll.n_work;
+      launches.push_back(ll);
+      walk_launch = true;
+    }
+  }
   bool path_launch = false;
   int path_buf_units = 0;
-  if (e->use_path && !chain_launch && !wave && !e->use_dmma && !e->rescale_active && e->comm.nranks <= 1 && recompute[e->root] &&
+  if (e->use_path && !chain_launch && !walk_launch && !wave && !e->use_dmma && !e->rescale_active && e->comm.nranks <= 1 && recompute[e->root] &&
       e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE) {
     std::vector<int> chain;
     bool ok = true;
@@ -2627,7 +2725,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   std::vector<int> lv_stream;
   int n_streams_used = 1;
   {
-    bool streams = e->use_streams && !e->rescale_active && wave == nullptr && !path_launch && !chain_launch && !e->use_flow &&
+    bool streams = e->use_streams && !e->rescale_active && wave == nullptr && !path_launch && !chain_launch && !walk_launch && !e->use_flow &&
                    !e->profiling && e->batch_mode == 0 && e->children[e->root].size() >= 2;
     if (streams) {
       // worth it only when at least two subtrees have a level that streams (more units than the cluster takes)
@@ -2668,7 +2766,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   // ---- recomputing launches: runs of consecutive small / medium levels, REC_DEPTH + 1 levels per launch -------
   std::vector<int> rec_phase(std::max(e->n_levels, n_groups) + 2, -1);  // level -> phase (launch) number, -1: the usual launches
   std::vector<int> rec_first;                        // first level of every phase
-  if (e->use_rec && by_level && !e->use_dmma && e->use_small && !e->rescale_active && !path_launch && !chain_launch) {
+  if (e->use_rec && by_level && !e->use_dmma && e->use_small && !e->rescale_active && !path_launch && !chain_launch && !walk_launch) {
     std::vector<int64_t> level_units(e->n_levels + 2, 0);
     std::vector<char> level_ok(e->n_levels + 2, 0);
     for (int l = 1; l <= e->n_levels; ++l) {
@@ -2917,7 +3015,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   // small problems whose root sits in the (last) small-levels launch: that launch also reduces
   // (prune4_small_kernel's tail: the same tiles and summation trees, one launch fewer)
   e->last_chain = chain_launch;
-  const bool fuse_reduce = path_launch || chain_launch ||
+  e->last_walk = walk_launch;
+  const bool fuse_reduce = path_launch || chain_launch || walk_launch ||
                            (e->use_small_reduce && !launches.empty() && launches.back().kind == 1 &&
                             launches.back().grid == 0 && launches.back().is_root && !e->rescale_active && comm.nranks <= 1 &&
                             e->n_rows[e->root] <= (int64_t)SMALL_REDUCE_MAX_TILES * REDUCE_ROWS_PER_TILE);
@@ -3065,7 +3164,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       a.bprobs = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
     }
     a.tl = tl_slot(ll.is_root ? 100 + ll.kind : ll.kind);
-    ProfScope ps(e, (ll.kind == 1 || ll.kind == 9 || ll.kind == 10 || ll.kind == 11) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
+    ProfScope ps(e, (ll.kind == 1 || ll.kind == 9 || ll.kind == 10 || ll.kind == 11 || ll.kind == 12) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
     if (ll.kind == 1) {
       const SmallLevel* d_small = reinterpret_cast<const SmallLevel*>(e->d_block + e->off_small) + ll.small_off;
       if (ll.grid > 0) {
@@ -3145,6 +3244,34 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       const int32_t* d_child = reinterpret_cast<const int32_t*>(e->d_block + e->off_rec) + (int64_t)ll.work_off * REC_MAX_CHILDREN;
       cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_rec_kernel, a, d_child);
       if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("rec launch: ") + cudaGetErrorString(err));
+    } else if (ll.kind == 12) {
+      const size_t smem = (size_t)walk_ops * sizeof(WalkOp) + (size_t)walk_slots * 2 * WALK_THREADS * sizeof(double2) +
+                          (size_t)walk_nP * K * 16 * sizeof(double) + (size_t)walk_nP * sizeof(double*);
+      static DeviceOnce walk_cfg;
+      if (walk_cfg.need(e->device)) {
+        int rc = set_max_smem(prune4_walk_kernel, (size_t)200 * 1024);
+        if (rc) return rc;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)((ll.total_tiles + WALK_THREADS - 1) / WALK_THREADS));
+      cfg.blockDim = dim3(WALK_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = e->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ReduceTail tail{};
+      tail.bprobs = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
+      tail.counts = e->d_counts;
+      tail.n_rows = e->n_rows[e->root];
+      tail.n_tiles = (int)((tail.n_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
+      tail.sink = sink;
+      const WalkOp* d_ops = reinterpret_cast<const WalkOp*>(e->d_block + e->off_ops);
+      cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_walk_kernel, a, d_ops, ll.n_work, walk_slots, walk_nP, tail,
+                                           e->d_chain_ctr, e->d_tile_sums);
+      if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("walk launch: ") + cudaGetErrorString(err));
     } else if (ll.kind == 11) {
       static DeviceOnce chain_cfg;
       if (chain_cfg.need(e->device)) {
@@ -3310,7 +3437,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     std::vector<int32_t> sig;
     sig.reserve(16 + 8 * launches.size() + w_off);
     sig.push_back(n_eigen); sig.push_back(n_pade); sig.push_back((int32_t)std::min(used, e->block_bytes));
-    sig.push_back((e->rescale_active ? 1 : 0) | (fuse_reduce ? 2 : 0) | (lean ? 4 : 0));
+    sig.push_back((e->rescale_active ? 1 : 0) | (fuse_reduce ? 2 : 0) | (lean ? 4 : 0) | (walk_slots << 8) | (walk_nP << 16));
     sig.push_back((int32_t)((uintptr_t)device_out & 0xffffffffu)); sig.push_back((int32_t)((uintptr_t)device_out >> 32));
     sig.push_back((blocking || deferred) ? 1 : 0);
     sig.push_back((int32_t)((uintptr_t)e->stream & 0xffffffffu)); sig.push_back((int32_t)((uintptr_t)e->stream >> 32));

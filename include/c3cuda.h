@@ -64,6 +64,7 @@ typedef struct c3_stats {
   int64_t wave_noops;         /* ... of which no-op positions                   */
   int64_t lean_evaluations;   /* evaluations whose root launch wrote the class mixture (8 B per row) instead of lh */
   int64_t chain_launches;     /* single-path updates walked per root row by the chain kernel (no level barriers) */
+  int64_t walk_launches;      /* other evaluations of small problems walked per root row (tree-walk kernel)     */
 } c3_stats;
 
 C3_API int c3_abi_version(void);

@@ -691,3 +691,78 @@ def test_chain_kernel_single_branch_updates_bit_identical(model, n_tips, L, bins
     last = a.get_log_likelihood()
     a.engine.invalidate()
     assert a.engine.evaluate() == last
+
+
+@pytest.mark.parametrize(
+    "model,n_tips,L,bins,rooted",
+    [("HKY85", 24, 3000, 1, False), ("GTR", 17, 1800, 4, False), ("HKY85", 9, 700, 2, True), ("GTR", 60, 1500, 4, False)],
+)
+def test_walk_kernel_bit_identical(model, n_tips, L, bins, rooted, monkeypatch):
+    """every evaluation of a small problem that is not a single path -- full sweeps, several branches at once, a
+    rate-matrix parameter -- by the tree-walk kernel (one launch, every root row evaluates the dirty nodes itself,
+    dirty children from a per-thread value stack) against the small-levels launch (C3_WALK=0, C3_CHAIN=0): lnL,
+    every partial row and lh bit-identical, through graph replays, with fixed motifs and ambiguity codes"""
+    from cogent3_b200.tree import Topology
+
+    m = hostmodels.get_model(model)
+    topo, lengths, codes = make_workload(n_tips, L, 4, kind="evolved", seed=33)
+    if rooted:
+        topo, lengths = Topology.from_newick("(((a:0.1,b:0.2):0.1,(c:0.3,d:0.2):0.05):0.1,((e:0.1,f:0.1):0.2,(g:0.2,(h:0.1,i:0.3):0.1):0.1):0.2);")
+        codes = codes[: int(np.sum(topo.is_tip))]
+    rows = np.vstack([np.eye(4), [[1.0, 0.0, 1.0, 0.0], [1.0, 1.0, 1.0, 1.0]]])
+    codes = codes.copy()
+    amb = np.random.default_rng(19).random(codes.shape)
+    codes[amb < 0.015] = 4
+    codes[amb > 0.985] = 5
+
+    def build(walk):
+        monkeypatch.setenv("C3_WALK", "1" if walk else "0")
+        monkeypatch.setenv("C3_CHAIN", "1" if walk else "0")
+        monkeypatch.setenv("C3_GRAPH_AFTER", "2")
+        lf = LikelihoodFunction(m, topo, bins=bins)
+        lf.set_alignment(codes.astype(np.int64), rows)
+        lf.set_motif_probs_from_data()
+        lf.lengths[:-1] = np.asarray(lengths)[:-1]
+        for k, p in enumerate(m.parameter_order):
+            lf.set_param_rule(p, value=0.5 + 0.37 * k)
+        if bins > 1:
+            lf.set_param_rule("rate_shape", value=0.6)
+        return lf
+
+    a, b = build(True), build(False)
+    assert a.get_log_likelihood() == b.get_log_likelihood()  # the first full sweep
+    rng = np.random.default_rng(4)
+    internal = [n for n in range(topo.n_nodes) if not topo.is_tip[n]]
+    edges = list(topo.edges)
+
+    def same_state():
+        for n in internal:
+            for bin_ in range(bins):
+                np.testing.assert_array_equal(a.engine.get_partials(n, bin_), b.engine.get_partials(n, bin_))
+        for bin_ in range(bins):
+            np.testing.assert_array_equal(a.engine.get_lh(bin_), b.engine.get_lh(bin_))
+
+    same_state()
+    for step in range(24):
+        if step % 4 == 0:  # a rate-matrix parameter: everything moves
+            for lf in (a, b):
+                lf.set_param_rule(m.parameter_order[0], value=0.4 + 0.05 * step)
+        else:  # two or three branches at once: the dirty set is a union of paths, the same structures revisited
+            pick = [edges[(7 * step + 3 * k) % len(edges)] for k in range(2 + step % 2)]
+            for n in pick:
+                v = float(rng.uniform(0.01, 0.6))
+                for lf in (a, b):
+                    lf.set_param_rule("length", edge=topo.names[n], value=v)
+        va, vb = a.get_log_likelihood(), b.get_log_likelihood()
+        assert va == vb, (step, va, vb)
+        if step == 9:
+            fm = np.full(topo.n_nodes, -1, np.int32)
+            fm[internal[len(internal) // 3]] = 1
+            for lf in (a, b):
+                lf.engine.set_fixed_motifs(fm)
+            assert a.engine.evaluate() == b.engine.evaluate()
+        if step in (3, 10, 23):
+            same_state()
+    sa, sb = a.engine.stats(), b.engine.stats()
+    assert sb["walk_launches"] == 0 and sb["chain_launches"] == 0
+    assert sa["walk_launches"] >= 12 and sa["graph_replays"] > 0  # (some picks of a small tree are a single path: chain launches)

@@ -23,10 +23,9 @@ except Exception as e: print('no line', e)
 PY
 )"
   grep "c3 hostprof" $OUT/${TAG}_${name}.err | sed -n 1,3p
-  grep "kind 111" $OUT/${TAG}_${name}.err | tail -3
+  grep "kind 11[12]" $OUT/${TAG}_${name}.err | tail -4
 }
 CFG="--config c1"
-run c1_fused C3_HOSTPROF=1
-run c1_fused_tl C3_TIMELINE=1
-run c1_unfused C3_CHAIN_FUSED=0 C3_HOSTPROF=1
-run c1_nochain C3_CHAIN=0
+run c1_walk C3_HOSTPROF=1
+run c1_walk_tl C3_TIMELINE=1
+run c1_nowalk C3_WALK=0 C3_HOSTPROF=1
