@@ -76,6 +76,8 @@ struct PruneArgs {
   // developer timeline (C3_TIMELINE=1): [entry_min, start_min (after the dependency wait), end_min, end_max] in
   // globaltimer ns, per launch
   unsigned long long* tl = nullptr;
+  // dynamic strips (prune4_reg2_kernel<..., DYN>): this launch's claim counter, zero at launch
+  int32_t* strip_ctr = nullptr;
 };
 
 // Site-pattern shards on several GPUs of one node: the reduction's last CTA exchanges the shard

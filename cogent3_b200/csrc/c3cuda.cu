@@ -177,6 +177,8 @@ struct c3_engine {
   // bytes in flight per SM in steps half as long -- the drain and the last-strip imbalance of a launch scale with
   // the step
   bool reg2_u2 = false;
+  bool use_dyn = false;   // C3_DYN=1: strips past a warp's first five are claimed from a per-launch counter
+  int64_t off_ctr = 0;    // [DYN_MAX_LAUNCHES] int32 zeros in the parameter block
   int root_u = 3;  // rows per lane of the three-children instance: 3 (8 warps, 255 registers) or 2 (12 warps, C3_ROOT_U=2)
   // lean root (C3_LEAN_ROOT=0 disables): the regpipe2 root launch writes mix[p] (8 B per row) instead of lh[p][K]
   // and the reduction reads mix + counts only; lh is recomputed by the root launch alone when an accessor asks for
@@ -496,6 +498,7 @@ int launch_flow(c3_engine* e, const PruneArgs& a, const int32_t* d_dep, unsigned
   return C3_OK;
 }
 
+constexpr int DYN_MAX_LAUNCHES = 64;
 template <int K, int NC, int U, int WARPS>
 int launch_reg2_cfg(c3_engine* e, const PruneArgs& a, bool is_root);
 
@@ -507,6 +510,24 @@ int launch_reg2(c3_engine* e, const PruneArgs& a, bool is_root) {
 
 template <int K, int NC, int U, int WARPS>
 int launch_reg2_cfg(c3_engine* e, const PruneArgs& a, bool is_root) {
+  const int grid0 = std::max(1, std::min(e->n_sm, (a.total_tiles + WARPS - 1) / WARPS));
+  if (e->use_dyn && a.strip_ctr != nullptr && a.total_tiles > 8 * grid0 * WARPS) {
+    // dynamic strips (C3_DYN=1): the same kernel, strips past a warp's first five claimed from a counter
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid0);
+    cfg.blockDim = dim3(WARPS * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t err = is_root ? cudaLaunchKernelEx(&cfg, prune4_reg2_kernel<K, NC, U, WARPS, true, true>, a)
+                              : cudaLaunchKernelEx(&cfg, prune4_reg2_kernel<K, NC, U, WARPS, false, true>, a);
+    if (err != cudaSuccess) return fail(C3_ERR_CUDA, std::string("regpipe2 (dynamic) launch: ") + cudaGetErrorString(err));
+    return C3_OK;
+  }
   const int grid = std::max(1, std::min(e->n_sm, (a.total_tiles + WARPS - 1) / WARPS));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -977,6 +998,7 @@ int c3_create(int device, int n_nodes, int n_states, int n_bins, const int32_t* 
   if (const char* env = getenv("C3_RING")) e->use_ring = atoi(env) != 0;
   if (const char* env = getenv("C3_REG1")) e->use_reg2 = atoi(env) == 0;
   if (const char* env = getenv("C3_REG2_U2")) e->reg2_u2 = atoi(env) != 0;
+  if (const char* env = getenv("C3_DYN")) e->use_dyn = atoi(env) != 0;
   if (const char* env = getenv("C3_ROOT_U")) e->root_u = atoi(env) == 2 ? 2 : 3;
   if (const char* env = getenv("C3_LEAN_ROOT")) e->lean_root = atoi(env) != 0;
   if (const char* env = getenv("C3_TIMELINE")) e->timeline = atoi(env) != 0;
@@ -1770,10 +1792,12 @@ int c3_finalize(c3_engine* e) {
   e->off_small = b;   b += align_up((int64_t)(e->n_levels + 1) * sizeof(SmallLevel), 16);
   e->off_dep = b;     b += align_up((int64_t)2 * n_internal * sizeof(int32_t), 16);
   e->off_rec = b;     b += align_up((int64_t)REC_MAX_CHILDREN * n_internal * sizeof(int32_t), 16);
+  e->off_ctr = b;     b += align_up((int64_t)DYN_MAX_LAUNCHES * sizeof(int32_t), 16);
   e->off_ops = b;     b += e->chain_ok ? align_up((int64_t)n_internal * sizeof(WalkOp), 16) : 0;
   e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
   e->block_bytes = b;
   C3_CUDA(cudaHostAlloc(&e->h_block, (size_t)b, cudaHostAllocDefault));
+  std::memset(e->h_block, 0, (size_t)b);  // (the claim counters of the dynamic-strip launches travel as zeros)
   C3_CUDA(cudaMalloc(&e->d_block, (size_t)b));
   C3_CUDA(cudaStreamSynchronize(e->stream));
 
@@ -3164,6 +3188,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
       a.bprobs = reinterpret_cast<const double*>(e->d_block + e->off_bprobs);
     }
     a.tl = tl_slot(ll.is_root ? 100 + ll.kind : ll.kind);
+    if (e->use_dyn && li < (size_t)DYN_MAX_LAUNCHES)
+      a.strip_ctr = reinterpret_cast<int32_t*>(e->d_block + e->off_ctr) + li;
     ProfScope ps(e, (ll.kind == 1 || ll.kind == 9 || ll.kind == 10 || ll.kind == 11 || ll.kind == 12) ? 5 : (ll.is_root ? 3 : 2), ll.bytes, ll.flops);
     if (ll.kind == 1) {
       const SmallLevel* d_small = reinterpret_cast<const SmallLevel*>(e->d_block + e->off_small) + ll.small_off;

@@ -291,7 +291,7 @@ __device__ __forceinline__ void tl_end(unsigned long long* tl) {
 // ---------------------------------------------------------------------------------------
 // Instantiated as <K, 2 children, U = 4 rows per lane, 8 warps> (248 registers) and, for the
 // trifurcating root, <K, 3, 2, 12> (strips of 64 units, 12 warps per SM instead of regpipe's 6).
-template <int K, int NC, int U, int WARPS, bool ROOT>
+template <int K, int NC, int U, int WARPS, bool ROOT, bool DYN = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneArgs a) {
   constexpr int ROWS = 32 * U / K;  // pattern rows per strip
   __shared__ StripSmem<NC> sd;
@@ -350,9 +350,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
     for (int c = 0; c < NC; ++c) gsrc[c] = sd.work[g_w].src[c];
   };
 
-  // compute strip s from x; refill x with strip s + 2 GW (indexes ix, requested two steps ago);
-  // then request the indexes of strip s + 4 GW into ix
-  auto step = [&](d4(&x)[NC][U], int32_t(&ix)[NC][U], int s) {
+  // compute strip s from x; refill x with strip s2 (= s + 2 GW; indexes ix, requested two steps ago);
+  // then request the indexes of strip s4 (= s + 4 GW) into ix
+  auto step = [&](d4(&x)[NC][U], int32_t(&ix)[NC][U], int s, int s2, int s4) {
     while (s >= sd.prefix[c_w + 1]) ++c_w;
     const WorkDesc<NC>& wd = sd.work[c_w];
     if (c_w != p_w) {
@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
       p_w = c_w;
       __syncwarp();
     }
-    const bool refill = s + 2 * GW < total;
-    if (refill) gather_seek(s + 2 * GW);
+    const bool refill = s2 < total;
+    if (refill) gather_seek(s2);
     d4 acc[U];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
         for (int u = 0; u < U; ++u) x[c][u] = ld256_nc(gsrc[c] + ((int64_t)ix[c][u] * K + b) * 4);
       }
     }
-    if (s + 4 * GW < total) load_idx(ix, s + 4 * GW);
+    if (s4 < total) load_idx(ix, s4);
     const int64_t node_row0 = (int64_t)(s - sd.prefix[c_w]) * ROWS;
     const int c_fixed = wd.fixed_motif;
 #pragma unroll
@@ -443,10 +443,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune4_reg2_kernel(const PruneA
   if (gw + 2 * GW < total) load_idx(ia, gw + 2 * GW);
   if (gw + 3 * GW < total) load_idx(ib, gw + 3 * GW);
 
+  if (!DYN) {
 #pragma unroll 1
-  for (int s = gw; s < total; s += 2 * GW) {
-    step(xa, ia, s);
-    if (s + GW < total) step(xb, ib, s + GW);
+    for (int s = gw; s < total; s += 2 * GW) {
+      step(xa, ia, s, s + 2 * GW, s + 4 * GW);
+      if (s + GW < total) step(xb, ib, s + GW, s + 3 * GW, s + 5 * GW);
+    }
+  } else {
+    // DYNAMIC strips (C3_DYN=1): the first five strips of a warp are the static ones (gw + k GW), every further
+    // one is claimed from a counter (a.strip_ctr, zeroed with the parameter block) one step before its indexes
+    // are requested -- five steps before it is computed.  A warp on a slow SM then simply claims fewer strips: the
+    // 4-9 us between the first and the last warp leaving a launch (lesson 17a) are what this is after.  Claims
+    // grow monotonically, so the forward cursors keep working; per-strip arithmetic is untouched: bit-identical.
+    int w0 = gw, w1 = gw + GW, w2 = gw + 2 * GW, w3 = gw + 3 * GW, w4 = gw + 4 * GW;
+    int claim = 0;
+    auto claim_next = [&]() {
+      if (lane == 0) claim = atomicAdd(a.strip_ctr, 1);
+    };
+    auto rotate = [&]() {
+      w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+      // (a negative sum after an overflow would restart at strip 0: clamp)
+      const int c = __shfl_sync(0xffffffffu, claim, 0);
+      w4 = (c < total) ? 5 * GW + c : total;
+    };
+#pragma unroll 1
+    while (w0 < total) {
+      claim_next();
+      step(xa, ia, w0, w2, w4);
+      rotate();
+      if (w0 >= total) break;
+      claim_next();
+      step(xb, ib, w0, w2, w4);
+      rotate();
+    }
   }
   if (lane == 0) tl_end(a.tl);
 }
@@ -823,7 +852,6 @@ prune4_chain_kernel(const PruneArgs a, const ChainParams cp,
   const int K = a.K, n_work = a.n_work, t = (int)threadIdx.x;
   pdl_trigger();
   if (t == 0) tl_first(a.tl, 0);
-  if (t < 4) s_bp[t] = cp.bprobs[t];
   for (int i = t; i < n_work; i += CHAIN_THREADS) {
     const int node = cp.work_node[i];
     const NodeDesc nd = a.nodes[node];
@@ -872,6 +900,14 @@ prune4_chain_kernel(const PruneArgs a, const ChainParams cp,
   }
   pdl_wait();  // the expm launch's P matrices / tip tables; the rows and counters of the previous evaluation
   if (t == 0) tl_first(a.tl, 1);
+  // pi and the bin probabilities are VALUES, not structure: a launch that is replayed from a CUDA graph (its
+  // arguments frozen at capture) must read them from the parameter block, which every replay copies afresh; only
+  // the fused launch -- never captured -- carries them by value.  (The path itself is structure: it is part of the
+  // graph's signature.)
+  double pi[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pi[q] = fused ? cp.pi[q] : a.pi[q];
+  if (t < 4) s_bp[t] = fused ? cp.bprobs[t] : (t < K ? tail.bprobs[t] : 0.0);
   const bool fused_tip = fused && sm.childs[cp.edge_slot].P == nullptr;  // the changed branch ends in a tip
   {
     const int per_item = CHAIN_MAX_CHILDREN * K * 16;
@@ -951,7 +987,7 @@ prune4_chain_kernel(const PruneArgs a, const ChainParams cp,
       if (active) {
         if (nd.out != nullptr && own[i] >= 0) st256(nd.out + ((int64_t)own[i] * K + b) * 4, acc);
         if (nd.is_root) {
-          const double lh = fma(acc.w, cp.pi[3], fma(acc.z, cp.pi[2], fma(acc.y, cp.pi[1], acc.x * cp.pi[0])));
+          const double lh = fma(acc.w, pi[3], fma(acc.z, pi[2], fma(acc.y, pi[1], acc.x * pi[0])));
           a.lh_out[p * K + b] = lh;
         }
       }
@@ -991,197 +1027,6 @@ prune4_chain_kernel(const PruneArgs a, const ChainParams cp,
     counters[0] = 0u;
     publish_result(tail.sink, result);
     tl_end(a.tl);  // (slot 3, the latest stamp: the result is out)
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// 4-state "tree walk" kernel: ANY evaluation of a small problem (full sweeps included) in one launch with no
-// barrier between the levels -- the chain kernel's idea for an arbitrary set of dirty nodes.
-//
-// The thread of (root row p, bin b) evaluates every dirty node, children before parents, for the ONE row of
-// each node that root row p looks at (map_n[p]).  A clean child's row (a tip's pre-multiplied row, an internal
-// node that did not change) is gathered from memory at map_child[p]; a dirty child's value was computed by this
-// very thread a few steps earlier and waits in a slot of a per-thread value stack in shared memory (slots
-// assigned by the host: a value's slot is free again once its parent is done).  Every node row is also stored
-// (later partial updates read it; root rows that share a lower row store the same bits), lh is written at the
-// root, the tiles are reduced as in the chain kernel.  The work is redundant -- a lower node has fewer distinct
-// rows than the root has patterns -- and irrelevant at this size: brca1 (35 internal nodes, 2764 x K units) is
-// ~100k matvecs more, against 11 levels x (cluster barrier + two dependent global latencies) saved.
-// Arithmetic per row as in every 4-state kernel: bit-identical.
-// ---------------------------------------------------------------------------------------
-constexpr int WALK_MAX_OPS = 224;    // dirty nodes one launch walks (descriptors staged in shared memory)
-constexpr int WALK_MAX_SLOTS = 20;   // live values per thread (8 KB of shared memory per slot)
-constexpr int WALK_THREADS = REDUCE_THREADS;
-
-struct WalkOp {
-  double* out;             // the node's rows (nullptr: the root's are not stored)
-  const int32_t* map_own;  // root row -> row of the node
-  const double* src[3];    // clean child: its rows
-  const double* P[3];      // P of the branch to child c (nullptr: the child's rows are already multiplied, tips)
-  const int32_t* map_child[3];
-  int8_t n_children;
-  int8_t slot[3];          // >= 0: child c is dirty, its value waits in this stack slot; -1: gather from memory
-  int8_t out_slot;         // where this node's value goes (-1: nobody above needs it, the root)
-  int8_t fixed_motif;
-  int8_t is_root;
-  int8_t pad;
-  int16_t p_idx[3];        // P[c] staged in shared memory: entry number ([K][16] doubles each), -1: none
-  int16_t pad2;
-  int64_t pad3;
-};
-static_assert(sizeof(WalkOp) == 112, "WalkOp layout");
-
-__global__ void __launch_bounds__(WALK_THREADS)
-prune4_walk_kernel(const PruneArgs a, const WalkOp* __restrict__ ops, int n_ops, int n_slots, int n_P, const ReduceTail tail,
-                   unsigned int* __restrict__ counters, double* __restrict__ tile_sums) {
-  extern __shared__ __align__(16) unsigned char walk_raw[];
-  // [n_ops] descriptors | [n_slots][2][threads] value stack | [n_P][K][16] P matrices | [n_P] their addresses
-  WalkOp* s_ops = reinterpret_cast<WalkOp*>(walk_raw);
-  double2* s_stack = reinterpret_cast<double2*>(walk_raw + (size_t)n_ops * sizeof(WalkOp));
-  double* s_P = reinterpret_cast<double*>(s_stack + (size_t)n_slots * 2 * WALK_THREADS);
-  const double** s_Pptr = reinterpret_cast<const double**>(s_P + (size_t)n_P * a.K * 16);
-  __shared__ double s_warp[WALK_THREADS / 32];
-  __shared__ bool s_last;
-  const int K = a.K, t = (int)threadIdx.x;
-  pdl_trigger();
-  if (t == 0) tl_first(a.tl, 0);
-  pdl_wait();  // the parameter block is this evaluation's; P matrices / tip tables of the expm launch
-  if (t == 0) tl_first(a.tl, 1);
-  {
-    const int4* g = reinterpret_cast<const int4*>(ops);
-    int4* d = reinterpret_cast<int4*>(s_ops);
-    for (int i = t; i < n_ops * (int)(sizeof(WalkOp) / 16); i += WALK_THREADS) d[i] = g[i];
-  }
-  __syncthreads();
-  const int64_t total = tail.n_rows * K;
-  const int64_t u = (int64_t)blockIdx.x * WALK_THREADS + t;
-  const bool active = u < total;
-  const int64_t p = active ? u / K : 0;
-  const int b = active ? (int)(u - p * K) : 0;
-  auto push = [&](int slot, const d4& v) {
-    s_stack[(slot * 2 + 0) * WALK_THREADS + t] = make_double2(v.x, v.y);
-    s_stack[(slot * 2 + 1) * WALK_THREADS + t] = make_double2(v.z, v.w);
-  };
-  auto pop = [&](int slot) {
-    const double2 lo = s_stack[(slot * 2 + 0) * WALK_THREADS + t], hi = s_stack[(slot * 2 + 1) * WALK_THREADS + t];
-    return d4{lo.x, lo.y, hi.x, hi.y};
-  };
-  // software pipeline over the ops (every address is static: it only depends on p)
-  auto load_idx = [&](int j, int32_t(&ix)[4]) {
-    if (j >= n_ops) return;
-    const WalkOp& op = s_ops[j];
-    ix[3] = (op.out != nullptr) ? __ldg(op.map_own + p) : -1;  // (negative: another root row stores this row)
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      if (c < op.n_children && op.slot[c] < 0) ix[c] = __ldg(op.map_child[c] + p);  // (top bit masked at use: no wait here)
-  };
-  auto load_rows = [&](int j, const int32_t(&ix)[4], d4(&x)[3]) {
-    if (j >= n_ops) return;
-    const WalkOp& op = s_ops[j];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      if (c < op.n_children && op.slot[c] < 0) x[c] = ld256(op.src[c] + ((int64_t)(ix[c] & 0x7fffffff) * K + b) * 4);
-  };
-  // the P matrices of the walk into shared memory (read at use from global memory they cost every op an L2 round
-  // trip per child -- a launch starts with a cold L1 -- which is what the first version spent its time on)
-  for (int i = t; i < n_ops * 3; i += WALK_THREADS) {
-    const int j = i / 3, c = i - j * 3;
-    if (s_ops[j].p_idx[c] >= 0) s_Pptr[s_ops[j].p_idx[c]] = s_ops[j].P[c];
-  }
-  __syncthreads();
-  for (int i = t; i < n_P * K * 16; i += WALK_THREADS) s_P[i] = s_Pptr[i / (K * 16)][i % (K * 16)];
-  __syncthreads();
-  // FOUR ops in flight per thread, each with its own row buffer and index set (no register is ever copied from one
-  // stage to the next: a move would wait for the load it moves): after op j is computed from buffer q, the rows
-  // of op j + 4 are requested into the same buffer with the indexes requested four ops earlier, and the indexes
-  // of op j + 8 are requested -- an op costs a quarter of an L2 round trip
-  auto step = [&](d4(&x)[3], int32_t(&ix)[4], int32_t& own, int j) {
-    const WalkOp& op = s_ops[j];
-    d4 acc{1.0, 1.0, 1.0, 1.0};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (c < op.n_children) {
-        const d4 v = (op.slot[c] >= 0) ? pop(op.slot[c]) : x[c];
-        d4 y = v;
-        if (op.p_idx[c] >= 0) y = matvec4(s_P + ((int)op.p_idx[c] * K + b) * 16, v);
-        if (c == 0) acc = y;
-        else { acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w; }
-      }
-    }
-    if (op.fixed_motif >= 0) {
-      if (op.fixed_motif != 0) acc.x = 0.0;
-      if (op.fixed_motif != 1) acc.y = 0.0;
-      if (op.fixed_motif != 2) acc.z = 0.0;
-      if (op.fixed_motif != 3) acc.w = 0.0;
-    }
-    if (op.out_slot >= 0) push(op.out_slot, acc);
-    if (active) {
-      if (own >= 0) st256(op.out + ((int64_t)own * K + b) * 4, acc);
-      if (op.is_root) {
-        const double lh = fma(acc.w, a.pi[3], fma(acc.z, a.pi[2], fma(acc.y, a.pi[1], acc.x * a.pi[0])));
-        a.lh_out[p * K + b] = lh;
-      }
-    }
-    if (j + 4 < n_ops) {
-      load_rows(j + 4, ix, x);
-      own = ix[3];
-      load_idx(j + 8, ix);
-    }
-  };
-  int32_t ia[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0}, ic[4] = {0, 0, 0, 0}, id[4] = {0, 0, 0, 0};
-  int32_t oa, ob, oc, od;
-  d4 xa[3], xb[3], xc[3], xd[3];
-  load_idx(0, ia);
-  load_idx(1, ib);
-  load_idx(2, ic);
-  load_idx(3, id);
-  load_rows(0, ia, xa);
-  load_rows(1, ib, xb);
-  load_rows(2, ic, xc);
-  load_rows(3, id, xd);
-  oa = ia[3]; ob = ib[3]; oc = ic[3]; od = id[3];
-  load_idx(4, ia);
-  load_idx(5, ib);
-  load_idx(6, ic);
-  load_idx(7, id);
-#pragma unroll 1
-  for (int j = 0; j < n_ops; j += 4) {
-    step(xa, ia, oa, j);
-    if (j + 1 < n_ops) step(xb, ib, ob, j + 1);
-    if (j + 2 < n_ops) step(xc, ic, oc, j + 2);
-    if (j + 3 < n_ops) step(xd, id, od, j + 3);
-  }
-  if (t == 0) tl_end(a.tl);
-  // ---- reduction: as in the chain kernel ----
-  __threadfence();
-  __syncthreads();
-  const int ctas_per_tile = REDUCE_ROWS_PER_TILE * K / WALK_THREADS;
-  const int tile = (int)blockIdx.x / ctas_per_tile;
-  const int ctas_here = min(ctas_per_tile, (int)gridDim.x - tile * ctas_per_tile);
-  if (t == 0) s_last = atomicAdd(counters + 1 + tile, 1u) == (unsigned)(ctas_here - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  {
-    const double acc = reduce_tile_partial(a.lh_out, tail.bprobs, tail.counts, tail.n_rows, K, tile, t, nullptr);
-    const double total_t = block_sum(acc, s_warp);
-    if (t == 0) {
-      tile_sums[tile] = total_t;
-      counters[1 + tile] = 0u;
-      __threadfence();
-      s_last = atomicAdd(counters, 1u) == (unsigned)(tail.n_tiles - 1);
-    }
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  double acc = 0.0;
-  for (int i = t; i < tail.n_tiles; i += REDUCE_THREADS) acc += __ldcg(tile_sums + i);
-  const double result = block_sum(acc, s_warp);
-  if (t == 0) {
-    counters[0] = 0u;
-    publish_result(tail.sink, result);
-    tl_end(a.tl);
   }
 }
 

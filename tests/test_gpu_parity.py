@@ -203,7 +203,7 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
         codes = codes[: int(np.sum(topo.is_tip))]
 
     def build(env):
-        for k in ("C3_FLOW", "C3_RING", "C3_NO_STRIP", "C3_NO_SMALL", "C3_REG1", "C3_REG2_U2", "C3_ROOT_U"):
+        for k in ("C3_FLOW", "C3_RING", "C3_NO_STRIP", "C3_NO_SMALL", "C3_REG1", "C3_REG2_U2", "C3_ROOT_U", "C3_DYN"):
             monkeypatch.delenv(k, raising=False)
         for k in env:
             name, _, value = k.partition("=")
@@ -219,7 +219,7 @@ def test_four_state_kernel_families_bit_identical(model, n_tips, L, bins, kind, 
         return lf
 
     variants = [(), ("C3_REG1",), ("C3_FLOW",), ("C3_RING",), ("C3_NO_STRIP",), ("C3_NO_SMALL",), ("C3_FLOW", "C3_NO_SMALL"),
-                ("C3_REG2_U2",), ("C3_ROOT_U=2",)]
+                ("C3_REG2_U2",), ("C3_ROOT_U=2",), ("C3_DYN",)]
     lfs = [build(v) for v in variants]
     vals = [lf.get_log_likelihood() for lf in lfs]
     assert len(set(vals)) == 1, vals
@@ -607,6 +607,10 @@ def test_phylo_hmm_reduction_over_the_sites(n_tips, L, rescale):
     assert abs(got - want) <= 1e-10 * abs(want), (got, want)
 
 
+def rng_bp(k, bins):
+    return np.random.default_rng(100 + k).dirichlet(np.ones(bins) * 6.0)
+
+
 @pytest.mark.parametrize(
     "model,n_tips,L,bins,rooted",
     [("HKY85", 24, 3000, 1, False), ("GTR", 17, 1800, 4, False), ("HKY85", 9, 700, 2, True), ("GTR", 40, 2000, 4, False)],
@@ -678,6 +682,23 @@ def test_chain_kernel_single_branch_updates_bit_identical(model, n_tips, L, bins
             for lf in (a, b, c):
                 lf.engine.set_fixed_motifs(fm)
             assert a.engine.evaluate() == b.engine.evaluate() == c.engine.evaluate()
+    # VALUES that are not structure -- the root motif probabilities, the bin probabilities -- must reach a launch
+    # that is replayed from a graph (a change of pi dirties the root alone: a one-node path, the same structure
+    # every time; this is what the reference's own test_discrete_vs_general1 found)
+    for k in range(6):
+        pi = rng.dirichlet(np.ones(4) * 8.0)
+        for lf in (a, b, c):
+            lf.engine.set_root_mprobs(pi)
+            if bins > 1 and k % 2:
+                lf.engine.set_bin_probs(rng_bp(k, bins))
+        va, vb, vc = a.engine.evaluate(), b.engine.evaluate(), c.engine.evaluate()
+        assert va == vb == vc, (k, va, vb, vc)
+        n = edges[k % len(edges)]
+        for lf in (a, b, c):
+            lf.set_param_rule("length", edge=topo.names[n], value=0.07 + 0.01 * k)
+        # (the mirror API re-sets its own pi / bprobs when it evaluates: compare at engine level again afterwards)
+        va, vb, vc = a.get_log_likelihood(), b.get_log_likelihood(), c.get_log_likelihood()
+        assert va == vb == vc, (k, va, vb, vc)
     # every branch moved: the next full sweep reads the tables the fused launches wrote back
     for lf in (a, b, c):
         lf.set_param_rule("rate_shape" if bins > 1 else m.parameter_order[0], value=0.77)
