@@ -588,16 +588,28 @@ def _build(cogent3_modules):
                 # (re)assign exponentiators to q slots: whenever a rate-matrix parameter moved.  The E*K
                 # entries name only a few DISTINCT objects (one for a time-homogeneous model, one per edge
                 # with per-edge Q), so the per-entry work is numpy's: ids -> unique -> slot of each
-                ids = np.fromiter(map(id, qds), dtype=np.int64, count=len(qds))
-                _uniq, first, inverse = np.unique(ids, return_index=True, return_inverse=True)
-                slot_of_uniq = np.empty(len(first), np.int32)
                 live, host = set(), {}
-                for u, f in enumerate(first):
-                    slot = self._slot_for(st, qds[int(f)])
-                    slot_of_uniq[u] = -1 if slot is None else slot
+                try:
+                    homogeneous = qds.count(qds[0]) == len(qds)
+                except Exception:  # noqa: BLE001 - an exotic exponentiator with an array-valued __eq__
+                    homogeneous = False
+                if homogeneous:
+                    # time-homogeneous model: ONE exponentiator for every (edge, bin) -- tuple.count compares by
+                    # identity first, a C loop; the general path below costs ~25 us of numpy per evaluation
+                    slot = self._slot_for(st, qds[0])
                     if slot is not None:
                         live.add(slot)
-                per_entry = slot_of_uniq[inverse.reshape(-1)].reshape(E, K)
+                    per_entry = np.full((E, K), -1 if slot is None else slot, np.int32)
+                else:
+                    ids = np.fromiter(map(id, qds), dtype=np.int64, count=len(qds))
+                    _uniq, first, inverse = np.unique(ids, return_index=True, return_inverse=True)
+                    slot_of_uniq = np.empty(len(first), np.int32)
+                    for u, f in enumerate(first):
+                        slot = self._slot_for(st, qds[int(f)])
+                        slot_of_uniq[u] = -1 if slot is None else slot
+                        if slot is not None:
+                            live.add(slot)
+                    per_entry = slot_of_uniq[inverse.reshape(-1)].reshape(E, K)
                 qslots[edge_ids, :] = per_entry
                 if (per_entry < 0).any():
                     # not an eigen / Pade exponentiator: P on the host for those (edge, bin)s

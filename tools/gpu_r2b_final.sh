@@ -12,7 +12,7 @@ timeout 900 python bench.py > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_benc
 tail -c 600 $OUT/${TAG}_bench_reference.json; echo
 CMD="python bench.py --steps 2 --warmup 3 --no-extra --no-dropin --no-cpu"
 $CMD > $OUT/${TAG}_ncu_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/r2b_launches_c2.csv $CMD > $OUT/${TAG}_ncu_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:prune|expm|lnl_reduce' -c 300 --csv --log-file $OUT/r2b_launches_c2.csv $CMD > $OUT/${TAG}_ncu_launch.log 2>&1
 echo "launch list rc=$?"
 $CMD > $OUT/${TAG}_ncu_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:prune4_reg2 -s 21 -c 7 -o $OUT/r2b_prune4_reg2 -f $CMD > $OUT/${TAG}_ncu_full.log 2>&1
