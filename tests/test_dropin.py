@@ -154,6 +154,36 @@ def test_fast_gamma_rates_bit_identical():
     pickle.loads(pickle.dumps(lf))
 
 
+def test_accessors_between_streaming_evaluations():
+    """an alignment large enough for the streaming kernels (more than 8192 root patterns): the root launch then only
+    writes the class mixture (lean root) and per-pattern likelihoods are recomputed when an accessor asks --
+    lnL, per-column likelihoods, posterior bin probabilities and the G statistic against the stock class between
+    optimiser-style updates, and again after them"""
+    tree, aln = small_problem(n_tips=10, L=30_000, seed=12)
+    mk = lambda: get_model("GTR", ordered_param="rate", distribution="gamma")  # noqa: E731
+    ref, lf = pair(mk, tree, aln, bins=4)
+    for f in (ref, lf):
+        f.set_param_rule("rate_shape", value=0.7)
+    assert_same(ref, lf)
+    names = [e.name for e in tree.postorder() if e.name != "root"]
+    for k in range(12):  # more evaluations than an lh request keeps lh materialised for
+        for f in (ref, lf):
+            f.set_param_rule("length", edge=names[k % len(names)], value=0.03 + 0.01 * k)
+            if k % 5 == 4:
+                f.set_param_rule("A/G", value=2.0 + 0.1 * k)
+        assert_same(ref, lf)
+        if k in (0, 1, 11):
+            np.testing.assert_allclose(
+                lf.get_full_length_likelihoods(), ref.get_full_length_likelihoods(), rtol=1e-12, atol=1e-15
+            )
+            assert_same(ref, lf)  # (the request neither committed nor lost anything)
+    np.testing.assert_allclose(lf.get_bin_probs().array, ref.get_bin_probs().array, atol=1e-13)
+    assert lf.get_G_statistic() == pytest.approx(ref.get_G_statistic(), rel=1e-10)
+    if ON_GPU:
+        st = lf._engine().stats()
+        assert st["lean_evaluations"] > 0, st
+
+
 def test_gn_time_heterogeneous_pade():
     tree, aln = small_problem(n_tips=6, L=150, seed=8)
     ref, lf = pair(lambda: get_model("GN"), tree, aln, expm="pade")
