@@ -1889,6 +1889,14 @@ int c3_set_psub(c3_engine* e, int node, int bin, const double* P) {
   std::vector<double> padded((size_t)MP * MP, 0.0);
   for (int i = 0; i < M; ++i)
     for (int j = 0; j < M; ++j) padded[i * MP + j] = P[i * M + j];
+  // (lean root: per-pattern likelihoods of the LAST evaluation are recomputed from the P matrices on the device when
+  //  an accessor asks -- materialise them before this call overwrites one of those matrices)
+  if (!e->lh_valid && e->have_cached) {
+    const int keep = e->lh_keep;
+    const int rc = ensure_lh(e);
+    e->lh_keep = keep;
+    if (rc) return rc;
+  }
   C3_CUDA(cudaStreamSynchronize(e->stream));
   C3_CUDA(cudaMemcpy(e->d_P + ((int64_t)node * e->K + bin) * MP * MP, padded.data(),
                      padded.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -178,6 +178,7 @@ def fast_likelihood_tree_leaf(likelihood_tree, sequence, alphabet, seq_name):
 # ``lf.set_alignment`` needs every tip's table twice: for the motif counts (set_motif_probs_from_data) and for
 # the ``leaf_likelihoods`` Defn.  Same alignment, same sequence, same alphabet -> the same (immutable) leaf.
 _LEAF_CACHE: dict = {}
+_LEAF_CACHE_LOCK = __import__("threading").Lock()
 
 
 def cached_likelihood_tree_leaf(likelihood_tree, align, seq_name, recode_gaps, alphabet):
@@ -190,15 +191,16 @@ def cached_likelihood_tree_leaf(likelihood_tree, align, seq_name, recode_gaps, a
         if ref() is align and (alpha is alphabet or alpha == alphabet):
             return leaf
     leaf = fast_likelihood_tree_leaf(likelihood_tree, align.get_gapped_seq(seq_name, recode_gaps), alphabet, seq_name)
-    if len(_LEAF_CACHE) > 2048:
-        for k in [k for k, (ref, _a, _l) in _LEAF_CACHE.items() if ref() is None]:
-            del _LEAF_CACHE[k]
+    with _LEAF_CACHE_LOCK:  # (leaves of a large alignment are built by several threads: build_leaves)
         if len(_LEAF_CACHE) > 2048:
-            _LEAF_CACHE.clear()
-    try:
-        _LEAF_CACHE[key] = (weakref.ref(align), alphabet, leaf)
-    except TypeError:  # an alignment type without weak references: no caching
-        pass
+            for k in [k for k, (ref, _a, _l) in list(_LEAF_CACHE.items()) if ref() is None]:
+                _LEAF_CACHE.pop(k, None)
+            if len(_LEAF_CACHE) > 2048:
+                _LEAF_CACHE.clear()
+        try:
+            _LEAF_CACHE[key] = (weakref.ref(align), alphabet, leaf)
+        except TypeError:  # an alignment type without weak references: no caching
+            pass
     return leaf
 
 
@@ -227,6 +229,39 @@ def fast_likelihood_tree_edge(likelihood_tree, children, edge_name):
     ambigs = [child.ambig[ix] for (ix, child) in e._indexed_children]
     e.ambig = np.prod(ambigs, axis=0)
     return e
+
+
+def build_leaves(likelihood_tree, alignment, names, recode_gaps, alphabet):
+    """{name: LikelihoodTreeLeaf} for the sequences of one alignment (cached per alignment object); the leaves are
+    independent of each other: from 10^5 columns on they are built in a thread pool"""
+    names = list(names)
+    workers = _table_workers(len(alignment)) if names else 1
+
+    def leaf(name):
+        return cached_likelihood_tree_leaf(likelihood_tree, alignment, name, recode_gaps, alphabet)
+
+    if workers > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            return dict(zip(names, pool.map(leaf, names), strict=True))
+    return {name: leaf(name) for name in names}
+
+
+def _table_workers(n_columns):
+    """threads for building the pattern tables of one alignment: 1 below 10^5 columns (the pool would cost more than
+    it saves), else up to 8 (C3_TABLE_THREADS overrides)"""
+    import os
+
+    env = os.environ.get("C3_TABLE_THREADS")
+    if env is not None:
+        try:
+            return max(1, int(env))
+        except ValueError:
+            return 1
+    if n_columns < 100_000:
+        return 1
+    return max(1, min(8, os.cpu_count() or 1))
 
 
 # identity-keyed memo of a Defn's last few results (one per locus + undo); strong references, so
@@ -276,10 +311,7 @@ def _build(cogent3_modules):
             if type(model).convert_sequence is not _reference_convert_sequence(model):
                 return model.convert_alignment(alignment)  # a model with its own conversion
             alphabet = model.get_alphabet()
-            leaves = {
-                name: cached_likelihood_tree_leaf(likelihood_tree, alignment, name, model.recode_gaps, alphabet)
-                for name in alignment.names
-            }
+            leaves = build_leaves(likelihood_tree, alignment, alignment.names, model.recode_gaps, alphabet)
             return _memo_put(self, (model, alignment), leaves)
 
         __getstate__ = _memo_free_state
@@ -312,7 +344,29 @@ def _build(cogent3_modules):
                 kids = [build(child) for child in edge.children]
                 return fast_likelihood_tree_edge(likelihood_tree, kids, edge.name)
 
-            return _memo_put(self, (leaves,), build(self.tree))
+            n_columns = max((len(leaf.index) for leaf in leaves.values()), default=0)
+            workers = _table_workers(n_columns)
+            if workers <= 1:
+                return _memo_put(self, (leaves,), build(self.tree))
+            # large alignments: the nodes of one tree level are independent, and the ranking of a node's columns
+            # (numpy scatter / pandas hash table over 10^5..10^7 keys) runs without the GIL -- level by level in a
+            # thread pool.  Same function per node, same tables.
+            height, order = {}, list(self.tree.postorder())
+            for edge in order:
+                height[id(edge)] = 0 if edge.istip() else 1 + max(height[id(c)] for c in edge.children)
+            done = {id(e): leaves[e.name] for e in order if e.istip()}
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                for h in range(1, height[id(self.tree)] + 1):
+                    level = [e for e in order if height[id(e)] == h]
+                    made = pool.map(
+                        lambda e: fast_likelihood_tree_edge(likelihood_tree, [done[id(c)] for c in e.children], e.name),
+                        level,
+                    )
+                    for e, lht_edge in zip(level, made, strict=True):
+                        done[id(e)] = lht_edge
+            return _memo_put(self, (leaves,), done[id(self.tree)])
 
         __getstate__ = _memo_free_state
 
@@ -803,8 +857,9 @@ def _build(cogent3_modules):
                 )  # fmt: skip
             alpha = mm.get_counted_alphabet()
             counts = None
+            leaves = build_leaves(likelihood_tree, align, align.names, self.model.recode_gaps, alpha)
             for seq_name in align.names:
-                leaf = cached_likelihood_tree_leaf(likelihood_tree, align, seq_name, self.model.recode_gaps, alpha)
+                leaf = leaves[seq_name]
                 count = leaf.get_motif_counts(include_ambiguity=include_ambiguity)
                 counts = count.copy() if counts is None else counts + count
             if is_constant is None:

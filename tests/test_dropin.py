@@ -289,12 +289,23 @@ def _same_lht(a, b):
     return n
 
 
+@pytest.mark.parametrize("threads", [None, "3"])
 @pytest.mark.parametrize(
     "model,data",
     [("HKY85", "brca1"), ("GTR", "ambiguous"), ("CNFGTR", "codon"), ("GN", "small"), ("dinuc", "small")],
 )
-def test_fast_compression_builds_the_reference_tables(model, data):
+def test_fast_compression_builds_the_reference_tables(model, data, threads, monkeypatch):
+    """every table of every node equal to the reference's; also when the nodes of a tree level (and the leaves) are
+    built in a thread pool, as they are from 10^5 columns on (C3_TABLE_THREADS forces it here)"""
     from cogent3.evolve import substitution_model
+
+    from cogent3_b200 import dropin
+
+    if threads is None:
+        monkeypatch.delenv("C3_TABLE_THREADS", raising=False)
+    else:
+        monkeypatch.setenv("C3_TABLE_THREADS", threads)
+    dropin._LEAF_CACHE.clear()
 
     if data == "brca1":
         aln, tree = get_dataset("brca1"), get_dataset("mammal-tree")
