@@ -3254,6 +3254,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
         tail.n_rows = e->n_rows[e->root];
         tail.n_tiles = (int)((tail.n_rows + REDUCE_ROWS_PER_TILE - 1) / REDUCE_ROWS_PER_TILE);
         tail.sink = sink;
+        tail.tile_sums = e->d_tile_sums;
       }
       cudaError_t err = cudaLaunchKernelEx(&cfg, prune4_small_kernel<false>, a, d_small, ll.n_small, ll.n_work,
                                            ll.n_work + ll.n_small, tail, (unsigned*)nullptr);

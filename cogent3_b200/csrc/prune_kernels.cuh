@@ -654,6 +654,7 @@ struct ReduceTail {
   int64_t n_rows;
   int n_tiles;  // 0: no fused reduction
   ResultSink sink;
+  double* tile_sums = nullptr;  // small-levels launch: scratch for the per-tile sums (global memory)
 };
 
 // n_work_total / n_prefix_total: sizes of the launch's work and prefix arrays.  When they
@@ -765,22 +766,24 @@ prune4_small_kernel(const PruneArgs a, const SmallLevel* __restrict__ levels, in
     // the root was in this launch and the problem is small: the site-weighted reduction right here
     // (same tiles, same per-thread rows, same summation trees as lnl_reduce_kernel: same bits), by
     // the cluster's first CTA once every CTA's lh values are there
+    // -- the tiles dealt to the cluster's CTAs (one 1024-row tile each at brca1's size, instead of the first CTA
+    // taking them one after the other), then the first CTA adds the tile sums in index order
     cluster_barrier();
-    if (cluster_ctarank() != 0) return;
     __shared__ double s_warp[SMALL_THREADS / 32];
-    __shared__ double s_tiles[SMALL_REDUCE_MAX_TILES];
     const int t = (int)threadIdx.x;
-    for (int tile = 0; tile < tail.n_tiles; ++tile) {
+    const int rank = (int)cluster_ctarank(), n_rank = (int)cluster_nctarank();
+    for (int tile = rank; tile < tail.n_tiles; tile += n_rank) {
       const double acc = (t < REDUCE_THREADS)
                              ? reduce_tile_partial(a.lh_out, tail.bprobs, tail.counts, tail.n_rows, K, tile, t, nullptr)
                              : 0.0;
       const double total = block_sum(acc, s_warp);  // (the warps past REDUCE_THREADS add +0.0)
-      if (t == 0) s_tiles[tile] = total;
+      if (t == 0) tail.tile_sums[tile] = total;
     }
-    __syncthreads();
+    cluster_barrier();  // (release / acquire at cluster scope: the tile sums are visible to the first CTA)
+    if (rank != 0) return;
     double acc = 0.0;
     if (t < REDUCE_THREADS)
-      for (int i = t; i < tail.n_tiles; i += REDUCE_THREADS) acc += s_tiles[i];
+      for (int i = t; i < tail.n_tiles; i += REDUCE_THREADS) acc += __ldcg(tail.tile_sums + i);
     const double total = block_sum(acc, s_warp);
     if (t == 0) publish_result(tail.sink, total);
   }
