@@ -13,7 +13,10 @@ metric   pattern.edge partial updates/s = U_gp / time, with U_gp = K * sum over 
          the pattern rows at the edge's PARENT node, counted from the reference's own
          per-node compression tables -- the same numerator for GPU and CPU.
 value    steps timed on the device (CUDA events on the engine's stream), pattern tables
-         and partials resident in HBM, parameters arriving from the host each step.
+         and partials resident in HBM, parameters arriving from the host each step; every
+         step is a BLOCKING evaluation (the result is back on the host before the next
+         step is issued, as in an optimiser).  `pipelined`: the same steps issued back to
+         back (c3_evaluate_device), one synchronisation at the end.
 e2e      the same metric END TO END THROUGH THE PRODUCT: unmodified cogent3 (baseline/_ref)
          with cogent3_b200.install(); `calc = lf.make_calculator(); calc(x_k)` with every
          optimisable parameter changed -- the call the reference arm times: cogent3's own
@@ -28,6 +31,9 @@ cpu_baseline  unmodified cogent3 (kind "reference") on a bounded sample of the c
 c4       (default config, N = 1) the CNFGTR 61-state config measured the same way, roofline
          bound "tensor" against max(DMMA issue-loop peak, cuBLAS DGEMM 8192^3) of this run.
 c5_strong  (default config) the ONE 10M-column C5 alignment split over the N ranks.
+c1       (default config, N = 1) brca1: full evaluations, single-branch updates, 64 engines at
+         once, and `e2e.optimise`: lf.optimise(local=True) through the drop-in and through
+         stock cogent3 in the same process.
 
 With N>1 (torchrun) every rank holds its own column shard of the same size (weak
 scaling); the sum over ranks of the scalar lnL is fused into the reduction
