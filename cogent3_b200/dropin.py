@@ -110,6 +110,7 @@ class LazyPsub:
 def fast_gamma_rates(weights, a):
     from scipy.special import gammaincinv
 
+    given = weights
     weights = weights / np.sum(weights)
     percentiles = np.add.accumulate(weights) - weights * 0.5
     shape = np.asarray(a)
@@ -117,7 +118,7 @@ def fast_gamma_rates(weights, a):
             or not ((percentiles > 0) & (percentiles < 1)).all()):  # fmt: skip
         from cogent3.recalculation.definition import GammaDefn
 
-        return GammaDefn.calc(None, weights, a)
+        return GammaDefn.calc(None, given, a)  # (the weights as they came: the reference normalises them itself)
     medians = gammaincinv(shape, percentiles) * np.asarray(1 / a) + 0
     scale = np.sum(medians * weights)
     return medians / scale

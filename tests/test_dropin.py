@@ -138,8 +138,8 @@ def test_fast_gamma_rates_bit_identical():
         want, got = GammaDefn.calc(None, w, a), fast_gamma_rates(w, a)
         assert want.dtype == got.dtype and want.tobytes() == got.tobytes(), (w, a)
     # outside the plain case the reference's own code answers (an empty last bin puts a percentile at 1)
-    w = np.array([0.5, 0.5, 0.0])
-    np.testing.assert_array_equal(fast_gamma_rates(w, 0.7), GammaDefn.calc(None, w, 0.7))
+    for w in (np.array([0.5, 0.5, 0.0]), np.array([0.3, 0.3, 0.1, 0.0]), np.array([1.7, 0.9, 0.0])):
+        np.testing.assert_array_equal(fast_gamma_rates(w, 0.7), GammaDefn.calc(None, w, 0.7))
     tree, aln = small_problem()
     mk = lambda: get_model("GTR", ordered_param="rate", distribution="gamma")  # noqa: E731
     ref, lf = pair(mk, tree, aln, bins=4)
