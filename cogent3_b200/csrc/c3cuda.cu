@@ -150,6 +150,7 @@ struct c3_engine {
   // chain kernel (prune4_chain_kernel): single-branch updates of small 4-state problems walked per ROOT row through
   // composed gather tables, no barrier between the levels (C3_CHAIN=0 disables)
   bool use_chain = true;
+  bool skip_block_copy = false;  // (inside a batch capture: the batch's copy kernel brings every engine's block)
   // tree-walk kernel (prune4_walk_kernel): every other evaluation of such a problem -- full sweeps included -- the
   // same way, with a per-thread value stack for the dirty children
   // OPT-IN (C3_WALK=1): bit-identical, but brca1's full sweep walks in 45 us against the small-levels launch's 40 --
@@ -864,6 +865,7 @@ struct BatchGraph {
   std::vector<int64_t> n_launch;
   cudaGraphExec_t exec = nullptr;
   int seen = 0;
+  void* d_copies = nullptr;  // [n] BatchCopy: the engines' parameter blocks, copied by ONE kernel at the head of the graph
 };
 std::unordered_map<uint64_t, BatchGraph> g_batches;  // (single-threaded use, like the engines themselves)
 cudaEvent_t g_fork = nullptr;
@@ -871,8 +873,10 @@ std::vector<cudaEvent_t> g_joins;
 
 void clear_batches() {
   std::lock_guard<std::recursive_mutex> lock(g_batch_mutex);
-  for (auto& b : g_batches)
+  for (auto& b : g_batches) {
     if (b.second.exec) cudaGraphExecDestroy(b.second.exec);
+    if (b.second.d_copies) cudaFree(b.second.d_copies);
+  }
   g_batches.clear();
 }
 
@@ -1796,7 +1800,8 @@ int c3_finalize(c3_engine* e) {
   e->off_ops = b;     b += e->chain_ok ? align_up((int64_t)n_internal * sizeof(WalkOp), 16) : 0;
   e->off_jobs = b;    b += align_up((int64_t)N * K * sizeof(ExpmJob), 16);
   e->block_bytes = b;
-  C3_CUDA(cudaHostAlloc(&e->h_block, (size_t)b, cudaHostAllocDefault));
+  // (mapped: the copy kernel of a batch graph reads the block straight from this buffer)
+  C3_CUDA(cudaHostAlloc(&e->h_block, (size_t)b, cudaHostAllocMapped | cudaHostAllocPortable));
   std::memset(e->h_block, 0, (size_t)b);  // (the claim counters of the dynamic-strip launches travel as zeros)
   C3_CUDA(cudaMalloc(&e->d_block, (size_t)b));
   C3_CUDA(cudaStreamSynchronize(e->stream));
@@ -3100,7 +3105,7 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     e->tl_launches = tl_n + 1;
     return e->d_tl + 4 * tl_n++;
   };
-  if (!chain_fused) {  // (the fused chain launch carries its parameters by value)
+  if (!chain_fused && !e->skip_block_copy) {  // (the fused chain launch carries its parameters by value)
   C3_CUDA(cudaMemcpyAsync(e->d_block, e->h_block, (size_t)std::min(used, e->block_bytes),
                           cudaMemcpyHostToDevice, e->stream));
   if (!capturing) C3_CUDA(cudaEventRecord(e->block_copied, e->stream));  // the staging buffer is free again
@@ -3698,6 +3703,21 @@ int finish_deferred(c3_engine* e, double* host_out) {
   return C3_OK;
 }
 
+struct BatchCopy {
+  const int4* src;  // an engine's pinned parameter staging buffer (device alias)
+  int4* dst;        // its device copy
+  int64_t n16;      // 16-byte words
+};
+__global__ void __launch_bounds__(256) batch_copy_kernel(const BatchCopy* __restrict__ copies) {
+  const BatchCopy c = copies[blockIdx.x];
+  for (int64_t i = threadIdx.x; i < c.n16; i += blockDim.x) c.dst[i] = c.src[i];
+}
+// C3_BATCH_ONE_COPY=0: one copy node per engine inside a batch graph (the first version)
+const bool g_batch_one_copy = [] {
+  const char* env = getenv("C3_BATCH_ONE_COPY");
+  return env == nullptr || atoi(env) != 0;
+}();
+
 // ---- c3_evaluate_many as ONE graph ---------------------------------------------------------------
 // Small alignments are bound by the host's launch calls (~14 us per engine even with per-engine
 // graphs).  When the same set of engines keeps being evaluated with the same structures (bootstraps,
@@ -3739,6 +3759,27 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
       g_joins.push_back(ev);
     }
     cudaStream_t s0 = engines[0]->stream;
+    // the parameter blocks of the whole batch by ONE kernel at the head of the graph (it reads every engine's
+    // pinned staging buffer directly and writes the device copy): n separate host-to-device copy nodes of a few KB
+    // each serialise on the copy engine -- a third of a 64-engine brca1 batch
+    bool one_copy = g_batch_one_copy;
+    if (one_copy && bg.d_copies == nullptr) {
+      std::vector<BatchCopy> copies(n);
+      for (int i = 0; i < n; ++i) {
+        void* dev_alias = nullptr;
+        if (cudaHostGetDevicePointer(&dev_alias, engines[i]->h_block, 0) != cudaSuccess) {
+          cudaGetLastError();
+          one_copy = false;
+          break;
+        }
+        copies[i] = BatchCopy{reinterpret_cast<const int4*>(dev_alias), reinterpret_cast<int4*>(engines[i]->d_block),
+                              engines[i]->block_bytes / 16};
+      }
+      if (one_copy) {
+        C3_CUDA(cudaMalloc(&bg.d_copies, (size_t)n * sizeof(BatchCopy)));
+        C3_CUDA(cudaMemcpy(bg.d_copies, copies.data(), (size_t)n * sizeof(BatchCopy), cudaMemcpyHostToDevice));
+      }
+    }
     if (cudaStreamBeginCapture(s0, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
       cudaGetLastError();
       bg.seen = -(1 << 30);  // never again for this set of engines
@@ -3746,6 +3787,7 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
     }
     int rc = C3_OK;
     bool skipped = false;
+    if (one_copy) batch_copy_kernel<<<n, 256, 0, s0>>>(reinterpret_cast<const BatchCopy*>(bg.d_copies));
     cudaError_t err = cudaEventRecord(g_fork, s0);
     std::vector<uint64_t> hashes(n);
     std::vector<int64_t> n_launch(n);
@@ -3754,7 +3796,9 @@ int evaluate_many_batched(c3_engine** engines, int n, double* lnL, int* used) {
       if (e->stream != s0) err = cudaStreamWaitEvent(e->stream, g_fork, 0);
       if (err != cudaSuccess) break;
       e->batch_mode = 1;
+      e->skip_block_copy = one_copy;
       rc = run_evaluation(e, nullptr, false, nullptr, true);
+      e->skip_block_copy = false;
       e->batch_mode = 0;
       skipped = skipped || e->last_skipped;
       hashes[i] = e->last_sig_hash;
