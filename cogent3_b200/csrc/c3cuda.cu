@@ -2677,6 +2677,8 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
           op.slot[c] = (int8_t)slot_of[ch];
           busy[slot_of[ch]] = 0;  // (read before this node's own value is pushed: the slot may be taken again)
         }
+        const int kind = recompute[ch] ? 3 : (op.P[c] != nullptr ? 2 : 1);
+        op.shape = (uint8_t)(op.shape | (kind << (2 * c)));
       }
       op.out_slot = -1;
       if (n != e->root) {

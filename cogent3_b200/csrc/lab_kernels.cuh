@@ -1578,7 +1578,8 @@ struct WalkOp {
   int8_t out_slot;         // where this node's value goes (-1: nobody above needs it, the root)
   int8_t fixed_motif;
   int8_t is_root;
-  int8_t pad;
+  uint8_t shape;           // kind of child 0 | kind of child 1 << 2 | kind of child 2 << 4: 0 none, 1 memory without P
+                           // (a tip's pre-multiplied row), 2 memory with P (a clean internal node), 3 stack (dirty, P)
   int16_t p_idx[3];        // P[c] staged in shared memory: entry number ([K][16] doubles each), -1: none
   int16_t pad2;
   int64_t pad3;
@@ -1625,16 +1626,22 @@ prune4_walk_kernel(const PruneArgs a, const WalkOp* __restrict__ ops, int n_ops,
     if (j >= n_ops) return;
     const WalkOp& op = s_ops[j];
     ix[3] = (op.out != nullptr) ? __ldg(op.map_own + p) : -1;  // (negative: another root row stores this row)
+    const unsigned shape = op.shape;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      if (c < op.n_children && op.slot[c] < 0) ix[c] = __ldg(op.map_child[c] + p);  // (top bit masked at use: no wait here)
+    for (int c = 0; c < 3; ++c) {
+      const unsigned kind = (shape >> (2 * c)) & 3u;  // 1, 2: gathered from memory
+      if (kind == 1u || kind == 2u) ix[c] = __ldg(op.map_child[c] + p);  // (top bit masked at use: no wait here)
+    }
   };
   auto load_rows = [&](int j, const int32_t(&ix)[4], d4(&x)[3]) {
     if (j >= n_ops) return;
     const WalkOp& op = s_ops[j];
+    const unsigned shape = op.shape;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      if (c < op.n_children && op.slot[c] < 0) x[c] = ld256(op.src[c] + ((int64_t)(ix[c] & 0x7fffffff) * K + b) * 4);
+    for (int c = 0; c < 3; ++c) {
+      const unsigned kind = (shape >> (2 * c)) & 3u;
+      if (kind == 1u || kind == 2u) x[c] = ld256(op.src[c] + ((int64_t)(ix[c] & 0x7fffffff) * K + b) * 4);
+    }
   };
   // the P matrices of the walk into shared memory (read at use from global memory they cost every op an L2 round
   // trip per child -- a launch starts with a cold L1 -- which is what the first version spent its time on)
@@ -1649,18 +1656,47 @@ prune4_walk_kernel(const PruneArgs a, const WalkOp* __restrict__ ops, int n_ops,
   // stage to the next: a move would wait for the load it moves): after op j is computed from buffer q, the rows
   // of op j + 4 are requested into the same buffer with the indexes requested four ops earlier, and the indexes
   // of op j + 8 are requested -- an op costs a quarter of an L2 round trip
+  // one child's contribution, specialised on its kind (std::integral_constant tag): no predicate survives
+  auto child = [&](auto tag, const WalkOp& op, int c, const d4& xc) -> d4 {
+    constexpr int KIND = decltype(tag)::value;
+    d4 v = xc;
+    if constexpr (KIND == 3) v = pop(op.slot[c]);
+    if constexpr (KIND >= 2) return matvec4(s_P + ((int)op.p_idx[c] * K + b) * 16, v);
+    return v;
+  };
+  auto binary = [&](auto t0, auto t1, const WalkOp& op, const d4(&x)[3]) -> d4 {
+    const d4 y0 = child(t0, op, 0, x[0]), y1 = child(t1, op, 1, x[1]);
+    return d4{y0.x * y1.x, y0.y * y1.y, y0.z * y1.z, y0.w * y1.w};
+  };
+  using k1 = std::integral_constant<int, 1>;
+  using k2 = std::integral_constant<int, 2>;
+  using k3 = std::integral_constant<int, 3>;
   auto step = [&](d4(&x)[3], int32_t(&ix)[4], int32_t& own, int j) {
     const WalkOp& op = s_ops[j];
     d4 acc{1.0, 1.0, 1.0, 1.0};
+    // binary nodes (every node but a trifurcating root) through a body specialised on the two children's kinds:
+    // the generic loop below spends most of its ~220 instructions per node on predicates and descriptor decoding
+    switch (op.shape) {
+      case 1 | 1 << 2: acc = binary(k1{}, k1{}, op, x); break;
+      case 2 | 1 << 2: acc = binary(k2{}, k1{}, op, x); break;
+      case 3 | 1 << 2: acc = binary(k3{}, k1{}, op, x); break;
+      case 1 | 2 << 2: acc = binary(k1{}, k2{}, op, x); break;
+      case 2 | 2 << 2: acc = binary(k2{}, k2{}, op, x); break;
+      case 3 | 2 << 2: acc = binary(k3{}, k2{}, op, x); break;
+      case 1 | 3 << 2: acc = binary(k1{}, k3{}, op, x); break;
+      case 2 | 3 << 2: acc = binary(k2{}, k3{}, op, x); break;
+      case 3 | 3 << 2: acc = binary(k3{}, k3{}, op, x); break;
+      default:
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (c < op.n_children) {
-        const d4 v = (op.slot[c] >= 0) ? pop(op.slot[c]) : x[c];
-        d4 y = v;
-        if (op.p_idx[c] >= 0) y = matvec4(s_P + ((int)op.p_idx[c] * K + b) * 16, v);
-        if (c == 0) acc = y;
-        else { acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w; }
-      }
+        for (int c = 0; c < 3; ++c) {
+          if (c < op.n_children) {
+            const d4 v = (op.slot[c] >= 0) ? pop(op.slot[c]) : x[c];
+            d4 y = v;
+            if (op.p_idx[c] >= 0) y = matvec4(s_P + ((int)op.p_idx[c] * K + b) * 16, v);
+            if (c == 0) acc = y;
+            else { acc.x *= y.x; acc.y *= y.y; acc.z *= y.z; acc.w *= y.w; }
+          }
+        }
     }
     if (op.fixed_motif >= 0) {
       if (op.fixed_motif != 0) acc.x = 0.0;
