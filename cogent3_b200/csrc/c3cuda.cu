@@ -153,9 +153,9 @@ struct c3_engine {
   bool skip_block_copy = false;  // (inside a batch capture: the batch's copy kernel brings every engine's block)
   // tree-walk kernel (prune4_walk_kernel): every other evaluation of such a problem -- full sweeps included -- the
   // same way, with a per-thread value stack for the dirty children
-  // OPT-IN (C3_WALK=1): bit-identical, but brca1's full sweep walks in 45 us against the small-levels launch's 40 --
-  // ~220 instructions per node with 88 warps on the whole GPU (K = 1: 2764 units): latency of one warp's
-  // instruction stream, ncu profiles/r2_prune4_walk_ncu.txt; DESIGN lesson 17h
+  // OPT-IN (C3_WALK=1): bit-identical; brca1's full sweep walks in 31-34 us against the small-levels launch's 40, but
+  // every root row recomputes every node -- 64 engines at once run at 100k against 153k evaluations/s, a 64-taxon
+  // problem at 104 against 74 us (DESIGN lesson 17h, ncu of the first version: profiles/r2_prune4_walk_ncu.txt)
   bool use_walk = false;
   int64_t off_ops = 0;
   // C3_CHAIN_FUSED=1: a single-branch update in the real eigen form as ONE launch -- parameters by value, the
