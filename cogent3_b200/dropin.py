@@ -572,11 +572,17 @@ def _build(cogent3_modules):
             eng.set_fixed_motifs(fm)
             return self._finish(eng, blh)
 
-        def _finish(self, eng, blh=None):
+        def _finish(self, eng, blh=None, dist=None):
             lockstep = _batch.current()
             # inside cogent3_b200.batch.run_lockstep the evaluations of several optimiser threads meet in one
-            # c3_evaluate_many call; otherwise the engine is evaluated right here
-            value = eng.evaluate() if lockstep is None else lockstep.evaluate(eng)
+            # c3_evaluate_many call; otherwise the engine is evaluated right here -- distances
+            # and evaluation in ONE FFI crossing (c3_update) when the caller has not handed them over yet
+            if lockstep is None:
+                value = eng.evaluate() if dist is None else eng.update(dist)
+            else:
+                if dist is not None:
+                    eng.set_distances(dist)
+                value = lockstep.evaluate(eng)
             if self.return_lh:
                 # SiteHmm.__call__ (evolve/likelihood_calculation.py:265-269): its reduction over the sites --
                 # log_dot_reduce, a Python loop over every column (evolve/likelihood_tree.py:168-176) -- runs on
@@ -689,7 +695,6 @@ def _build(cogent3_modules):
                 if prev is None or prev[0] is not key[0] or prev[1] != key[1]:
                     eng.set_psub(node, b, np.asarray(ex(key[1]), float))
                     st["psub_obj"][(node, b)] = key
-            eng.set_distances(dist)
             # unchanged inputs keep object identity between calls (calculation.py:431-438)
             if st.get("last_mprobs") is not mprobs:
                 eng.set_root_mprobs(np.asarray(mprobs, float))
@@ -703,7 +708,7 @@ def _build(cogent3_modules):
                     fm[node] = -1 if f in (None, -1) else int(f)
                 eng.set_fixed_motifs(fm)
                 st["last_fixed"] = fixed
-            return self._finish(eng, blh)
+            return self._finish(eng, blh, dist=dist)
 
     def make_total_loglikelihood_defn(tree, leaves, psubs, mprobs, bprobs, bin_names, locus_names,
                                       sites_independent, engine_factory, device, factors=None, devices=None):  # fmt: skip

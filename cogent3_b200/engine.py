@@ -300,7 +300,11 @@ class LikelihoodEngine:
         return out.value
 
     def update(self, dist) -> float:
-        d = np.ascontiguousarray(np.broadcast_to(dist, (self.n_nodes, self.n_bins)), np.float64)
+        d = dist
+        if not (isinstance(d, np.ndarray) and d.dtype == np.float64 and d.shape == (self.n_nodes, self.n_bins)
+                and d.flags.c_contiguous):
+            d = np.ascontiguousarray(np.broadcast_to(dist, (self.n_nodes, self.n_bins)), np.float64)
+        self._dist = d
         out = c_double(0.0)
         _lib.check(self._lib.c3_update(self._h, _dptr(d), byref(out)))
         return out.value
