@@ -237,6 +237,7 @@ struct c3_engine {
   unsigned int* d_done = nullptr;  // per work item completion counters of the dataflow launches
   int64_t off_dep = 0;
   cudaEvent_t block_copied = nullptr;
+  bool block_free = false;  // the last evaluation's result has been collected: the staging buffer is free without asking
   // mapped pinned result: the value and, after it, the sequence number of the evaluation that wrote it
   // (the blocking path spins on that word instead of synchronising the stream)
   double* h_lnl = nullptr;
@@ -2400,7 +2401,10 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
   }
 
   // ---- expm jobs ----------------------------------------------------------------
-  C3_CUDA(cudaEventSynchronize(e->block_copied));  // staging buffer free again
+  // staging buffer free again?  (after a blocking evaluation whose result has been collected the stream is idle:
+  // nothing to wait for -- one driver call less on the latency path)
+  if (!e->block_free) C3_CUDA(cudaEventSynchronize(e->block_copied));
+  e->block_free = false;
   ExpmJob* jobs = reinterpret_cast<ExpmJob*>(e->h_block + e->off_jobs);
   int n_eigen = 0, n_pade = 0;
   std::vector<char> edge_touched(N, 0);
@@ -2777,7 +2781,9 @@ int run_evaluation(c3_engine* e, double* device_out, bool blocking, double* host
     }
     lv_nodes.emplace_back();
     lv_stream.push_back(0);
-    if (!streams) {
+    if (chain_launch || walk_launch || path_launch) {
+      // (every dirty node is in that one launch: nothing left to plan level by level)
+    } else if (!streams) {
       for (int l = 1; l <= e->n_levels; ++l) {
         lv_nodes.push_back(e->level_nodes[l]);
         lv_stream.push_back(0);
@@ -3654,6 +3660,7 @@ int collect_result(c3_engine* e) {
   if (synced) e->seq_issued = *e->h_seq;  // stream order: the words hold the last result whatever its number
   for (auto& r : e->prof) cudaEventElapsedTime(&r.ms, r.a, r.b);
   e->async_pending = false;  // stream order: everything issued before the reduction is through as well
+  e->block_free = true;      // ... the copy of the parameter block included
   e->cached_lnl = *e->h_lnl;
   e->have_cached = true;
   unsigned long long bits;
