@@ -243,7 +243,12 @@ C3_API int c3_update_many(c3_engine** engines, int n, const double* distances, i
 
 /* ---- accessors (what likelihood_function.py reads back) -------------------------
  * c3_get_lh: per-pattern root likelihood of one bin, "lh" Defn
- *             (likelihood_function.py:415-425); n_rows = root rows.
+ *             (likelihood_function.py:415-425); n_rows = root rows.  The values are those of
+ *             the LAST evaluation.  On large problems the root launch only keeps the class
+ *             mixture (nothing on the hot path reads lh[p][K]); the first accessor that asks
+ *             (c3_get_lh, c3_get_site_lh, c3_get_scaled_lh, c3_hmm_reduce) re-runs that one
+ *             launch with the lh output -- nothing is committed, pending input changes stay
+ *             pending -- and the next few evaluations write lh themselves.
  * c3_get_psub: "psubs" value (likelihood_function.py:272-320).
  * c3_get_partials: "plh" of one node and bin [n_rows x M].                     */
 C3_API int c3_get_lh(c3_engine* e, int bin, double* out, int64_t n_rows);
